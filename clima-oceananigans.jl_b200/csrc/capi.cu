@@ -1,0 +1,774 @@
+// capi.cu -- C ABI (include/ocean_b200.h), handles and the host-side orchestration of the
+// NonhydrostaticModel time step.  No torch types, no CPU fallback.
+#include "../../include/ocean_b200.h"
+#include "internal.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace ob {
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+static cudaStream_t g_stream = nullptr;
+static bool g_inited = false;
+
+void count_launch(int n) { g_launches += n; }
+cudaStream_t stream() { return g_stream; }
+
+static void ensure_device() {
+    if (g_inited) return;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw Error(std::string("no usable CUDA device (libocean_b200 has no CPU fallback): ") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    g_inited = true;
+}
+}  // namespace ob
+
+using namespace ob;
+
+#define API_BEGIN try {
+#define API_END                                              \
+    return 0;                                                \
+    }                                                        \
+    catch (const std::exception& e) {                        \
+        ob::g_err = e.what();                                \
+        return 1;                                            \
+    }                                                        \
+    catch (...) {                                            \
+        ob::g_err = "unknown error";                         \
+        return 2;                                            \
+    }
+
+// ---------------------------------------------------------------------------------------------
+// handle types
+// ---------------------------------------------------------------------------------------------
+struct ob200_grid {
+    int ftype;
+    ob200_grid_desc desc;                   // host copy (pointers cleared)
+    GridD<float> g32;
+    GridD<double> g64;
+    std::vector<void*> owned;
+    std::vector<double> dzF_h, dzC_h;       // Julia indices 0..Nz+1 (for the tridiagonal solver)
+    ~ob200_grid() { for (void* p : owned) cudaFree(p); }
+};
+
+struct ob200_field {
+    const ob200_grid* grid;
+    int loc[3];
+    ob200_bc bcs[6];
+    void* base = nullptr;                   // current buffer
+    void* alt = nullptr;                    // second buffer (prognostic fields of a model)
+    bool owns = true;
+    int psize[3];
+    ~ob200_field() {
+        if (owns) { if (base) cudaFree(base); if (alt) cudaFree(alt); }
+    }
+    template <class FT> FT* p0() const {
+        return (FT*)base + (grid->ftype == OB200_F32 ? grid->g32.off0 : grid->g64.off0);
+    }
+    template <class FT> FT* alt0() const {
+        return (FT*)alt + (grid->ftype == OB200_F32 ? grid->g32.off0 : grid->g64.off0);
+    }
+};
+
+struct ob200_poisson {
+    const ob200_grid* grid;
+    int kind;
+    PoissonPlan<float>* p32 = nullptr;
+    PoissonPlan<double>* p64 = nullptr;
+    ~ob200_poisson() { poisson_plan_destroy(p32); poisson_plan_destroy(p64); }
+};
+
+template <class FT> static const GridD<FT>& gridD(const ob200_grid* g);
+template <> const GridD<float>& gridD<float>(const ob200_grid* g) { return g->g32; }
+template <> const GridD<double>& gridD<double>(const ob200_grid* g) { return g->g64; }
+template <class FT> static PoissonPlan<FT>* planOf(ob200_poisson* s);
+template <> PoissonPlan<float>* planOf<float>(ob200_poisson* s) { return s->p32; }
+template <> PoissonPlan<double>* planOf<double>(ob200_poisson* s) { return s->p64; }
+
+static size_t fsize(const ob200_grid* g) { return g->ftype == OB200_F32 ? 4 : 8; }
+static size_t gtotal(const ob200_grid* g) { return (size_t)(g->ftype == OB200_F32 ? g->g32.total : g->g64.total); }
+
+// ---------------------------------------------------------------------------------------------
+// library / memory
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t ob200_version(void) { return OB200_VERSION; }
+
+extern "C" int32_t ob200_init(int32_t device) {
+    API_BEGIN
+    ensure_device();
+    OB_CUDA(cudaSetDevice(device));
+    OB_CUDA(cudaFree(0));
+    API_END
+}
+extern "C" int32_t ob200_set_stream(void* s) { ob::g_stream = (cudaStream_t)s; return 0; }
+extern "C" int32_t ob200_sync(void) {
+    API_BEGIN
+    ensure_device();
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    API_END
+}
+extern "C" size_t ob200_last_error(char* buf, size_t len) {
+    size_t n = ob::g_err.size();
+    if (buf && len) {
+        size_t m = std::min(n, len - 1);
+        memcpy(buf, ob::g_err.data(), m);
+        buf[m] = 0;
+    }
+    return n;
+}
+extern "C" int64_t ob200_launch_count(void) { return ob::g_launches.load(); }
+
+extern "C" int32_t ob200_malloc(void** p, size_t bytes) {
+    API_BEGIN
+    ensure_device();
+    OB_CUDA(cudaMalloc(p, std::max<size_t>(bytes, 1)));
+    API_END
+}
+extern "C" int32_t ob200_free(void* p) { API_BEGIN OB_CUDA(cudaFree(p)); API_END }
+extern "C" int32_t ob200_memset(void* p, int32_t v, size_t bytes) {
+    API_BEGIN OB_CUDA(cudaMemsetAsync(p, v, bytes, stream())); API_END
+}
+extern "C" int32_t ob200_upload(void* dst, const void* src, size_t bytes) {
+    API_BEGIN
+    OB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    API_END
+}
+extern "C" int32_t ob200_download(void* dst, const void* src, size_t bytes) {
+    API_BEGIN
+    OB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+static void build_gridD(ob200_grid* G, GridD<FT>& g) {
+    const ob200_grid_desc& D = G->desc;
+    int align = sizeof(FT) == 8 ? 4 : 8;       // 32-byte sectors
+    for (int d = 0; d < 3; ++d) {
+        g.N[d] = D.N[d]; g.H[d] = D.H[d]; g.topo[d] = D.topology[d];
+        g.regular[d] = D.regular[d];
+        g.L[d] = (FT)D.L[d];
+        g.d[d] = (FT)D.delta[d];
+        g.dC[d] = g.dF[d] = nullptr;
+        if (D.topology[d] == OB200_FLAT) {
+            if (D.N[d] != 1 || D.H[d] != 0) throw Error("Flat dimensions must have N = 1 and H = 0");
+            g.O[d] = 0; g.S[d] = 1; g.regular[d] = 1; g.d[d] = 1; g.L[d] = 1;
+        } else {
+            if (D.N[d] < 1 || D.H[d] < 1) throw Error("non-Flat dimensions need N >= 1 and H >= 1");
+            g.O[d] = d == 0 ? ((D.H[d] + align - 1) / align) * align : D.H[d];
+            g.S[d] = g.O[d] + D.N[d] + D.H[d] + 1;
+            if (d == 0) g.S[d] = ((g.S[d] + align - 1) / align) * align;
+        }
+    }
+    g.st[0] = 1; g.st[1] = g.S[0]; g.st[2] = (long long)g.S[0] * g.S[1];
+    g.total = (long long)g.S[0] * g.S[1] * g.S[2];
+    g.off0 = (g.O[0] - 1) * g.st[0] + (g.O[1] - 1) * g.st[1] + (g.O[2] - 1) * g.st[2];
+}
+
+template <class FT>
+static void upload_metrics(ob200_grid* G, GridD<FT>& g, const ob200_grid_desc* src) {
+    for (int d = 0; d < 3; ++d) {
+        if (g.regular[d]) continue;
+        for (int w = 0; w < 2; ++w) {
+            const double* h = w == 0 ? src->dC[d] : src->dF[d];
+            int first = w == 0 ? src->dC_first[d] : src->dF_first[d];
+            int len = w == 0 ? src->dC_len[d] : src->dF_len[d];
+            if (!h || len <= 0) throw Error("stretched dimension without metric vectors");
+            // need indices 1-H .. N+H for centers, 1-H .. N+H+1 for faces (when Bounded); clamp-extend
+            int lo = std::min(first, -g.H[d] - 1), hi = std::max(first + len - 1, g.N[d] + g.H[d] + 2);
+            std::vector<FT> v(hi - lo + 1);
+            for (int q = lo; q <= hi; ++q) {
+                int c = std::min(std::max(q, first), first + len - 1);
+                v[q - lo] = (FT)h[c - first];
+            }
+            FT* dptr = nullptr;
+            OB_CUDA(cudaMalloc(&dptr, v.size() * sizeof(FT)));
+            OB_CUDA(cudaMemcpy(dptr, v.data(), v.size() * sizeof(FT), cudaMemcpyHostToDevice));
+            G->owned.push_back(dptr);
+            (w == 0 ? g.dC[d] : g.dF[d]) = dptr - lo;
+        }
+    }
+}
+
+extern "C" int32_t ob200_grid_create(const ob200_grid_desc* desc, ob200_grid** out) {
+    API_BEGIN
+    ensure_device();
+    if (!desc || !out) throw Error("null argument");
+    if (desc->ftype != OB200_F32 && desc->ftype != OB200_F64) throw Error("ftype must be OB200_F32 or OB200_F64");
+    auto G = std::make_unique<ob200_grid>();
+    G->ftype = desc->ftype;
+    G->desc = *desc;
+    build_gridD(G.get(), G->g32);
+    build_gridD(G.get(), G->g64);
+    if (G->ftype == OB200_F32) upload_metrics(G.get(), G->g32, desc);
+    else upload_metrics(G.get(), G->g64, desc);
+    // vertical spacings on the host for the Fourier-tridiagonal solver (Julia indices 0..Nz+1)
+    int Nz = desc->N[2];
+    G->dzF_h.assign(Nz + 2, desc->delta[2]);
+    G->dzC_h.assign(Nz + 2, desc->delta[2]);
+    if (!desc->regular[2] && desc->topology[2] != OB200_FLAT) {
+        for (int k = 0; k <= Nz + 1; ++k) {
+            int cf = std::min(std::max(k, desc->dF_first[2]), desc->dF_first[2] + desc->dF_len[2] - 1);
+            int cc = std::min(std::max(k, desc->dC_first[2]), desc->dC_first[2] + desc->dC_len[2] - 1);
+            G->dzF_h[k] = desc->dF[2][cf - desc->dF_first[2]];
+            G->dzC_h[k] = desc->dC[2][cc - desc->dC_first[2]];
+        }
+    }
+    for (int d = 0; d < 3; ++d) { G->desc.dC[d] = nullptr; G->desc.dF[d] = nullptr; }
+    *out = G.release();
+    API_END
+}
+extern "C" int32_t ob200_grid_destroy(ob200_grid* g) { delete g; return 0; }
+
+// ---------------------------------------------------------------------------------------------
+// fields
+// ---------------------------------------------------------------------------------------------
+static void parent_size(const ob200_grid* g, const int loc[3], int ps[3]) {
+    for (int d = 0; d < 3; ++d) {
+        const ob200_grid_desc& D = g->desc;
+        if (D.topology[d] == OB200_FLAT) ps[d] = D.N[d];
+        else ps[d] = D.N[d] + 2 * D.H[d] + ((loc[d] == OB200_FACE && D.topology[d] == OB200_BOUNDED) ? 1 : 0);
+    }
+}
+
+static ob200_field* make_field(const ob200_grid* g, const int32_t loc[3], const ob200_bc bcs[6], bool two) {
+    auto f = std::make_unique<ob200_field>();
+    f->grid = g;
+    for (int d = 0; d < 3; ++d) f->loc[d] = loc[d];
+    for (int s = 0; s < 6; ++s) {
+        if (bcs) f->bcs[s] = bcs[s];
+        else {     // defaults: field_boundary_conditions.jl:13-30
+            int d = s / 2, t = g->desc.topology[d];
+            f->bcs[s].value = 0;
+            f->bcs[s].kind = t == OB200_PERIODIC ? OB200_BC_PERIODIC
+                           : t == OB200_FLAT ? OB200_BC_NONE
+                           : (loc[d] == OB200_CENTER ? OB200_BC_FLUX : OB200_BC_OPEN);
+        }
+    }
+    parent_size(g, f->loc, f->psize);
+    size_t bytes = gtotal(g) * fsize(g);
+    OB_CUDA(cudaMalloc(&f->base, bytes));
+    OB_CUDA(cudaMemsetAsync(f->base, 0, bytes, stream()));
+    if (two) {
+        OB_CUDA(cudaMalloc(&f->alt, bytes));
+        OB_CUDA(cudaMemsetAsync(f->alt, 0, bytes, stream()));
+    }
+    return f.release();
+}
+
+extern "C" int32_t ob200_field_create(const ob200_grid* g, const int32_t loc[3], const ob200_bc bcs[6],
+                                      ob200_field** out) {
+    API_BEGIN
+    if (!g || !loc || !out) throw Error("null argument");
+    *out = make_field(g, loc, bcs, false);
+    API_END
+}
+extern "C" int32_t ob200_field_destroy(ob200_field* f) { delete f; return 0; }
+extern "C" int32_t ob200_field_parent_size(const ob200_field* f, int32_t out[3]) {
+    for (int d = 0; d < 3; ++d) out[d] = f->psize[d];
+    return 0;
+}
+
+template <class FT>
+static void field_set_parent(ob200_field* f, const void* host) {
+    const GridD<FT>& g = gridD<FT>(f->grid);
+    size_t n = (size_t)f->psize[0] * f->psize[1] * f->psize[2];
+    FT* tmp = nullptr;
+    OB_CUDA(cudaMalloc(&tmp, n * sizeof(FT)));
+    OB_CUDA(cudaMemcpyAsync(tmp, host, n * sizeof(FT), cudaMemcpyHostToDevice, stream()));
+    launch_to_internal<FT>(g, f->psize, f->loc, tmp, (FT*)f->base);
+    if (f->alt) launch_to_internal<FT>(g, f->psize, f->loc, tmp, (FT*)f->alt);
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    cudaFree(tmp);
+}
+template <class FT>
+static void field_get_parent(const ob200_field* f, void* host) {
+    const GridD<FT>& g = gridD<FT>(f->grid);
+    size_t n = (size_t)f->psize[0] * f->psize[1] * f->psize[2];
+    FT* tmp = nullptr;
+    OB_CUDA(cudaMalloc(&tmp, n * sizeof(FT)));
+    launch_from_internal<FT>(g, f->psize, f->loc, (const FT*)f->base, tmp);
+    OB_CUDA(cudaMemcpyAsync(host, tmp, n * sizeof(FT), cudaMemcpyDeviceToHost, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    cudaFree(tmp);
+}
+extern "C" int32_t ob200_field_set_parent(ob200_field* f, const void* host) {
+    API_BEGIN
+    if (f->grid->ftype == OB200_F32) field_set_parent<float>(f, host);
+    else field_set_parent<double>(f, host);
+    API_END
+}
+extern "C" int32_t ob200_field_get_parent(const ob200_field* f, void* host) {
+    API_BEGIN
+    if (f->grid->ftype == OB200_F32) field_get_parent<float>(f, host);
+    else field_get_parent<double>(f, host);
+    API_END
+}
+extern "C" int32_t ob200_field_device_view(const ob200_field* f, void** base, int64_t off[1], int64_t st[3]) {
+    const ob200_grid* G = f->grid;
+    bool s = G->ftype == OB200_F32;
+    *base = f->base;
+    off[0] = s ? G->g32.off0 + G->g32.st[0] + G->g32.st[1] + G->g32.st[2]
+               : G->g64.off0 + G->g64.st[0] + G->g64.st[1] + G->g64.st[2];
+    for (int d = 0; d < 3; ++d) st[d] = s ? G->g32.st[d] : G->g64.st[d];
+    return 0;
+}
+
+template <class FT>
+static void fill_halos(ob200_field* const* fields, int n) {
+    if (n == 0) return;
+    const ob200_grid* G = fields[0]->grid;
+    const GridD<FT>& g = gridD<FT>(G);
+    for (int start = 0; start < n; start += MAXF) {
+        HaloBatch<FT> hb;
+        hb.n = std::min(MAXF, n - start);
+        for (int q = 0; q < hb.n; ++q) {
+            ob200_field* f = fields[start + q];
+            if (f->grid != G) throw Error("fill_halo_regions: fields live on different grids");
+            hb.p0[q] = f->p0<FT>();
+            for (int d = 0; d < 3; ++d) hb.loc[q][d] = f->loc[d];
+            for (int s = 0; s < 6; ++s) { hb.bc_kind[q][s] = f->bcs[s].kind; hb.bc_val[q][s] = (FT)f->bcs[s].value; }
+        }
+        launch_fill_halos<FT>(g, hb);
+    }
+}
+extern "C" int32_t ob200_fill_halo_regions(ob200_field* const* fields, int32_t n) {
+    API_BEGIN
+    if (n <= 0) return 0;
+    if (fields[0]->grid->ftype == OB200_F32) fill_halos<float>(fields, n);
+    else fill_halos<double>(fields, n);
+    API_END
+}
+
+static double* g_red = nullptr;
+static double* red_buf() {
+    if (!g_red) OB_CUDA(cudaMalloc(&g_red, 8 * sizeof(double)));
+    return g_red;
+}
+extern "C" int32_t ob200_field_reduce(const ob200_field* f, double* sum, double* sumsq, double* maxabs,
+                                      int32_t* has_nan) {
+    API_BEGIN
+    int n[3];
+    for (int d = 0; d < 3; ++d) {
+        const ob200_grid_desc& D = f->grid->desc;
+        n[d] = D.N[d] + ((f->loc[d] == OB200_FACE && D.topology[d] == OB200_BOUNDED) ? 1 : 0);
+    }
+    double* r = red_buf();
+    if (f->grid->ftype == OB200_F32) launch_reduce<float>(f->grid->g32, f->p0<float>(), n, r);
+    else launch_reduce<double>(f->grid->g64, f->p0<double>(), n, r);
+    double h[4];
+    OB_CUDA(cudaMemcpyAsync(h, r, sizeof(h), cudaMemcpyDeviceToHost, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    if (sum) *sum = h[0];
+    if (sumsq) *sumsq = h[1];
+    if (maxabs) *maxabs = h[2];
+    if (has_nan) *has_nan = h[3] > 0;
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// Poisson solvers
+// ---------------------------------------------------------------------------------------------
+static int pick_solver(const ob200_grid* g, int kind) {
+    const ob200_grid_desc& D = g->desc;
+    if (kind == OB200_SOLVER_AUTO)     // NonhydrostaticModels.jl:18-27
+        kind = (D.regular[0] && D.regular[1] && D.regular[2]) ? OB200_SOLVER_FFT : OB200_SOLVER_FOURIER_TRIDIAGONAL;
+    if (kind == OB200_SOLVER_FFT && !(D.regular[0] && D.regular[1] && D.regular[2]))
+        throw Error("FFTBasedPoissonSolver requires a regular grid");
+    if (kind == OB200_SOLVER_FOURIER_TRIDIAGONAL) {
+        if (D.topology[2] != OB200_BOUNDED)
+            throw Error("FourierTridiagonalPoissonSolver can only be used with a Bounded z topology.");
+        if (!(D.regular[0] && D.regular[1])) throw Error("FourierTridiagonalPoissonSolver requires regular x and y");
+    }
+    return kind;
+}
+extern "C" int32_t ob200_poisson_create(const ob200_grid* g, int32_t kind, ob200_poisson** out) {
+    API_BEGIN
+    ensure_device();
+    auto s = std::make_unique<ob200_poisson>();
+    s->grid = g;
+    s->kind = pick_solver(g, kind);
+    if (g->ftype == OB200_F32) s->p32 = poisson_plan_create<float>(g->g32, s->kind, g->dzF_h.data(), g->dzC_h.data());
+    else s->p64 = poisson_plan_create<double>(g->g64, s->kind, g->dzF_h.data(), g->dzC_h.data());
+    *out = s.release();
+    API_END
+}
+extern "C" int32_t ob200_poisson_destroy(ob200_poisson* s) { delete s; return 0; }
+
+template <class FT> struct C2 { FT x, y; };
+
+template <class FT>
+static void poisson_solve_host(ob200_poisson* s, ob200_field* phi, const void* rhs_host) {
+    const ob200_grid* G = s->grid;
+    const GridD<FT>& g = gridD<FT>(G);
+    PoissonPlan<FT>* p = planOf<FT>(s);
+    if (rhs_host) {
+        size_t n = (size_t)g.N[0] * g.N[1] * g.N[2];
+        std::vector<C2<FT>> h(n);
+        const FT* r = (const FT*)rhs_host;
+        for (size_t q = 0; q < n; ++q) {
+            FT v = r[q];
+            if (s->kind == OB200_SOLVER_FOURIER_TRIDIAGONAL) {       // set_source_term!: times Δzᶜ
+                int k = (int)(q / ((size_t)g.N[0] * g.N[1]));
+                v = v * (FT)G->dzC_h[k + 1];
+            }
+            h[q].x = v; h[q].y = 0;
+        }
+        OB_CUDA(cudaMemcpyAsync(poisson_storage(p), h.data(), n * sizeof(C2<FT>), cudaMemcpyHostToDevice, stream()));
+        OB_CUDA(cudaStreamSynchronize(stream()));
+    }
+    poisson_solve<FT>(p, g, phi->p0<FT>());
+}
+extern "C" int32_t ob200_poisson_solve(ob200_poisson* s, ob200_field* phi, const void* rhs_host) {
+    API_BEGIN
+    if (s->grid != phi->grid) throw Error("solver and field live on different grids");
+    if (s->grid->ftype == OB200_F32) poisson_solve_host<float>(s, phi, rhs_host);
+    else poisson_solve_host<double>(s, phi, rhs_host);
+    API_END
+}
+
+template <class FT>
+static void solve_for_pressure_T(ob200_poisson* s, ob200_field* p, double dt, const ob200_field* u,
+                                 const ob200_field* v, const ob200_field* w) {
+    using CT = typename std::conditional<sizeof(FT) == 4, float2, double2>::type;
+    const GridD<FT>& g = gridD<FT>(s->grid);
+    PoissonPlan<FT>* pl = planOf<FT>(s);
+    launch_pressure_rhs<FT, CT>(g, u->p0<FT>(), v->p0<FT>(), w->p0<FT>(), (FT)dt,
+                                s->kind == OB200_SOLVER_FOURIER_TRIDIAGONAL, (CT*)poisson_storage(pl));
+    poisson_solve<FT>(pl, g, p->p0<FT>());
+}
+extern "C" int32_t ob200_solve_for_pressure(ob200_poisson* s, ob200_field* p, double dt, const ob200_field* u,
+                                            const ob200_field* v, const ob200_field* w) {
+    API_BEGIN
+    if (s->grid->ftype == OB200_F32) solve_for_pressure_T<float>(s, p, dt, u, v, w);
+    else solve_for_pressure_T<double>(s, p, dt, u, v, w);
+    API_END
+}
+
+template <class FT>
+static void tridiag_host(int cplx, int Nx, int Ny, int Nz, const double* a, const double* b, const double* c,
+                         const void* rhs, void* phi) {
+    size_t n = (size_t)Nx * Ny * Nz, es = sizeof(FT) * (cplx ? 2 : 1);
+    double *da, *db, *dc;
+    void *dr, *dp;
+    FT* dt;
+    OB_CUDA(cudaMalloc(&da, std::max(1, Nz - 1) * sizeof(double)));
+    OB_CUDA(cudaMalloc(&dc, std::max(1, Nz - 1) * sizeof(double)));
+    OB_CUDA(cudaMalloc(&db, n * sizeof(double)));
+    OB_CUDA(cudaMalloc(&dr, n * es));
+    OB_CUDA(cudaMalloc(&dp, n * es));
+    OB_CUDA(cudaMalloc(&dt, n * sizeof(FT)));
+    OB_CUDA(cudaMemcpy(da, a, (Nz - 1) * sizeof(double), cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemcpy(dc, c, (Nz - 1) * sizeof(double), cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemcpy(db, b, n * sizeof(double), cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemcpy(dr, rhs, n * es, cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemset(dp, 0, n * es));
+    OB_CUDA(cudaMemset(dt, 0, n * sizeof(FT)));
+    batched_tridiagonal<FT>(Nx, Ny, Nz, cplx != 0, da, db, dc, dr, dp, dt);
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    OB_CUDA(cudaMemcpy(phi, dp, n * es, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dc); cudaFree(dr); cudaFree(dp); cudaFree(dt);
+}
+extern "C" int32_t ob200_batched_tridiagonal_solve(int32_t ftype, int32_t cplx, int32_t Nx, int32_t Ny, int32_t Nz,
+                                                   const double* a, const double* b, const double* c,
+                                                   const void* rhs, void* phi) {
+    API_BEGIN
+    ensure_device();
+    if (ftype == OB200_F32) tridiag_host<float>(cplx, Nx, Ny, Nz, a, b, c, rhs, phi);
+    else tridiag_host<double>(cplx, Nx, Ny, Nz, a, b, c, rhs, phi);
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------
+struct ob200_model {
+    ob200_model_desc desc;
+    const ob200_grid* grid;
+    int nf;                                         // prognostic fields: 3 + ntracers
+    std::vector<std::unique_ptr<ob200_field>> F;    // state (two buffers each)
+    std::vector<std::unique_ptr<ob200_field>> Gn, Gm;
+    std::unique_ptr<ob200_field> pNHS, pHY;
+    std::unique_ptr<ob200_poisson> solver;
+    std::vector<void*> owned;
+    Phys<float> P32;
+    Phys<double> P64;
+    double time = 0, previous_dt = 1.0 / 0.0;
+    long long iteration = 0;
+    bool use_fast = true;
+    ~ob200_model() { for (void* p : owned) cudaFree(p); }
+};
+template <class FT> static Phys<FT>& physOf(ob200_model* m);
+template <> Phys<float>& physOf<float>(ob200_model* m) { return m->P32; }
+template <> Phys<double>& physOf<double>(ob200_model* m) { return m->P64; }
+
+template <class FT>
+static void build_phys(ob200_model* m) {
+    Phys<FT>& P = physOf<FT>(m);
+    const ob200_model_desc& D = m->desc;
+    P.g = gridD<FT>(m->grid);
+    P.scheme = D.advection;
+    P.zweno = D.weno_zweno;
+    static const int buf[7] = {0, 0, 1, 1, 1, 2, 2};
+    P.buffer = buf[D.advection];
+    for (int d = 0; d < 3; ++d)
+        for (int l = 0; l < 2; ++l) {
+            P.wc[d][l] = nullptr;
+            if (D.advection == OB200_ADV_WENO5 && D.weno_coeff[d][l]) {
+                size_t n = 4 * (size_t)(P.g.N[d] + 2) * 3;
+                std::vector<FT> h(n);
+                for (size_t q = 0; q < n; ++q) h[q] = (FT)D.weno_coeff[d][l][q];
+                FT* dp = nullptr;
+                OB_CUDA(cudaMalloc(&dp, n * sizeof(FT)));
+                OB_CUDA(cudaMemcpy(dp, h.data(), n * sizeof(FT), cudaMemcpyHostToDevice));
+                m->owned.push_back(dp);
+                P.wc[d][l] = dp;
+            }
+        }
+    P.closure = D.closure;
+    P.nu = (FT)D.nu;
+    for (int t = 0; t < 8; ++t) P.kappa[t] = (FT)D.kappa[t];
+    P.fplane = D.coriolis_fplane;
+    P.f = (FT)D.f;
+    P.btr = D.buoyancy_tracer;
+    P.tilted = D.gravity_tilted;
+    for (int d = 0; d < 3; ++d) P.ghat[d] = (FT)D.g_hat[d];
+    P.ntr = D.ntracers;
+}
+
+extern "C" int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model** out) {
+    API_BEGIN
+    ensure_device();
+    if (!desc || !desc->grid || !out) throw Error("null argument");
+    if (desc->ntracers < 0 || desc->ntracers > OB200_MAX_TRACERS) throw Error("too many tracers");
+    if (desc->advection < 0 || desc->advection > OB200_ADV_WENO5) throw Error("unsupported advection scheme");
+    if (desc->closure < 0 || desc->closure > OB200_CLOSURE_VERTICAL) throw Error("unsupported closure");
+    if (desc->buoyancy_tracer >= desc->ntracers) throw Error("buoyancy tracer index out of range");
+    const ob200_grid_desc& GD = desc->grid->desc;
+    // required halo: Advection.jl:40 (buffer + 1), closures need 1
+    static const int need[7] = {1, 1, 2, 2, 2, 3, 3};
+    for (int d = 0; d < 3; ++d)
+        if (GD.topology[d] != OB200_FLAT && GD.H[d] < need[desc->advection])
+            throw Error("grid halo too small for the advection scheme (the host shim must inflate it, "
+                        "nonhydrostatic_model.jl:140-148)");
+    auto m = std::make_unique<ob200_model>();
+    m->desc = *desc;
+    m->grid = desc->grid;
+    m->nf = 3 + desc->ntracers;
+    for (int q = 0; q < m->nf; ++q) {
+        int32_t loc[3] = {OB200_CENTER, OB200_CENTER, OB200_CENTER};
+        if (q < 3) loc[q] = OB200_FACE;
+        m->F.emplace_back(make_field(m->grid, loc, desc->bcs[q], true));
+        m->Gn.emplace_back(make_field(m->grid, loc, nullptr, false));
+        m->Gm.emplace_back(make_field(m->grid, loc, nullptr, false));
+    }
+    int32_t ccc[3] = {0, 0, 0};
+    m->pNHS.reset(make_field(m->grid, ccc, nullptr, false));
+    if (GD.topology[2] != OB200_FLAT) m->pHY.reset(make_field(m->grid, ccc, nullptr, false));
+    ob200_poisson* s = nullptr;
+    if (ob200_poisson_create(m->grid, desc->pressure_solver, &s)) throw Error(ob::g_err);
+    m->solver.reset(s);
+    if (m->grid->ftype == OB200_F32) build_phys<float>(m.get());
+    else build_phys<double>(m.get());
+    for (int d = 0; d < 3; ++d) for (int l = 0; l < 2; ++l) m->desc.weno_coeff[d][l] = nullptr;
+    *out = m.release();
+    if (ob200_model_update_state(*out)) { delete *out; *out = nullptr; throw Error(ob::g_err); }
+    API_END
+}
+extern "C" int32_t ob200_model_destroy(ob200_model* m) { delete m; return 0; }
+
+extern "C" int32_t ob200_model_field(ob200_model* m, const char* name, ob200_field** out) {
+    API_BEGIN
+    std::string s(name);
+    auto idx = [&](const std::string& t) -> int {
+        if (t == "u") return 0;
+        if (t == "v") return 1;
+        if (t == "w") return 2;
+        if (t.size() >= 2 && t[0] == 'c') {
+            int k = std::stoi(t.substr(1));
+            if (k >= 0 && k < m->desc.ntracers) return 3 + k;
+        }
+        return -1;
+    };
+    ob200_field* f = nullptr;
+    if (s == "pNHS") f = m->pNHS.get();
+    else if (s == "pHY") f = m->pHY.get();
+    else if (s.rfind("Gn_", 0) == 0) { int q = idx(s.substr(3)); if (q >= 0) f = m->Gn[q].get(); }
+    else if (s.rfind("Gm_", 0) == 0) { int q = idx(s.substr(3)); if (q >= 0) f = m->Gm[q].get(); }
+    else { int q = idx(s); if (q >= 0) f = m->F[q].get(); }
+    if (!f) throw Error("no such model field: " + s);
+    *out = f;
+    API_END
+}
+
+template <class FT>
+static void model_fill_state_halos(ob200_model* m, int first, int last) {
+    std::vector<ob200_field*> v;
+    for (int q = first; q < last; ++q) v.push_back(m->F[q].get());
+    fill_halos<FT>(v.data(), (int)v.size());
+}
+
+template <class FT>
+static void model_update_state(ob200_model* m, bool tracers_too = true) {
+    // update_nonhydrostatic_model_state.jl:14-37
+    model_fill_state_halos<FT>(m, 0, tracers_too ? m->nf : 3);
+    if (m->pHY) {
+        const GridD<FT>& g = gridD<FT>(m->grid);
+        Phys<FT>& P = physOf<FT>(m);
+        bool has_b = P.btr >= 0;
+        const FT* b = has_b ? m->F[3 + P.btr]->template p0<FT>() : nullptr;
+        FT gz = (has_b && P.tilted) ? P.ghat[2] : FT(1);
+        launch_hydrostatic_pressure<FT>(g, b, gz, has_b, m->pHY->template p0<FT>());
+        ob200_field* ph = m->pHY.get();
+        fill_halos<FT>(&ph, 1);
+    }
+}
+extern "C" int32_t ob200_model_update_state(ob200_model* m) {
+    API_BEGIN
+    if (m->grid->ftype == OB200_F32) model_update_state<float>(m);
+    else model_update_state<double>(m);
+    API_END
+}
+
+template <class FT>
+static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
+    Phys<FT>& P = physOf<FT>(m);
+    const FT* U[3] = {m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(), m->F[2]->template p0<FT>()};
+    const FT* pHY = m->pHY ? m->pHY->template p0<FT>() : nullptr;
+    const FT* b = P.btr >= 0 ? m->F[3 + P.btr]->template p0<FT>() : nullptr;
+    for (int q = 0; q < m->nf; ++q) {
+        ob200_field* f = m->F[q].get();
+        FluxBC<FT> fbc;
+        for (int s = 0; s < 6; ++s) { fbc.kind[s] = f->bcs[s].kind; fbc.val[s] = (FT)f->bcs[s].value; }
+        FT* newp = ss.mode == SUB_NONE ? nullptr : f->template alt0<FT>();
+        bool done = false;
+        if (m->use_fast)
+            done = launch_tendency_fast<FT>(P, q, U, f->template p0<FT>(), pHY, m->Gn[q]->template p0<FT>(),
+                                            m->Gm[q]->template p0<FT>(), newp, ss);
+        if (!done)
+            launch_tendency_general<FT>(P, q, U, f->template p0<FT>(), pHY, b, fbc, m->Gn[q]->template p0<FT>(),
+                                        m->Gm[q]->template p0<FT>(), newp, ss);
+    }
+    if (ss.mode != SUB_NONE) {
+        // the out-of-place substep wrote the new state into the second buffer: swap.  Cells the
+        // kernels never write (wall faces, outer halos of Bounded dims) are refreshed by the halo
+        // fill that always follows, or are never read, exactly as in the reference.
+        for (int q = 0; q < m->nf; ++q) std::swap(m->F[q]->base, m->F[q]->alt);
+    }
+}
+extern "C" int32_t ob200_model_calculate_tendencies(ob200_model* m) {
+    API_BEGIN
+    if (m->grid->ftype == OB200_F32) { Substep<float> s{SUB_NONE, 0, 0, 0}; model_tendencies<float>(m, s); }
+    else { Substep<double> s{SUB_NONE, 0, 0, 0}; model_tendencies<double>(m, s); }
+    API_END
+}
+
+template <class FT>
+static void model_pressure_step(ob200_model* m, FT dt) {
+    // calculate_pressure_correction! + pressure_correct_velocities! (pressure_correction.jl:10-56)
+    const GridD<FT>& g = gridD<FT>(m->grid);
+    model_fill_state_halos<FT>(m, 0, 3);
+    solve_for_pressure_T<FT>(m->solver.get(), m->pNHS.get(), (double)dt, m->F[0].get(), m->F[1].get(), m->F[2].get());
+    ob200_field* pn = m->pNHS.get();
+    fill_halos<FT>(&pn, 1);
+    launch_pressure_correct<FT>(g, m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(),
+                                m->F[2]->template p0<FT>(), m->pNHS->template p0<FT>(), dt);
+}
+extern "C" int32_t ob200_model_pressure_project(ob200_model* m, double dt) {
+    API_BEGIN
+    if (m->grid->ftype == OB200_F32) model_pressure_step<float>(m, (float)dt);
+    else model_pressure_step<double>(m, dt);
+    API_END
+}
+
+template <class FT>
+static void model_time_step(ob200_model* m, double dt_in, bool euler) {
+    FT dt = (FT)dt_in;
+    if (m->desc.timestepper == OB200_TS_RK3) {
+        // runge_kutta_3.jl:81-152; γ, ζ stored as FT (:57-66)
+        if (m->iteration == 0) model_update_state<FT>(m);
+        const FT g1 = FT(8.0 / 15.0), g2 = FT(5.0 / 12.0), g3 = FT(3.0 / 4.0);
+        const FT z2 = FT(-17.0 / 60.0), z3 = FT(-5.0 / 12.0);
+        FT sdt[3] = {g1 * dt, (g2 + z2) * dt, (g3 + z3) * dt};
+        Substep<FT> ss[3] = {{SUB_RK3_FIRST, dt, dt * g1, 0}, {SUB_RK3, dt, g2, z2}, {SUB_RK3, dt, g3, z3}};
+        for (int s = 0; s < 3; ++s) {
+            model_tendencies<FT>(m, ss[s]);
+            model_pressure_step<FT>(m, sdt[s]);
+            m->time += (double)sdt[s];
+            if (s < 2) for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);   // store_tendencies!
+            model_update_state<FT>(m);
+        }
+        m->iteration += 1;
+    } else {
+        // quasi_adams_bashforth_2.jl:70-104
+        euler = euler || (dt_in != m->previous_dt);
+        FT chi = euler ? FT(-0.5) : (FT)m->desc.chi;
+        if (euler)
+            for (int q = 0; q < m->nf; ++q)
+                OB_CUDA(cudaMemsetAsync(m->Gm[q]->base, 0, gtotal(m->grid) * sizeof(FT), stream()));
+        m->previous_dt = dt_in;
+        if (m->iteration == 0) model_update_state<FT>(m);
+        Substep<FT> ss{SUB_AB2, dt, FT(1.5) + chi, FT(0.5) + chi};
+        model_tendencies<FT>(m, ss);
+        model_pressure_step<FT>(m, dt);
+        for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);
+        m->time += (double)dt;
+        m->iteration += 1;
+        model_update_state<FT>(m);
+    }
+}
+extern "C" int32_t ob200_model_time_step(ob200_model* m, double dt, int32_t euler) {
+    API_BEGIN
+    if (m->grid->ftype == OB200_F32) model_time_step<float>(m, dt, euler != 0);
+    else model_time_step<double>(m, dt, euler != 0);
+    API_END
+}
+
+extern "C" int32_t ob200_model_clock(const ob200_model* m, double* t, int64_t* it) {
+    if (t) *t = m->time;
+    if (it) *it = m->iteration;
+    return 0;
+}
+extern "C" int32_t ob200_model_set_clock(ob200_model* m, double t, int64_t it, double pdt) {
+    m->time = t; m->iteration = it; m->previous_dt = pdt;
+    return 0;
+}
+
+extern "C" int32_t ob200_model_diagnostics(ob200_model* m, double* maxdiv, double* ke) {
+    API_BEGIN
+    double* r = red_buf();
+    double h[4];
+    if (maxdiv) {
+        if (m->grid->ftype == OB200_F32)
+            launch_max_divergence<float>(m->grid->g32, m->F[0]->p0<float>(), m->F[1]->p0<float>(), m->F[2]->p0<float>(), r);
+        else
+            launch_max_divergence<double>(m->grid->g64, m->F[0]->p0<double>(), m->F[1]->p0<double>(), m->F[2]->p0<double>(), r);
+        OB_CUDA(cudaMemcpyAsync(h, r, sizeof(h), cudaMemcpyDeviceToHost, stream()));
+        OB_CUDA(cudaStreamSynchronize(stream()));
+        *maxdiv = h[3] > 0 ? (0.0 / 0.0) : h[2];
+    }
+    if (ke) {
+        double acc = 0;
+        for (int q = 0; q < 3; ++q) {
+            double s2 = 0;
+            if (ob200_field_reduce(m->F[q].get(), nullptr, &s2, nullptr, nullptr)) throw Error(ob::g_err);
+            acc += s2;
+        }
+        *ke = 0.5 * acc;
+    }
+    API_END
+}
+
+// knob used by tests to force the general kernels
+extern "C" int32_t ob200_model_use_fast_kernels(ob200_model* m, int32_t on) { m->use_fast = on != 0; return 0; }

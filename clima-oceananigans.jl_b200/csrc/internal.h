@@ -1,0 +1,77 @@
+// internal.h -- host-side launcher declarations shared by the translation units.
+#pragma once
+#include "common.cuh"
+#include "physics.cuh"
+
+namespace ob {
+
+constexpr int MAXF = 12;   // max fields in one batched halo launch
+
+// ---- kernels.cu ---------------------------------------------------------------------------
+template <class FT>
+struct HaloBatch {
+    int n;
+    FT* p0[MAXF];          // Julia-(0,0,0) pointers
+    int loc[MAXF][3];
+    int bc_kind[MAXF][6];
+    FT bc_val[MAXF][6];
+};
+template <class FT> void launch_fill_halos(const GridD<FT>& g, const HaloBatch<FT>& hb);
+
+// substep modes for the fused tendency kernels
+enum { SUB_NONE = 0, SUB_RK3_FIRST = 1, SUB_RK3 = 2, SUB_AB2 = 3 };
+template <class FT>
+struct Substep {
+    int mode;
+    FT dt, c1, c2;         // RK3_FIRST: unew = u + c1*G (c1 = dt*γ) ; RK3: u + dt*(c1*G + c2*Gm)
+                           // AB2: u + dt*(c1*G - c2*Gm)
+};
+template <class FT>
+struct FluxBC {            // constant Flux boundary conditions of the field being stepped
+    int kind[6];
+    FT val[6];
+};
+// general tendency (+ optional fused substep) for prognostic field `comp`
+template <class FT>
+void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi,
+                             const FT* pHY, const FT* b, const FluxBC<FT>& fbc, FT* Gn,
+                             const FT* Gm, FT* psi_new, const Substep<FT>& ss);
+// fast path (triply periodic, regular, WENO5 uniform, no closure/coriolis); returns false if
+// the configuration is not covered
+template <class FT>
+bool launch_tendency_fast(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi,
+                          const FT* pHY, FT* Gn, const FT* Gm, FT* psi_new, const Substep<FT>& ss);
+
+template <class FT, class CT>
+void launch_pressure_rhs(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,
+                         bool times_dz, CT* rhs);
+template <class FT>
+void launch_pressure_correct(const GridD<FT>& g, FT* u, FT* v, FT* w, const FT* p, FT dt);
+template <class FT>
+void launch_hydrostatic_pressure(const GridD<FT>& g, const FT* b, FT gz, bool has_b, FT* pHY);
+template <class FT>
+void launch_to_internal(const GridD<FT>& g, const int psize[3], const int loc[3], const FT* parent, FT* base);
+template <class FT>
+void launch_from_internal(const GridD<FT>& g, const int psize[3], const int loc[3], const FT* base, FT* parent);
+// reductions over Julia box [1..n0]x[1..n1]x[1..n2]; out (device, 4 doubles): sum, sumsq, maxabs, nan
+template <class FT>
+void launch_reduce(const GridD<FT>& g, const FT* p0, const int n[3], double* out4);
+template <class FT>
+void launch_max_divergence(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, double* out4);
+
+// ---- fft.cu ---------------------------------------------------------------------------------
+template <class FT>
+struct PoissonPlan;      // opaque
+template <class FT> PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind,
+                                                         const double* dzF_host, const double* dzC_host);
+template <class FT> void poisson_plan_destroy(PoissonPlan<FT>* p);
+template <class FT> void* poisson_storage(PoissonPlan<FT>* p);          // complex Nx*Ny*Nz (device)
+template <class FT> int poisson_kind(PoissonPlan<FT>* p);
+// solve with the rhs already in storage; writes the real solution into phi (internal layout)
+template <class FT> void poisson_solve(PoissonPlan<FT>* p, const GridD<FT>& g, FT* phi_p0);
+template <class FT>
+void batched_tridiagonal(int Nx, int Ny, int Nz, bool is_complex, const double* a_dev,
+                         const double* b_dev, const double* c_dev, const void* rhs_dev,
+                         void* phi_dev, FT* scratch_dev);
+
+}  // namespace ob

@@ -1,0 +1,371 @@
+// kernels.cu -- halo fills, general tendency(+substep), pressure rhs / correction, hydrostatic
+// pressure, layout conversion and reductions.  sm_100a.
+#include "internal.h"
+
+namespace ob {
+
+// =============================================================================================
+// fill_halo_regions!  (BoundaryConditions/fill_halo_regions*.jl)
+// One launch per dimension for ALL fields of the batch.  Periodic dims copy H planes over the
+// full allocated extent of the other two dims (fills edges/corners when applied dim after dim);
+// Bounded dims act on the interior extent of the other dims only, first halo cell only.
+// =============================================================================================
+template <class FT>
+__global__ void fill_halo_kernel(GridD<FT> g, HaloBatch<FT> hb, int d, int a, int b, int alo, int ahi,
+                                 int blo, int bhi) {
+    int ia = alo + blockIdx.x * blockDim.x + threadIdx.x;
+    int ib = blo + blockIdx.y * blockDim.y + threadIdx.y;
+    if (ia > ahi || ib > bhi) return;
+    long long base = ia * g.st[a] + ib * g.st[b];
+    long long s = g.st[d];
+    int N = g.N[d], H = g.H[d];
+    if (g.topo[d] == OB_PERIODIC) {
+        for (int n = 0; n < hb.n; ++n) {
+            FT* f = hb.p0[n] + base;
+            for (int h = 1; h <= H; ++h) {
+                f[(h - H) * s] = f[(N + h - H) * s];        // c[i] = c[N+i], i = 1-H..0
+                f[(N + h) * s] = f[h * s];                  // c[N+i] = c[i], i = 1..H
+            }
+        }
+    } else if (g.topo[d] == OB_BOUNDED) {
+        for (int n = 0; n < hb.n; ++n) {
+            FT* f = hb.p0[n] + base;
+            for (int side = 0; side < 2; ++side) {
+                int kind = hb.bc_kind[n][2 * d + side];
+                FT val = hb.bc_val[n][2 * d + side];
+                if (kind == 2) {                            // Flux: mirror (fill_halo_regions_flux.jl:16-28)
+                    if (side == 0) f[0] = f[s];
+                    else f[(N + 1) * s] = f[N * s];
+                } else if (kind == 5) {                     // Open (fill_halo_regions_open.jl:34-39)
+                    f[(side == 0 ? 1 : N + 1) * s] = val;
+                } else if (kind == 3 || kind == 4) {        // Value / Gradient (…_value_gradient.jl:7-99)
+                    int iB = side == 0 ? 1 : N + 1, iI = side == 0 ? 1 : N, iH = side == 0 ? 0 : N + 1;
+                    FT D = spacing(g, d, hb.loc[n][d] == OB_C ? OB_F : OB_C, iB);
+                    FT cI = f[iI * s];
+                    FT grad = kind == 4 ? val : (side == 0 ? (cI - val) / (D / 2) : (val - cI) / (D / 2));
+                    f[iH * s] = cI + grad * (side == 0 ? -D : D);
+                }
+            }
+        }
+    }
+}
+
+template <class FT>
+void launch_fill_halos(const GridD<FT>& g, const HaloBatch<FT>& hb) {
+    if (hb.n == 0) return;
+    // non-periodic first, then periodic (fill_halo_regions.jl:56-102)
+    for (int pass = 0; pass < 2; ++pass)
+        for (int d = 0; d < 3; ++d) {
+            if (g.topo[d] == OB_FLAT) continue;
+            bool per = g.topo[d] == OB_PERIODIC;
+            if ((pass == 0) == per) continue;
+            if (per && g.H[d] == 0) continue;
+            int a = d == 0 ? 1 : 0, b = d == 2 ? 1 : 2;
+            int lo[2], hi[2], ab[2] = {a, b};
+            for (int q = 0; q < 2; ++q) {
+                int e = ab[q];
+                if (g.topo[e] == OB_FLAT) { lo[q] = hi[q] = 1; }
+                else if (per) { lo[q] = 1 - g.H[e]; hi[q] = g.N[e] + g.H[e] + 1; }
+                else { lo[q] = 1; hi[q] = g.N[e]; }
+            }
+            dim3 blk(a == 0 ? 64 : 16, a == 0 ? 4 : 16);
+            dim3 grd(cdiv(hi[0] - lo[0] + 1, blk.x), cdiv(hi[1] - lo[1] + 1, blk.y));
+            fill_halo_kernel<FT><<<grd, blk, 0, stream()>>>(g, hb, d, a, b, lo[0], hi[0], lo[1], hi[1]);
+            OB_LAUNCH_CHECK();
+        }
+}
+template void launch_fill_halos<float>(const GridD<float>&, const HaloBatch<float>&);
+template void launch_fill_halos<double>(const GridD<double>&, const HaloBatch<double>&);
+
+// =============================================================================================
+// general tendency kernel, one thread per cell, fused substep (out of place)
+// =============================================================================================
+template <class FT>
+struct TendArgs {
+    const FT* U[3];
+    const FT* psi;
+    const FT* pHY;
+    const FT* b;
+    FT* Gn;
+    const FT* Gm;
+    FT* psi_new;
+    Substep<FT> ss;
+    FluxBC<FT> fbc;
+    int comp;
+};
+
+template <class FT>
+__global__ void __launch_bounds__(128) tendency_general_kernel(Phys<FT> P, TendArgs<FT> A) {
+    const GridD<FT>& g = P.g;
+    int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    int k = 1 + blockIdx.z;
+    if (i > g.N[0] || j > g.N[1]) return;
+    Pt q;
+    q.i[0] = i; q.i[1] = j; q.i[2] = k;
+    q.p = i * g.st[0] + j * g.st[1] + k * g.st[2];
+    const FT* U[3] = {A.U[0], A.U[1], A.U[2]};
+    FT G = tendency(P, A.comp, U, A.psi, A.pHY, A.b, q);
+    // apply_x/y/z_bcs! (apply_flux_bcs.jl:35-160): constant Flux BCs of this field
+    int l[3] = {OB_C, OB_C, OB_C};
+    if (A.comp < 3) l[A.comp] = OB_F;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (g.topo[d] != OB_BOUNDED) continue;
+        int lf[3] = {l[0], l[1], l[2]};
+        lf[d] = l[d] == OB_C ? OB_F : OB_C;
+        if (A.fbc.kind[2 * d] == 2 && q.i[d] == 1 && A.fbc.val[2 * d] != FT(0))
+            G += A.fbc.val[2 * d] * areaA(g, d, q, lf[0], lf[1], lf[2]) / volume(g, q, l[0], l[1], l[2]);
+        if (A.fbc.kind[2 * d + 1] == 2 && q.i[d] == g.N[d] && A.fbc.val[2 * d + 1] != FT(0))
+            G -= A.fbc.val[2 * d + 1] * areaA(g, d, sh(g, q, d, 1), lf[0], lf[1], lf[2]) /
+                 volume(g, q, l[0], l[1], l[2]);
+    }
+    A.Gn[q.p] = G;
+    const Substep<FT>& s = A.ss;
+    if (s.mode == SUB_RK3_FIRST) A.psi_new[q.p] = A.psi[q.p] + s.c1 * G;
+    else if (s.mode == SUB_RK3) A.psi_new[q.p] = A.psi[q.p] + s.dt * (s.c1 * G + s.c2 * A.Gm[q.p]);
+    else if (s.mode == SUB_AB2) A.psi_new[q.p] = A.psi[q.p] + s.dt * (s.c1 * G - s.c2 * A.Gm[q.p]);
+}
+
+template <class FT>
+void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi,
+                             const FT* pHY, const FT* b, const FluxBC<FT>& fbc, FT* Gn,
+                             const FT* Gm, FT* psi_new, const Substep<FT>& ss) {
+    TendArgs<FT> A;
+    for (int d = 0; d < 3; ++d) A.U[d] = U[d];
+    A.psi = psi; A.pHY = pHY; A.b = b; A.Gn = Gn; A.Gm = Gm; A.psi_new = psi_new;
+    A.ss = ss; A.fbc = fbc; A.comp = comp;
+    dim3 blk(32, 4, 1);
+    dim3 grd(cdiv(P.g.N[0], 32), cdiv(P.g.N[1], 4), P.g.N[2]);
+    tendency_general_kernel<FT><<<grd, blk, 0, stream()>>>(P, A);
+    OB_LAUNCH_CHECK();
+}
+template void launch_tendency_general<float>(const Phys<float>&, int, const float* const[3], const float*,
+                                             const float*, const float*, const FluxBC<float>&, float*,
+                                             const float*, float*, const Substep<float>&);
+template void launch_tendency_general<double>(const Phys<double>&, int, const double* const[3], const double*,
+                                              const double*, const double*, const FluxBC<double>&, double*,
+                                              const double*, double*, const Substep<double>&);
+
+// =============================================================================================
+// pressure source term: rhs = div(U*) / dt (x Δzᶜ for the tridiagonal solver)
+// solve_for_pressure.jl:15-33, divergence_operators.jl:16-19
+// =============================================================================================
+template <class FT>
+__device__ __forceinline__ FT div_ccc(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, Pt q) {
+    FT t[3];
+    const FT* U[3] = {u, v, w};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (g.topo[d] == OB_FLAT) { t[d] = FT(0); continue; }
+        int l[3] = {OB_C, OB_C, OB_C};
+        l[d] = OB_F;
+        Pt q1 = sh(g, q, d, 1);
+        t[d] = areaA(g, d, q1, l[0], l[1], l[2]) * U[d][q1.p] - areaA(g, d, q, l[0], l[1], l[2]) * U[d][q.p];
+    }
+    return (1 / volume(g, q, OB_C, OB_C, OB_C)) * ((t[0] + t[1]) + t[2]);
+}
+
+template <class FT, class CT>
+__global__ void pressure_rhs_kernel(GridD<FT> g, const FT* u, const FT* v, const FT* w, FT dt,
+                                    bool times_dz, CT* rhs) {
+    int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    int k = 1 + blockIdx.z;
+    if (i > g.N[0] || j > g.N[1]) return;
+    Pt q;
+    q.i[0] = i; q.i[1] = j; q.i[2] = k;
+    q.p = i * g.st[0] + j * g.st[1] + k * g.st[2];
+    FT dv = div_ccc(g, u, v, w, q);
+    FT r = times_dz ? (spacing(g, 2, OB_C, k) * dv) / dt : dv / dt;
+    CT c;
+    c.x = r; c.y = 0;
+    rhs[(i - 1) + (long long)g.N[0] * ((j - 1) + (long long)g.N[1] * (k - 1))] = c;
+}
+template <class FT, class CT>
+void launch_pressure_rhs(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,
+                         bool times_dz, CT* rhs) {
+    dim3 blk(64, 4, 1), grd(cdiv(g.N[0], 64), cdiv(g.N[1], 4), g.N[2]);
+    pressure_rhs_kernel<FT, CT><<<grd, blk, 0, stream()>>>(g, u, v, w, dt, times_dz, rhs);
+    OB_LAUNCH_CHECK();
+}
+template void launch_pressure_rhs<float, float2>(const GridD<float>&, const float*, const float*, const float*,
+                                                 float, bool, float2*);
+template void launch_pressure_rhs<double, double2>(const GridD<double>&, const double*, const double*,
+                                                   const double*, double, bool, double2*);
+
+// _pressure_correct_velocities! pressure_correction.jl:34-40
+template <class FT>
+__global__ void pressure_correct_kernel(GridD<FT> g, FT* u, FT* v, FT* w, const FT* p, FT dt) {
+    int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    int k = 1 + blockIdx.z;
+    if (i > g.N[0] || j > g.N[1]) return;
+    Pt q;
+    q.i[0] = i; q.i[1] = j; q.i[2] = k;
+    q.p = i * g.st[0] + j * g.st[1] + k * g.st[2];
+    u[q.p] -= deriv(g, p, q, 0, OB_F) * dt;
+    v[q.p] -= deriv(g, p, q, 1, OB_F) * dt;
+    w[q.p] -= deriv(g, p, q, 2, OB_F) * dt;
+}
+template <class FT>
+void launch_pressure_correct(const GridD<FT>& g, FT* u, FT* v, FT* w, const FT* p, FT dt) {
+    dim3 blk(64, 4, 1), grd(cdiv(g.N[0], 64), cdiv(g.N[1], 4), g.N[2]);
+    pressure_correct_kernel<FT><<<grd, blk, 0, stream()>>>(g, u, v, w, p, dt);
+    OB_LAUNCH_CHECK();
+}
+template void launch_pressure_correct<float>(const GridD<float>&, float*, float*, float*, const float*, float);
+template void launch_pressure_correct<double>(const GridD<double>&, double*, double*, double*, const double*, double);
+
+// _update_hydrostatic_pressure! update_hydrostatic_pressure.jl:10-18 : one column per thread
+template <class FT>
+__global__ void hydrostatic_kernel(GridD<FT> g, const FT* b, FT gz, bool has_b, bool tilted, FT* pHY) {
+    int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > g.N[0] || j > g.N[1]) return;
+    long long p = i * g.st[0] + j * g.st[1];
+    long long sz = g.st[2];
+    int Nz = g.N[2];
+    auto zb = [&](int k) -> FT {
+        if (!has_b) return FT(0);
+        FT v = b[p + k * sz];
+        return tilted ? gz * v : v;
+    };
+    FT acc = -(FT(0.5) * (zb(Nz) + zb(Nz + 1))) * spacing(g, 2, OB_F, Nz + 1);
+    pHY[p + Nz * sz] = acc;
+    for (int k = Nz - 1; k >= 1; --k) {
+        acc = acc - (FT(0.5) * (zb(k) + zb(k + 1))) * spacing(g, 2, OB_F, k + 1);
+        pHY[p + k * sz] = acc;
+    }
+}
+template <class FT>
+void launch_hydrostatic_pressure(const GridD<FT>& g, const FT* b, FT gz, bool has_b, FT* pHY) {
+    dim3 blk(64, 2), grd(cdiv(g.N[0], 64), cdiv(g.N[1], 2));
+    hydrostatic_kernel<FT><<<grd, blk, 0, stream()>>>(g, b, gz, has_b, gz != FT(1), pHY);
+    OB_LAUNCH_CHECK();
+}
+template void launch_hydrostatic_pressure<float>(const GridD<float>&, const float*, float, bool, float*);
+template void launch_hydrostatic_pressure<double>(const GridD<double>&, const double*, double, bool, double*);
+
+// =============================================================================================
+// reference parent layout <-> internal layout
+// =============================================================================================
+template <class FT, bool TO_INTERNAL>
+__global__ void convert_kernel(GridD<FT> g, int p0, int p1, int p2, const FT* src, FT* dst) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.y * blockDim.y + threadIdx.y;
+    int c = blockIdx.z;
+    if (a >= p0 || b >= p1 || c >= p2) return;
+    long long ip = a + (long long)p0 * (b + (long long)p1 * c);           // parent (reference) index
+    long long ii = (a - g.H[0] + g.O[0]) * g.st[0] + (b - g.H[1] + g.O[1]) * g.st[1] +
+                   (c - g.H[2] + g.O[2]) * g.st[2];
+    if (TO_INTERNAL) dst[ii] = src[ip];
+    else dst[ip] = src[ii];
+}
+template <class FT>
+void launch_to_internal(const GridD<FT>& g, const int ps[3], const int loc[3], const FT* parent, FT* base) {
+    dim3 blk(64, 4, 1), grd(cdiv(ps[0], 64), cdiv(ps[1], 4), ps[2]);
+    convert_kernel<FT, true><<<grd, blk, 0, stream()>>>(g, ps[0], ps[1], ps[2], parent, base);
+    OB_LAUNCH_CHECK();
+}
+template <class FT>
+void launch_from_internal(const GridD<FT>& g, const int ps[3], const int loc[3], const FT* base, FT* parent) {
+    dim3 blk(64, 4, 1), grd(cdiv(ps[0], 64), cdiv(ps[1], 4), ps[2]);
+    convert_kernel<FT, false><<<grd, blk, 0, stream()>>>(g, ps[0], ps[1], ps[2], base, parent);
+    OB_LAUNCH_CHECK();
+}
+template void launch_to_internal<float>(const GridD<float>&, const int[3], const int[3], const float*, float*);
+template void launch_to_internal<double>(const GridD<double>&, const int[3], const int[3], const double*, double*);
+template void launch_from_internal<float>(const GridD<float>&, const int[3], const int[3], const float*, float*);
+template void launch_from_internal<double>(const GridD<double>&, const int[3], const int[3], const double*, double*);
+
+// =============================================================================================
+// reductions
+// =============================================================================================
+__device__ __forceinline__ void block_reduce_store(double s, double s2, double mx, int nan, double* out4) {
+    __shared__ double sh[4][32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffff, s, o);
+        s2 += __shfl_down_sync(0xffffffff, s2, o);
+        mx = fmax(mx, __shfl_down_sync(0xffffffff, mx, o));
+        nan |= __shfl_down_sync(0xffffffff, nan, o);
+    }
+    if (lane == 0) { sh[0][wid] = s; sh[1][wid] = s2; sh[2][wid] = mx; sh[3][wid] = nan; }
+    __syncthreads();
+    if (wid == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        s = lane < nw ? sh[0][lane] : 0; s2 = lane < nw ? sh[1][lane] : 0;
+        mx = lane < nw ? sh[2][lane] : 0; double nn = lane < nw ? sh[3][lane] : 0;
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_down_sync(0xffffffff, s, o);
+            s2 += __shfl_down_sync(0xffffffff, s2, o);
+            mx = fmax(mx, __shfl_down_sync(0xffffffff, mx, o));
+            nn += __shfl_down_sync(0xffffffff, nn, o);
+        }
+        if (lane == 0) {
+            atomicAdd(out4 + 0, s);
+            atomicAdd(out4 + 1, s2);
+            atomicMax((unsigned long long*)(out4 + 2), (unsigned long long)__double_as_longlong(mx));
+            if (nn > 0) atomicAdd(out4 + 3, 1.0);
+        }
+    }
+}
+
+template <class FT>
+__global__ void reduce_kernel(GridD<FT> g, const FT* p0, int n0, int n1, int n2, double* out4) {
+    long long total = (long long)n0 * n1 * n2;
+    double s = 0, s2 = 0, mx = 0;
+    int nan = 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int i = 1 + (int)(t % n0);
+        int j = 1 + (int)((t / n0) % n1);
+        int k = 1 + (int)(t / ((long long)n0 * n1));
+        double v = (double)p0[i * g.st[0] + j * g.st[1] + k * g.st[2]];
+        if (v != v) nan = 1;
+        else { s += v; s2 += v * v; mx = fmax(mx, fabs(v)); }
+    }
+    block_reduce_store(s, s2, mx, nan, out4);
+}
+template <class FT>
+void launch_reduce(const GridD<FT>& g, const FT* p0, const int n[3], double* out4) {
+    OB_CUDA(cudaMemsetAsync(out4, 0, 4 * sizeof(double), stream()));
+    long long total = (long long)n[0] * n[1] * n[2];
+    int blocks = (int)std::min<long long>(148 * 8, (total + 255) / 256);
+    reduce_kernel<FT><<<blocks, 256, 0, stream()>>>(g, p0, n[0], n[1], n[2], out4);
+    OB_LAUNCH_CHECK();
+}
+template void launch_reduce<float>(const GridD<float>&, const float*, const int[3], double*);
+template void launch_reduce<double>(const GridD<double>&, const double*, const int[3], double*);
+
+template <class FT>
+__global__ void maxdiv_kernel(GridD<FT> g, const FT* u, const FT* v, const FT* w, double* out4) {
+    long long total = (long long)g.N[0] * g.N[1] * g.N[2];
+    double s = 0, s2 = 0, mx = 0;
+    int nan = 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        Pt q;
+        q.i[0] = 1 + (int)(t % g.N[0]);
+        q.i[1] = 1 + (int)((t / g.N[0]) % g.N[1]);
+        q.i[2] = 1 + (int)(t / ((long long)g.N[0] * g.N[1]));
+        q.p = q.i[0] * g.st[0] + q.i[1] * g.st[1] + q.i[2] * g.st[2];
+        double dv = (double)div_ccc(g, u, v, w, q);
+        if (dv != dv) nan = 1;
+        else { mx = fmax(mx, fabs(dv)); s += dv; s2 += dv * dv; }
+    }
+    block_reduce_store(s, s2, mx, nan, out4);
+}
+template <class FT>
+void launch_max_divergence(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, double* out4) {
+    OB_CUDA(cudaMemsetAsync(out4, 0, 4 * sizeof(double), stream()));
+    long long total = (long long)g.N[0] * g.N[1] * g.N[2];
+    int blocks = (int)std::min<long long>(148 * 8, (total + 255) / 256);
+    maxdiv_kernel<FT><<<blocks, 256, 0, stream()>>>(g, u, v, w, out4);
+    OB_LAUNCH_CHECK();
+}
+template void launch_max_divergence<float>(const GridD<float>&, const float*, const float*, const float*, double*);
+template void launch_max_divergence<double>(const GridD<double>&, const double*, const double*, const double*, double*);
+
+}  // namespace ob

@@ -1,0 +1,430 @@
+// physics.cuh -- pointwise operators, advection schemes, closure and tendency functions.
+//
+// This is the GENERAL path: every topology (Periodic/Bounded/Flat per dimension), every
+// in-scope scheme and closure, regular and stretched spacings.  It follows the reference's
+// operation order term by term (files cited at each function; paths relative to
+// /root/reference/src).  The specialised fast kernels in tendency_fast.cuh compute the
+// same quantities for the headline configuration with shared sub-expressions.
+#pragma once
+#include "common.cuh"
+
+namespace ob {
+
+#define OBD __device__ __forceinline__
+
+enum { ADV_NONE = 0, ADV_C2 = 1, ADV_C4 = 2, ADV_U1 = 3, ADV_U3 = 4, ADV_U5 = 5, ADV_WENO5 = 6 };
+enum { CLO_NONE = 0, CLO_3D = 1, CLO_H = 2, CLO_V = 3 };
+enum { SIDE_LEFT = 0, SIDE_RIGHT = 1 };
+
+template <class FT>
+struct Phys {
+    GridD<FT> g;
+    int scheme, zweno, buffer;       // buffer = Nᴮ of the scheme (Advection.jl:36-40)
+    const FT* wc[3][2];              // stretched WENO tables [dim][0 = Face, 1 = Center] or null
+    int closure;
+    FT nu, kappa[8];
+    int fplane;
+    FT f;
+    int btr, tilted;                 // buoyancy tracer index (-1 none); tilted gravity flag
+    FT ghat[3];
+    int ntr;
+};
+
+struct Pt {
+    long long p;   // linear offset from the Julia-(0,0,0) pointer
+    int i[3];      // Julia indices
+};
+
+template <class FT>
+OBD Pt sh(const GridD<FT>& g, Pt q, int d, int n) {
+    q.p += n * g.st[d];
+    q.i[d] += n;
+    return q;
+}
+
+#ifdef OB200_STRICT
+template <class FT> OBD FT div6(FT x) { return x / FT(6); }
+template <class FT> OBD FT div60(FT x) { return x / FT(60); }
+#else
+template <class FT> OBD FT div6(FT x) { return x * FT(1.0 / 6.0); }
+template <class FT> OBD FT div60(FT x) { return x * FT(1.0 / 60.0); }
+#endif
+
+// ---- Operators/difference_operators.jl:7-49, interpolation_operators.jl:20-114 ------------
+template <class FT> OBD FT dC(const GridD<FT>& g, const FT* f, Pt q, int d) {   // δxᶜᵃᵃ
+    return g.topo[d] == OB_FLAT ? FT(0) : f[q.p + g.st[d]] - f[q.p];
+}
+template <class FT> OBD FT dFc(const GridD<FT>& g, const FT* f, Pt q, int d) {  // δxᶠᵃᵃ
+    return g.topo[d] == OB_FLAT ? FT(0) : f[q.p] - f[q.p - g.st[d]];
+}
+template <class FT> OBD FT IC(const GridD<FT>& g, const FT* f, Pt q, int d) {   // ℑxᶜᵃᵃ
+    return g.topo[d] == OB_FLAT ? f[q.p] : FT(0.5) * (f[q.p] + f[q.p + g.st[d]]);
+}
+template <class FT> OBD FT IF(const GridD<FT>& g, const FT* f, Pt q, int d) {   // ℑxᶠᵃᵃ
+    return g.topo[d] == OB_FLAT ? f[q.p] : FT(0.5) * (f[q.p - g.st[d]] + f[q.p]);
+}
+template <class FT> OBD FT I2(const GridD<FT>& g, const FT* f, Pt q, int d, int loc) {
+    return loc == OB_C ? IC(g, f, q, d) : IF(g, f, q, d);
+}
+// ∂ at result location loc along d: δ / Δ (derivative_operators.jl:6-29)
+template <class FT> OBD FT deriv(const GridD<FT>& g, const FT* f, Pt q, int d, int loc) {
+    FT del = loc == OB_C ? dC(g, f, q, d) : dFc(g, f, q, d);
+    return del / spacing(g, d, loc, q.i[d]);
+}
+
+// ---- metrics (spacings_and_areas_and_volumes.jl:173-236) ---------------------------------
+template <class FT> OBD FT areaA(const GridD<FT>& g, int d, Pt q, int lx, int ly, int lz) {
+    if (d == 0) return spacing(g, 1, ly, q.i[1]) * spacing(g, 2, lz, q.i[2]);
+    if (d == 1) return spacing(g, 0, lx, q.i[0]) * spacing(g, 2, lz, q.i[2]);
+    return spacing(g, 0, lx, q.i[0]) * spacing(g, 1, ly, q.i[1]);
+}
+template <class FT> OBD FT volume(const GridD<FT>& g, Pt q, int lx, int ly, int lz) {
+    return (spacing(g, 0, lx, q.i[0]) * spacing(g, 1, ly, q.i[1])) * spacing(g, 2, lz, q.i[2]);
+}
+
+// ---- centered_fourth_order.jl:17-33 ------------------------------------------------------
+template <class FT> OBD FT I3(const GridD<FT>& g, const FT* c, Pt q, int d) {
+    // ℑ³: c[i] - δ(δ c)(i) / 6 ; identical operation order for the ᶜ and ᶠ variants
+    if (g.topo[d] == OB_FLAT) return c[q.p];
+    long long s = g.st[d];
+    FT c0 = c[q.p];
+    return c0 - div6((c[q.p + s] - c0) - (c0 - c[q.p - s]));
+}
+template <class FT> OBD FT sym4(const GridD<FT>& g, const FT* c, Pt q, int d, int loc) {
+    if (g.topo[d] == OB_FLAT) return c[q.p];
+    if (loc == OB_C) return FT(0.5) * (I3(g, c, q, d) + I3(g, c, sh(g, q, d, 1), d));
+    return FT(0.5) * (I3(g, c, sh(g, q, d, -1), d) + I3(g, c, q, d));
+}
+
+// ---- WENO5: weno_fifth_order.jl:266-272,299-317,380-403,489-532 ----------------------------
+// v = psi at offsets (-3..+1) for LEFT, (-2..+2) for RIGHT relative to the face index.
+// cf = 9 coefficients (p0: 3, p1: 3, p2: 3) for the three sub-stencils psi0, psi1, psi2.
+template <class FT>
+OBD FT weno5_core(int side, int zweno, FT a, FT b, FT c, FT d, FT e, const FT* cf) {
+    // LEFT : psi2=(a,b,c) psi1=(b,c,d) psi0=(c,d,e);  RIGHT: same with the right-shifted window
+    const FT c1312 = FT(13.0 / 12.0), c14 = FT(0.25);
+    FT t2 = (a - 2 * b) + c, t1 = (b - 2 * c) + d, t0 = (c - 2 * d) + e;
+    FT s0, s1, s2;
+    FT C0, C1, C2;
+    s1 = b - d;
+    if (side == SIDE_LEFT) {            // :311-313
+        s0 = (3 * c - 4 * d) + e;       // psi0: 3ψ1 - 4ψ2 + ψ3
+        s2 = (a - 4 * b) + 3 * c;       // psi2: ψ1 - 4ψ2 + 3ψ3
+        C0 = FT(3.0 / 10.0); C1 = FT(3.0 / 5.0); C2 = FT(1.0 / 10.0);
+    } else {                            // :315-317 (not the mirror image)
+        s0 = (c - 4 * d) + 3 * e;       // psi0: ψ1 - 4ψ2 + 3ψ3
+        s2 = (3 * a - 4 * b) + c;       // psi2: 3ψ1 - 4ψ2 + ψ3
+        C0 = FT(1.0 / 10.0); C1 = FT(3.0 / 5.0); C2 = FT(3.0 / 10.0);
+    }
+    FT b0 = c1312 * (t0 * t0) + c14 * (s0 * s0);
+    FT b1 = c1312 * (t1 * t1) + c14 * (s1 * s1);
+    FT b2 = c1312 * (t2 * t2) + c14 * (s2 * s2);
+    const FT eps = FT(1e-6);
+    FT a0, a1, a2;
+    if (zweno) {                        // :386-390
+        FT tau = fabs(b2 - b0);
+        FT q0 = tau / (b0 + eps), q1 = tau / (b1 + eps), q2 = tau / (b2 + eps);
+        a0 = C0 * (1 + q0 * q0);
+        a1 = C1 * (1 + q1 * q1);
+        a2 = C2 * (1 + q2 * q2);
+    } else {                            // :392-394
+        FT d0 = b0 + eps, d1 = b1 + eps, d2 = b2 + eps;
+        a0 = C0 / (d0 * d0);
+        a1 = C1 / (d1 * d1);
+        a2 = C2 / (d2 * d2);
+    }
+    FT sa = (a0 + a1) + a2;
+    FT w0 = a0 / sa, w1 = a1 / sa, w2 = a2 / sa;
+    FT p0 = (cf[0] * c + cf[1] * d) + cf[2] * e;
+    FT p1 = (cf[3] * b + cf[4] * c) + cf[5] * d;
+    FT p2 = (cf[6] * a + cf[7] * b) + cf[8] * c;
+    return (w0 * p0 + w1 * p1) + w2 * p2;
+}
+
+template <class FT>
+OBD void weno_uniform_coeffs(int side, FT* cf) {
+    // coeff_left_p0..p2 :518-520 ; right = reversed (:522-524)
+    if (side == SIDE_LEFT) {
+        cf[0] = FT(1.0 / 3.0);  cf[1] = FT(5.0 / 6.0);  cf[2] = -FT(1.0 / 6.0);
+        cf[3] = -FT(1.0 / 6.0); cf[4] = FT(5.0 / 6.0);  cf[5] = FT(1.0 / 3.0);
+        cf[6] = FT(1.0 / 3.0);  cf[7] = -FT(7.0 / 6.0); cf[8] = FT(11.0 / 6.0);
+    } else {
+        cf[0] = FT(11.0 / 6.0); cf[1] = -FT(7.0 / 6.0); cf[2] = FT(1.0 / 3.0);
+        cf[3] = FT(1.0 / 3.0);  cf[4] = FT(5.0 / 6.0);  cf[5] = -FT(1.0 / 6.0);
+        cf[6] = -FT(1.0 / 6.0); cf[7] = FT(5.0 / 6.0);  cf[8] = FT(1.0 / 3.0);
+    }
+}
+
+// left/right_biased_interpolate at location loc along d (raw, no boundary fallback)
+template <class FT>
+OBD FT biased_raw(const Phys<FT>& P, int side, const FT* psi, Pt q, int d, int loc) {
+    const GridD<FT>& g = P.g;
+    int idx = q.i[d];                       // table index keeps the un-shifted index (:257-263)
+    if (loc == OB_C) q = sh(g, q, d, 1);    // *_xᶜᵃᵃ(i) = *_xᶠᵃᵃ(i+1)
+    long long s = g.st[d];
+    const FT* f = psi + q.p;
+    switch (P.scheme) {
+        case ADV_WENO5: {
+            FT cf[9];
+            const FT* tab = P.wc[d][loc == OB_F ? 0 : 1];
+            if (tab == nullptr) {
+                weno_uniform_coeffs(side, cf);
+            } else {                       // retrieve_coeff :526-539: table[r+2][idx]
+                int n2 = g.N[d] + 2;
+                int r0 = side == SIDE_LEFT ? 1 : 0;     // p0 -> r=0 (left) / r=-1 (right)
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) cf[3 * m + c] = tab[((r0 + m) * n2 + idx) * 3 + c];
+            }
+            if (side == SIDE_LEFT)
+                return weno5_core(side, P.zweno, f[-3 * s], f[-2 * s], f[-s], f[0], f[s], cf);
+            return weno5_core(side, P.zweno, f[-2 * s], f[-s], f[0], f[s], f[2 * s], cf);
+        }
+        case ADV_U5:                       // upwind_biased_fifth_order.jl:24-46
+            if (side == SIDE_LEFT)
+                return div60((((-3 * f[s] + 27 * f[0]) + 47 * f[-s]) - 13 * f[-2 * s]) + 2 * f[-3 * s]);
+            return div60((((2 * f[2 * s] - 13 * f[s]) + 47 * f[0]) + 27 * f[-s]) - 3 * f[-2 * s]);
+        case ADV_U3:
+            if (side == SIDE_LEFT) return div6((2 * f[0] + 5 * f[-s]) - f[-2 * s]);
+            return div6((-f[s] + 5 * f[0]) + 2 * f[-s]);
+        default:                           // ADV_U1
+            return side == SIDE_LEFT ? f[-s] : f[0];
+    }
+}
+
+template <class FT>
+OBD FT sym_raw(const Phys<FT>& P, const FT* c, Pt q, int d, int loc) {
+    if (P.scheme == ADV_C4 || P.scheme == ADV_U5 || P.scheme == ADV_WENO5) return sym4(P.g, c, q, d, loc);
+    return I2(P.g, c, q, d, loc);
+}
+
+// ---- topologically_conditional_interpolation.jl:19-80 ------------------------------------
+template <class FT>
+OBD FT sym_c(const Phys<FT>& P, const FT* c, Pt q, int d, int loc) {
+    const GridD<FT>& g = P.g;
+    FT hi = sym_raw(P, c, q, d, loc);
+    if (g.topo[d] != OB_BOUNDED) return hi;
+    int i = q.i[d], N = g.N[d], NB = P.buffer;
+    bool out = (i > NB) && (i < N + 1 - NB);
+    return out ? hi : I2(g, c, q, d, loc);
+}
+template <class FT>
+OBD FT biased_c(const Phys<FT>& P, int side, const FT* c, Pt q, int d, int loc) {
+    const GridD<FT>& g = P.g;
+    if (g.topo[d] != OB_BOUNDED) return biased_raw(P, side, c, q, d, loc);
+    int i = q.i[d], N = g.N[d], NB = P.buffer;
+    bool out = side == SIDE_LEFT ? ((i > NB) && (i < N + 1 - (NB - 1)))
+                                 : ((i > NB - 1) && (i < N + 1 - NB));
+    // the reference's ifelse evaluates both branches; the halo is wide enough for the
+    // high-order one everywhere it is evaluated, so we may skip it when it is not selected.
+    return out ? biased_raw(P, side, c, q, d, loc) : I2(g, c, q, d, loc);
+}
+
+// upwind_biased_advective_fluxes.jl:10
+template <class FT> OBD FT upwind_product(FT u, FT pl, FT pr) {
+    FT au = fabs(u);
+    return ((u + au) * pl + (u - au) * pr) * FT(0.5);
+}
+
+// advection OF component B BY component A, evaluated at q (momentum); all fluxes include the area
+template <class FT>
+OBD FT momentum_flux(const Phys<FT>& P, int A, int B, const FT* Ua, const FT* psi, Pt q) {
+    const GridD<FT>& g = P.g;
+    int fl[3] = {OB_C, OB_C, OB_C};
+    int ul, ud;
+    if (A == B) { ul = OB_C; ud = A; }
+    else { fl[A] = OB_F; fl[B] = OB_F; ul = OB_F; ud = B; }
+    int pl = ul;
+    if (P.scheme == ADV_C2) {          // centered_second_order.jl:16-26: ℑ(A_q U) * ℑ(ψ)
+        int nat[3] = {OB_C, OB_C, OB_C};
+        nat[A] = OB_F;
+        FT t0, t1;
+        if (g.topo[ud] == OB_FLAT) {
+            t0 = areaA(g, A, q, nat[0], nat[1], nat[2]) * Ua[q.p];
+        } else {
+            Pt q1 = ul == OB_C ? q : sh(g, q, ud, -1);
+            Pt q2 = sh(g, q1, ud, 1);
+            t0 = FT(0.5) * (areaA(g, A, q1, nat[0], nat[1], nat[2]) * Ua[q1.p] +
+                            areaA(g, A, q2, nat[0], nat[1], nat[2]) * Ua[q2.p]);
+        }
+        t1 = I2(g, psi, q, A, pl);
+        return t0 * t1;
+    }
+    FT Ar = areaA(g, A, q, fl[0], fl[1], fl[2]);
+    FT ut = sym_c(P, Ua, q, ud, ul);
+    if (P.scheme >= ADV_U1) {          // upwind_biased_advective_fluxes.jl:18-97
+        FT L = biased_c(P, SIDE_LEFT, psi, q, A, pl);
+        FT R = biased_c(P, SIDE_RIGHT, psi, q, A, pl);
+        return Ar * upwind_product(ut, L, R);
+    }
+    return (Ar * ut) * sym_c(P, psi, q, A, pl);     // centered_advective_fluxes.jl:15-27
+}
+
+template <class FT>
+OBD FT tracer_flux(const Phys<FT>& P, int A, const FT* Ua, const FT* c, Pt q) {
+    const GridD<FT>& g = P.g;
+    int fl[3] = {OB_C, OB_C, OB_C};
+    fl[A] = OB_F;
+    FT Ar = areaA(g, A, q, fl[0], fl[1], fl[2]);
+    if (P.scheme == ADV_C2) return (Ar * Ua[q.p]) * IF(g, c, q, A);
+    if (P.scheme >= ADV_U1) {          // :103-128
+        FT L = biased_c(P, SIDE_LEFT, c, q, A, OB_F);
+        FT R = biased_c(P, SIDE_RIGHT, c, q, A, OB_F);
+        return Ar * upwind_product(Ua[q.p], L, R);
+    }
+    return (Ar * Ua[q.p]) * sym_c(P, c, q, A, OB_F);
+}
+
+// div_𝐯u/v/w (momentum_advection_operators.jl:52-86), B = advected component
+template <class FT>
+OBD FT div_Uu(const Phys<FT>& P, int B, const FT* const* U, const FT* psi, Pt q) {
+    if (P.scheme == ADV_NONE) return FT(0);
+    const GridD<FT>& g = P.g;
+    FT t[3];
+#pragma unroll
+    for (int A = 0; A < 3; ++A) {
+        if (g.topo[A] == OB_FLAT) { t[A] = FT(0); continue; }
+        if (A == B)    // δ to the Face location: f(i) - f(i-1)
+            t[A] = momentum_flux(P, A, B, U[A], psi, q) - momentum_flux(P, A, B, U[A], psi, sh(g, q, A, -1));
+        else           // δ to the Center location: f(i+1) - f(i)
+            t[A] = momentum_flux(P, A, B, U[A], psi, sh(g, q, A, 1)) - momentum_flux(P, A, B, U[A], psi, q);
+    }
+    int l[3] = {OB_C, OB_C, OB_C};
+    l[B] = OB_F;
+    return (1 / volume(g, q, l[0], l[1], l[2])) * ((t[0] + t[1]) + t[2]);
+}
+
+// div_Uc (tracer_advection_operators.jl:31-35)
+template <class FT>
+OBD FT div_Uc(const Phys<FT>& P, const FT* const* U, const FT* c, Pt q) {
+    if (P.scheme == ADV_NONE) return FT(0);
+    const GridD<FT>& g = P.g;
+    FT t[3];
+#pragma unroll
+    for (int A = 0; A < 3; ++A) {
+        if (g.topo[A] == OB_FLAT) { t[A] = FT(0); continue; }
+        t[A] = tracer_flux(P, A, U[A], c, sh(g, q, A, 1)) - tracer_flux(P, A, U[A], c, q);
+    }
+    return (1 / volume(g, q, OB_C, OB_C, OB_C)) * ((t[0] + t[1]) + t[2]);
+}
+
+// ---- ScalarDiffusivity: closure_kernel_operators.jl:22-48, abstract_scalar_diffusivity_closure.jl:172-207
+// strain rates velocity_tracer_gradients.jl:25-43 (location of the strain given by (comp, dir))
+template <class FT>
+OBD FT strain(const GridD<FT>& g, int comp, int dir, const FT* const* U, Pt q) {
+    if (comp == dir) return deriv(g, U[comp], q, comp, OB_C);            // Σ11, Σ22, Σ33 at ccc
+    // Σ_ab = 0.5 (∂_b u_a + ∂_a u_b), both derivatives to the Face location
+    int a = comp < dir ? comp : dir, b = comp < dir ? dir : comp;
+    return FT(0.5) * (deriv(g, U[a], q, b, OB_F) + deriv(g, U[b], q, a, OB_F));
+}
+
+template <class FT>
+OBD FT div_xy(const GridD<FT>& g, const FT* const* U, Pt q) {            // div_xyᶜᶜᶜ
+    FT tx = g.topo[0] == OB_FLAT ? FT(0)
+          : spacing(g, 1, OB_C, q.i[1]) * U[0][q.p + g.st[0]] - spacing(g, 1, OB_C, q.i[1]) * U[0][q.p];
+    FT ty = g.topo[1] == OB_FLAT ? FT(0)
+          : spacing(g, 0, OB_C, q.i[0]) * U[1][q.p + g.st[1]] - spacing(g, 0, OB_C, q.i[0]) * U[1][q.p];
+    return (1 / (spacing(g, 0, OB_C, q.i[0]) * spacing(g, 1, OB_C, q.i[1]))) * (tx + ty);
+}
+template <class FT>
+OBD FT zeta3(const GridD<FT>& g, const FT* const* U, Pt q) {             // ζ₃ᶠᶠᶜ
+    FT a = g.topo[0] == OB_FLAT ? FT(0)
+         : spacing(g, 1, OB_F, q.i[1]) * U[1][q.p] - spacing(g, 1, OB_F, q.i[1]) * U[1][q.p - g.st[0]];
+    FT b = g.topo[1] == OB_FLAT ? FT(0)
+         : spacing(g, 0, OB_F, q.i[0]) * U[0][q.p] - spacing(g, 0, OB_F, q.i[0]) * U[0][q.p - g.st[1]];
+    return (a - b) / (spacing(g, 0, OB_F, q.i[0]) * spacing(g, 1, OB_F, q.i[1]));
+}
+
+// A * viscous_flux_{comp}{dir} at q
+template <class FT>
+OBD FT viscous_Aflux(const Phys<FT>& P, int comp, int dir, const FT* const* U, Pt q) {
+    const GridD<FT>& g = P.g;
+    int fl[3] = {OB_C, OB_C, OB_C};
+    if (comp != dir) { fl[comp] = OB_F; fl[dir] = OB_F; }
+    FT Ar = areaA(g, dir, q, fl[0], fl[1], fl[2]);
+    FT fx = FT(0);
+    if (P.closure == CLO_3D) {
+        fx = -2 * (P.nu * strain(g, comp, dir, U, q));
+    } else if (P.closure == CLO_H) {
+        if (comp < 2 && comp == dir) fx = -(P.nu * div_xy(g, U, q));
+        else if (comp == 1 && dir == 0) fx = -(P.nu * zeta3(g, U, q));
+        else if (comp == 0 && dir == 1) fx = P.nu * zeta3(g, U, q);
+        else if (comp == 2 && dir < 2) fx = -(P.nu * deriv(g, U[2], q, dir, OB_F));
+    } else if (P.closure == CLO_V) {
+        if (dir == 2) fx = -(P.nu * deriv(g, U[comp], q, 2, comp == 2 ? OB_C : OB_F));
+    }
+    return Ar * fx;
+}
+
+template <class FT>
+OBD FT div_tau(const Phys<FT>& P, int comp, const FT* const* U, Pt q) {
+    if (P.closure == CLO_NONE) return FT(0);
+    const GridD<FT>& g = P.g;
+    FT t[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (g.topo[d] == OB_FLAT) { t[d] = FT(0); continue; }
+        if (d == comp) t[d] = viscous_Aflux(P, comp, d, U, q) - viscous_Aflux(P, comp, d, U, sh(g, q, d, -1));
+        else t[d] = viscous_Aflux(P, comp, d, U, sh(g, q, d, 1)) - viscous_Aflux(P, comp, d, U, q);
+    }
+    int l[3] = {OB_C, OB_C, OB_C};
+    l[comp] = OB_F;
+    return (1 / volume(g, q, l[0], l[1], l[2])) * ((t[0] + t[1]) + t[2]);
+}
+
+template <class FT>
+OBD FT diffusive_Aflux(const Phys<FT>& P, int d, FT kappa, const FT* c, Pt q) {
+    const GridD<FT>& g = P.g;
+    int fl[3] = {OB_C, OB_C, OB_C};
+    fl[d] = OB_F;
+    FT Ar = areaA(g, d, q, fl[0], fl[1], fl[2]);
+    bool active = P.closure == CLO_3D || (P.closure == CLO_H && d < 2) || (P.closure == CLO_V && d == 2);
+    return active ? Ar * (-kappa * deriv(g, c, q, d, OB_F)) : Ar * FT(0);
+}
+template <class FT>
+OBD FT div_q(const Phys<FT>& P, FT kappa, const FT* c, Pt q) {
+    if (P.closure == CLO_NONE) return FT(0);
+    const GridD<FT>& g = P.g;
+    FT t[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (g.topo[d] == OB_FLAT) { t[d] = FT(0); continue; }
+        t[d] = diffusive_Aflux(P, d, kappa, c, sh(g, q, d, 1)) - diffusive_Aflux(P, d, kappa, c, q);
+    }
+    return (1 / volume(g, q, OB_C, OB_C, OB_C)) * ((t[0] + t[1]) + t[2]);
+}
+
+// ---- tendencies: nonhydrostatic_tendency_kernel_functions.jl:44-232 (term order kept) -------
+// comp 0,1,2 = u,v,w ; comp >= 3 = tracer (comp-3)
+template <class FT>
+OBD FT tendency(const Phys<FT>& P, int comp, const FT* const* U, const FT* psi, const FT* pHY,
+                const FT* b, Pt q) {
+    const GridD<FT>& g = P.g;
+    if (comp >= 3) {
+        FT G = -div_Uc(P, U, psi, q);
+        G = G - div_q(P, P.kappa[comp - 3], psi, q);
+        return G;
+    }
+    FT G = -div_Uu(P, comp, U, psi, q);
+    if (comp == 0) {
+        if (P.fplane) {          // x_f_cross_U = -f ℑxyᶠᶜᵃ(v) = -f ℑyᵃᶜᵃ(ℑxᶠᵃᵃ v)   (f_plane.jl:42)
+            FT a0 = IF(g, U[1], q, 0);
+            FT v = g.topo[1] == OB_FLAT ? a0 : FT(0.5) * (a0 + IF(g, U[1], sh(g, q, 1, 1), 0));
+            G = G - (-P.f * v);
+        }
+        if (pHY) G = G - deriv(g, pHY, q, 0, OB_F);
+    } else if (comp == 1) {
+        if (P.fplane) {          // y_f_cross_U = f ℑxyᶜᶠᵃ(u) = f ℑyᵃᶠᵃ(ℑxᶜᵃᵃ u)       (f_plane.jl:43)
+            FT a1 = IC(g, U[0], q, 0);
+            FT u = g.topo[1] == OB_FLAT ? a1 : FT(0.5) * (IC(g, U[0], sh(g, q, 1, -1), 0) + a1);
+            G = G - (P.f * u);
+        }
+        if (pHY) G = G - deriv(g, pHY, q, 1, OB_F);
+    }
+    G = G - div_tau(P, comp, U, q);
+    if (comp < 2 && P.tilted && b) G = G + P.ghat[comp] * b[q.p];      // x/y_dot_g_b (g_dot_b.jl:1-3)
+    return G;
+}
+
+}  // namespace ob

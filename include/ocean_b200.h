@@ -1,0 +1,188 @@
+/*
+ * ocean_b200.h -- C ABI of libocean_b200.so: the B200-native NonhydrostaticModel time step
+ * behind Oceananigans' architecture dispatch (a new `B200()` next to `CPU()`/`GPU()`,
+ * reference src/Architectures.jl:68-143).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, POD descriptors copied on entry.
+ *   - every function returns int32 status: 0 = OK, nonzero = error; the message is
+ *     retrieved with ob200_last_error() (thread-local).  No exceptions cross the boundary.
+ *   - host pointers are borrowed for the duration of the call only.
+ *   - device memory is owned by the handle that allocated it and released by *_destroy.
+ *   - all work is enqueued on one CUDA stream per process (ob200_set_stream); entry points
+ *     that return data to the host synchronise that stream, the others do not.
+ *   - arrays are column-major, x fastest.  "parent" arrays have the reference's layout:
+ *     (Nx+2Hx) x (Ny+2Hy) x (Nz+2Hz), +1 along a Bounded dimension for Face-located fields,
+ *     extent N and halo 0 along Flat dimensions (reference src/Grids/new_data.jl:16-22,56-61).
+ *     Internally fields live in a padded, sector-aligned layout; upload/download convert.
+ *   - there is NO CPU fallback: every entry point fails if no CUDA device is usable.
+ *
+ * Each entry point cites the reference interface (path relative to /root/reference/src) it
+ * replaces.  INTEGRATION.md shows the Julia `ccall` shim that binds them.
+ */
+#ifndef OCEAN_B200_H
+#define OCEAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OB200_VERSION 100
+
+/* ---- enums ---------------------------------------------------------------------------- */
+enum { OB200_F32 = 0, OB200_F64 = 1 };                       /* eltype(grid)                   */
+enum { OB200_PERIODIC = 0, OB200_BOUNDED = 1, OB200_FLAT = 2 }; /* Grids topology              */
+enum { OB200_CENTER = 0, OB200_FACE = 1 };                   /* Center / Face                  */
+enum { OB200_BC_NONE = 0, OB200_BC_PERIODIC = 1, OB200_BC_FLUX = 2, OB200_BC_VALUE = 3,
+       OB200_BC_GRADIENT = 4, OB200_BC_OPEN = 5 };           /* BoundaryConditions classes     */
+enum { OB200_ADV_NONE = 0, OB200_ADV_CENTERED2 = 1, OB200_ADV_CENTERED4 = 2, OB200_ADV_UPWIND1 = 3,
+       OB200_ADV_UPWIND3 = 4, OB200_ADV_UPWIND5 = 5, OB200_ADV_WENO5 = 6 };   /* Advection      */
+enum { OB200_CLOSURE_NONE = 0, OB200_CLOSURE_3D = 1, OB200_CLOSURE_HORIZONTAL = 2,
+       OB200_CLOSURE_VERTICAL = 3 };                         /* ScalarDiffusivity formulations */
+enum { OB200_TS_AB2 = 0, OB200_TS_RK3 = 1 };                 /* :QuasiAdamsBashforth2 / :RungeKutta3 */
+enum { OB200_SIDE_WEST = 0, OB200_SIDE_EAST = 1, OB200_SIDE_SOUTH = 2, OB200_SIDE_NORTH = 3,
+       OB200_SIDE_BOTTOM = 4, OB200_SIDE_TOP = 5 };
+enum { OB200_SOLVER_AUTO = 0, OB200_SOLVER_FFT = 1, OB200_SOLVER_FOURIER_TRIDIAGONAL = 2 };
+
+typedef struct ob200_grid ob200_grid;
+typedef struct ob200_field ob200_field;
+typedef struct ob200_model ob200_model;
+typedef struct ob200_poisson ob200_poisson;
+
+/* ---- descriptors ---------------------------------------------------------------------- */
+
+/* RectilinearGrid (Grids/rectilinear_grid.jl:1-47).  For a regular dimension `delta` is the
+ * spacing already rounded to the grid's float type by the host (grid_generation.jl:83-107).
+ * For a stretched dimension the host passes the reference's own metric vectors (parents of
+ * the OffsetArrays grid.Δzᵃᵃᶜ / grid.Δzᵃᵃᶠ, halos included) with the Julia index of their
+ * first element (grid_generation.jl:28-80).  Values are passed as double whatever `ftype`. */
+typedef struct {
+    int32_t ftype;
+    int32_t N[3];
+    int32_t H[3];
+    int32_t topology[3];
+    double  L[3];
+    int32_t regular[3];
+    double  delta[3];
+    const double* dC[3];  int32_t dC_first[3]; int32_t dC_len[3];   /* Δ at centers  */
+    const double* dF[3];  int32_t dF_first[3]; int32_t dF_len[3];   /* Δ at faces    */
+} ob200_grid_desc;
+
+/* One boundary condition (BoundaryConditions/boundary_condition.jl): class + constant value.
+ * Function-valued conditions cannot cross a C ABI and are rejected by the shim. */
+typedef struct { int32_t kind; double value; } ob200_bc;
+
+#define OB200_MAX_TRACERS 8
+
+/* NonhydrostaticModel(; grid, advection, closure, coriolis, buoyancy, tracers, timestepper,
+ * boundary_conditions) (Models/NonhydrostaticModels/nonhydrostatic_model.jl:102-203). */
+typedef struct {
+    const ob200_grid* grid;
+    int32_t timestepper;            /* OB200_TS_*                                              */
+    double  chi;                    /* AB2 χ (quasi_adams_bashforth_2.jl:6-40), default 0.1    */
+    int32_t advection;              /* OB200_ADV_*                                             */
+    int32_t weno_zweno;             /* WENO5(zweno=true) default (weno_fifth_order.jl:167)     */
+    /* WENO5(grid=grid) ENO coefficient tables for stretched dimensions, else NULL:
+     * weno_coeff[d][loc] -> 4 tables (r=-1,0,1,2) x (N[d]+2) entries (index 0..N+1) x 3 doubles
+     * (weno_fifth_order.jl:562-584), loc 0 = Face table (coeff_xᶠᵃᵃ), 1 = Center table. */
+    const double* weno_coeff[3][2];
+    int32_t closure;                /* OB200_CLOSURE_*                                         */
+    double  nu;                     /* ScalarDiffusivity ν                                     */
+    double  kappa[OB200_MAX_TRACERS];
+    int32_t coriolis_fplane;        /* 0 = nothing, 1 = FPlane                                 */
+    double  f;
+    int32_t buoyancy_tracer;        /* -1 = buoyancy nothing, else index of tracer :b          */
+    int32_t gravity_tilted;         /* 0 = ZDirection, 1 = gravity_unit_vector given           */
+    double  g_hat[3];
+    int32_t ntracers;
+    ob200_bc bcs[3 + OB200_MAX_TRACERS][6];   /* per prognostic field (u,v,w,tracers...), per side */
+    int32_t pressure_solver;        /* OB200_SOLVER_AUTO picks as NonhydrostaticModels.jl:18-27 */
+} ob200_model_desc;
+
+/* ---- library / device ----------------------------------------------------------------- */
+int32_t ob200_version(void);
+/* Architectures.jl device(arch): select the CUDA device for this process. */
+int32_t ob200_init(int32_t device);
+/* All subsequent work is enqueued on `cuda_stream` (a cudaStream_t; NULL = legacy default). */
+int32_t ob200_set_stream(void* cuda_stream);
+int32_t ob200_sync(void);
+size_t  ob200_last_error(char* buf, size_t len);
+/* number of kernels launched by the library so far in this process (bench evidence) */
+int64_t ob200_launch_count(void);
+
+/* ---- raw memory: Architectures.jl array_type / arch_array / zeros / unsafe_free! -------- */
+int32_t ob200_malloc(void** dev_ptr, size_t bytes);
+int32_t ob200_free(void* dev_ptr);
+int32_t ob200_memset(void* dev_ptr, int32_t value, size_t bytes);
+int32_t ob200_upload(void* dst_dev, const void* src_host, size_t bytes);     /* arch_array(arch, a) */
+int32_t ob200_download(void* dst_host, const void* src_dev, size_t bytes);   /* Array(a)            */
+
+/* ---- grid ----------------------------------------------------------------------------- */
+int32_t ob200_grid_create(const ob200_grid_desc* desc, ob200_grid** out);
+int32_t ob200_grid_destroy(ob200_grid* g);
+
+/* ---- fields: Fields/field.jl:16-31,165-194 --------------------------------------------- */
+int32_t ob200_field_create(const ob200_grid* g, const int32_t loc[3], const ob200_bc bcs[6],
+                           ob200_field** out);
+int32_t ob200_field_destroy(ob200_field* f);
+/* size(parent(field)) in the reference layout */
+int32_t ob200_field_parent_size(const ob200_field* f, int32_t out[3]);
+/* parent(field) .= host array  /  Array(parent(field)); element type = grid ftype */
+int32_t ob200_field_set_parent(ob200_field* f, const void* host_parent);
+int32_t ob200_field_get_parent(const ob200_field* f, void* host_parent);
+/* internal device storage: base pointer, index of Julia (1,1,1), strides in elements */
+int32_t ob200_field_device_view(const ob200_field* f, void** base, int64_t offset111[1],
+                                int64_t strides[3]);
+/* fill_halo_regions!(fields) BoundaryConditions/fill_halo_regions.jl:34-82 */
+int32_t ob200_fill_halo_regions(ob200_field* const* fields, int32_t n);
+/* device reductions over the interior (Simulations NaNChecker / wizard / diagnostics) */
+int32_t ob200_field_reduce(const ob200_field* f, double* sum, double* sumsq, double* maxabs,
+                           int32_t* has_nan);
+
+/* ---- Poisson solvers: Solvers/fft_based_poisson_solver.jl, fourier_tridiagonal_poisson_solver.jl */
+int32_t ob200_poisson_create(const ob200_grid* g, int32_t kind, ob200_poisson** out);
+int32_t ob200_poisson_destroy(ob200_poisson* s);
+/* solve!(ϕ, solver, rhs): rhs is a real host array Nx*Ny*Nz of the grid's float type
+ * (the real part of solver.storage; for the Fourier-tridiagonal solver it is the source term
+ * BEFORE multiplication by Δzᶜ, i.e. the argument of set_source_term!). */
+int32_t ob200_poisson_solve(ob200_poisson* s, ob200_field* phi, const void* rhs_host);
+/* solve_for_pressure!(pressure, solver, Δt, U★) Models/NonhydrostaticModels/solve_for_pressure.jl:55-89 */
+int32_t ob200_solve_for_pressure(ob200_poisson* s, ob200_field* pressure, double dt,
+                                 const ob200_field* u, const ob200_field* v, const ob200_field* w);
+/* solve!(ϕ, ::BatchedTridiagonalSolver, rhs) Solvers/batched_tridiagonal_solver.jl:74-122:
+ * a, c: Nz-1 doubles; b: Nx*Ny*Nz doubles; rhs/phi: Nx*Ny*Nz (complex if is_complex) host arrays
+ * of the float type `ftype`. */
+int32_t ob200_batched_tridiagonal_solve(int32_t ftype, int32_t is_complex, int32_t Nx, int32_t Ny,
+                                        int32_t Nz, const double* a, const double* b,
+                                        const double* c, const void* rhs_host, void* phi_host);
+
+/* ---- model ---------------------------------------------------------------------------- */
+int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model** out);
+int32_t ob200_model_destroy(ob200_model* m);
+/* model.velocities.u / model.tracers.b / model.pressures.pNHS / timestepper.Gⁿ.u ...
+ * names: "u","v","w","c<k>" (k-th tracer, 0-based),"pNHS","pHY","Gn_u",...,"Gm_c0".
+ * The returned handle is borrowed (owned by the model). */
+int32_t ob200_model_field(ob200_model* m, const char* name, ob200_field** out);
+/* update_state!(model) update_nonhydrostatic_model_state.jl:14-37 */
+int32_t ob200_model_update_state(ob200_model* m);
+/* calculate_tendencies!(model) calculate_nonhydrostatic_tendencies.jl:12-36 (Gⁿ only) */
+int32_t ob200_model_calculate_tendencies(ob200_model* m);
+/* calculate_pressure_correction! + pressure_correct_velocities! pressure_correction.jl:10-56;
+ * with update_state!, this is the projection `set!(model; ...)` applies (set_nonhydrostatic_model.jl:51-56) */
+int32_t ob200_model_pressure_project(ob200_model* m, double dt);
+/* time_step!(model, Δt) TimeSteppers/runge_kutta_3.jl:81-152, quasi_adams_bashforth_2.jl:70-104.
+ * `euler` forces a forward-Euler step (AB2 only).  Enqueues the whole step; does not sync. */
+int32_t ob200_model_time_step(ob200_model* m, double dt, int32_t euler);
+/* model.clock (TimeSteppers/clock.jl) */
+int32_t ob200_model_clock(const ob200_model* m, double* time, int64_t* iteration);
+int32_t ob200_model_set_clock(ob200_model* m, double time, int64_t iteration, double previous_dt);
+/* max |div U| and kinetic energy 0.5*sum(u^2+v^2+w^2) over the interior (diagnostics) */
+int32_t ob200_model_diagnostics(ob200_model* m, double* max_abs_div, double* kinetic_energy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCEAN_B200_H */

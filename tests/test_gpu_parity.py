@@ -1,0 +1,351 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (via the ctypes host mirror), against
+the oracle on identical seeded inputs.  Tolerances are BASELINE.json's: max relative error per
+step <= 1e-12 in Float64 and <= 1e-5 in Float32 (relative to the field's max magnitude)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import ocean_b200 as ob
+    ob.arch = ob.B200()
+    return ob
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b)) / scale)
+
+
+def make_pair(ob, FT, size, topology, coords=None, extent=None, halo=None):
+    kw = dict(size=size, topology=topology)
+    if extent is not None:
+        kw["extent"] = extent
+    if coords:
+        kw.update(coords)
+    if halo is not None:
+        kw["halo"] = halo
+    return O.RectilinearGrid(FT, **kw), ob.RectilinearGrid(ob.arch, FT, **kw)
+
+
+LOCS = [("f", "c", "c"), ("c", "f", "c"), ("c", "c", "f"), ("c", "c", "c")]
+LMAP = {"c": "Center", "f": "Face"}
+
+
+# ---- halos -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("topo", [(O.Periodic, O.Periodic, O.Periodic), (O.Periodic, O.Periodic, O.Bounded),
+                                  (O.Bounded, O.Periodic, O.Bounded), (O.Bounded, O.Bounded, O.Bounded),
+                                  (O.Periodic, O.Bounded, O.Flat)])
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_fill_halo_regions_bit_exact(ob, topo, FT):
+    rng = np.random.default_rng(11)
+    size = tuple(n for n, t in zip((9, 6, 5), topo) if t != O.Flat)
+    halo = tuple(h for h, t in zip((3, 2, 1), topo) if t != O.Flat)
+    go, gb = make_pair(ob, FT, size, topo, extent=tuple(1.0 for _ in size), halo=halo)
+    fo_list, fb_list = [], []
+    for loc in LOCS:
+        fo = O.Field(go, loc)
+        fb = ob.Field(tuple(LMAP[l] for l in loc), gb)
+        assert fb.parent_size == fo.parent.shape
+        a = rng.random(fo.parent.shape).astype(FT)
+        fo.parent[...] = a
+        fb.set_parent(a)
+        assert np.array_equal(fb.parent(), a)           # layout round trip
+        fo_list.append(fo), fb_list.append(fb)
+    O.fill_halo_regions(fo_list)
+    ob.fill_halo_regions(fb_list)
+    for fo, fb in zip(fo_list, fb_list):
+        assert np.array_equal(fb.parent(), fo.parent)
+
+
+def test_fill_halo_value_gradient_bcs(ob):
+    rng = np.random.default_rng(12)
+    zF = -np.linspace(1, 0, 8) ** 1.5
+    topo = (O.Periodic, O.Periodic, O.Bounded)
+    go, gb = make_pair(ob, np.float64, (6, 5, 7), topo, coords=dict(x=(0, 1), y=(0, 1), z=zF))
+    bo = O.FieldBoundaryConditions(go, ("c", "c", "c"), top=O.BoundaryCondition("Value", 2.0),
+                                   bottom=O.BoundaryCondition("Gradient", -0.5))
+    fo = O.Field(go, ("c", "c", "c"), bo)
+    fb = ob.CenterField(gb, dict(top=ob.ValueBoundaryCondition(2.0), bottom=ob.GradientBoundaryCondition(-0.5)))
+    a = rng.random(fo.parent.shape)
+    fo.parent[...] = a
+    fb.set_parent(a)
+    O.fill_halo_regions(fo)
+    ob.fill_halo_regions(fb)
+    assert relerr(fb.parent(), fo.parent) < 1e-15
+
+
+# ---- Poisson solvers ---------------------------------------------------------------------------
+def _rhs(go, rng):
+    u, v, w = O.Field(go, LOCS[0]), O.Field(go, LOCS[1]), O.Field(go, LOCS[2])
+    for f in (u, v, w):
+        f.set(rng.random(f.size()))
+    O.fill_halo_regions([u, v, w])
+    i, j, k = O.R(1, go.Nx), O.R(1, go.Ny), O.R(1, go.Nz)
+    from oracle.operators import div_ccc
+    return np.array(div_ccc(i, j, k, go, u, v, w)), (u, v, w)
+
+
+TOPOS8 = [(a, b, c) for a in (O.Periodic, O.Bounded) for b in (O.Periodic, O.Bounded) for c in (O.Periodic, O.Bounded)]
+
+
+@pytest.mark.parametrize("topo", TOPOS8)
+@pytest.mark.parametrize("N", [(16, 8, 32), (7, 11, 6)])
+def test_fft_poisson_matches_oracle_and_laplacian(ob, topo, N):
+    rng = np.random.default_rng(13)
+    go, gb = make_pair(ob, np.float64, N, topo, extent=(1.0, 2.0, 3.0))
+    rhs, _ = _rhs(go, rng)
+    so = O.FFTBasedPoissonSolver(go)
+    ϕo = O.Field(go, auxiliary=True)
+    so.storage[...] = rhs
+    so.solve(ϕo)
+    sb = ob.FFTBasedPoissonSolver(gb)
+    ϕb = ob.CenterField(gb)
+    ob.solve(ϕb, sb, rhs)
+    assert relerr(ϕb.interior(), ϕo.interior) < 1e-12
+    # reference's own check: lap(phi) == rhs (test/dependencies_for_poisson_solvers.jl:86-104)
+    ob.fill_halo_regions(ϕb)
+    ϕo.parent[...] = ϕb.parent()
+    from oracle.operators import laplacian_ccc
+    lap = laplacian_ccc(O.R(1, go.Nx), O.R(1, go.Ny), O.R(1, go.Nz), go, ϕo)
+    assert np.linalg.norm(lap - rhs) <= 1e-8 * np.linalg.norm(rhs)
+
+
+def test_fft_poisson_float32_flat(ob):
+    rng = np.random.default_rng(14)
+    go, gb = make_pair(ob, np.float32, (32, 16), (O.Periodic, O.Bounded, O.Flat), extent=(1.0, 1.0))
+    rhs, _ = _rhs(go, rng)
+    so = O.FFTBasedPoissonSolver(go)
+    ϕo = O.Field(go, auxiliary=True)
+    so.storage[...] = rhs
+    so.solve(ϕo)
+    ϕb = ob.CenterField(gb)
+    ob.solve(ϕb, ob.FFTBasedPoissonSolver(gb), rhs)
+    assert relerr(ϕb.interior(), ϕo.interior) < 1e-5
+
+
+@pytest.mark.parametrize("topo", [(a, b, O.Bounded) for a in (O.Periodic, O.Bounded) for b in (O.Periodic, O.Bounded)])
+def test_fourier_tridiagonal_matches_oracle(ob, topo):
+    rng = np.random.default_rng(15)
+    zF = np.concatenate([[0.0], np.cumsum(0.5 + rng.random(12))])
+    zF = zF / zF[-1] - 1
+    go, gb = make_pair(ob, np.float64, (16, 8, 12), topo, coords=dict(x=(0, 1), y=(0, 2), z=zF))
+    rhs, _ = _rhs(go, rng)
+    ϕo = O.Field(go, auxiliary=True)
+    O.FourierTridiagonalPoissonSolver(go).solve(ϕo, rhs)
+    ϕb = ob.CenterField(gb)
+    ob.solve(ϕb, ob.FourierTridiagonalPoissonSolver(gb), rhs)
+    assert relerr(ϕb.interior(), ϕo.interior) < 1e-11
+
+
+def test_batched_tridiagonal_vs_dense(ob):
+    rng = np.random.default_rng(16)
+    Nx, Ny, Nz = 5, 4, 9
+    _, gb = make_pair(ob, np.float64, (Nx, Ny, Nz), (O.Periodic, O.Periodic, O.Bounded), extent=(1, 1, 1))
+    a, c = rng.random(Nz - 1), rng.random(Nz - 1)
+    b = 3 + rng.random((Nx, Ny, Nz))
+    f = rng.random((Nx, Ny, Nz)) + 1j * rng.random((Nx, Ny, Nz))
+    ϕ = ob.BatchedTridiagonalSolver(gb, a, b, c).solve(f)
+    for i in range(Nx):
+        for j in range(Ny):
+            M = np.diag(b[i, j]) + np.diag(a, -1) + np.diag(c, 1)
+            assert np.allclose(np.linalg.solve(M, f[i, j]), ϕ[i, j], rtol=1e-12)
+
+
+# ---- model configurations ------------------------------------------------------------------------
+def _zf(n, p=1.5):
+    return -np.linspace(1, 0, n + 1) ** p
+
+
+CONFIGS = {
+    # headline physics at a small size: triply periodic, WENO5, buoyancy tracer, RK3
+    "c2_periodic_weno_rk3": dict(size=(16, 12, 10), topology=(O.Periodic,) * 3, extent=(1, 1, 1),
+                                 adv="WENO5", tracers=("b",), buoyancy=True, ts="RungeKutta3", dt=2e-3),
+    "periodic_weno_closure_fplane_ab2": dict(size=(12, 16, 8), topology=(O.Periodic,) * 3, extent=(1, 2, 1),
+                                             adv="WENO5", tracers=("b", "c"), buoyancy=True, closure=("ThreeDimensional", 1e-3, 2e-3),
+                                             f=0.7, ts="QuasiAdamsBashforth2", dt=2e-3),
+    # config 1 physics: 2-D periodic turbulence, Flat z, AB2 (README example)
+    "c1_2d_flat_weno_ab2": dict(size=(32, 24), topology=(O.Periodic, O.Periodic, O.Flat), extent=(2 * np.pi, 2 * np.pi),
+                                adv="WENO5", tracers=(), buoyancy=False, ts="QuasiAdamsBashforth2", dt=5e-3),
+    # config 3 physics: bounded stretched z, WENO5(grid), Fourier-tridiagonal, flux/gradient BCs
+    "c3_stretched_weno_rk3": dict(size=(12, 8, 14), topology=(O.Periodic, O.Periodic, O.Bounded),
+                                  coords=dict(x=(0, 1), y=(0, 1), z=_zf(14)), adv="WENO5grid", tracers=("b",),
+                                  buoyancy=True, closure=("ThreeDimensional", 1e-4, 1e-4), f=1e-2, ts="RungeKutta3", dt=5e-3,
+                                  bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"top": ("Flux", 1e-4), "bottom": ("Gradient", 1e-2)}}),
+    "channel_bounded_yz_weno": dict(size=(8, 12, 10), topology=(O.Periodic, O.Bounded, O.Bounded), extent=(1, 1, 1),
+                                    adv="WENO5", tracers=("b",), buoyancy=True, closure=("Horizontal", 1e-3, 1e-3),
+                                    ts="RungeKutta3", dt=2e-3),
+    "box_bbb_upwind5_vertical": dict(size=(8, 9, 10), topology=(O.Bounded,) * 3, extent=(1, 1, 1), adv="UpwindBiasedFifthOrder",
+                                     tracers=("b",), buoyancy=True, closure=("Vertical", 1e-3, 1e-3), ts="QuasiAdamsBashforth2", dt=2e-3),
+    "centered2_default": dict(size=(8, 8, 8), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(1, 1, 1),
+                              adv="CenteredSecondOrder", tracers=("b",), buoyancy=True, ts="QuasiAdamsBashforth2", dt=2e-3),
+    "centered4_tilted": dict(size=(8, 10, 8), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(1, 1, 1),
+                             adv="CenteredFourthOrder", tracers=("b",), buoyancy=True, tilt=(0.0, 0.6, 0.8),
+                             ts="RungeKutta3", dt=2e-3),
+    "upwind3_jsweno_none": dict(size=(8, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="UpwindBiasedThirdOrder",
+                                tracers=("c",), buoyancy=False, ts="RungeKutta3", dt=2e-3),
+    "weno_js": dict(size=(10, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="WENO5js",
+                    tracers=("b",), buoyancy=True, ts="RungeKutta3", dt=2e-3),
+}
+
+
+def build_models(ob, cfg, FT):
+    go, gb = make_pair(ob, FT, cfg["size"], cfg["topology"], coords=cfg.get("coords"), extent=cfg.get("extent"))
+    adv = cfg["adv"]
+    if adv == "WENO5":
+        ao, ab = O.WENO5(FT), ob.WENO5(FT)
+    elif adv == "WENO5js":
+        ao, ab = O.WENO5(FT, zweno=False), ob.WENO5(FT, zweno=False)
+    elif adv == "WENO5grid":
+        ao, ab = O.WENO5(grid=go), ob.WENO5(grid=gb)
+    else:
+        ao, ab = getattr(O, adv)(), getattr(ob, adv)()
+    clo_o = clo_b = None
+    if cfg.get("closure"):
+        form, nu, ka = cfg["closure"]
+        clo_o, clo_b = O.ScalarDiffusivity(form, ν=nu, κ=ka), ob.ScalarDiffusivity(form, ν=nu, κ=ka)
+    cor_o = O.FPlane(cfg["f"]) if cfg.get("f") else None
+    cor_b = ob.FPlane(cfg["f"]) if cfg.get("f") else None
+    bu_o = bu_b = None
+    if cfg.get("buoyancy"):
+        bu_o = O.Buoyancy(O.BuoyancyTracer(), cfg.get("tilt"))
+        bu_b = ob.Buoyancy(ob.BuoyancyTracer(), cfg.get("tilt"))
+    bcs_o = bcs_b = None
+    if cfg.get("bcs"):
+        bcs_o = {n: {s: O.BoundaryCondition(*kv) for s, kv in d.items()} for n, d in cfg["bcs"].items()}
+        bcs_b = {n: {s: ob.BoundaryCondition(*kv) for s, kv in d.items()} for n, d in cfg["bcs"].items()}
+    mo = O.NonhydrostaticModel(go, advection=ao, closure=clo_o, coriolis=cor_o, buoyancy=bu_o,
+                               tracers=cfg["tracers"], timestepper=cfg["ts"], boundary_conditions=bcs_o)
+    mb = ob.NonhydrostaticModel(gb, advection=ab, closure=clo_b, coriolis=cor_b, buoyancy=bu_b,
+                                tracers=cfg["tracers"], timestepper=cfg["ts"], boundary_conditions=bcs_b)
+    return mo, mb
+
+
+def init_state(mo, mb, ob, seed):
+    rng = np.random.default_rng(seed)
+    vals = {}
+    for n in mo.names:
+        f = mo.fields[n]
+        a = rng.uniform(-1, 1, f.size())
+        if n in "uvw":
+            a = a - a.mean()
+        else:
+            z = mo.grid.nodes(f.loc)[2]
+            a = 0.5 * z + 0.1 * a
+        vals[n] = a.astype(mo.grid.FT)
+    mo.set(**vals)
+    ob.set_model(mb, **vals)
+
+
+def compare_fields(mo, mb, tol, what="state"):
+    worst = 0.0
+    for n in mo.names:
+        e = relerr(mb.fields[n].interior(), mo.fields[n].interior)
+        worst = max(worst, e)
+        assert e < tol, f"{what}: field {n} differs: rel err {e:.3e}"
+    return worst
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_tendencies_and_steps_match_oracle_f64(ob, name):
+    cfg = CONFIGS[name]
+    FT = np.float64
+    mo, mb = build_models(ob, cfg, FT)
+    init_state(mo, mb, ob, 21)
+    compare_fields(mo, mb, 1e-12, "after set!/projection")
+    if mo.pHY is not None:
+        assert relerr(mb.pressures["pHY′"].interior(), mo.pHY.interior) < 1e-13
+    # tendencies alone
+    mo.calculate_tendencies()
+    ob.calculate_tendencies(mb)
+    g = mo.grid
+    for n in mo.names:
+        Go = mo.Gn[n][O.R(1, g.Nx), O.R(1, g.Ny), O.R(1, g.Nz)]
+        Gb = mb.Gn[n].interior()[:g.Nx, :g.Ny, :g.Nz]
+        assert relerr(Gb, Go) < 1e-12, f"tendency {n}"
+    # time steps, checked after every step
+    for step in range(4):
+        mo.time_step(cfg["dt"])
+        ob.time_step(mb, cfg["dt"])
+        compare_fields(mo, mb, 1e-12, f"step {step + 1}")
+        assert relerr(mb.pressures["pNHS"].interior(), mo.pNHS.interior) < 1e-9
+    d = mb.diagnostics()
+    assert d["max_abs_div"] < 1e-10
+    assert abs(d["kinetic_energy"] - mo.kinetic_energy()) <= 1e-11 * mo.kinetic_energy()
+    assert abs(mb.clock.time - mo.clock.time) < 1e-15 and mb.clock.iteration == 4
+
+
+@pytest.mark.parametrize("name", ["c2_periodic_weno_rk3", "c3_stretched_weno_rk3", "c1_2d_flat_weno_ab2"])
+def test_steps_match_oracle_f32(ob, name):
+    cfg = CONFIGS[name]
+    mo, mb = build_models(ob, cfg, np.float32)
+    init_state(mo, mb, ob, 22)
+    for step in range(3):
+        mo.time_step(cfg["dt"])
+        ob.time_step(mb, cfg["dt"])
+        compare_fields(mo, mb, 1e-5, f"f32 step {step + 1}")
+
+
+def test_fast_and_general_kernels_agree(ob):
+    """the specialised headline kernels against the general ones on the same state"""
+    cfg = CONFIGS["c2_periodic_weno_rk3"]
+    mo, m1 = build_models(ob, cfg, np.float64)
+    _, m2 = build_models(ob, cfg, np.float64)
+    m2.use_fast_kernels(False)
+    init_state(mo, m1, ob, 23)
+    init_state(mo, m2, ob, 23)
+    for _ in range(3):
+        ob.time_step(m1, cfg["dt"])
+        ob.time_step(m2, cfg["dt"])
+    for n in m1.names:
+        assert relerr(m1.fields[n].interior(), m2.fields[n].interior()) < 1e-13
+
+
+def test_ab2_first_step_is_euler_and_simulation_runs(ob):
+    cfg = CONFIGS["c1_2d_flat_weno_ab2"]
+    mo, mb = build_models(ob, cfg, np.float64)
+    init_state(mo, mb, ob, 24)
+    sim = ob.Simulation(mb, Δt=cfg["dt"], stop_iteration=6)
+    ob.run(sim)
+    for _ in range(6):
+        mo.time_step(cfg["dt"])
+    compare_fields(mo, mb, 1e-11, "run!")
+    assert mb.clock.iteration == 6
+
+
+# ---- full-size properties (BASELINE.json config 2: 256^3) ----------------------------------------
+def test_full_size_256_properties(ob):
+    """size-independent properties at the headline size: the projected state is divergence free,
+    tracer mean is conserved by flux-form advection on a periodic domain, and halos are periodic."""
+    N = 256
+    gb = ob.RectilinearGrid(ob.arch, np.float64, size=(N, N, N), extent=(1, 1, 1), topology=("Periodic",) * 3)
+    m = ob.NonhydrostaticModel(gb, advection=ob.WENO5(), tracers=("b",), buoyancy=ob.BuoyancyTracer(),
+                               timestepper="RungeKutta3")
+    rng = np.random.default_rng(2)
+    vals = {}
+    for n in "uvw":
+        a = rng.uniform(-1, 1, (N, N, N))
+        vals[n] = a - a.mean()
+    z = gb.nodes(("Center",) * 3)[2]
+    vals["b"] = 1e-5 * z + 1e-3 * rng.uniform(-1, 1, (N, N, N))
+    ob.set_model(m, **vals)
+    b0 = m.tracers["b"].reduce()["sum"]
+    d0 = m.diagnostics()
+    assert d0["max_abs_div"] < 1e-9
+    dt = 0.1 / N
+    for _ in range(2):
+        ob.time_step(m, dt)
+    d1 = m.diagnostics()
+    assert d1["max_abs_div"] < 1e-9
+    assert 0 < d1["kinetic_energy"] <= d0["kinetic_energy"] * (1 + 1e-12)     # WENO is dissipative
+    b1 = m.tracers["b"].reduce()["sum"]
+    assert abs(b1 - b0) <= 1e-10 * (abs(b0) + N ** 3 * 1e-3)
+    p = m.velocities["u"].parent()
+    assert np.array_equal(p[:3], p[N:N + 3]) and np.array_equal(p[:, :, N + 3:], p[:, :, 3:6])
