@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point updates/sec of one RK3 step of NonhydrostaticModel (256^3 triply periodic,
+WENO5 + buoyancy tracer + FFT pressure solve, Float64) on B200, plus HBM roofline fraction of the
+dominant kernel and a CPU baseline.  Contract: see the task statement / DESIGN.md section 6.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 256] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU).  One "step" = one full RK3 time step (3 stages,
+3 pressure solves) of every cell of the workload.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "clima-oceananigans.jl_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "grid-point updates/sec (RK3 step, 256^3 WENO5+FFT)"
+UNIT = "grid-point updates/s"
+
+
+def synthetic_state(N, seed=2):
+    """uniform(-1,1) velocities with the mean removed, b = N^2 z + noise."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    vals = {}
+    for n in "uvw":
+        a = rng.uniform(-1, 1, (N, N, N))
+        vals[n] = a - a.mean()
+    z = (np.arange(N) + 0.5) / N
+    vals["b"] = 1e-5 * z.reshape(1, 1, N) + 1e-3 * rng.uniform(-1, 1, (N, N, N))
+    return vals
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_run(steps, warmup, sample_n=48):
+    """The reference's CPU path is pure Julia and cannot run here (no Julia toolchain).
+    What is timed is the oracle port (numpy restatement, oracle/) on a bounded sample of the same
+    workload: one RK3 step of the triply periodic WENO5 + b + FFT model at sample_n^3."""
+    import numpy as np
+    import oracle as O
+    N = sample_n
+    g = O.RectilinearGrid(np.float64, size=(N, N, N), extent=(1, 1, 1), topology=(O.Periodic,) * 3)
+    m = O.NonhydrostaticModel(g, advection=O.WENO5(), tracers=("b",), buoyancy=O.BuoyancyTracer(),
+                              timestepper="RungeKutta3")
+    m.set(**synthetic_state(N))
+    dt = 0.1 / N
+    for _ in range(warmup):
+        m.time_step(dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.time_step(dt)
+    el = time.perf_counter() - t0
+    return N ** 3 * steps / el, el / steps, f"{steps} RK3 step(s) of the same model at {N}^3 (numpy oracle port, 1 thread)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N = a.size
+    workload = f"C2: {N}^3 triply-periodic NonhydrostaticModel, WENO5 + tracer b + BuoyancyTracer, FFT pressure solve, RK3, Float64"
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(a.steps, 3))
+        v, spstep, sample = cpu_reference_run(steps, min(a.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": min(a.warmup, 1), "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import numpy as np
+    import torch
+    import ocean_b200 as ob
+    from ocean_b200._lib import lib
+    import ctypes as C
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    arch = ob.B200(local_rank)
+    stream = torch.cuda.current_stream()
+    lib.ob200_set_stream(C.c_void_p(stream.cuda_stream))
+
+    # weak scaling: every rank advances its own N^3 domain (see DESIGN.md section 7 for the status of
+    # the slab-decomposed path); per-GPU work is fixed as N grows
+    grid = ob.RectilinearGrid(arch, np.float64, size=(N, N, N), extent=(1, 1, 1), topology=("Periodic",) * 3)
+    model = ob.NonhydrostaticModel(grid, advection=ob.WENO5(), tracers=("b",), buoyancy=ob.BuoyancyTracer(),
+                                   timestepper="RungeKutta3")
+    vals = synthetic_state(N, seed=2 + rank)
+    ob.set_model(model, **vals)
+    dt = 0.1 / N          # CFL ~ 0.1-0.3 for |u| <~ 1..3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        ob.time_step(model, dt)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.ob200_profile_reset()
+    lib.ob200_profile_enable(1)
+    n0 = ob.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(a.steps):
+        ob.time_step(model, dt)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ob.launch_count() - n0
+    lib.ob200_profile_enable(0)
+    phases = {}
+    for ph in ("tendency", "poisson", "halo", "pressure_correct", "hydrostatic"):
+        t, c = C.c_double(), C.c_int64()
+        lib.ob200_profile_query(ph.encode(), C.byref(t), C.byref(c))
+        phases[ph] = {"ms_total": t.value, "count": c.value}
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = world * N ** 3 * a.steps / (ms * 1e-3)
+    d = model.diagnostics()
+    assert np.isfinite(d["kinetic_energy"]) and d["max_abs_div"] < 1e-8, d
+
+    # ---- roofline of the dominant kernel: the fused tendency+substep kernel (one launch per field) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    F = 4
+    tend = phases["tendency"]
+    # algorithmic words per point per launch: (4F+1)/F for stages 2,3 and (3F+1)/F for stage 1
+    words = ((3 * F + 1) + 2 * (4 * F + 1)) / 3.0 / F
+    alg_bytes = words * 8 * N ** 3
+    avg_ms = tend["ms_total"] / max(1, tend["count"])
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "tendency+substep (per prognostic field)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "avg_launch_ms": avg_ms, "launches": tend["count"],
+                "share_of_step": tend["ms_total"] / ms if ms > 0 else None,
+                "whole_step": {"algorithmic_GB_per_step": 880.0 * N ** 3 / 1e9,
+                               "achieved_GBps": 880.0 * N ** 3 * a.steps / (ms * 1e-3) / 1e9,
+                               "frac": 880.0 * N ** 3 * a.steps / (ms * 1e-3) / 1e9 / peak},
+                "phases_ms_per_step": {k: v["ms_total"] / a.steps for k, v in phases.items()}}
+
+    # ---- e2e: host buffers in, host buffers out, every step (pinned; copies inside the timed region) ----
+    e2e = None
+    if not a.no_e2e:
+        names = list(model.names)
+        hin = {n: torch.from_numpy(np.asfortranarray(model.fields[n].parent()).ravel(order="K").copy()).pin_memory()
+               for n in names}
+        hout = {n: torch.empty_like(hin[n]).pin_memory() for n in names}
+        nbytes = sum(t.numel() * 8 for t in hin.values())
+        ksteps = max(2, min(a.steps, 5))
+
+        def one():
+            for n in names:
+                lib.ob200_field_set_parent_async(model.fields[n].handle, C.c_void_p(hin[n].data_ptr()))
+            ob.time_step(model, dt)
+            for n in names:
+                lib.ob200_field_get_parent_async(model.fields[n].handle, C.c_void_p(hout[n].data_ptr()))
+            lib.ob200_sync()
+        one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            one()
+        barrier()
+        el = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([el], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el = float(tt.item())
+        # resident-state variant: the call a user of the B200() architecture makes inside run!:
+        # time_step!(model, dt) + the per-step scalar diagnostics read back (NaN check / CFL)
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            ob.time_step(model, dt)
+            model.velocities["u"].reduce()
+        barrier()
+        el_res = time.perf_counter() - t0
+        e2e = {"value": world * N ** 3 * ksteps / el, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "steps": ksteps,
+               "note": "every step: H2D of u,v,w,b parent arrays from pinned host memory, time_step!, D2H of the same",
+               "resident_state": {"value": world * N ** 3 * ksteps / el_res, "d2h_bytes_per_step": 32,
+                                  "note": "state stays on the device (how run! uses the architecture); per step a scalar reduction is read back"}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, spstep, sample = cpu_reference_run(1, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "grid": [N, N, N], "timestepper": "RungeKutta3", "advection": "WENO5 (Z)",
+                       "fields": F, "dt": dt, "l2": "inputs larger than L2 (14 fields x 144 MB)",
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent {N}^3 domains (weak; no data-path collective yet)"},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

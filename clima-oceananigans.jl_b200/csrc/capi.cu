@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -27,6 +28,51 @@ static void ensure_device() {
         throw Error(std::string("no usable CUDA device (libocean_b200 has no CPU fallback): ") +
                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
     g_inited = true;
+}
+
+// ---- optional per-phase timing with CUDA events on the library stream (bench evidence) ----
+struct Phase {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double total_ms = 0;
+    long long count = 0;
+};
+static bool g_profile = false;
+static std::map<std::string, Phase> g_phases;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t get_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    OB_CUDA(cudaEventCreate(&e));
+    return e;
+}
+struct ScopedPhase {
+    Phase* ph = nullptr;
+    cudaEvent_t a, b;
+    explicit ScopedPhase(const char* name) {
+        if (!g_profile) return;
+        ph = &g_phases[name];
+        a = get_event(); b = get_event();
+        cudaEventRecord(a, g_stream);
+    }
+    ~ScopedPhase() {
+        if (!ph) return;
+        cudaEventRecord(b, g_stream);
+        ph->pending.emplace_back(a, b);
+    }
+};
+static void resolve_phases() {
+    cudaStreamSynchronize(g_stream);
+    for (auto& kv : g_phases) {
+        for (auto& pr : kv.second.pending) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, pr.first, pr.second);
+            kv.second.total_ms += ms;
+            kv.second.count += 1;
+            g_event_pool.push_back(pr.first);
+            g_event_pool.push_back(pr.second);
+        }
+        kv.second.pending.clear();
+    }
 }
 }  // namespace ob
 
@@ -66,8 +112,10 @@ struct ob200_field {
     void* alt = nullptr;                    // second buffer (prognostic fields of a model)
     bool owns = true;
     int psize[3];
+    void* staging = nullptr;                // device copy in the reference's parent layout
     ~ob200_field() {
         if (owns) { if (base) cudaFree(base); if (alt) cudaFree(alt); }
+        if (staging) cudaFree(staging);
     }
     template <class FT> FT* p0() const {
         return (FT*)base + (grid->ftype == OB200_F32 ? grid->g32.off0 : grid->g64.off0);
@@ -281,38 +329,46 @@ extern "C" int32_t ob200_field_parent_size(const ob200_field* f, int32_t out[3])
 }
 
 template <class FT>
-static void field_set_parent(ob200_field* f, const void* host) {
+static void field_set_parent(ob200_field* f, const void* host, bool sync) {
     const GridD<FT>& g = gridD<FT>(f->grid);
     size_t n = (size_t)f->psize[0] * f->psize[1] * f->psize[2];
-    FT* tmp = nullptr;
-    OB_CUDA(cudaMalloc(&tmp, n * sizeof(FT)));
-    OB_CUDA(cudaMemcpyAsync(tmp, host, n * sizeof(FT), cudaMemcpyHostToDevice, stream()));
-    launch_to_internal<FT>(g, f->psize, f->loc, tmp, (FT*)f->base);
-    if (f->alt) launch_to_internal<FT>(g, f->psize, f->loc, tmp, (FT*)f->alt);
-    OB_CUDA(cudaStreamSynchronize(stream()));
-    cudaFree(tmp);
+    if (!f->staging) OB_CUDA(cudaMalloc(&f->staging, n * sizeof(FT)));
+    OB_CUDA(cudaMemcpyAsync(f->staging, host, n * sizeof(FT), cudaMemcpyHostToDevice, stream()));
+    launch_to_internal<FT>(g, f->psize, f->loc, (const FT*)f->staging, (FT*)f->base);
+    if (f->alt) launch_to_internal<FT>(g, f->psize, f->loc, (const FT*)f->staging, (FT*)f->alt);
+    if (sync) OB_CUDA(cudaStreamSynchronize(stream()));
 }
 template <class FT>
-static void field_get_parent(const ob200_field* f, void* host) {
+static void field_get_parent(ob200_field* f, void* host, bool sync) {
     const GridD<FT>& g = gridD<FT>(f->grid);
     size_t n = (size_t)f->psize[0] * f->psize[1] * f->psize[2];
-    FT* tmp = nullptr;
-    OB_CUDA(cudaMalloc(&tmp, n * sizeof(FT)));
-    launch_from_internal<FT>(g, f->psize, f->loc, (const FT*)f->base, tmp);
-    OB_CUDA(cudaMemcpyAsync(host, tmp, n * sizeof(FT), cudaMemcpyDeviceToHost, stream()));
-    OB_CUDA(cudaStreamSynchronize(stream()));
-    cudaFree(tmp);
+    if (!f->staging) OB_CUDA(cudaMalloc(&f->staging, n * sizeof(FT)));
+    launch_from_internal<FT>(g, f->psize, f->loc, (const FT*)f->base, (FT*)f->staging);
+    OB_CUDA(cudaMemcpyAsync(host, f->staging, n * sizeof(FT), cudaMemcpyDeviceToHost, stream()));
+    if (sync) OB_CUDA(cudaStreamSynchronize(stream()));
 }
 extern "C" int32_t ob200_field_set_parent(ob200_field* f, const void* host) {
     API_BEGIN
-    if (f->grid->ftype == OB200_F32) field_set_parent<float>(f, host);
-    else field_set_parent<double>(f, host);
+    if (f->grid->ftype == OB200_F32) field_set_parent<float>(f, host, true);
+    else field_set_parent<double>(f, host, true);
     API_END
 }
 extern "C" int32_t ob200_field_get_parent(const ob200_field* f, void* host) {
     API_BEGIN
-    if (f->grid->ftype == OB200_F32) field_get_parent<float>(f, host);
-    else field_get_parent<double>(f, host);
+    if (f->grid->ftype == OB200_F32) field_get_parent<float>(const_cast<ob200_field*>(f), host, true);
+    else field_get_parent<double>(const_cast<ob200_field*>(f), host, true);
+    API_END
+}
+extern "C" int32_t ob200_field_set_parent_async(ob200_field* f, const void* host) {
+    API_BEGIN
+    if (f->grid->ftype == OB200_F32) field_set_parent<float>(f, host, false);
+    else field_set_parent<double>(f, host, false);
+    API_END
+}
+extern "C" int32_t ob200_field_get_parent_async(const ob200_field* f, void* host) {
+    API_BEGIN
+    if (f->grid->ftype == OB200_F32) field_get_parent<float>(const_cast<ob200_field*>(f), host, false);
+    else field_get_parent<double>(const_cast<ob200_field*>(f), host, false);
     API_END
 }
 extern "C" int32_t ob200_field_device_view(const ob200_field* f, void** base, int64_t off[1], int64_t st[3]) {
@@ -622,8 +678,9 @@ static void model_fill_state_halos(ob200_model* m, int first, int last) {
 template <class FT>
 static void model_update_state(ob200_model* m, bool tracers_too = true) {
     // update_nonhydrostatic_model_state.jl:14-37
-    model_fill_state_halos<FT>(m, 0, tracers_too ? m->nf : 3);
+    { ScopedPhase ph("halo"); model_fill_state_halos<FT>(m, 0, tracers_too ? m->nf : 3); }
     if (m->pHY) {
+        ScopedPhase phase_timer("hydrostatic");
         const GridD<FT>& g = gridD<FT>(m->grid);
         Phys<FT>& P = physOf<FT>(m);
         bool has_b = P.btr >= 0;
@@ -653,6 +710,7 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
         for (int s = 0; s < 6; ++s) { fbc.kind[s] = f->bcs[s].kind; fbc.val[s] = (FT)f->bcs[s].value; }
         FT* newp = ss.mode == SUB_NONE ? nullptr : f->template alt0<FT>();
         bool done = false;
+        ScopedPhase ph("tendency");
         if (m->use_fast)
             done = launch_tendency_fast<FT>(P, q, U, f->template p0<FT>(), pHY, m->Gn[q]->template p0<FT>(),
                                             m->Gm[q]->template p0<FT>(), newp, ss);
@@ -678,10 +736,12 @@ template <class FT>
 static void model_pressure_step(ob200_model* m, FT dt) {
     // calculate_pressure_correction! + pressure_correct_velocities! (pressure_correction.jl:10-56)
     const GridD<FT>& g = gridD<FT>(m->grid);
-    model_fill_state_halos<FT>(m, 0, 3);
-    solve_for_pressure_T<FT>(m->solver.get(), m->pNHS.get(), (double)dt, m->F[0].get(), m->F[1].get(), m->F[2].get());
+    { ScopedPhase ph("halo"); model_fill_state_halos<FT>(m, 0, 3); }
+    { ScopedPhase ph("poisson");
+      solve_for_pressure_T<FT>(m->solver.get(), m->pNHS.get(), (double)dt, m->F[0].get(), m->F[1].get(), m->F[2].get()); }
     ob200_field* pn = m->pNHS.get();
-    fill_halos<FT>(&pn, 1);
+    { ScopedPhase ph("halo"); fill_halos<FT>(&pn, 1); }
+    ScopedPhase ph("pressure_correct");
     launch_pressure_correct<FT>(g, m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(),
                                 m->F[2]->template p0<FT>(), m->pNHS->template p0<FT>(), dt);
 }
@@ -772,3 +832,23 @@ extern "C" int32_t ob200_model_diagnostics(ob200_model* m, double* maxdiv, doubl
 
 // knob used by tests to force the general kernels
 extern "C" int32_t ob200_model_use_fast_kernels(ob200_model* m, int32_t on) { m->use_fast = on != 0; return 0; }
+
+// ---- profiling knobs (not part of the reference interface; bench evidence only) ---------------
+extern "C" int32_t ob200_profile_enable(int32_t on) {
+    ob::g_profile = on != 0;
+    return 0;
+}
+extern "C" int32_t ob200_profile_reset(void) {
+    API_BEGIN
+    resolve_phases();
+    ob::g_phases.clear();
+    API_END
+}
+extern "C" int32_t ob200_profile_query(const char* phase, double* total_ms, int64_t* count) {
+    API_BEGIN
+    resolve_phases();
+    auto it = ob::g_phases.find(phase);
+    if (total_ms) *total_ms = it == ob::g_phases.end() ? 0.0 : it->second.total_ms;
+    if (count) *count = it == ob::g_phases.end() ? 0 : it->second.count;
+    API_END
+}

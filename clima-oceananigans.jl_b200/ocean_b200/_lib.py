@@ -61,6 +61,8 @@ SYMBOLS = {
     "ob200_field_parent_size": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ob200_field_set_parent": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "ob200_field_get_parent": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "ob200_field_set_parent_async": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "ob200_field_get_parent_async": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "ob200_field_device_view": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ob200_fill_halo_regions": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int32]),
     "ob200_field_reduce": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -81,10 +83,12 @@ SYMBOLS = {
     "ob200_model_clock": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ob200_model_set_clock": (C.c_int32, [C.c_void_p, C.c_double, C.c_int64, C.c_double]),
     "ob200_model_diagnostics": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
-}
-EXTRA_SYMBOLS = {
     "ob200_model_use_fast_kernels": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "ob200_profile_enable": (C.c_int32, [C.c_int32]),
+    "ob200_profile_reset": (C.c_int32, []),
+    "ob200_profile_query": (C.c_int32, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
+EXTRA_SYMBOLS = {}
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

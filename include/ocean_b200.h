@@ -133,6 +133,10 @@ int32_t ob200_field_parent_size(const ob200_field* f, int32_t out[3]);
 /* parent(field) .= host array  /  Array(parent(field)); element type = grid ftype */
 int32_t ob200_field_set_parent(ob200_field* f, const void* host_parent);
 int32_t ob200_field_get_parent(const ob200_field* f, void* host_parent);
+/* same, enqueued on the stream without a final synchronisation: the host buffer (pinned for a
+ * truly asynchronous copy) must stay valid until ob200_sync() */
+int32_t ob200_field_set_parent_async(ob200_field* f, const void* host_parent);
+int32_t ob200_field_get_parent_async(const ob200_field* f, void* host_parent);
 /* internal device storage: base pointer, index of Julia (1,1,1), strides in elements */
 int32_t ob200_field_device_view(const ob200_field* f, void** base, int64_t offset111[1],
                                 int64_t strides[3]);
@@ -181,6 +185,15 @@ int32_t ob200_model_clock(const ob200_model* m, double* time, int64_t* iteration
 int32_t ob200_model_set_clock(ob200_model* m, double time, int64_t iteration, double previous_dt);
 /* max |div U| and kinetic energy 0.5*sum(u^2+v^2+w^2) over the interior (diagnostics) */
 int32_t ob200_model_diagnostics(ob200_model* m, double* max_abs_div, double* kinetic_energy);
+
+/* ---- measurement knobs (no reference counterpart; used by bench.py and the tests) ---------- */
+/* force the general kernels (on = 0) instead of the specialised headline kernels */
+int32_t ob200_model_use_fast_kernels(ob200_model* m, int32_t on);
+/* per-phase CUDA-event timing on the library stream: phases "tendency" (one event pair per
+ * tendency-kernel launch), "poisson", "halo", "pressure_correct", "hydrostatic" */
+int32_t ob200_profile_enable(int32_t on);
+int32_t ob200_profile_reset(void);
+int32_t ob200_profile_query(const char* phase, double* total_ms, int64_t* count);
 
 #ifdef __cplusplus
 }
