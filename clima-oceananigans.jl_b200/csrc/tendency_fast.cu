@@ -8,8 +8,9 @@
 //     thread marches up its column, x / y faces go through shared memory; the one extra column
 //     and row of faces a 32x8 tile needs are computed by two otherwise idle warps
 //     (the reference evaluates every face twice, momentum_advection_operators.jl:52-56);
-//   * the left- and right-biased WENO reconstructions at a face share their curvature terms
-//     and two of their three candidate polynomials (weno_fifth_order.jl:311-317,518-524);
+//   * only the UPWIND-side WENO reconstruction is evaluated: ((u+|u|) L + (u-|u|) R)/2 is exactly
+//     u*L or u*R (upwind_biased_advective_fluxes.jl:10), chosen per thread by address selection of
+//     a mirrored 5-point window (the reference always evaluates both sides);
 //   * in Float64 the six divisions of the weight computation (:386-400) are folded into one
 //     reciprocal:  sum_k w_k p_k = (sum_k g_k p_k) / (sum_k g_k),
 //     g_k = C_k (E_k + tau^2) prod_{j != k} E_j,  E_k = (beta_k + eps)^2   (Z weights), which is
@@ -21,7 +22,10 @@ namespace ob {
 
 namespace fast {
 
-constexpr int TX = 32, TY = 8;
+#ifndef OB_ROWS
+#define OB_ROWS 1
+#endif
+constexpr int TX = 32, TY = 8, ROWS = OB_ROWS;   // tile = TX x (ROWS*TY) cells, TX*TY threads
 
 template <class FT>
 struct Ctx {
@@ -86,29 +90,26 @@ __device__ __forceinline__ FT weno_combine(FT C0, FT C1, FT C2, FT b0, FT b1, FT
     }
 }
 
-// left- and right-biased reconstructions at a face from psi[f-3..f+2]
+// One-sided reconstruction.  The upwind flux ((u+|u|) L + (u-|u|) R)/2 equals u*L for u > 0 and
+// u*R otherwise EXACTLY (one product is 0), so only the upwind side is evaluated.  The window is
+// passed towards the face: (a,b,c,d,e) = psi[f-3..f+1] for the left-biased side and
+// psi[f+2..f-2] (mirrored) for the right-biased one.  In mirrored form the right-biased candidate
+// polynomials and linear weights coincide with the left-biased ones; the smoothness slopes do not
+// (weno_fifth_order.jl:315-317 are not the mirror image of :311-313): the outer stencils use
+// (k1,-4,k3) with (k1,k3) = (1,3) on the left side and (3,1) on the right side.
 template <class FT, bool ZW>
-__device__ __forceinline__ void weno_LR(FT m3, FT m2, FT m1, FT c0, FT p1, FT p2, FT& L, FT& R) {
+__device__ __forceinline__ FT weno_side(FT a, FT b, FT c, FT d, FT e, FT k1, FT k3) {
     const FT c1312 = FT(13.0 / 12.0), c14 = FT(0.25);
     const FT a13 = FT(1.0 / 3.0), a56 = FT(5.0 / 6.0), a16 = FT(1.0 / 6.0), a76 = FT(7.0 / 6.0), a116 = FT(11.0 / 6.0);
-    FT tA = (m3 - 2 * m2) + m1, tB = (m2 - 2 * m1) + c0, tC = (m1 - 2 * c0) + p1, tD = (c0 - 2 * p1) + p2;
-    FT cA = c1312 * (tA * tA), cB = c1312 * (tB * tB), cC = c1312 * (tC * tC), cD = c1312 * (tD * tD);
-    FT s;
-    // left: psi0 = (m1,c0,p1), psi1 = (m2,m1,c0), psi2 = (m3,m2,m1)   (weno_fifth_order.jl:311-313)
-    s = (3 * m1 - 4 * c0) + p1;  FT bL0 = cC + c14 * (s * s);
-    s = m2 - c0;                 FT bL1 = cB + c14 * (s * s);
-    s = (m3 - 4 * m2) + 3 * m1;  FT bL2 = cA + c14 * (s * s);
-    // right: psi0 = (c0,p1,p2), psi1 = (m1,c0,p1), psi2 = (m2,m1,c0)  (:315-317, non-mirrored forms)
-    s = (c0 - 4 * p1) + 3 * p2;  FT bR0 = cD + c14 * (s * s);
-    s = m1 - p1;                 FT bR1 = cC + c14 * (s * s);
-    s = (3 * m2 - 4 * m1) + c0;  FT bR2 = cB + c14 * (s * s);
-    // candidate polynomials (:518-524); qA and qB are shared by the two sides
-    FT qA = (a13 * m1 + a56 * c0) - a16 * p1;        // left p0 = right p1
-    FT qB = (-a16 * m2 + a56 * m1) + a13 * c0;       // left p1 = right p2
-    FT qC = (a13 * m3 - a76 * m2) + a116 * m1;       // left p2
-    FT qD = (a116 * c0 - a76 * p1) + a13 * p2;       // right p0
-    L = weno_combine<FT, ZW>(FT(3.0 / 10.0), FT(3.0 / 5.0), FT(1.0 / 10.0), bL0, bL1, bL2, qA, qB, qC);
-    R = weno_combine<FT, ZW>(FT(1.0 / 10.0), FT(3.0 / 5.0), FT(3.0 / 10.0), bR0, bR1, bR2, qD, qA, qB);
+    FT t2 = (a - 2 * b) + c, t1 = (b - 2 * c) + d, t0 = (c - 2 * d) + e;
+    FT s2 = (k1 * a - 4 * b) + k3 * c, s1 = b - d, s0 = (k3 * c - 4 * d) + k1 * e;
+    FT b2 = c1312 * (t2 * t2) + c14 * (s2 * s2);
+    FT b1 = c1312 * (t1 * t1) + c14 * (s1 * s1);
+    FT b0 = c1312 * (t0 * t0) + c14 * (s0 * s0);
+    FT p0 = (a13 * c + a56 * d) - a16 * e;
+    FT p1 = (-a16 * b + a56 * c) + a13 * d;
+    FT p2 = (a13 * a - a76 * b) + a116 * c;
+    return weno_combine<FT, ZW>(FT(3.0 / 10.0), FT(3.0 / 5.0), FT(1.0 / 10.0), b0, b1, b2, p0, p1, p2);
 }
 
 template <class FT, bool HASZ, int D>
@@ -136,77 +137,96 @@ __device__ __forceinline__ FT flux_at(const Ctx<FT>& c, long long p) {
         if (!HASZ && BB == 2) ut = c.U[A][p];
         else ut = FT(0.5) * (I3f<FT, HASZ, BB>(c.U[A], p - sB, sB) + I3f<FT, HASZ, BB>(c.U[A], p, sB));
     }
+    // all six loads are issued independently of ut (no dependent second memory round trip);
+    // the upwind window is then selected in registers
     const FT* q = c.psi + pf;
-    FT L, R;
-    weno_LR<FT, ZW>(q[-3 * sA], q[-2 * sA], q[-sA], q[0], q[sA], q[2 * sA], L, R);
-    FT au = fabs(ut);
-    return c.area[A] * (((ut + au) * L + (ut - au) * R) * FT(0.5));
+    const FT w0 = q[-3 * sA], w1 = q[-2 * sA], w2 = q[-sA], w3 = q[0], w4 = q[sA], w5 = q[2 * sA];
+    const bool pos = ut > FT(0);
+    FT rec = weno_side<FT, ZW>(pos ? w0 : w5, pos ? w1 : w4, pos ? w2 : w3, pos ? w3 : w2, pos ? w4 : w1,
+                               pos ? FT(1) : FT(3), pos ? FT(3) : FT(1));
+    return c.area[A] * (ut * rec);
 }
 
 template <class FT, bool ZW, bool HASZ, int B>
 __global__ void __launch_bounds__(TX* TY, 2) tendency_fast_kernel(Ctx<FT> c) {
-    __shared__ FT sFx[2][TY][TX + 1];
-    __shared__ FT sFy[2][TY + 1][TX];
+    // tile = TX x (ROWS*TY) cells; thread (tx, ty) owns rows ty and ty + TY of the tile
+    __shared__ FT sFx[2][ROWS * TY][TX + 1];
+    __shared__ FT sFy[2][ROWS * TY + 1][TX];
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
-    const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * TY;
-    const int i = i0 + tx, j = j0 + ty;
+    const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * (ROWS * TY);
+    const int i = i0 + tx;
     const int k0 = 1 + blockIdx.z * c.Kc;
     const long long sx = c.s[0], sy = c.s[1], sz = c.s[2];
     // x: B == 0 needs F(i) - F(i-1) (extra column at i0-1), otherwise F(i+1) - F(i) (extra at i0+TX)
     constexpr bool XLOW = (B == 0), YLOW = (B == 1), ZLOW = (B == 2);
-    long long p = i * sx + j * sy + k0 * sz;
-    // extra faces: warp 0 lanes 0..TY-1 -> x column ; warp 1 -> y row
-    const bool xextra = tid < TY, yextra = tid >= 32 && tid < 32 + TX;
+    long long p0 = i * sx + (j0 + ty) * sy + k0 * sz;
+    // extra faces: warp 0 lanes 0..ROWS*TY-1 -> x column ; warp 1 -> y row
+    const bool xextra = tid < ROWS * TY, yextra = tid >= 32 && tid < 32 + TX;
     long long pxe = (XLOW ? (i0 - 1) : (i0 + TX)) * sx + (j0 + tid) * sy + k0 * sz;
-    long long pye = (i0 + (tid - 32)) * sx + (YLOW ? (j0 - 1) : (j0 + TY)) * sy + k0 * sz;
+    long long pye = (i0 + (tid - 32)) * sx + (YLOW ? (j0 - 1) : (j0 + ROWS * TY)) * sy + k0 * sz;
 
-    FT Fz_carry = FT(0);
-    if (HASZ) Fz_carry = flux_at<FT, ZW, HASZ, 2, B>(c, ZLOW ? p - sz : p);
+    FT Fz_carry[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        long long p = p0 + r * TY * sy;
+        Fz_carry[r] = HASZ ? flux_at<FT, ZW, HASZ, 2, B>(c, ZLOW ? p - sz : p) : FT(0);
+    }
 
     for (int kk = 0; kk < c.Kc; ++kk) {
         const int buf = kk & 1;
-        FT Fx = flux_at<FT, ZW, HASZ, 0, B>(c, p);
-        FT Fy = flux_at<FT, ZW, HASZ, 1, B>(c, p);
-        sFx[buf][ty][XLOW ? tx + 1 : tx] = Fx;
-        sFy[buf][YLOW ? ty + 1 : ty][tx] = Fy;
+        FT Fx[ROWS], Fy[ROWS], dFz[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            long long p = p0 + r * TY * sy;
+            const int row = ty + r * TY;
+            Fx[r] = flux_at<FT, ZW, HASZ, 0, B>(c, p);
+            Fy[r] = flux_at<FT, ZW, HASZ, 1, B>(c, p);
+            sFx[buf][row][XLOW ? tx + 1 : tx] = Fx[r];
+            sFy[buf][YLOW ? row + 1 : row][tx] = Fy[r];
+            dFz[r] = FT(0);
+            if (HASZ) {
+                FT Fz_new = flux_at<FT, ZW, HASZ, 2, B>(c, ZLOW ? p : p + sz);
+                dFz[r] = Fz_new - Fz_carry[r];
+                Fz_carry[r] = Fz_new;
+            }
+        }
         if (xextra) sFx[buf][tid][XLOW ? 0 : TX] = flux_at<FT, ZW, HASZ, 0, B>(c, pxe);
-        if (yextra) sFy[buf][YLOW ? 0 : TY][tid - 32] = flux_at<FT, ZW, HASZ, 1, B>(c, pye);
-        FT dFz = FT(0);
-        if (HASZ) {
-            FT Fz_new = flux_at<FT, ZW, HASZ, 2, B>(c, ZLOW ? p : p + sz);
-            dFz = Fz_new - Fz_carry;
-            Fz_carry = Fz_new;
-        }
+        if (yextra) sFy[buf][YLOW ? 0 : ROWS * TY][tid - 32] = flux_at<FT, ZW, HASZ, 1, B>(c, pye);
         __syncthreads();
-        FT dFx = XLOW ? (Fx - sFx[buf][ty][tx]) : (sFx[buf][ty][tx + 1] - Fx);
-        FT dFy = YLOW ? (Fy - sFy[buf][ty][tx]) : (sFy[buf][ty + 1][tx] - Fy);
-        FT G = -(c.invV * ((dFx + dFy) + dFz));
-        if (B == 0) {
-            if (c.fplane) {      // - x_f_cross_U = + f * ℑxyᶠᶜᵃ(v)
-                const FT* v = c.U[1];
-                FT a0 = FT(0.5) * (v[p - sx] + v[p]), a1 = FT(0.5) * (v[p - sx + sy] + v[p + sy]);
-                G = G - (-c.f * (FT(0.5) * (a0 + a1)));
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            long long p = p0 + r * TY * sy;
+            const int row = ty + r * TY;
+            FT dFx = XLOW ? (Fx[r] - sFx[buf][row][tx]) : (sFx[buf][row][tx + 1] - Fx[r]);
+            FT dFy = YLOW ? (Fy[r] - sFy[buf][row][tx]) : (sFy[buf][row + 1][tx] - Fy[r]);
+            FT G = -(c.invV * ((dFx + dFy) + dFz[r]));
+            if (B == 0) {
+                if (c.fplane) {      // - x_f_cross_U = + f * ℑxyᶠᶜᵃ(v)
+                    const FT* v = c.U[1];
+                    FT a0 = FT(0.5) * (v[p - sx] + v[p]), a1 = FT(0.5) * (v[p - sx + sy] + v[p + sy]);
+                    G = G - (-c.f * (FT(0.5) * (a0 + a1)));
+                }
+                if (c.pHY) G = G - (c.pHY[p] - c.pHY[p - sx]) * c.invd[0];
+            } else if (B == 1) {
+                if (c.fplane) {      // - y_f_cross_U = - f * ℑxyᶜᶠᵃ(u)
+                    const FT* u = c.U[0];
+                    FT a0 = FT(0.5) * (u[p - sy] + u[p + sx - sy]), a1 = FT(0.5) * (u[p] + u[p + sx]);
+                    G = G - (c.f * (FT(0.5) * (a0 + a1)));
+                }
+                if (c.pHY) G = G - (c.pHY[p] - c.pHY[p - sy]) * c.invd[1];
             }
-            if (c.pHY) G = G - (c.pHY[p] - c.pHY[p - sx]) * c.invd[0];
-        } else if (B == 1) {
-            if (c.fplane) {      // - y_f_cross_U = - f * ℑxyᶜᶠᵃ(u)
-                const FT* u = c.U[0];
-                FT a0 = FT(0.5) * (u[p - sy] + u[p + sx - sy]), a1 = FT(0.5) * (u[p] + u[p + sx]);
-                G = G - (c.f * (FT(0.5) * (a0 + a1)));
-            }
-            if (c.pHY) G = G - (c.pHY[p] - c.pHY[p - sy]) * c.invd[1];
+            c.Gn[p] = G;
+            if (c.ss.mode == SUB_RK3_FIRST) c.psi_new[p] = c.psi[p] + c.ss.c1 * G;
+            else if (c.ss.mode == SUB_RK3) c.psi_new[p] = c.psi[p] + c.ss.dt * (c.ss.c1 * G + c.ss.c2 * c.Gm[p]);
+            else if (c.ss.mode == SUB_AB2) c.psi_new[p] = c.psi[p] + c.ss.dt * (c.ss.c1 * G - c.ss.c2 * c.Gm[p]);
         }
-        c.Gn[p] = G;
-        if (c.ss.mode == SUB_RK3_FIRST) c.psi_new[p] = c.psi[p] + c.ss.c1 * G;
-        else if (c.ss.mode == SUB_RK3) c.psi_new[p] = c.psi[p] + c.ss.dt * (c.ss.c1 * G + c.ss.c2 * c.Gm[p]);
-        else if (c.ss.mode == SUB_AB2) c.psi_new[p] = c.psi[p] + c.ss.dt * (c.ss.c1 * G - c.ss.c2 * c.Gm[p]);
-        p += sz; pxe += sz; pye += sz;
+        p0 += sz; pxe += sz; pye += sz;
     }
 }
 
 template <class FT, bool ZW, bool HASZ>
 void launch(const Ctx<FT>& c, int comp) {
-    dim3 blk(TX, TY), grd(c.N[0] / TX, c.N[1] / TY, HASZ ? c.N[2] / c.Kc : 1);
+    dim3 blk(TX, TY), grd(c.N[0] / TX, c.N[1] / (ROWS * TY), HASZ ? c.N[2] / c.Kc : 1);
     switch (comp) {
         case 0: tendency_fast_kernel<FT, ZW, HASZ, 0><<<grd, blk, 0, stream()>>>(c); break;
         case 1: tendency_fast_kernel<FT, ZW, HASZ, 1><<<grd, blk, 0, stream()>>>(c); break;
@@ -230,7 +250,7 @@ bool launch_tendency_fast(const Phys<FT>& P, int comp, const FT* const U[3], con
         if (P.wc[d][0] || P.wc[d][1]) return false;
         if (g.topo[d] != OB_FLAT && g.H[d] < 3) return false;
     }
-    if (g.N[0] % fast::TX || g.N[1] % fast::TY) return false;
+    if (g.N[0] % fast::TX || g.N[1] % (fast::ROWS * fast::TY)) return false;
     fast::Ctx<FT> c;
     for (int d = 0; d < 3; ++d) { c.U[d] = U[d]; c.s[d] = g.st[d]; c.N[d] = g.N[d]; c.invd[d] = 1 / g.d[d]; }
     c.psi = psi; c.pHY = pHY; c.Gm = Gm; c.Gn = Gn; c.psi_new = psi_new; c.ss = ss;
@@ -238,7 +258,7 @@ bool launch_tendency_fast(const Phys<FT>& P, int comp, const FT* const U[3], con
     c.invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
     c.f = P.f; c.fplane = P.fplane;
     int Kc = 1;
-    if (hasz) { Kc = 32; while (g.N[2] % Kc) Kc >>= 1; }
+    if (hasz) { Kc = 16; while (g.N[2] % Kc) Kc >>= 1; }
     c.Kc = Kc;
     if (hasz) { if (P.zweno) fast::launch<FT, true, true>(c, comp); else fast::launch<FT, false, true>(c, comp); }
     else { if (P.zweno) fast::launch<FT, true, false>(c, comp); else fast::launch<FT, false, false>(c, comp); }
