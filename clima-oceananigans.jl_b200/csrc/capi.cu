@@ -469,6 +469,16 @@ static void poisson_solve_host(ob200_poisson* s, ob200_field* phi, const void* r
     const ob200_grid* G = s->grid;
     const GridD<FT>& g = gridD<FT>(G);
     PoissonPlan<FT>* p = planOf<FT>(s);
+    if (rhs_host && poisson_has_fast<FT>(p)) {
+        size_t n = (size_t)g.N[0] * g.N[1] * g.N[2];
+        FT* tmp = nullptr;
+        OB_CUDA(cudaMalloc(&tmp, n * sizeof(FT)));
+        OB_CUDA(cudaMemcpyAsync(tmp, rhs_host, n * sizeof(FT), cudaMemcpyHostToDevice, stream()));
+        poisson_solve_real<FT>(p, g, tmp, phi->p0<FT>());
+        OB_CUDA(cudaStreamSynchronize(stream()));
+        cudaFree(tmp);
+        return;
+    }
     if (rhs_host) {
         size_t n = (size_t)g.N[0] * g.N[1] * g.N[2];
         std::vector<C2<FT>> h(n);
@@ -500,6 +510,10 @@ static void solve_for_pressure_T(ob200_poisson* s, ob200_field* p, double dt, co
     using CT = typename std::conditional<sizeof(FT) == 4, float2, double2>::type;
     const GridD<FT>& g = gridD<FT>(s->grid);
     PoissonPlan<FT>* pl = planOf<FT>(s);
+    if (poisson_has_fast<FT>(pl)) {
+        poisson_solve_velocities<FT>(pl, g, u->p0<FT>(), v->p0<FT>(), w->p0<FT>(), (FT)dt, p->p0<FT>());
+        return;
+    }
     launch_pressure_rhs<FT, CT>(g, u->p0<FT>(), v->p0<FT>(), w->p0<FT>(), (FT)dt,
                                 s->kind == OB200_SOLVER_FOURIER_TRIDIAGONAL, (CT*)poisson_storage(pl));
     poisson_solve<FT>(pl, g, p->p0<FT>());

@@ -19,6 +19,7 @@
 #include <vector>
 #include <cmath>
 #include <algorithm>
+#include <cstdlib>
 
 namespace ob {
 
@@ -363,6 +364,7 @@ struct PoissonPlan {
     double* dzC = nullptr;
     double* lower = nullptr;   // 1/ΔzF(k), k = 2..Nz
     double* msum = nullptr;
+    ff::FastPoisson<FT>* fast = nullptr;
     std::vector<void*> owned;
 };
 
@@ -382,6 +384,8 @@ PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double*
     using CT = typename Cx<FT>::T;
     auto* p = new PoissonPlan<FT>();
     p->kind = kind;
+    if (kind == 1 && ff::fast_poisson_supported<FT>(g) && getenv("OB200_NO_FAST_FFT") == nullptr)
+        p->fast = ff::fast_poisson_create<FT>(g);
     const double PI = 3.14159265358979323846;
     size_t tot = (size_t)g.N[0] * g.N[1] * g.N[2];
     OB_CUDA(cudaMalloc(&p->storage, tot * sizeof(CT)));
@@ -439,6 +443,7 @@ PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double*
 }
 template <class FT> void poisson_plan_destroy(PoissonPlan<FT>* p) {
     if (!p) return;
+    ff::fast_poisson_destroy(p->fast);
     cudaFree(p->storage);
     if (p->source) cudaFree(p->source);
     if (p->scratch) cudaFree(p->scratch);
@@ -526,7 +531,22 @@ void poisson_solve(PoissonPlan<FT>* p, const GridD<FT>& g, FT* phi_p0) {
     OB_LAUNCH_CHECK();
 }
 
+template <class FT> bool poisson_has_fast(PoissonPlan<FT>* p) { return p->fast != nullptr; }
+template <class FT>
+void poisson_solve_velocities(PoissonPlan<FT>* p, const GridD<FT>& g, const FT* u, const FT* v, const FT* w,
+                              FT dt, FT* phi_p0) {
+    ff::fast_poisson_solve<FT>(p->fast, g, u, v, w, dt, nullptr, phi_p0);
+}
+template <class FT>
+void poisson_solve_real(PoissonPlan<FT>* p, const GridD<FT>& g, const FT* rhs, FT* phi_p0) {
+    ff::fast_poisson_solve<FT>(p->fast, g, nullptr, nullptr, nullptr, FT(1), rhs, phi_p0);
+}
+
 #define INST(FT)                                                                                           \
+    template bool poisson_has_fast<FT>(PoissonPlan<FT>*);                                                  \
+    template void poisson_solve_velocities<FT>(PoissonPlan<FT>*, const GridD<FT>&, const FT*, const FT*,   \
+                                               const FT*, FT, FT*);                                        \
+    template void poisson_solve_real<FT>(PoissonPlan<FT>*, const GridD<FT>&, const FT*, FT*);              \
     template PoissonPlan<FT>* poisson_plan_create<FT>(const GridD<FT>&, int, const double*, const double*); \
     template void poisson_plan_destroy<FT>(PoissonPlan<FT>*);                                              \
     template void* poisson_storage<FT>(PoissonPlan<FT>*);                                                  \

@@ -1,0 +1,539 @@
+// fft_fast.cu -- fast path of the FFT-based Poisson solver for Periodic power-of-two dimensions:
+// real-to-complex in x (half spectrum, Nx/2+1 modes), register-radix passes, fused
+// divergence -> first pass, eigenvalue divide between the forward and backward transform of the
+// last axis, and real part -> pressure field (+ periodic x halo) on the last pass.
+//
+// Reference semantics: Solvers/fft_based_poisson_solver.jl:93-125 with the pressure source term of
+// Models/NonhydrostaticModels/solve_for_pressure.jl:15-18.  The reference runs an in-place c2c
+// transform over a complex Nx*Ny*Nz array (6 full passes, 24 words per point); for a real source
+// the half spectrum carries the same information (10-12 words per point).
+//
+// In-block engine: n = R1*R2(*R3) with radices <= 16; each thread does a radix-R butterfly in
+// registers, data is exchanged through shared memory once per pass (2 round trips for n <= 256
+// instead of log2 n for a radix-2 kernel).  Forward passes are decimation in frequency, backward
+// passes decimation in time, so spectral data stays in digit-reversed order along y and z and no
+// reordering pass exists; eigenvalue tables are uploaded in that order.
+#include "internal.h"
+#include <vector>
+#include <cmath>
+#include <algorithm>
+
+namespace ob {
+namespace ff {
+
+template <class FT> struct Cx;
+template <> struct Cx<float> { using T = float2; };
+template <> struct Cx<double> { using T = double2; };
+
+template <int LOG2N> struct Rad;
+template <> struct Rad<4> { static constexpr int R1 = 16, R2 = 1, R3 = 1; };
+template <> struct Rad<5> { static constexpr int R1 = 8, R2 = 4, R3 = 1; };
+template <> struct Rad<6> { static constexpr int R1 = 8, R2 = 8, R3 = 1; };
+template <> struct Rad<7> { static constexpr int R1 = 16, R2 = 8, R3 = 1; };
+template <> struct Rad<8> { static constexpr int R1 = 16, R2 = 16, R3 = 1; };
+template <> struct Rad<9> { static constexpr int R1 = 8, R2 = 8, R3 = 8; };
+template <> struct Rad<10> { static constexpr int R1 = 16, R2 = 8, R3 = 8; };
+
+template <int LOG2N> struct Geo {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int RL = Rad<LOG2N>::R3 > 1 ? Rad<LOG2N>::R3 : (Rad<LOG2N>::R2 > 1 ? Rad<LOG2N>::R2 : Rad<LOG2N>::R1);
+    static constexpr int LS = N + N / RL + 1;          // padded, odd line stride (in complex elements)
+    __host__ __device__ static constexpr int pos(int idx) { return idx + idx / RL; }
+};
+
+template <class CT> __device__ __forceinline__ CT cadd(CT a, CT b) { CT r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <class CT> __device__ __forceinline__ CT csub(CT a, CT b) { CT r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <class CT> __device__ __forceinline__ CT cmul(CT a, CT b) { CT r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+template <class CT> __device__ __forceinline__ CT cmulc(CT a, CT b) { CT r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r; }
+
+// cos/sin(2 pi k / 16), k = 0..7
+__device__ constexpr double C16[8] = {1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173,
+                                      0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128673848};
+__device__ constexpr double S16[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848,
+                                      1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173};
+
+__host__ __device__ constexpr int brev(int x, int bits) {
+    int r = 0;
+    for (int b = 0; b < bits; ++b) if (x & (1 << b)) r |= 1 << (bits - 1 - b);
+    return r;
+}
+__host__ __device__ constexpr int ilog2c(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+// in-register DFT of length R (2,4,8,16), DIF; result y[s] = x[brev(s)].  INV uses conjugate twiddles.
+template <int R, bool INV, class CT>
+__device__ __forceinline__ void dft_reg(CT* x) {
+    using FT = decltype(x[0].x);
+#pragma unroll
+    for (int len = R; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+#pragma unroll
+        for (int blk = 0; blk < R / len; ++blk) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                CT a = x[blk * len + j], b = x[blk * len + j + half];
+                x[blk * len + j] = cadd(a, b);
+                CT d = csub(a, b);
+                const int tk = j * (16 / len);            // twiddle exp(-+ 2 pi i tk / 16)
+                if (tk == 0) {
+                    x[blk * len + j + half] = d;
+                } else if (tk == 4) {                     // -i (forward) / +i (inverse)
+                    CT r;
+                    if (!INV) { r.x = d.y; r.y = -d.x; } else { r.x = -d.y; r.y = d.x; }
+                    x[blk * len + j + half] = r;
+                } else {
+                    CT w;
+                    w.x = (FT)C16[tk]; w.y = (FT)(INV ? S16[tk] : -S16[tk]);
+                    x[blk * len + j + half] = cmul(d, w);
+                }
+            }
+        }
+    }
+}
+
+// one forward (DIF) pass of radix R on blocks of size m = R*S of every line; tw = exp(-2 pi i t / n)
+template <int R, int LOG2N, class CT>
+__device__ __forceinline__ void pass_fwd(CT* s, const CT* tw, int S, int nlines) {
+    using G = Geo<LOG2N>;
+    constexpr int nb = G::N / R, LB = ilog2c(R);
+    const int m = R * S;
+    for (int w = threadIdx.x; w < nlines * nb; w += blockDim.x) {
+        int t = w / nb, b = w - t * nb;
+        int blk = b / S, j = b - blk * S;
+        CT* line = s + t * G::LS;
+        int base = blk * m + j;
+        CT x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = line[G::pos(base + q * S)];
+        dft_reg<R, false>(x);
+        const int tstep = j * (G::N / m);
+#pragma unroll
+        for (int sidx = 0; sidx < R; ++sidx) {
+            CT v = x[brev(sidx, LB)];
+            if (sidx > 0 && S > 1) v = cmul(v, tw[tstep * sidx]);
+            line[G::pos(base + sidx * S)] = v;
+        }
+    }
+}
+// the exact inverse of pass_fwd (up to the factor R): conjugate twiddles first, then conjugate DFT
+template <int R, int LOG2N, class CT>
+__device__ __forceinline__ void pass_inv(CT* s, const CT* tw, int S, int nlines) {
+    using G = Geo<LOG2N>;
+    constexpr int nb = G::N / R, LB = ilog2c(R);
+    const int m = R * S;
+    for (int w = threadIdx.x; w < nlines * nb; w += blockDim.x) {
+        int t = w / nb, b = w - t * nb;
+        int blk = b / S, j = b - blk * S;
+        CT* line = s + t * G::LS;
+        int base = blk * m + j;
+        const int tstep = j * (G::N / m);
+        CT x[R];
+#pragma unroll
+        for (int sidx = 0; sidx < R; ++sidx) {
+            CT v = line[G::pos(base + sidx * S)];
+            if (sidx > 0 && S > 1) v = cmulc(v, tw[tstep * sidx]);
+            x[sidx] = v;
+        }
+        dft_reg<R, true>(x);
+#pragma unroll
+        for (int q = 0; q < R; ++q) line[G::pos(base + q * S)] = x[brev(q, LB)];
+    }
+}
+
+template <int LOG2N, class CT>
+__device__ __forceinline__ void fft_fwd(CT* s, const CT* tw, int nlines) {
+    using R = Rad<LOG2N>;
+    constexpr int N = 1 << LOG2N;
+    pass_fwd<R::R1, LOG2N>(s, tw, N / R::R1, nlines);
+    __syncthreads();
+    if constexpr (R::R2 > 1) { pass_fwd<R::R2, LOG2N>(s, tw, N / (R::R1 * R::R2), nlines); __syncthreads(); }
+    if constexpr (R::R3 > 1) { pass_fwd<R::R3, LOG2N>(s, tw, 1, nlines); __syncthreads(); }
+}
+template <int LOG2N, class CT>
+__device__ __forceinline__ void fft_inv(CT* s, const CT* tw, int nlines) {
+    using R = Rad<LOG2N>;
+    constexpr int N = 1 << LOG2N;
+    if constexpr (R::R3 > 1) { pass_inv<R::R3, LOG2N>(s, tw, 1, nlines); __syncthreads(); }
+    if constexpr (R::R2 > 1) { pass_inv<R::R2, LOG2N>(s, tw, N / (R::R1 * R::R2), nlines); __syncthreads(); }
+    pass_inv<R::R1, LOG2N>(s, tw, N / R::R1, nlines);
+    __syncthreads();
+}
+// frequency index held at position P after fft_fwd
+static int freq_of_pos(int log2n, int P) {
+    int R1, R2, R3;
+    switch (log2n) {
+        case 4: R1 = 16; R2 = 1; R3 = 1; break;
+        case 5: R1 = 8; R2 = 4; R3 = 1; break;
+        case 6: R1 = 8; R2 = 8; R3 = 1; break;
+        case 7: R1 = 16; R2 = 8; R3 = 1; break;
+        case 8: R1 = 16; R2 = 16; R3 = 1; break;
+        case 9: R1 = 8; R2 = 8; R3 = 8; break;
+        default: R1 = 16; R2 = 8; R3 = 8; break;
+    }
+    int n = 1 << log2n, S1 = n / R1, S2 = S1 / R2;
+    int s1 = P / S1, rem = P % S1, s2 = rem / S2, s3 = rem % S2;
+    (void)R3;
+    return s1 + R1 * (s2 + R2 * s3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+struct XArgs {
+    typename Cx<FT>::T* spec;       // half spectrum, [Nz][Ny][NXP]
+    int Nx, Ny, Nz, NXP, T;
+    const typename Cx<FT>::T* twM;  // exp(-2 pi i t / M), M = Nx/2
+    const typename Cx<FT>::T* twN;  // exp(-2 pi i k / Nx), k = 0..M
+    const int* kpos;                // position (in the M-point engine) of frequency k
+    // forward input: divergence of (u, v, w) / dt  (Julia-(0,0,0) pointers, strides) or a real array
+    const FT* u; const FT* v; const FT* w; const FT* real_in;
+    long long st[3];
+    FT ax, ay, az, invV, dt;
+    int has_z;
+    // backward output
+    FT* phi_p0;
+    int Hx;
+    FT scale;
+};
+
+// forward x: real line -> half spectrum (natural kx order)
+template <class FT, int LOG2M>
+__global__ void __launch_bounds__(256) x_r2c_kernel(XArgs<FT> A) {
+    using CT = typename Cx<FT>::T;
+    using G = Geo<LOG2M>;
+    constexpr int M = 1 << LOG2M;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CT* s = reinterpret_cast<CT*>(smem_raw);
+    CT* stw = s + A.T * G::LS;
+    for (int w = threadIdx.x; w < M; w += blockDim.x) stw[w] = A.twM[w];
+    const int j0 = blockIdx.x * A.T, k = blockIdx.y;
+    const int nl = min(A.T, A.Ny - j0);
+    const int Nx = A.Nx;
+    // stage the real source term, two consecutive reals = one complex
+    for (int w = threadIdx.x; w < nl * M; w += blockDim.x) {
+        int t = w / M, m = w - t * M;
+        int j = j0 + t;
+        FT r[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int i = 2 * m + h;
+            if (A.real_in) {
+                r[h] = A.real_in[i + (long long)Nx * (j + (long long)A.Ny * k)];
+            } else {
+                long long p = (i + 1) * A.st[0] + (j + 1) * A.st[1] + (k + 1) * A.st[2];
+                // divᶜᶜᶜ on a regular grid: 1/V (Ax δx u + Ay δy v + Az δz w); kept as in kernels.cu
+                FT tx = A.ax * A.u[p + A.st[0]] - A.ax * A.u[p];
+                FT ty = A.ay * A.v[p + A.st[1]] - A.ay * A.v[p];
+                FT tz = A.has_z ? (A.az * A.w[p + A.st[2]] - A.az * A.w[p]) : FT(0);
+                r[h] = (A.invV * ((tx + ty) + tz)) / A.dt;
+            }
+        }
+        CT c; c.x = r[0]; c.y = r[1];
+        s[t * G::LS + G::pos(m)] = c;
+    }
+    __syncthreads();
+    fft_fwd<LOG2M>(s, stw, nl);
+    // untangle: X[k] = E[k] + w_N^k O[k], E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / (2i)
+    for (int w = threadIdx.x; w < nl * (M + 1); w += blockDim.x) {
+        int t = w / (M + 1), kk = w - t * (M + 1);
+        const CT* line = s + t * G::LS;
+        CT a = line[G::pos(A.kpos[kk & (M - 1)])];
+        CT b = line[G::pos(A.kpos[(M - kk) & (M - 1)])];
+        CT E, O;
+        E.x = FT(0.5) * (a.x + b.x); E.y = FT(0.5) * (a.y - b.y);
+        O.x = FT(0.5) * (a.y + b.y); O.y = FT(-0.5) * (a.x - b.x);
+        CT X = cadd(E, cmul(O, A.twN[kk]));
+        A.spec[kk + (long long)A.NXP * ((j0 + t) + (long long)A.Ny * k)] = X;
+    }
+}
+
+// backward x: half spectrum -> real line, written into the haloed field (+ periodic x halos)
+template <class FT, int LOG2M>
+__global__ void __launch_bounds__(256) x_c2r_kernel(XArgs<FT> A) {
+    using CT = typename Cx<FT>::T;
+    using G = Geo<LOG2M>;
+    constexpr int M = 1 << LOG2M;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CT* s = reinterpret_cast<CT*>(smem_raw);
+    CT* stw = s + A.T * G::LS;
+    for (int w = threadIdx.x; w < M; w += blockDim.x) stw[w] = A.twM[w];
+    const int j0 = blockIdx.x * A.T, k = blockIdx.y;
+    const int nl = min(A.T, A.Ny - j0);
+    // tangle: Z[k] = E[k] + i O[k], E = (X[k] + conj X[M-k]) / 2, O = conj(w_N^k) (X[k] - conj X[M-k]) / 2
+    for (int w = threadIdx.x; w < nl * M; w += blockDim.x) {
+        int t = w / M, kk = w - t * M;
+        const CT* row = A.spec + (long long)A.NXP * ((j0 + t) + (long long)A.Ny * k);
+        CT a = row[kk], b = row[M - kk];
+        CT E, D;
+        E.x = FT(0.5) * (a.x + b.x); E.y = FT(0.5) * (a.y - b.y);
+        D.x = FT(0.5) * (a.x - b.x); D.y = FT(0.5) * (a.y + b.y);
+        CT O = cmulc(D, A.twN[kk]);
+        CT Z; Z.x = E.x - O.y; Z.y = E.y + O.x;
+        s[t * G::LS + G::pos(A.kpos[kk])] = Z;
+    }
+    __syncthreads();
+    fft_inv<LOG2M>(s, stw, nl);
+    const int Nx = A.Nx, H = A.Hx;
+    for (int w = threadIdx.x; w < nl * M; w += blockDim.x) {
+        int t = w / M, m = w - t * M;
+        CT z = s[t * G::LS + G::pos(m)];
+        FT r0 = z.x * A.scale, r1 = z.y * A.scale;
+        FT* row = A.phi_p0 + (j0 + t + 1) * A.st[1] + (k + 1) * A.st[2];
+        int i = 2 * m + 1;                       // Julia index of the first of the two reals
+        row[i * A.st[0]] = r0;
+        row[(i + 1) * A.st[0]] = r1;
+        // periodic halos in x (fill_halo_regions_periodic.jl:37-46)
+        if (i > Nx - H) row[(i - Nx) * A.st[0]] = r0;
+        if (i + 1 > Nx - H) row[(i + 1 - Nx) * A.st[0]] = r1;
+        if (i <= H) row[(i + Nx) * A.st[0]] = r0;
+        if (i + 1 <= H) row[(i + 1 + Nx) * A.st[0]] = r1;
+    }
+}
+
+template <class FT>
+struct LArgs {
+    typename Cx<FT>::T* spec;
+    int n, NXH, NXP, nOther;       // lines: kx in [0, NXH), other index in [0, nOther)
+    long long stride, strideOther; // in complex elements
+    int T;
+    const typename Cx<FT>::T* tw;
+    FT scale;
+    const double* lamx;            // natural kx
+    const double* lamL;            // along the line, position order
+    const double* lamO;            // along the other (non-x) dimension, its storage order
+    int line_is_y;                 // 1: line along y (other = z) ; 0: line along z (other = y)
+};
+
+enum { LM_FWD = 0, LM_INV = 1, LM_FWD_DIV_INV = 2 };
+
+template <class FT, int LOG2N, int MODE>
+__global__ void __launch_bounds__(256) line_kernel(LArgs<FT> A) {
+    using CT = typename Cx<FT>::T;
+    using G = Geo<LOG2N>;
+    constexpr int N = 1 << LOG2N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CT* s = reinterpret_cast<CT*>(smem_raw);
+    CT* stw = s + A.T * G::LS;
+    for (int w = threadIdx.x; w < N; w += blockDim.x) stw[w] = A.tw[w];
+    const int x0 = blockIdx.x * A.T, o = blockIdx.y;
+    const int nl = min(A.T, A.NXH - x0);
+    CT* g = A.spec + x0 + o * A.strideOther;
+    for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
+        int m = w / nl, t = w - m * nl;
+        s[t * G::LS + G::pos(m)] = g[t + m * A.stride];
+    }
+    __syncthreads();
+    if (MODE == LM_FWD || MODE == LM_FWD_DIV_INV) fft_fwd<LOG2N>(s, stw, nl);
+    if (MODE == LM_FWD_DIV_INV) {
+        // phi_hat = -b_hat / (lx + ly + lz), zero mode = 0 (fft_based_poisson_solver.jl:106-111)
+        for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
+            int m = w / nl, t = w - m * nl;
+            double lx = A.lamx[x0 + t], lL = A.lamL[m], lO = A.lamO ? A.lamO[o] : 0.0;
+            double lam = A.line_is_y ? ((lx + lL) + lO) : ((lx + lO) + lL);
+            CT v = s[t * G::LS + G::pos(m)];
+            CT r;
+            if (x0 + t == 0 && m == 0 && o == 0) { r.x = 0; r.y = 0; }
+            else { r.x = (FT)(-(double)v.x / lam); r.y = (FT)(-(double)v.y / lam); }
+            s[t * G::LS + G::pos(m)] = r;
+        }
+        __syncthreads();
+    }
+    if (MODE == LM_INV || MODE == LM_FWD_DIV_INV) fft_inv<LOG2N>(s, stw, nl);
+    for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
+        int m = w / nl, t = w - m * nl;
+        CT v = s[t * G::LS + G::pos(m)];
+        if (MODE != LM_FWD) { v.x *= A.scale; v.y *= A.scale; }
+        g[t + m * A.stride] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+struct FastPoisson {
+    using CT = typename Cx<FT>::T;
+    int N[3], log2[3], has_z, NXH, NXP;
+    CT* spec = nullptr;
+    CT* twM = nullptr; CT* twN = nullptr; CT* twY = nullptr; CT* twZ = nullptr;
+    int* kpos = nullptr;
+    double *lamx = nullptr, *lamy = nullptr, *lamz = nullptr;
+    std::vector<void*> owned;
+};
+
+template <class T> static T* up(const std::vector<T>& h, std::vector<void*>& owned) {
+    T* d = nullptr;
+    OB_CUDA(cudaMalloc(&d, std::max<size_t>(1, h.size()) * sizeof(T)));
+    OB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    owned.push_back(d);
+    return d;
+}
+static bool pow2(int n) { return n >= 2 && (n & (n - 1)) == 0; }
+
+template <class FT>
+bool fast_poisson_supported(const GridD<FT>& g) {
+    if (g.topo[0] != OB_PERIODIC || g.topo[1] != OB_PERIODIC) return false;
+    if (g.topo[2] == OB_BOUNDED) return false;
+    if (!pow2(g.N[0]) || g.N[0] < 32 || g.N[0] > 2048) return false;
+    if (!pow2(g.N[1]) || g.N[1] < 16 || g.N[1] > 1024) return false;
+    if (g.topo[2] == OB_PERIODIC && (!pow2(g.N[2]) || g.N[2] < 16 || g.N[2] > 1024)) return false;
+    for (int d = 0; d < 3; ++d) if (!g.regular[d]) return false;
+    return true;
+}
+
+template <class FT>
+FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
+    using CT = typename Cx<FT>::T;
+    auto* p = new FastPoisson<FT>();
+    const long double PI = 3.14159265358979323846264338327950288L;
+    for (int d = 0; d < 3; ++d) { p->N[d] = g.N[d]; p->log2[d] = ilog2c(g.N[d]); }
+    p->has_z = g.topo[2] != OB_FLAT;
+    int Nx = g.N[0], M = Nx / 2, lm = p->log2[0] - 1;
+    p->NXH = M + 1;
+    p->NXP = ((p->NXH + 7) / 8) * 8;
+    size_t tot = (size_t)p->NXP * g.N[1] * g.N[2];
+    OB_CUDA(cudaMalloc(&p->spec, tot * sizeof(CT)));
+    OB_CUDA(cudaMemset(p->spec, 0, tot * sizeof(CT)));
+    auto twid = [&](int n, int count) {
+        std::vector<CT> t(count);
+        for (int k = 0; k < count; ++k) {
+            long double a = -2.0L * PI * k / n;
+            t[k].x = (FT)cosl(a); t[k].y = (FT)sinl(a);
+        }
+        return t;
+    };
+    p->twM = up(twid(M, M), p->owned);
+    p->twN = up(twid(Nx, M + 1), p->owned);
+    p->twY = up(twid(g.N[1], g.N[1]), p->owned);
+    if (p->has_z) p->twZ = up(twid(g.N[2], g.N[2]), p->owned);
+    std::vector<int> kp(M);
+    for (int P = 0; P < M; ++P) kp[freq_of_pos(lm, P)] = P;
+    p->kpos = up(kp, p->owned);
+    // eigenvalues (poisson_eigenvalues.jl:8-11), Float64
+    auto lam = [&](int d, int i) {
+        double L = (double)g.L[d];
+        int n = g.N[d];
+        double v = 2 * sin(i * (double)PI / n) / (L / n);
+        return v * v;
+    };
+    std::vector<double> lx(p->NXP, 1.0), ly(g.N[1]), lz(std::max(1, g.N[2]), 0.0);
+    for (int k = 0; k <= M; ++k) lx[k] = lam(0, k);
+    for (int P = 0; P < g.N[1]; ++P) ly[P] = lam(1, freq_of_pos(p->log2[1], P));
+    if (p->has_z) for (int P = 0; P < g.N[2]; ++P) lz[P] = lam(2, freq_of_pos(p->log2[2], P));
+    p->lamx = up(lx, p->owned); p->lamy = up(ly, p->owned); p->lamz = up(lz, p->owned);
+    return p;
+}
+template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
+    if (!p) return;
+    cudaFree(p->spec);
+    for (void* q : p->owned) cudaFree(q);
+    delete p;
+}
+
+template <class FT, int MODE>
+static void launch_line(const LArgs<FT>& A, int log2n, dim3 grd, size_t smem) {
+    auto go = [&](auto kern) {
+        OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        kern<<<grd, 256, smem, stream()>>>(A);
+        OB_LAUNCH_CHECK();
+    };
+    switch (log2n) {
+        case 4: go(line_kernel<FT, 4, MODE>); break;
+        case 5: go(line_kernel<FT, 5, MODE>); break;
+        case 6: go(line_kernel<FT, 6, MODE>); break;
+        case 7: go(line_kernel<FT, 7, MODE>); break;
+        case 8: go(line_kernel<FT, 8, MODE>); break;
+        case 9: go(line_kernel<FT, 9, MODE>); break;
+        default: go(line_kernel<FT, 10, MODE>); break;
+    }
+}
+static size_t line_smem(int log2n, int T, size_t csize) {
+    int n = 1 << log2n;
+    int RL = log2n == 4 ? 16 : (log2n == 5 ? 4 : (log2n == 8 ? 16 : 8));
+    int LS = n + n / RL + 1;
+    return ((size_t)T * LS + n) * csize;
+}
+
+template <class FT>
+static void run_line(FastPoisson<FT>* p, int dim, int mode) {
+    using CT = typename Cx<FT>::T;
+    LArgs<FT> A;
+    int Ny = p->N[1], Nz = p->N[2];
+    A.spec = p->spec; A.NXH = p->NXH; A.NXP = p->NXP;
+    A.n = p->N[dim];
+    A.line_is_y = dim == 1;
+    A.stride = dim == 1 ? p->NXP : (long long)p->NXP * Ny;
+    A.nOther = dim == 1 ? Nz : Ny;
+    A.strideOther = dim == 1 ? (long long)p->NXP * Ny : p->NXP;
+    A.tw = dim == 1 ? p->twY : p->twZ;
+    A.scale = (FT)(1.0 / A.n);
+    A.lamx = p->lamx;
+    A.lamL = dim == 1 ? p->lamy : p->lamz;
+    A.lamO = dim == 1 ? p->lamz : p->lamy;
+    int T = 16;
+    while (T > 1 && line_smem(p->log2[dim], T, sizeof(CT)) > 100 * 1024) T >>= 1;
+    A.T = T;
+    dim3 grd(cdiv(p->NXH, T), A.nOther);
+    size_t smem = line_smem(p->log2[dim], T, sizeof(CT));
+    if (mode == LM_FWD) launch_line<FT, LM_FWD>(A, p->log2[dim], grd, smem);
+    else if (mode == LM_INV) launch_line<FT, LM_INV>(A, p->log2[dim], grd, smem);
+    else launch_line<FT, LM_FWD_DIV_INV>(A, p->log2[dim], grd, smem);
+}
+
+template <class FT, bool FWD>
+static void run_x(FastPoisson<FT>* p, XArgs<FT>& A) {
+    using CT = typename Cx<FT>::T;
+    int lm = p->log2[0] - 1;
+    A.spec = p->spec; A.Nx = p->N[0]; A.Ny = p->N[1]; A.Nz = p->N[2]; A.NXP = p->NXP;
+    A.twM = p->twM; A.twN = p->twN; A.kpos = p->kpos;
+    A.scale = (FT)(1.0 / (p->N[0] / 2));
+    int T = 32;
+    while (T > 1 && line_smem(lm, T, sizeof(CT)) > 100 * 1024) T >>= 1;
+    A.T = T;
+    dim3 grd(cdiv(A.Ny, T), A.Nz);
+    size_t smem = line_smem(lm, T, sizeof(CT));
+    auto go = [&](auto kern) {
+        OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        kern<<<grd, 256, smem, stream()>>>(A);
+        OB_LAUNCH_CHECK();
+    };
+#define XCASE(L)                                                             \
+    case L: if (FWD) go(x_r2c_kernel<FT, L>); else go(x_c2r_kernel<FT, L>); break;
+    switch (lm) { XCASE(4) XCASE(5) XCASE(6) XCASE(7) XCASE(8) XCASE(9) default: if (FWD) go(x_r2c_kernel<FT, 10>); else go(x_c2r_kernel<FT, 10>); break; }
+#undef XCASE
+}
+
+// source term from the velocities (u, v, w Julia-(0,0,0) pointers) or from a real array; result in phi
+template <class FT>
+void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,
+                        const FT* real_in, FT* phi_p0) {
+    XArgs<FT> A{};
+    A.u = u; A.v = v; A.w = w; A.real_in = real_in;
+    for (int d = 0; d < 3; ++d) A.st[d] = g.st[d];
+    // divᶜᶜᶜ (divergence_operators.jl:16-19): 1/V * (δx(Ax u) + δy(Ay v) + δz(Az w)), then / Δt
+    A.ax = g.d[1] * g.d[2]; A.ay = g.d[0] * g.d[2]; A.az = g.d[0] * g.d[1];
+    A.invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
+    A.dt = dt;
+    A.has_z = p->has_z;
+    A.phi_p0 = phi_p0; A.Hx = g.H[0];
+    run_x<FT, true>(p, A);
+    if (p->has_z) {
+        run_line(p, 1, LM_FWD);
+        run_line(p, 2, LM_FWD_DIV_INV);
+        run_line(p, 1, LM_INV);
+    } else {
+        run_line(p, 1, LM_FWD_DIV_INV);
+    }
+    run_x<FT, false>(p, A);
+}
+
+#define INST(FT)                                                                                   \
+    template bool fast_poisson_supported<FT>(const GridD<FT>&);                                     \
+    template FastPoisson<FT>* fast_poisson_create<FT>(const GridD<FT>&);                            \
+    template void fast_poisson_destroy<FT>(FastPoisson<FT>*);                                       \
+    template void fast_poisson_solve<FT>(FastPoisson<FT>*, const GridD<FT>&, const FT*, const FT*, \
+                                         const FT*, FT, const FT*, FT*);
+INST(float)
+INST(double)
+}  // namespace ff
+}  // namespace ob

@@ -69,6 +69,24 @@ template <class FT> void* poisson_storage(PoissonPlan<FT>* p);          // compl
 template <class FT> int poisson_kind(PoissonPlan<FT>* p);
 // solve with the rhs already in storage; writes the real solution into phi (internal layout)
 template <class FT> void poisson_solve(PoissonPlan<FT>* p, const GridD<FT>& g, FT* phi_p0);
+// ---- fft_fast.cu: half-spectrum / register-radix fast path (Periodic power-of-two dims) ---------
+namespace ff {
+template <class FT> struct FastPoisson;
+template <class FT> bool fast_poisson_supported(const GridD<FT>& g);
+template <class FT> FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g);
+template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p);
+// source term = div(u,v,w)/dt computed on the fly, or a real Nx*Ny*Nz device array `real_in`
+template <class FT>
+void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,
+                        const FT* real_in, FT* phi_p0);
+}  // namespace ff
+// true if the plan owns a fast path; then the two entry points below may be used
+template <class FT> bool poisson_has_fast(PoissonPlan<FT>* p);
+template <class FT>
+void poisson_solve_velocities(PoissonPlan<FT>* p, const GridD<FT>& g, const FT* u, const FT* v, const FT* w,
+                              FT dt, FT* phi_p0);
+template <class FT>
+void poisson_solve_real(PoissonPlan<FT>* p, const GridD<FT>& g, const FT* rhs_real_dev, FT* phi_p0);
 template <class FT>
 void batched_tridiagonal(int Nx, int Ny, int Nz, bool is_complex, const double* a_dev,
                          const double* b_dev, const double* c_dev, const void* rhs_dev,
