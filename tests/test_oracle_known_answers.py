@@ -353,3 +353,27 @@ def test_weno5_stretched_model_runs_and_stays_divergence_free():
         m.time_step(0.1)
     assert m.max_divergence() < 1e-12
     assert np.isfinite(m.kinetic_energy())
+
+
+# ---- the compiled twin (oracle/oracle_cpu.c) restates the same arithmetic --------------------
+@pytest.mark.parametrize("N,zweno", [((16, 8, 32), True), ((8, 16, 16), False), ((16, 16, 1), True)])
+def test_c_twin_matches_numpy_oracle(N, zweno):
+    from oracle import cpu_twin
+    flat = N[2] == 1
+    topo = (Periodic, Periodic, Flat if flat else Periodic)
+    size = N[:2] if flat else N
+    L = (1.0, 2.0, 1.5)
+    g = RectilinearGrid(size=size, extent=L[:len(size)], topology=topo)
+    m = NonhydrostaticModel(g, advection=WENO5(zweno=zweno), tracers=("b",), buoyancy=BuoyancyTracer(),
+                            timestepper="RungeKutta3")
+    rng = np.random.default_rng(9)
+    vals = {n: rng.uniform(-1, 1, N) for n in "uvw"}
+    vals["b"] = 0.5 * g.nodes(("c", "c", "c"))[2] + 0.1 * rng.uniform(-1, 1, N)
+    m.set(**vals)
+    for _ in range(3):
+        m.time_step(2e-3)
+    out = cpu_twin.rk3_run(N, L, vals["u"], vals["v"], vals["w"], vals["b"], 3, 2e-3, zweno=zweno)
+    for n, a in zip("uvwb", out):
+        r = m.fields[n].interior
+        if np.max(np.abs(r)) > 0:
+            assert np.max(np.abs(a - r)) <= 1e-13 * np.max(np.abs(r)), n
