@@ -17,8 +17,15 @@
 //     the same rational function evaluated with ~1e-16 relative differences.
 // Parity with the oracle stays <= 1e-12 per step (tests/test_gpu_parity.py).
 #include "internal.h"
+#include <cstdlib>
 
 namespace ob {
+
+namespace tma {   // tendency_tma.cu
+template <class FT>
+bool launch(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi, const FT* pHY, FT* Gn, const FT* Gm,
+            FT* psi_new, const Substep<FT>& ss);
+}
 
 namespace fast {
 
@@ -251,6 +258,7 @@ bool launch_tendency_fast(const Phys<FT>& P, int comp, const FT* const U[3], con
         if (g.topo[d] != OB_FLAT && g.H[d] < 3) return false;
     }
     if (g.N[0] % fast::TX || g.N[1] % (fast::ROWS * fast::TY)) return false;
+    if (hasz && getenv("OB200_NO_TMA") == nullptr && tma::launch<FT>(P, comp, U, psi, pHY, Gn, Gm, psi_new, ss)) return true;
     fast::Ctx<FT> c;
     for (int d = 0; d < 3; ++d) { c.U[d] = U[d]; c.s[d] = g.st[d]; c.N[d] = g.N[d]; c.invd[d] = 1 / g.d[d]; }
     c.psi = psi; c.pHY = pHY; c.Gm = Gm; c.Gn = Gn; c.psi_new = psi_new; c.ss = ss;

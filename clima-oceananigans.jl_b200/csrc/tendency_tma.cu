@@ -1,0 +1,398 @@
+// tendency_tma.cu -- TMA-staged variant of the specialised tendency (+ substep) kernel.
+//
+// Same arithmetic as tendency_fast.cu (one-sided WENO5, faces shared through registers / shared
+// memory, single-reciprocal Float64 weights).  What changes is the data path: the ncu capture of the
+// direct-load kernel (profiles/r1_tendency_v2_summary.md) shows the FP64 pipe only ~45 % busy with
+// long-scoreboard (global load latency) as the top stall.  Here every operand of the stencils is
+// staged in shared memory by the Tensor Memory Accelerator:
+//   * each block owns a 32 x 8 column tile and marches in k; for every array it reads it keeps a RING
+//     of (32+6) x (8+6) halo'd planes in shared memory (psi: levels k-3..k+3, advecting velocities:
+//     the 1-4 levels their interpolation needs);
+//   * one elected thread issues `cp.async.bulk.tensor.3d` (SASS UTMALDG) for the planes of level k+1
+//     while all warps compute level k; completion is tracked with two alternating mbarriers
+//     (expect_tx / try_wait.parity), so no warp ever waits on a global load;
+//   * the z-direction stencil reads the ring, the x/y stencils read the level-k plane.
+// Tensor maps describe the padded internal layout (common.cuh): 3-D, box (40, 14, 1), no swizzle.
+#include "internal.h"
+#include <cuda.h>
+#include <map>
+#include <mutex>
+
+namespace ob {
+namespace tma {
+
+constexpr int TX = 32, TY = 8, HALO = 3, BY = TY + 2 * HALO, COL0 = HALO + 1;
+template <class FT> struct Box {
+    // The box must START on a 16-byte boundary in x (measured on B200: an odd FP64 start coordinate raises
+    // "illegal instruction", tools/tma_probe4.cu), so it starts one column left of the halo: 1 + 3 + 32 + 3 + 1.
+    static constexpr int BX = TX + 2 * HALO + 2;
+    static constexpr int PLANE_BYTES = ((BX * BY * (int)sizeof(FT) + 127) / 128) * 128;
+    static constexpr int PE = PLANE_BYTES / (int)sizeof(FT);
+};
+
+// rings per advected component B: psi + auxiliary advecting velocities.
+// aux a of B:      component            level range lo..hi      slots (power of two >= hi-lo+2)
+//   B=0 (u):  v [0,0] 2,  w [0,1] 4          B=1 (v):  u [0,0] 2,  w [0,1] 4
+//   B=2 (w):  u [-2,1] 8, v [-2,1] 8         B=3 (c):  u [0,0] 2,  v [0,0] 2,  w [0,1] 4
+template <int B> struct Cfg {
+    static constexpr int NA = B == 3 ? 3 : 2;
+    __host__ __device__ static constexpr int comp(int a) {
+        return B == 0 ? (a == 0 ? 1 : 2) : B == 1 ? (a == 0 ? 0 : 2) : B == 2 ? (a == 0 ? 0 : 1) : a;
+    }
+    __host__ __device__ static constexpr int lo(int a) { return B == 2 ? -2 : 0; }
+    __host__ __device__ static constexpr int hi(int a) { return B == 2 ? 1 : (comp(a) == 2 ? 1 : 0); }
+    __host__ __device__ static constexpr int sl(int a) { return a >= NA ? 0 : (B == 2 ? 8 : (comp(a) == 2 ? 4 : 2)); }
+};
+constexpr int PSI_LO = -3, PSI_HI = 3, PSI_SL = 8;
+
+template <class FT>
+struct Ctx {
+    CUtensorMap tm_psi, tm_aux[3];
+    const FT* psi;        // Julia-(0,0,0) pointers for the pointwise (non-stencil) reads / writes
+    const FT* pHY;
+    const FT* Gm;
+    const FT* cor;        // the velocity the Coriolis term interpolates (v for B = 0, u for B = 1)
+    FT* Gn;
+    FT* psi_new;
+    long long s[3];
+    int O[3];
+    FT area[3], invV, invd[3], f;
+    int fplane, Kc;
+    Substep<FT> ss;
+};
+
+// ---- PTX helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+template <class FT, bool ZW>
+__device__ __forceinline__ FT weno_combine(FT C0, FT C1, FT C2, FT b0, FT b1, FT b2, FT p0, FT p1, FT p2) {
+    const FT eps = FT(1e-6);
+    if constexpr (sizeof(FT) == 8) {
+        FT D0 = b0 + eps, D1 = b1 + eps, D2 = b2 + eps;
+        FT E0 = D0 * D0, E1 = D1 * D1, E2 = D2 * D2;
+        FT g0, g1, g2;
+        if (ZW) {
+            FT tau = fabs(b2 - b0), t2 = tau * tau;
+            g0 = (C0 * (E0 + t2)) * (E1 * E2);
+            g1 = (C1 * (E1 + t2)) * (E0 * E2);
+            g2 = (C2 * (E2 + t2)) * (E0 * E1);
+        } else {
+            g0 = C0 * (E1 * E2); g1 = C1 * (E0 * E2); g2 = C2 * (E0 * E1);
+        }
+        FT den = (g0 + g1) + g2;
+        FT num = (g0 * p0 + g1 * p1) + g2 * p2;
+        return (FT)(num * fast_rcp((double)den));
+    } else {
+        FT a0, a1, a2;
+        if (ZW) {
+            FT tau = fabs(b2 - b0);
+            FT q0 = tau / (b0 + eps), q1 = tau / (b1 + eps), q2 = tau / (b2 + eps);
+            a0 = C0 * (1 + q0 * q0); a1 = C1 * (1 + q1 * q1); a2 = C2 * (1 + q2 * q2);
+        } else {
+            FT d0 = b0 + eps, d1 = b1 + eps, d2 = b2 + eps;
+            a0 = C0 / (d0 * d0); a1 = C1 / (d1 * d1); a2 = C2 / (d2 * d2);
+        }
+        FT sa = (a0 + a1) + a2;
+        return ((a0 * p0 + a1 * p1) + a2 * p2) / sa;
+    }
+}
+// one-sided reconstruction, window ordered towards the face (see tendency_fast.cu)
+template <class FT, bool ZW>
+__device__ __forceinline__ FT weno_side(FT a, FT b, FT c, FT d, FT e, FT k1, FT k3) {
+    const FT c1312 = FT(13.0 / 12.0), c14 = FT(0.25);
+    const FT a13 = FT(1.0 / 3.0), a56 = FT(5.0 / 6.0), a16 = FT(1.0 / 6.0), a76 = FT(7.0 / 6.0), a116 = FT(11.0 / 6.0);
+    FT t2 = (a - 2 * b) + c, t1 = (b - 2 * c) + d, t0 = (c - 2 * d) + e;
+    FT s2 = (k1 * a - 4 * b) + k3 * c, s1 = b - d, s0 = (k3 * c - 4 * d) + k1 * e;
+    FT b2 = c1312 * (t2 * t2) + c14 * (s2 * s2);
+    FT b1 = c1312 * (t1 * t1) + c14 * (s1 * s1);
+    FT b0 = c1312 * (t0 * t0) + c14 * (s0 * s0);
+    FT p0 = (a13 * c + a56 * d) - a16 * e;
+    FT p1 = (-a16 * b + a56 * c) + a13 * d;
+    FT p2 = (a13 * a - a76 * b) + a116 * c;
+    return weno_combine<FT, ZW>(FT(3.0 / 10.0), FT(3.0 / 5.0), FT(1.0 / 10.0), b0, b1, b2, p0, p1, p2);
+}
+
+// position inside the staged data: level L (Julia k), tile row / column including the halo offset
+struct P3 { int L, row, col; };
+template <int D> __device__ __forceinline__ P3 shp(P3 q, int n) {
+    if (D == 0) q.col += n; else if (D == 1) q.row += n; else q.L += n;
+    return q;
+}
+
+template <class FT, int B>
+struct Rings {
+    const FT* psi;
+    const FT* aux[3];
+    __device__ __forceinline__ FT P(P3 q) const {
+        return psi[((q.L + 8) & (PSI_SL - 1)) * Box<FT>::PE + q.row * Box<FT>::BX + q.col];
+    }
+    template <int COMP> __device__ __forceinline__ FT V(P3 q) const {
+        if constexpr (COMP == B) return P(q);
+        else {
+            constexpr int a = Cfg<B>::comp(0) == COMP ? 0 : (Cfg<B>::comp(1) == COMP ? 1 : 2);
+            return aux[a][((q.L + 8) & (Cfg<B>::sl(a) - 1)) * Box<FT>::PE + q.row * Box<FT>::BX + q.col];
+        }
+    }
+};
+
+template <class FT, int B, int COMP, int D>
+__device__ __forceinline__ FT I3r(const Rings<FT, B>& r, P3 q) {
+    FT c0 = r.template V<COMP>(q);
+    return c0 - ((r.template V<COMP>(shp<D>(q, 1)) - c0) - (c0 - r.template V<COMP>(shp<D>(q, -1)))) * FT(1.0 / 6.0);
+}
+
+// area * upwind flux of psi (component B or tracer) in direction A at position q
+// (A == B: cell-centre index; otherwise face index along A)
+template <class FT, bool ZW, int A, int B>
+__device__ __forceinline__ FT flux_at(const Rings<FT, B>& r, const Ctx<FT>& c, P3 q) {
+    FT ut;
+    P3 pf = q;
+    if constexpr (B == 3) {
+        ut = r.template V<A>(q);
+    } else if constexpr (A == B) {
+        ut = FT(0.5) * (I3r<FT, B, A, A>(r, q) + I3r<FT, B, A, A>(r, shp<A>(q, 1)));
+        pf = shp<A>(q, 1);
+    } else {
+        ut = FT(0.5) * (I3r<FT, B, A, B>(r, shp<B>(q, -1)) + I3r<FT, B, A, B>(r, q));
+    }
+    const FT w0 = r.P(shp<A>(pf, -3)), w1 = r.P(shp<A>(pf, -2)), w2 = r.P(shp<A>(pf, -1)), w3 = r.P(pf),
+             w4 = r.P(shp<A>(pf, 1)), w5 = r.P(shp<A>(pf, 2));
+    const bool pos = ut > FT(0);
+    FT rec = weno_side<FT, ZW>(pos ? w0 : w5, pos ? w1 : w4, pos ? w2 : w3, pos ? w3 : w2, pos ? w4 : w1,
+                               pos ? FT(1) : FT(3), pos ? FT(3) : FT(1));
+    return c.area[A] * (ut * rec);
+}
+
+template <class FT, bool ZW, int B>
+__global__ void __launch_bounds__(TX* TY, 2) tendency_tma_kernel(const __grid_constant__ Ctx<FT> c) {
+    using BXs = Box<FT>;
+    using CF = Cfg<B>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ FT sFx[2][TY][TX + 1];
+    __shared__ FT sFy[2][TY + 1][TX];
+    __shared__ __align__(8) unsigned long long bars[2];
+
+    FT* ring_psi = reinterpret_cast<FT*>(smem_raw);
+    FT* ring_aux[3];
+    {
+        FT* q = ring_psi + PSI_SL * BXs::PE;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { ring_aux[a] = q; q += CF::sl(a) * BXs::PE; }
+    }
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * TY, k0 = 1 + blockIdx.z * c.Kc;
+    const int cx = i0 - HALO - 2 + c.O[0], cy = j0 - HALO - 1 + c.O[1], cz0 = c.O[2] - 1;   // array coords
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto load_psi = [&](int L, unsigned long long* bar) {
+        tma_load_3d(ring_psi + ((L + 8) & (PSI_SL - 1)) * BXs::PE, &c.tm_psi, cx, cy, L + cz0, bar);
+    };
+    auto load_aux = [&](int a, int L, unsigned long long* bar) {
+        tma_load_3d(ring_aux[a] + ((L + 8) & (CF::sl(a) - 1)) * BXs::PE, &c.tm_aux[a], cx, cy, L + cz0, bar);
+    };
+    if (tid == 0) {
+        // prologue: everything iteration 0 (and the carried z face) needs
+        int planes = (PSI_HI - PSI_LO + 1);
+#pragma unroll
+        for (int a = 0; a < CF::NA; ++a) planes += CF::hi(a) - CF::lo(a) + 1;
+        mbar_expect_tx(&bars[0], planes * BXs::BX * BY * (unsigned)sizeof(FT));
+        for (int L = k0 + PSI_LO; L <= k0 + PSI_HI; ++L) load_psi(L, &bars[0]);
+#pragma unroll
+        for (int a = 0; a < CF::NA; ++a)
+            for (int L = k0 + CF::lo(a); L <= k0 + CF::hi(a); ++L) load_aux(a, L, &bars[0]);
+    }
+
+    Rings<FT, B> R;
+    R.psi = ring_psi;
+    R.aux[0] = ring_aux[0]; R.aux[1] = ring_aux[1]; R.aux[2] = ring_aux[2];
+
+    constexpr bool XLOW = (B == 0), YLOW = (B == 1), ZLOW = (B == 2);
+    const bool xextra = tid < TY, yextra = tid >= 32 && tid < 32 + TX;
+    const long long sx = c.s[0], sy = c.s[1], sz = c.s[2];
+    long long p = (i0 + tx) * sx + (j0 + ty) * sy + k0 * sz;
+    FT Fz_carry = FT(0);
+
+    for (int it = 0; it < c.Kc; ++it) {
+        const int k = k0 + it, buf = it & 1;
+        if (tid == 0 && it + 1 < c.Kc) {      // prefetch the planes level k+1 adds
+            unsigned long long* nb = &bars[(it + 1) & 1];
+            mbar_expect_tx(nb, (1 + CF::NA) * BXs::BX * BY * (unsigned)sizeof(FT));
+            load_psi(k + 1 + PSI_HI, nb);
+#pragma unroll
+            for (int a = 0; a < CF::NA; ++a) load_aux(a, k + 1 + CF::hi(a), nb);
+        }
+        mbar_wait(&bars[it & 1], (it >> 1) & 1);
+
+        P3 q{k, ty + HALO, tx + COL0};
+        if (it == 0) Fz_carry = flux_at<FT, ZW, 2, B>(R, c, ZLOW ? shp<2>(q, -1) : q);
+        FT Fx = flux_at<FT, ZW, 0, B>(R, c, q);
+        FT Fy = flux_at<FT, ZW, 1, B>(R, c, q);
+        sFx[buf][ty][XLOW ? tx + 1 : tx] = Fx;
+        sFy[buf][YLOW ? ty + 1 : ty][tx] = Fy;
+        if (xextra) {
+            P3 e{k, tid + HALO, (XLOW ? -1 : TX) + COL0};
+            sFx[buf][tid][XLOW ? 0 : TX] = flux_at<FT, ZW, 0, B>(R, c, e);
+        }
+        if (yextra) {
+            P3 e{k, (YLOW ? -1 : TY) + HALO, (tid - 32) + COL0};
+            sFy[buf][YLOW ? 0 : TY][tid - 32] = flux_at<FT, ZW, 1, B>(R, c, e);
+        }
+        FT Fz_new = flux_at<FT, ZW, 2, B>(R, c, ZLOW ? q : shp<2>(q, 1));
+        FT dFz = Fz_new - Fz_carry;
+        Fz_carry = Fz_new;
+        __syncthreads();
+        FT dFx = XLOW ? (Fx - sFx[buf][ty][tx]) : (sFx[buf][ty][tx + 1] - Fx);
+        FT dFy = YLOW ? (Fy - sFy[buf][ty][tx]) : (sFy[buf][ty + 1][tx] - Fy);
+        FT G = -(c.invV * ((dFx + dFy) + dFz));
+        if (B == 0) {
+            if (c.fplane) {
+                const FT* v = c.cor;
+                FT a0 = FT(0.5) * (v[p - sx] + v[p]), a1 = FT(0.5) * (v[p - sx + sy] + v[p + sy]);
+                G = G - (-c.f * (FT(0.5) * (a0 + a1)));
+            }
+            if (c.pHY) G = G - (c.pHY[p] - c.pHY[p - sx]) * c.invd[0];
+        } else if (B == 1) {
+            if (c.fplane) {
+                const FT* u = c.cor;
+                FT a0 = FT(0.5) * (u[p - sy] + u[p + sx - sy]), a1 = FT(0.5) * (u[p] + u[p + sx]);
+                G = G - (c.f * (FT(0.5) * (a0 + a1)));
+            }
+            if (c.pHY) G = G - (c.pHY[p] - c.pHY[p - sy]) * c.invd[1];
+        }
+        c.Gn[p] = G;
+        const FT ps = R.P(q);
+        if (c.ss.mode == SUB_RK3_FIRST) c.psi_new[p] = ps + c.ss.c1 * G;
+        else if (c.ss.mode == SUB_RK3) c.psi_new[p] = ps + c.ss.dt * (c.ss.c1 * G + c.ss.c2 * c.Gm[p]);
+        else if (c.ss.mode == SUB_AB2) c.psi_new[p] = ps + c.ss.dt * (c.ss.c1 * G - c.ss.c2 * c.Gm[p]);
+        p += sz;
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        OB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+        if (!p || qr != cudaDriverEntryPointSuccess) throw Error("cuTensorMapEncodeTiled not available");
+        fn = (EncodeFn)p;
+    }
+    return fn;
+}
+
+template <class FT>
+static CUtensorMap make_map(const GridD<FT>& g, const FT* base) {
+    static std::map<std::pair<const void*, long long>, CUtensorMap> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair((const void*)base, (long long)g.total * (long long)sizeof(FT) + g.S[0]);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)g.S[0], (cuuint64_t)g.S[1], (cuuint64_t)g.S[2]};
+    cuuint64_t strides[2] = {(cuuint64_t)g.S[0] * sizeof(FT), (cuuint64_t)g.S[0] * g.S[1] * sizeof(FT)};
+    cuuint32_t box[3] = {(cuuint32_t)Box<FT>::BX, (cuuint32_t)BY, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = get_encode()(&m, sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                              (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    cache[key] = m;
+    return m;
+}
+
+template <class FT, bool ZW, int B>
+static void launch_one(Ctx<FT>& c, const GridD<FT>& g, const FT* const U[3]) {
+    using CF = Cfg<B>;
+    int slots = PSI_SL;
+    for (int a = 0; a < CF::NA; ++a) {
+        slots += CF::sl(a);
+        c.tm_aux[a] = make_map<FT>(g, U[CF::comp(a)] - g.off0);
+    }
+    size_t smem = (size_t)slots * Box<FT>::PLANE_BYTES;
+    auto kern = tendency_tma_kernel<FT, ZW, B>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        attr_set = true;
+    }
+    dim3 blk(TX, TY), grd(g.N[0] / TX, g.N[1] / TY, g.N[2] / c.Kc);
+    kern<<<grd, blk, smem, stream()>>>(c);
+    OB_LAUNCH_CHECK();
+}
+
+template <class FT>
+bool launch(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi, const FT* pHY, FT* Gn, const FT* Gm,
+            FT* psi_new, const Substep<FT>& ss) {
+    const GridD<FT>& g = P.g;
+    if (g.topo[2] == OB_FLAT || g.N[0] % TX || g.N[1] % TY) return false;
+    if ((g.S[0] * sizeof(FT)) % 16) return false;
+    Ctx<FT> c;
+    c.tm_psi = make_map<FT>(g, psi - g.off0);
+    c.psi = psi; c.pHY = pHY; c.Gm = Gm; c.Gn = Gn; c.psi_new = psi_new; c.ss = ss;
+    c.cor = comp == 0 ? U[1] : U[0];
+    for (int d = 0; d < 3; ++d) { c.s[d] = g.st[d]; c.O[d] = g.O[d]; c.invd[d] = 1 / g.d[d]; }
+    c.area[0] = g.d[1] * g.d[2]; c.area[1] = g.d[0] * g.d[2]; c.area[2] = g.d[0] * g.d[1];
+    c.invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
+    c.f = P.f; c.fplane = P.fplane;
+    int Kc = 32;
+    while (g.N[2] % Kc) Kc >>= 1;
+    c.Kc = Kc;
+#define GO(ZWV)                                                         \
+    switch (comp) {                                                     \
+        case 0: launch_one<FT, ZWV, 0>(c, g, U); break;                 \
+        case 1: launch_one<FT, ZWV, 1>(c, g, U); break;                 \
+        case 2: launch_one<FT, ZWV, 2>(c, g, U); break;                 \
+        default: launch_one<FT, ZWV, 3>(c, g, U); break;                \
+    }
+    if (P.zweno) { GO(true) } else { GO(false) }
+#undef GO
+    return true;
+}
+template bool launch<float>(const Phys<float>&, int, const float* const[3], const float*, const float*, float*,
+                            const float*, float*, const Substep<float>&);
+template bool launch<double>(const Phys<double>&, int, const double* const[3], const double*, const double*, double*,
+                             const double*, double*, const Substep<double>&);
+}  // namespace tma
+}  // namespace ob
