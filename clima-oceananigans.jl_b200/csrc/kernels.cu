@@ -233,6 +233,7 @@ __global__ void hydrostatic_kernel(GridD<FT> g, const FT* b, FT gz, bool has_b, 
     };
     FT acc = -(FT(0.5) * (zb(Nz) + zb(Nz + 1))) * spacing(g, 2, OB_F, Nz + 1);
     pHY[p + Nz * sz] = acc;
+#pragma unroll 8
     for (int k = Nz - 1; k >= 1; --k) {
         acc = acc - (FT(0.5) * (zb(k) + zb(k + 1))) * spacing(g, 2, OB_F, k + 1);
         pHY[p + k * sz] = acc;

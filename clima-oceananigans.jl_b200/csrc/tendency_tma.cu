@@ -32,8 +32,8 @@ template <class FT> struct Box {
 
 // rings per advected component B: psi + auxiliary advecting velocities.
 // aux a of B:      component            level range lo..hi      slots (power of two >= hi-lo+2)
-//   B=0 (u):  v [0,0] 2,  w [0,1] 4          B=1 (v):  u [0,0] 2,  w [0,1] 4
-//   B=2 (w):  u [-2,1] 8, v [-2,1] 8         B=3 (c):  u [0,0] 2,  v [0,0] 2,  w [0,1] 4
+//   B=0 (u):  v [0,0] 2,  w [0,1] 3          B=1 (v):  u [0,0] 2,  w [0,1] 3
+//   B=2 (w):  u [-2,1] 5, v [-2,1] 5         B=3 (c):  u [0,0] 2,  v [0,0] 2,  w [0,1] 3
 template <int B> struct Cfg {
     static constexpr int NA = B == 3 ? 3 : 2;
     __host__ __device__ static constexpr int comp(int a) {
@@ -41,7 +41,8 @@ template <int B> struct Cfg {
     }
     __host__ __device__ static constexpr int lo(int a) { return B == 2 ? -2 : 0; }
     __host__ __device__ static constexpr int hi(int a) { return B == 2 ? 1 : (comp(a) == 2 ? 1 : 0); }
-    __host__ __device__ static constexpr int sl(int a) { return a >= NA ? 0 : (B == 2 ? 8 : (comp(a) == 2 ? 4 : 2)); }
+    // slots >= live levels + 1 prefetched level (any count: the slot index is a compile-time modulo)
+    __host__ __device__ static constexpr int sl(int a) { return a >= NA ? 0 : (B == 2 ? 5 : (comp(a) == 2 ? 3 : 2)); }
 };
 constexpr int PSI_LO = -3, PSI_HI = 3, PSI_SL = 8;
 
@@ -160,7 +161,7 @@ struct Rings {
         if constexpr (COMP == B) return P(q);
         else {
             constexpr int a = Cfg<B>::comp(0) == COMP ? 0 : (Cfg<B>::comp(1) == COMP ? 1 : 2);
-            return aux[a][((q.L + 8) & (Cfg<B>::sl(a) - 1)) * Box<FT>::PE + q.row * Box<FT>::BX + q.col];
+            return aux[a][((q.L + 60) % Cfg<B>::sl(a)) * Box<FT>::PE + q.row * Box<FT>::BX + q.col];
         }
     }
 };
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(TX* TY, 2) tendency_tma_kernel(const __grid_co
         tma_load_3d(ring_psi + ((L + 8) & (PSI_SL - 1)) * BXs::PE, &c.tm_psi, cx, cy, L + cz0, bar);
     };
     auto load_aux = [&](int a, int L, unsigned long long* bar) {
-        tma_load_3d(ring_aux[a] + ((L + 8) & (CF::sl(a) - 1)) * BXs::PE, &c.tm_aux[a], cx, cy, L + cz0, bar);
+        tma_load_3d(ring_aux[a] + ((L + 60) % CF::sl(a)) * BXs::PE, &c.tm_aux[a], cx, cy, L + cz0, bar);
     };
     if (tid == 0) {
         // prologue: everything iteration 0 (and the carried z face) needs
