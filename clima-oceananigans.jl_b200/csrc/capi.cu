@@ -299,7 +299,7 @@ static ob200_field* make_field(const ob200_grid* g, const int32_t loc[3], const 
         else {     // defaults: field_boundary_conditions.jl:13-30
             int d = s / 2, t = g->desc.topology[d];
             f->bcs[s].value = 0;
-            f->bcs[s].kind = t == OB200_PERIODIC ? OB200_BC_PERIODIC
+            f->bcs[s].kind = (t == OB200_PERIODIC || t == OB200_FULLY_CONNECTED) ? OB200_BC_PERIODIC
                            : t == OB200_FLAT ? OB200_BC_NONE
                            : (loc[d] == OB200_CENTER ? OB200_BC_FLUX : OB200_BC_OPEN);
         }
@@ -864,5 +864,39 @@ extern "C" int32_t ob200_profile_query(const char* phase, double* total_ms, int6
     auto it = ob::g_phases.find(phase);
     if (total_ms) *total_ms = it == ob::g_phases.end() ? 0.0 : it->second.total_ms;
     if (count) *count = it == ob::g_phases.end() ? 0 : it->second.count;
+    API_END
+}
+
+// ---- slab decomposition over several GPUs (reference: src/Distributed/multi_architectures.jl:7-137) -----
+namespace ob { namespace comm {
+void unique_id(char out[128]); void init(int nranks, int rank, const char id[128]); void destroy();
+int rank(); int size(); bool active(); void allreduce_f64(double* buf, size_t n, bool max);
+} }
+extern "C" int32_t ob200_comm_unique_id(char out[128]) {
+    API_BEGIN
+    ob::comm::unique_id(out);
+    API_END
+}
+extern "C" int32_t ob200_comm_init(int32_t nranks, int32_t rank, const char id[128]) {
+    API_BEGIN
+    ensure_device();
+    ob::comm::init(nranks, rank, id);
+    API_END
+}
+extern "C" int32_t ob200_comm_destroy(void) {
+    API_BEGIN
+    ob::comm::destroy();
+    API_END
+}
+// sum (op = 0) or max (op = 1) of n host doubles over all ranks (diagnostics: KE, max |div|, CFL)
+extern "C" int32_t ob200_comm_allreduce(double* values, int32_t n, int32_t op) {
+    API_BEGIN
+    if (!ob::comm::active()) return 0;
+    double* r = red_buf();
+    if (n > 8) throw Error("at most 8 values");
+    OB_CUDA(cudaMemcpyAsync(r, values, n * sizeof(double), cudaMemcpyHostToDevice, stream()));
+    ob::comm::allreduce_f64(r, n, op == 1);
+    OB_CUDA(cudaMemcpyAsync(values, r, n * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
     API_END
 }

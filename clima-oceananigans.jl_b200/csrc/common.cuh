@@ -15,6 +15,7 @@
 #define OB_PERIODIC 0
 #define OB_BOUNDED 1
 #define OB_FLAT 2
+#define OB_COMM 3      // FullyConnected: periodic-like, halos filled by neighbour exchange
 #define OB_C 0
 #define OB_F 1
 

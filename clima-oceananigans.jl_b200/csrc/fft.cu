@@ -386,6 +386,14 @@ PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double*
     p->kind = kind;
     if (kind == 1 && ff::fast_poisson_supported<FT>(g) && getenv("OB200_NO_FAST_FFT") == nullptr)
         p->fast = ff::fast_poisson_create<FT>(g);
+    if (g.topo[0] == OB_COMM || g.topo[1] == OB_COMM || g.topo[2] == OB_COMM) {
+        if (!p->fast) {
+            delete p;
+            throw Error("the slab-decomposed Poisson solver needs Periodic power-of-two x, z and a y decomposition "
+                        "(FullyConnected y) with 2, 4 or 8 ranks");
+        }
+        return p;
+    }
     const double PI = 3.14159265358979323846;
     size_t tot = (size_t)g.N[0] * g.N[1] * g.N[2];
     OB_CUDA(cudaMalloc(&p->storage, tot * sizeof(CT)));

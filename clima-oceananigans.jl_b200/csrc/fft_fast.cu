@@ -19,6 +19,11 @@
 #include <algorithm>
 
 namespace ob {
+namespace comm {
+bool active(); int rank(); int size();
+void group_start(); void group_end();
+void send(const void*, size_t, int); void recv(void*, size_t, int);
+}
 namespace ff {
 
 template <class FT> struct Cx;
@@ -290,15 +295,28 @@ __global__ void __launch_bounds__(256) x_c2r_kernel(XArgs<FT> A) {
     }
 }
 
+// address of spectral element (kx, m, o): kx blocked by kxb (for the all-to-all chunks), the line
+// index m optionally split in (m / split, m % split) (y lines gathered from R ranks)
+struct Lay {
+    int kxb, split;
+    long long s_blk, s_ml, s_mh, s_o;
+    __device__ __forceinline__ long long at(int kx, int m, int o) const {
+        int kb = kx / kxb, kl = kx - kb * kxb, mh = m / split, ml = m - mh * split;
+        return kb * s_blk + kl + ml * s_ml + mh * s_mh + o * s_o;
+    }
+};
+
 template <class FT>
 struct LArgs {
-    typename Cx<FT>::T* spec;
-    int n, NXH, NXP, nOther;       // lines: kx in [0, NXH), other index in [0, nOther)
-    long long stride, strideOther; // in complex elements
+    const typename Cx<FT>::T* in;
+    typename Cx<FT>::T* out;
+    Lay lin, lout;
+    int n, NXH, nOther;            // lines: kx in [0, NXH), other index in [0, nOther)
+    int kx0;                       // global kx of local kx 0 (slab-decomposed spectral space)
     int T;
     const typename Cx<FT>::T* tw;
     FT scale;
-    const double* lamx;            // natural kx
+    const double* lamx;            // natural kx (global)
     const double* lamL;            // along the line, position order
     const double* lamO;            // along the other (non-x) dimension, its storage order
     int line_is_y;                 // 1: line along y (other = z) ; 0: line along z (other = y)
@@ -317,10 +335,9 @@ __global__ void __launch_bounds__(256) line_kernel(LArgs<FT> A) {
     for (int w = threadIdx.x; w < N; w += blockDim.x) stw[w] = A.tw[w];
     const int x0 = blockIdx.x * A.T, o = blockIdx.y;
     const int nl = min(A.T, A.NXH - x0);
-    CT* g = A.spec + x0 + o * A.strideOther;
     for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
         int m = w / nl, t = w - m * nl;
-        s[t * G::LS + G::pos(m)] = g[t + m * A.stride];
+        s[t * G::LS + G::pos(m)] = A.in[A.lin.at(x0 + t, m, o)];
     }
     __syncthreads();
     if (MODE == LM_FWD || MODE == LM_FWD_DIV_INV) fft_fwd<LOG2N>(s, stw, nl);
@@ -328,11 +345,12 @@ __global__ void __launch_bounds__(256) line_kernel(LArgs<FT> A) {
         // phi_hat = -b_hat / (lx + ly + lz), zero mode = 0 (fft_based_poisson_solver.jl:106-111)
         for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
             int m = w / nl, t = w - m * nl;
-            double lx = A.lamx[x0 + t], lL = A.lamL[m], lO = A.lamO ? A.lamO[o] : 0.0;
+            int kx = A.kx0 + x0 + t;
+            double lx = A.lamx[kx], lL = A.lamL[m], lO = A.lamO ? A.lamO[o] : 0.0;
             double lam = A.line_is_y ? ((lx + lL) + lO) : ((lx + lO) + lL);
             CT v = s[t * G::LS + G::pos(m)];
             CT r;
-            if (x0 + t == 0 && m == 0 && o == 0) { r.x = 0; r.y = 0; }
+            if (kx == 0 && m == 0 && o == 0) { r.x = 0; r.y = 0; }
             else { r.x = (FT)(-(double)v.x / lam); r.y = (FT)(-(double)v.y / lam); }
             s[t * G::LS + G::pos(m)] = r;
         }
@@ -343,7 +361,7 @@ __global__ void __launch_bounds__(256) line_kernel(LArgs<FT> A) {
         int m = w / nl, t = w - m * nl;
         CT v = s[t * G::LS + G::pos(m)];
         if (MODE != LM_FWD) { v.x *= A.scale; v.y *= A.scale; }
-        g[t + m * A.stride] = v;
+        A.out[A.lout.at(x0 + t, m, o)] = v;
     }
 }
 
@@ -354,6 +372,8 @@ template <class FT>
 struct FastPoisson {
     using CT = typename Cx<FT>::T;
     int N[3], log2[3], has_z, NXH, NXP;
+    int R = 1, rank = 0, NyG = 0, KXB = 0;      // slab decomposition in y: NyG = R * N[1], KXB = NXP / R
+    CT* bufA = nullptr; CT* bufB = nullptr;     // all-to-all staging (distributed only)
     CT* spec = nullptr;
     CT* twM = nullptr; CT* twN = nullptr; CT* twY = nullptr; CT* twZ = nullptr;
     int* kpos = nullptr;
@@ -361,6 +381,7 @@ struct FastPoisson {
     std::vector<void*> owned;
 };
 
+namespace cm = ::ob::comm;
 template <class T> static T* up(const std::vector<T>& h, std::vector<void*>& owned) {
     T* d = nullptr;
     OB_CUDA(cudaMalloc(&d, std::max<size_t>(1, h.size()) * sizeof(T)));
@@ -372,10 +393,12 @@ static bool pow2(int n) { return n >= 2 && (n & (n - 1)) == 0; }
 
 template <class FT>
 bool fast_poisson_supported(const GridD<FT>& g) {
-    if (g.topo[0] != OB_PERIODIC || g.topo[1] != OB_PERIODIC) return false;
+    if (g.topo[0] != OB_PERIODIC || (g.topo[1] != OB_PERIODIC && g.topo[1] != OB_COMM)) return false;
     if (g.topo[2] == OB_BOUNDED) return false;
+    int R = g.topo[1] == OB_COMM ? comm::size() : 1;
+    if (g.topo[1] == OB_COMM && (g.topo[2] != OB_PERIODIC || !pow2(R) || R > 8)) return false;
     if (!pow2(g.N[0]) || g.N[0] < 32 || g.N[0] > 2048) return false;
-    if (!pow2(g.N[1]) || g.N[1] < 16 || g.N[1] > 1024) return false;
+    if (!pow2(g.N[1]) || g.N[1] * R < 16 || g.N[1] * R > 1024) return false;
     if (g.topo[2] == OB_PERIODIC && (!pow2(g.N[2]) || g.N[2] < 16 || g.N[2] > 1024)) return false;
     for (int d = 0; d < 3; ++d) if (!g.regular[d]) return false;
     return true;
@@ -388,12 +411,22 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
     const long double PI = 3.14159265358979323846264338327950288L;
     for (int d = 0; d < 3; ++d) { p->N[d] = g.N[d]; p->log2[d] = ilog2c(g.N[d]); }
     p->has_z = g.topo[2] != OB_FLAT;
+    if (g.topo[1] == OB_COMM) { p->R = cm::size(); p->rank = cm::rank(); }
+    p->NyG = p->R * g.N[1];
+    p->log2[1] = ilog2c(p->NyG);
     int Nx = g.N[0], M = Nx / 2, lm = p->log2[0] - 1;
     p->NXH = M + 1;
-    p->NXP = ((p->NXH + 7) / 8) * 8;
+    p->NXP = ((p->NXH + 7) / 8) * 8;           // multiple of 8 hence of R (R in {1,2,4,8})
+    p->KXB = p->NXP / p->R;
     size_t tot = (size_t)p->NXP * g.N[1] * g.N[2];
     OB_CUDA(cudaMalloc(&p->spec, tot * sizeof(CT)));
     OB_CUDA(cudaMemset(p->spec, 0, tot * sizeof(CT)));
+    if (p->R > 1) {
+        OB_CUDA(cudaMalloc(&p->bufA, tot * sizeof(CT)));
+        OB_CUDA(cudaMalloc(&p->bufB, tot * sizeof(CT)));
+        OB_CUDA(cudaMemset(p->bufA, 0, tot * sizeof(CT)));
+        OB_CUDA(cudaMemset(p->bufB, 0, tot * sizeof(CT)));
+    }
     auto twid = [&](int n, int count) {
         std::vector<CT> t(count);
         for (int k = 0; k < count; ++k) {
@@ -404,21 +437,22 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
     };
     p->twM = up(twid(M, M), p->owned);
     p->twN = up(twid(Nx, M + 1), p->owned);
-    p->twY = up(twid(g.N[1], g.N[1]), p->owned);
+    p->twY = up(twid(p->NyG, p->NyG), p->owned);
     if (p->has_z) p->twZ = up(twid(g.N[2], g.N[2]), p->owned);
     std::vector<int> kp(M);
     for (int P = 0; P < M; ++P) kp[freq_of_pos(lm, P)] = P;
     p->kpos = up(kp, p->owned);
     // eigenvalues (poisson_eigenvalues.jl:8-11), Float64
     auto lam = [&](int d, int i) {
-        double L = (double)g.L[d];
-        int n = g.N[d];
+        // global extent and size of the dimension (the local slab holds 1/R of y)
+        double L = (double)g.L[d] * (d == 1 ? p->R : 1);
+        int n = d == 1 ? p->NyG : g.N[d];
         double v = 2 * sin(i * (double)PI / n) / (L / n);
         return v * v;
     };
-    std::vector<double> lx(p->NXP, 1.0), ly(g.N[1]), lz(std::max(1, g.N[2]), 0.0);
+    std::vector<double> lx(p->NXP, 1.0), ly(p->NyG), lz(std::max(1, g.N[2]), 0.0);
     for (int k = 0; k <= M; ++k) lx[k] = lam(0, k);
-    for (int P = 0; P < g.N[1]; ++P) ly[P] = lam(1, freq_of_pos(p->log2[1], P));
+    for (int P = 0; P < p->NyG; ++P) ly[P] = lam(1, freq_of_pos(p->log2[1], P));
     if (p->has_z) for (int P = 0; P < g.N[2]; ++P) lz[P] = lam(2, freq_of_pos(p->log2[2], P));
     p->lamx = up(lx, p->owned); p->lamy = up(ly, p->owned); p->lamz = up(lz, p->owned);
     return p;
@@ -426,6 +460,8 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
 template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
     if (!p) return;
     cudaFree(p->spec);
+    if (p->bufA) cudaFree(p->bufA);
+    if (p->bufB) cudaFree(p->bufB);
     for (void* q : p->owned) cudaFree(q);
     delete p;
 }
@@ -454,30 +490,88 @@ static size_t line_smem(int log2n, int T, size_t csize) {
     return ((size_t)T * LS + n) * csize;
 }
 
+static Lay natural_lay(int NXP, long long s_m, long long s_o) {
+    Lay l; l.kxb = 1 << 30; l.split = 1 << 30; l.s_blk = 0; l.s_ml = s_m; l.s_mh = 0; l.s_o = s_o;
+    return l;
+}
+
 template <class FT>
-static void run_line(FastPoisson<FT>* p, int dim, int mode) {
+static void launch_line_any(FastPoisson<FT>* p, LArgs<FT>& A, int log2n, int mode) {
     using CT = typename Cx<FT>::T;
-    LArgs<FT> A;
-    int Ny = p->N[1], Nz = p->N[2];
-    A.spec = p->spec; A.NXH = p->NXH; A.NXP = p->NXP;
-    A.n = p->N[dim];
-    A.line_is_y = dim == 1;
-    A.stride = dim == 1 ? p->NXP : (long long)p->NXP * Ny;
-    A.nOther = dim == 1 ? Nz : Ny;
-    A.strideOther = dim == 1 ? (long long)p->NXP * Ny : p->NXP;
-    A.tw = dim == 1 ? p->twY : p->twZ;
+    int T = 16;
+    while (T > 1 && line_smem(log2n, T, sizeof(CT)) > 100 * 1024) T >>= 1;
+    A.T = T;
     A.scale = (FT)(1.0 / A.n);
     A.lamx = p->lamx;
+    dim3 grd(cdiv(A.NXH, T), A.nOther);
+    size_t smem = line_smem(log2n, T, sizeof(CT));
+    if (mode == LM_FWD) launch_line<FT, LM_FWD>(A, log2n, grd, smem);
+    else if (mode == LM_INV) launch_line<FT, LM_INV>(A, log2n, grd, smem);
+    else launch_line<FT, LM_FWD_DIV_INV>(A, log2n, grd, smem);
+}
+
+// single-GPU passes on the natural [Nz][Ny][NXP] layout, in place
+template <class FT>
+static void run_line(FastPoisson<FT>* p, int dim, int mode) {
+    LArgs<FT> A;
+    int Ny = p->N[1], Nz = p->N[2];
+    A.in = p->spec; A.out = p->spec;
+    A.NXH = p->NXH; A.kx0 = 0;
+    A.n = p->N[dim];
+    A.line_is_y = dim == 1;
+    long long s_m = dim == 1 ? p->NXP : (long long)p->NXP * Ny;
+    long long s_o = dim == 1 ? (long long)p->NXP * Ny : p->NXP;
+    A.lin = A.lout = natural_lay(p->NXP, s_m, s_o);
+    A.nOther = dim == 1 ? Nz : Ny;
+    A.tw = dim == 1 ? p->twY : p->twZ;
     A.lamL = dim == 1 ? p->lamy : p->lamz;
     A.lamO = dim == 1 ? p->lamz : p->lamy;
-    int T = 16;
-    while (T > 1 && line_smem(p->log2[dim], T, sizeof(CT)) > 100 * 1024) T >>= 1;
-    A.T = T;
-    dim3 grd(cdiv(p->NXH, T), A.nOther);
-    size_t smem = line_smem(p->log2[dim], T, sizeof(CT));
-    if (mode == LM_FWD) launch_line<FT, LM_FWD>(A, p->log2[dim], grd, smem);
-    else if (mode == LM_INV) launch_line<FT, LM_INV>(A, p->log2[dim], grd, smem);
-    else launch_line<FT, LM_FWD_DIV_INV>(A, p->log2[dim], grd, smem);
+    launch_line_any(p, A, p->log2[dim], mode);
+}
+
+// slab-decomposed solve (y split over R ranks): x and z transforms are local; the y transform needs
+// the lines gathered, i.e. one all-to-all that turns y-slabs into kx-slabs and one that turns them back
+// (reference: Distributed/distributed_fft_based_poisson_solver.jl:50-93,146-196 via PencilFFTs).
+// The z passes write / read the all-to-all chunk layout directly, so no pack or unpack kernel exists.
+template <class FT>
+static void all_to_all(FastPoisson<FT>* p, const typename Cx<FT>::T* src, typename Cx<FT>::T* dst) {
+    using CT = typename Cx<FT>::T;
+    size_t chunk = (size_t)p->KXB * p->N[1] * p->N[2];
+    cm::group_start();
+    for (int r = 0; r < p->R; ++r) {
+        cm::send(src + r * chunk, chunk * sizeof(CT), r);
+        cm::recv(dst + r * chunk, chunk * sizeof(CT), r);
+    }
+    cm::group_end();
+}
+
+template <class FT>
+static void distributed_middle(FastPoisson<FT>* p) {
+    int NyL = p->N[1], Nz = p->N[2], KXB = p->KXB;
+    long long chunk = (long long)KXB * NyL * Nz;
+    Lay nat = natural_lay(p->NXP, (long long)p->NXP * NyL, p->NXP);          // z lines on [Nz][NyL][NXP]
+    Lay blk;                                                                  // [R][Nz][NyL][KXB]
+    blk.kxb = KXB; blk.split = 1 << 30; blk.s_blk = chunk; blk.s_ml = (long long)NyL * KXB; blk.s_mh = 0; blk.s_o = KXB;
+    LArgs<FT> A;
+    // forward z: natural -> chunk layout
+    A.in = p->spec; A.out = p->bufA; A.lin = nat; A.lout = blk;
+    A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;
+    A.tw = p->twZ; A.lamL = p->lamz; A.lamO = nullptr;
+    launch_line_any(p, A, p->log2[2], LM_FWD);
+    all_to_all(p, p->bufA, p->bufB);
+    // y lines gathered from the R source ranks: m = s * NyL + yl, other = z, kx local to this rank
+    Lay gy;
+    gy.kxb = 1 << 30; gy.split = NyL; gy.s_blk = 0; gy.s_ml = KXB; gy.s_mh = chunk; gy.s_o = (long long)NyL * KXB;
+    A.in = p->bufB; A.out = p->bufB; A.lin = A.lout = gy;
+    A.NXH = KXB; A.kx0 = p->rank * KXB; A.n = p->NyG; A.line_is_y = 1; A.nOther = Nz;
+    A.tw = p->twY; A.lamL = p->lamy; A.lamO = p->lamz;
+    launch_line_any(p, A, p->log2[1], LM_FWD_DIV_INV);
+    all_to_all(p, p->bufB, p->bufA);
+    // backward z: chunk layout -> natural
+    A.in = p->bufA; A.out = p->spec; A.lin = blk; A.lout = nat;
+    A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;
+    A.tw = p->twZ; A.lamL = p->lamz; A.lamO = nullptr;
+    launch_line_any(p, A, p->log2[2], LM_INV);
 }
 
 template <class FT, bool FWD>
@@ -517,7 +611,9 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
     A.has_z = p->has_z;
     A.phi_p0 = phi_p0; A.Hx = g.H[0];
     run_x<FT, true>(p, A);
-    if (p->has_z) {
+    if (p->R > 1) {
+        distributed_middle(p);
+    } else if (p->has_z) {
         run_line(p, 1, LM_FWD);
         run_line(p, 2, LM_FWD_DIV_INV);
         run_line(p, 1, LM_INV);

@@ -50,16 +50,85 @@ __global__ void fill_halo_kernel(GridD<FT> g, HaloBatch<FT> hb, int d, int a, in
     }
 }
 
+// ---- halo exchange for a FullyConnected (slab-decomposed) dimension ---------------------------
+// Reference: Distributed/halo_communication.jl:62-183 sends strided views per field and side with
+// MPI.Isend/Irecv.  Here all fields' H boundary planes are packed into one contiguous buffer per
+// side, exchanged with one grouped ncclSend/ncclRecv pair per side, and unpacked; the planes span
+// the FULL extent of the other two dimensions so that edges and corners come out as in the
+// single-process x -> y -> z sequence (fill_halo_regions_periodic.jl:15-31).
+template <class FT, bool PACK>
+__global__ void halo_pack_kernel(GridD<FT> g, HaloBatch<FT> hb, int d, int a, int b, int alo, int nA, int blo, int nB,
+                                 FT* buf_lo, FT* buf_hi) {
+    int ia = blockIdx.x * blockDim.x + threadIdx.x;
+    int ib = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ia >= nA || ib >= nB) return;
+    long long base = (alo + ia) * g.st[a] + (blo + ib) * g.st[b];
+    long long s = g.st[d];
+    int N = g.N[d], H = g.H[d];
+    for (int n = 0; n < hb.n; ++n) {
+        FT* f = hb.p0[n] + base;
+        for (int h = 0; h < H; ++h) {
+            long long q = (((long long)n * H + h) * nB + ib) * nA + ia;
+            if (PACK) {
+                buf_lo[q] = f[(1 + h) * s];               // rows 1..H       -> low-side neighbour's high halo
+                buf_hi[q] = f[(N - H + 1 + h) * s];       // rows N-H+1..N   -> high-side neighbour's low halo
+            } else {
+                f[(1 - H + h) * s] = buf_lo[q];           // low halo  <- low-side neighbour's rows N-H+1..N
+                f[(N + 1 + h) * s] = buf_hi[q];           // high halo <- high-side neighbour's rows 1..H
+            }
+        }
+    }
+}
+
+namespace comm {
+bool active(); int rank(); int size();
+void group_start(); void group_end();
+void send(const void*, size_t, int); void recv(void*, size_t, int);
+}
+
+template <class FT>
+static void exchange_halos(const GridD<FT>& g, const HaloBatch<FT>& hb, int d) {
+    if (!comm::active()) throw Error("FullyConnected topology without an initialised communicator");
+    int a = d == 0 ? 1 : 0, b = d == 2 ? 1 : 2;
+    int ab[2] = {a, b}, lo[2], n[2];
+    for (int q = 0; q < 2; ++q) {
+        int e = ab[q];
+        if (g.topo[e] == OB_FLAT) { lo[q] = 1; n[q] = 1; }
+        else { lo[q] = 1 - g.H[e]; n[q] = g.N[e] + 2 * g.H[e] + 1; }
+    }
+    size_t elems = (size_t)hb.n * g.H[d] * n[0] * n[1], bytes = elems * sizeof(FT);
+    static FT* buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    static size_t cap = 0;
+    if (bytes > cap) {
+        for (int q = 0; q < 4; ++q) { if (buf[q]) cudaFree(buf[q]); OB_CUDA(cudaMalloc(&buf[q], bytes)); }
+        cap = bytes;
+    }
+    dim3 blk(a == 0 ? 64 : 16, a == 0 ? 4 : 16), grd(cdiv(n[0], blk.x), cdiv(n[1], blk.y));
+    halo_pack_kernel<FT, true><<<grd, blk, 0, stream()>>>(g, hb, d, a, b, lo[0], n[0], lo[1], n[1], buf[0], buf[1]);
+    OB_LAUNCH_CHECK();
+    int R = comm::size(), r = comm::rank();
+    int below = (r - 1 + R) % R, above = (r + 1) % R;
+    comm::group_start();
+    comm::send(buf[0], bytes, below);       // my low rows   -> neighbour below (its high halo)
+    comm::send(buf[1], bytes, above);       // my high rows  -> neighbour above (its low halo)
+    comm::recv(buf[3], bytes, above);       // high halo     <- neighbour above's low rows  (its first send)
+    comm::recv(buf[2], bytes, below);       // low halo      <- neighbour below's high rows (its second send)
+    comm::group_end();
+    halo_pack_kernel<FT, false><<<grd, blk, 0, stream()>>>(g, hb, d, a, b, lo[0], n[0], lo[1], n[1], buf[2], buf[3]);
+    OB_LAUNCH_CHECK();
+}
+
 template <class FT>
 void launch_fill_halos(const GridD<FT>& g, const HaloBatch<FT>& hb) {
     if (hb.n == 0) return;
-    // non-periodic first, then periodic (fill_halo_regions.jl:56-102)
+    // non-periodic first, then periodic / connected dimensions in x, y, z order (fill_halo_regions.jl:56-102)
     for (int pass = 0; pass < 2; ++pass)
         for (int d = 0; d < 3; ++d) {
             if (g.topo[d] == OB_FLAT) continue;
-            bool per = g.topo[d] == OB_PERIODIC;
+            bool per = g.topo[d] == OB_PERIODIC || g.topo[d] == OB_COMM;
             if ((pass == 0) == per) continue;
             if (per && g.H[d] == 0) continue;
+            if (g.topo[d] == OB_COMM) { exchange_halos<FT>(g, hb, d); continue; }
             int a = d == 0 ? 1 : 0, b = d == 2 ? 1 : 2;
             int lo[2], hi[2], ab[2] = {a, b};
             for (int q = 0; q < 2; ++q) {

@@ -251,7 +251,7 @@ bool launch_tendency_fast(const Phys<FT>& P, int comp, const FT* const U[3], con
     const GridD<FT>& g = P.g;
     if (P.scheme != ADV_WENO5 || P.closure != CLO_NONE || P.tilted) return false;
     bool hasz = g.topo[2] != OB_FLAT;
-    if (g.topo[0] != OB_PERIODIC || g.topo[1] != OB_PERIODIC || (hasz && g.topo[2] != OB_PERIODIC)) return false;
+    if (g.topo[0] != OB_PERIODIC || (g.topo[1] != OB_PERIODIC && g.topo[1] != OB_COMM) || (hasz && g.topo[2] != OB_PERIODIC)) return false;
     for (int d = 0; d < 3; ++d) {
         if (!g.regular[d]) return false;
         if (P.wc[d][0] || P.wc[d][1]) return false;

@@ -3,7 +3,8 @@ Oceananigans NonhydrostaticModel operator interface on the new `B200()` architec
 arithmetic runs in libocean_b200.so (hand-written sm_100a CUDA); importing this package fails
 if that library has not been built, and nothing here falls back to the CPU."""
 from ._lib import lib, B200Error, LIB_PATH, SYMBOLS, last_error  # noqa: F401
-from .grids import B200, RectilinearGrid, Periodic, Bounded, Flat, Center, Face  # noqa: F401
+from .grids import B200, RectilinearGrid, Periodic, Bounded, Flat, FullyConnected, Center, Face  # noqa: F401
+from .distributed import MultiArch  # noqa: F401
 from .model import (Field, CenterField, XFaceField, YFaceField, ZFaceField, fill_halo_regions,  # noqa: F401
                     FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver, BatchedTridiagonalSolver,
                     solve, solve_for_pressure, NonhydrostaticModel, WENO5, CenteredSecondOrder,

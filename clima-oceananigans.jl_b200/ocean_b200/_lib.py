@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libocean_b200.so")
 
 F32, F64 = 0, 1
-PERIODIC, BOUNDED, FLAT = 0, 1, 2
+PERIODIC, BOUNDED, FLAT, FULLY_CONNECTED = 0, 1, 2, 3
 CENTER, FACE = 0, 1
 BC_NONE, BC_PERIODIC, BC_FLUX, BC_VALUE, BC_GRADIENT, BC_OPEN = range(6)
 ADV = {"none": 0, "CenteredSecondOrder": 1, "CenteredFourthOrder": 2, "UpwindBiasedFirstOrder": 3,
@@ -83,6 +83,10 @@ SYMBOLS = {
     "ob200_model_clock": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ob200_model_set_clock": (C.c_int32, [C.c_void_p, C.c_double, C.c_int64, C.c_double]),
     "ob200_model_diagnostics": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ob200_comm_unique_id": (C.c_int32, [C.c_char_p]),
+    "ob200_comm_init": (C.c_int32, [C.c_int32, C.c_int32, C.c_char_p]),
+    "ob200_comm_destroy": (C.c_int32, []),
+    "ob200_comm_allreduce": (C.c_int32, [C.POINTER(C.c_double), C.c_int32, C.c_int32]),
     "ob200_model_use_fast_kernels": (C.c_int32, [C.c_void_p, C.c_int32]),
     "ob200_profile_enable": (C.c_int32, [C.c_int32]),
     "ob200_profile_reset": (C.c_int32, []),

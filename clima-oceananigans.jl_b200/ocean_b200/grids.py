@@ -14,9 +14,9 @@ import numpy as np
 from . import _lib as L
 from ._lib import lib, check
 
-Periodic, Bounded, Flat = "Periodic", "Bounded", "Flat"
+Periodic, Bounded, Flat, FullyConnected = "Periodic", "Bounded", "Flat", "FullyConnected"
 Center, Face = "Center", "Face"
-_TOPO = {Periodic: L.PERIODIC, Bounded: L.BOUNDED, Flat: L.FLAT}
+_TOPO = {Periodic: L.PERIODIC, Bounded: L.BOUNDED, Flat: L.FLAT, FullyConnected: L.FULLY_CONNECTED}
 
 
 class B200:
@@ -97,6 +97,33 @@ def _stretched(FT, topo, N, H, coord):
 class RectilinearGrid:
     def __init__(self, architecture=None, FT=np.float64, size=None, x=None, y=None, z=None, extent=None,
                  topology=(Periodic, Periodic, Bounded), halo=None):
+        self.global_size, self.multi = None, None
+        if hasattr(architecture, "ranks") and hasattr(architecture, "child"):
+            # RectilinearGrid(arch::MultiArch, ...) takes GLOBAL size / extent and builds the local slab
+            # (reference src/Distributed/distributed_grids.jl:16-60)
+            from . import distributed as D
+            multi = architecture
+            if multi.R > 1:
+                if topology[1] != Periodic:
+                    raise ValueError("slab decomposition needs a Periodic y topology")
+                if extent is not None:
+                    ext = (extent,) if np.isscalar(extent) else tuple(extent)
+                    it = iter(ext)
+                    cs = [x, y, z]
+                    for d, t in enumerate(topology):
+                        if t != Flat:
+                            cs[d] = (0.0, float(next(it)))
+                    x, y, z = cs
+                    extent = None
+                if not (isinstance(y, tuple) and len(y) == 2):
+                    raise ValueError("the decomposed dimension must be regular")
+                gsize = (size,) if np.isscalar(size) else tuple(size)
+                self.global_size = gsize
+                size = D.local_size(gsize, multi.ranks, 1)
+                y = D.local_interval(y, multi.R, multi.local_rank)
+                topology = (topology[0], FullyConnected, topology[2])
+                self.multi = multi
+            architecture = multi.child
         if not isinstance(architecture, B200):
             raise TypeError("this package only provides the B200() architecture")
         self.architecture = architecture
@@ -179,8 +206,17 @@ class RectilinearGrid:
                 cs.append(self._coords[d])
             else:
                 cs.append(np.array(self.F[d].span(1, self.N[d] + 1)))
-        return RectilinearGrid(self.architecture, self.FT, size=size, x=cs[0], y=cs[1], z=cs[2],
-                               topology=self.topology, halo=hl)
+        g = RectilinearGrid(self.architecture, self.FT, size=size, x=cs[0], y=cs[1], z=cs[2],
+                            topology=self.topology, halo=hl)
+        g.multi, g.global_size = self.multi, self.global_size
+        return g
+
+    def local_slice(self):
+        """index slices of this rank's slab inside GLOBAL interior arrays"""
+        if self.multi is None:
+            return (slice(None),) * 3
+        r, n = self.multi.local_rank, self.N[1]
+        return (slice(None), slice(r * n, (r + 1) * n), slice(None))
 
     def nodes(self, loc):
         """xnodes/ynodes/znodes of the interior points of a field at `loc`, broadcast-shaped."""

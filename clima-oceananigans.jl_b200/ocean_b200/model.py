@@ -42,7 +42,7 @@ _SIDES = ("west", "east", "south", "north", "bottom", "top")
 
 def _default_bc(topo, loc, auxiliary=False):
     """default_prognostic_bc / default_auxiliary_bc (field_boundary_conditions.jl:13-34)."""
-    if topo == Periodic:
+    if topo in (Periodic, "FullyConnected"):
         return BoundaryCondition("Periodic")
     if topo == Flat:
         return BoundaryCondition(None)

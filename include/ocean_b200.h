@@ -34,7 +34,8 @@ extern "C" {
 
 /* ---- enums ---------------------------------------------------------------------------- */
 enum { OB200_F32 = 0, OB200_F64 = 1 };                       /* eltype(grid)                   */
-enum { OB200_PERIODIC = 0, OB200_BOUNDED = 1, OB200_FLAT = 2 }; /* Grids topology              */
+enum { OB200_PERIODIC = 0, OB200_BOUNDED = 1, OB200_FLAT = 2,
+       OB200_FULLY_CONNECTED = 3 };   /* Grids topology; FullyConnected = split over ranks (Distributed) */
 enum { OB200_CENTER = 0, OB200_FACE = 1 };                   /* Center / Face                  */
 enum { OB200_BC_NONE = 0, OB200_BC_PERIODIC = 1, OB200_BC_FLUX = 2, OB200_BC_VALUE = 3,
        OB200_BC_GRADIENT = 4, OB200_BC_OPEN = 5 };           /* BoundaryConditions classes     */
@@ -185,6 +186,17 @@ int32_t ob200_model_clock(const ob200_model* m, double* time, int64_t* iteration
 int32_t ob200_model_set_clock(ob200_model* m, double time, int64_t iteration, double previous_dt);
 /* max |div U| and kinetic energy 0.5*sum(u^2+v^2+w^2) over the interior (diagnostics) */
 int32_t ob200_model_diagnostics(ob200_model* m, double* max_abs_div, double* kinetic_energy);
+
+/* ---- several GPUs: MultiArch(ranks=(1,R,1)) slab decomposition in y (src/Distributed) -------------
+ * One process per GPU.  Rank 0 creates the NCCL id, the host distributes it (MPI.bcast in the Julia shim,
+ * torch.distributed / a file here), every rank calls ob200_comm_init BEFORE creating grids whose y topology
+ * is OB200_FULLY_CONNECTED.  Such a grid describes the LOCAL slab (N[1] = Ny/R, L[1] = Ly/R); halos in y are
+ * exchanged with the neighbouring ranks (halo_communication.jl:62-183) and the Poisson solver transposes
+ * between y-slabs and kx-slabs with all-to-all exchanges (distributed_fft_based_poisson_solver.jl:146-196). */
+int32_t ob200_comm_unique_id(char out[128]);
+int32_t ob200_comm_init(int32_t nranks, int32_t rank, const char id[128]);
+int32_t ob200_comm_destroy(void);
+int32_t ob200_comm_allreduce(double* values, int32_t n, int32_t op);
 
 /* ---- measurement knobs (no reference counterpart; used by bench.py and the tests) ---------- */
 /* force the general kernels (on = 0) instead of the specialised headline kernels */

@@ -392,3 +392,19 @@ def test_full_size_256_properties(ob):
     assert abs(b1 - b0) <= 1e-10 * (abs(b0) + N ** 3 * 1e-3)
     p = m.velocities["u"].parent()
     assert np.array_equal(p[:3], p[N:N + 3]) and np.array_equal(p[:, :, N + 3:], p[:, :, 3:6])
+
+
+def test_slab_decomposition_two_gpus_matches_oracle():
+    """runs tests/dist_check.py under torchrun when the box has >= 2 GPUs (skipped otherwise)"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tests", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
