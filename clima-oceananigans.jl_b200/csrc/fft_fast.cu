@@ -38,6 +38,7 @@ template <> struct Rad<7> { static constexpr int R1 = 16, R2 = 8, R3 = 1; };
 template <> struct Rad<8> { static constexpr int R1 = 16, R2 = 16, R3 = 1; };
 template <> struct Rad<9> { static constexpr int R1 = 8, R2 = 8, R3 = 8; };
 template <> struct Rad<10> { static constexpr int R1 = 16, R2 = 8, R3 = 8; };
+template <> struct Rad<11> { static constexpr int R1 = 16, R2 = 16, R3 = 8; };
 
 template <int LOG2N> struct Geo {
     static constexpr int N = 1 << LOG2N;
@@ -172,7 +173,8 @@ static int freq_of_pos(int log2n, int P) {
         case 7: R1 = 16; R2 = 8; R3 = 1; break;
         case 8: R1 = 16; R2 = 16; R3 = 1; break;
         case 9: R1 = 8; R2 = 8; R3 = 8; break;
-        default: R1 = 16; R2 = 8; R3 = 8; break;
+        case 10: R1 = 16; R2 = 8; R3 = 8; break;
+        default: R1 = 16; R2 = 16; R3 = 8; break;
     }
     int n = 1 << log2n, S1 = n / R1, S2 = S1 / R2;
     int s1 = P / S1, rem = P % S1, s2 = rem / S2, s3 = rem % S2;
@@ -398,7 +400,7 @@ bool fast_poisson_supported(const GridD<FT>& g) {
     int R = g.topo[1] == OB_COMM ? comm::size() : 1;
     if (g.topo[1] == OB_COMM && (g.topo[2] != OB_PERIODIC || !pow2(R) || R > 8)) return false;
     if (!pow2(g.N[0]) || g.N[0] < 32 || g.N[0] > 2048) return false;
-    if (!pow2(g.N[1]) || g.N[1] * R < 16 || g.N[1] * R > 1024) return false;
+    if (!pow2(g.N[1]) || g.N[1] * R < 16 || g.N[1] * R > 2048) return false;
     if (g.topo[2] == OB_PERIODIC && (!pow2(g.N[2]) || g.N[2] < 16 || g.N[2] > 1024)) return false;
     for (int d = 0; d < 3; ++d) if (!g.regular[d]) return false;
     return true;
@@ -480,7 +482,8 @@ static void launch_line(const LArgs<FT>& A, int log2n, dim3 grd, size_t smem) {
         case 7: go(line_kernel<FT, 7, MODE>); break;
         case 8: go(line_kernel<FT, 8, MODE>); break;
         case 9: go(line_kernel<FT, 9, MODE>); break;
-        default: go(line_kernel<FT, 10, MODE>); break;
+        case 10: go(line_kernel<FT, 10, MODE>); break;
+        default: go(line_kernel<FT, 11, MODE>); break;
     }
 }
 static size_t line_smem(int log2n, int T, size_t csize) {
