@@ -705,6 +705,25 @@ static void model_update_state(ob200_model* m, bool tracers_too = true) {
         fill_halos<FT>(&ph, 1);
     }
 }
+// update_state! as it runs inside time_step!, after model_pressure_step(..., tracers_too = true): tracer halos are
+// already valid, so pHY' is integrated first and velocities + pHY' share ONE halo fill (one neighbour exchange
+// on the slab-decomposed path instead of two).  Same values as the reference sequence.
+template <class FT>
+static void model_update_state_after_projection(ob200_model* m) {
+    std::vector<ob200_field*> v = {m->F[0].get(), m->F[1].get(), m->F[2].get()};
+    if (m->pHY) {
+        ScopedPhase phase_timer("hydrostatic");
+        const GridD<FT>& g = gridD<FT>(m->grid);
+        Phys<FT>& P = physOf<FT>(m);
+        bool has_b = P.btr >= 0;
+        const FT* b = has_b ? m->F[3 + P.btr]->template p0<FT>() : nullptr;
+        FT gz = (has_b && P.tilted) ? P.ghat[2] : FT(1);
+        launch_hydrostatic_pressure<FT>(g, b, gz, has_b, m->pHY->template p0<FT>());
+        v.push_back(m->pHY.get());
+    }
+    ScopedPhase ph("halo");
+    fill_halos<FT>(v.data(), (int)v.size());
+}
 extern "C" int32_t ob200_model_update_state(ob200_model* m) {
     API_BEGIN
     if (m->grid->ftype == OB200_F32) model_update_state<float>(m);
@@ -747,10 +766,12 @@ extern "C" int32_t ob200_model_calculate_tendencies(ob200_model* m) {
 }
 
 template <class FT>
-static void model_pressure_step(ob200_model* m, FT dt) {
-    // calculate_pressure_correction! + pressure_correct_velocities! (pressure_correction.jl:10-56)
+static void model_pressure_step(ob200_model* m, FT dt, bool tracers_too = false) {
+    // calculate_pressure_correction! + pressure_correct_velocities! (pressure_correction.jl:10-56).
+    // Inside time_step! the tracers' halos are filled here as well (they do not change until the next
+    // substep), which lets the update_state! that follows merge its two halo fills into one.
     const GridD<FT>& g = gridD<FT>(m->grid);
-    { ScopedPhase ph("halo"); model_fill_state_halos<FT>(m, 0, 3); }
+    { ScopedPhase ph("halo"); model_fill_state_halos<FT>(m, 0, tracers_too ? m->nf : 3); }
     { ScopedPhase ph("poisson");
       solve_for_pressure_T<FT>(m->solver.get(), m->pNHS.get(), (double)dt, m->F[0].get(), m->F[1].get(), m->F[2].get()); }
     ob200_field* pn = m->pNHS.get();
@@ -778,10 +799,10 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
         Substep<FT> ss[3] = {{SUB_RK3_FIRST, dt, dt * g1, 0}, {SUB_RK3, dt, g2, z2}, {SUB_RK3, dt, g3, z3}};
         for (int s = 0; s < 3; ++s) {
             model_tendencies<FT>(m, ss[s]);
-            model_pressure_step<FT>(m, sdt[s]);
+            model_pressure_step<FT>(m, sdt[s], true);
             m->time += (double)sdt[s];
             if (s < 2) for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);   // store_tendencies!
-            model_update_state<FT>(m);
+            model_update_state_after_projection<FT>(m);
         }
         m->iteration += 1;
     } else {
@@ -795,11 +816,11 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
         if (m->iteration == 0) model_update_state<FT>(m);
         Substep<FT> ss{SUB_AB2, dt, FT(1.5) + chi, FT(0.5) + chi};
         model_tendencies<FT>(m, ss);
-        model_pressure_step<FT>(m, dt);
+        model_pressure_step<FT>(m, dt, true);
         for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);
         m->time += (double)dt;
         m->iteration += 1;
-        model_update_state<FT>(m);
+        model_update_state_after_projection<FT>(m);
     }
 }
 extern "C" int32_t ob200_model_time_step(ob200_model* m, double dt, int32_t euler) {

@@ -24,6 +24,7 @@ struct Api {
     ncclResult_t (*GroupStart)();
     ncclResult_t (*GroupEnd)();
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
     const char* (*GetErrorString)(ncclResult_t);
 };
 static Api api;
@@ -48,6 +49,7 @@ static void load() {
     api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
     api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
     api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     loaded = true;
 }
@@ -85,5 +87,17 @@ void allreduce_f64(double* buf, size_t n, bool max) {
     count_launch(1);
 }
 
+void allgather_bytes(const void* send_dev, void* recv_dev, size_t bytes_per_rank) {
+    ck(api.AllGather(send_dev, recv_dev, bytes_per_rank, ncclInt8, g_comm, stream()), "ncclAllGather");
+    count_launch(1);
+}
+// stream-ordered barrier over all ranks: every rank's preceding work on the library stream has completed
+// (and its peer-memory stores are visible) before any rank's following work starts
+void barrier() {
+    static double* tok = nullptr;
+    if (!tok) { OB_CUDA(cudaMalloc(&tok, 8)); OB_CUDA(cudaMemset(tok, 0, 8)); }
+    ck(api.AllReduce(tok, tok, 1, ncclFloat64, ncclSum, g_comm, stream()), "ncclAllReduce(barrier)");
+    count_launch(1);
+}
 }  // namespace comm
 }  // namespace ob

@@ -17,12 +17,14 @@
 #include <vector>
 #include <cmath>
 #include <algorithm>
+#include <cstdlib>
 
 namespace ob {
 namespace comm {
 bool active(); int rank(); int size();
 void group_start(); void group_end();
 void send(const void*, size_t, int); void recv(void*, size_t, int);
+void allgather_bytes(const void*, void*, size_t); void barrier();
 }
 namespace ff {
 
@@ -302,9 +304,21 @@ __global__ void __launch_bounds__(256) x_c2r_kernel(XArgs<FT> A) {
 struct Lay {
     int kxb, split;
     long long s_blk, s_ml, s_mh, s_o;
-    __device__ __forceinline__ long long at(int kx, int m, int o) const {
-        int kb = kx / kxb, kl = kx - kb * kxb, mh = m / split, ml = m - mh * split;
-        return kb * s_blk + kl + ml * s_ml + mh * s_mh + o * s_o;
+    // optional per-block base pointers (peer memory of the other ranks, mapped with CUDA IPC): the block id is
+    // the kx block (pmode 1) or the upper part of the split line index (pmode 2); the block stride is then unused
+    int pmode;
+    float inv_kxb, inv_split;
+    void* ptr[8];
+    template <class CT> __device__ __forceinline__ CT* addr(CT* base, int kx, int m, int o) const {
+        if (pmode == 0 && kxb >= (1 << 30) && split >= (1 << 30)) return base + (kx + m * s_ml + o * s_o);   // natural
+        // exact small-integer division by multiplication with a float reciprocal ((k + 1/2) / d is never
+        // within rounding distance of an integer for k < 2^12)
+        int kb = kxb >= (1 << 30) ? 0 : __float2int_rz(((float)kx + 0.5f) * inv_kxb);
+        int mh = split >= (1 << 30) ? 0 : __float2int_rz(((float)m + 0.5f) * inv_split);
+        int kl = kx - kb * kxb, ml = m - mh * split;
+        if (pmode == 1) return (CT*)ptr[kb] + (kl + ml * s_ml + mh * s_mh + o * s_o);
+        if (pmode == 2) return (CT*)ptr[mh] + (kb * s_blk + kl + ml * s_ml + o * s_o);
+        return base + (kb * s_blk + kl + ml * s_ml + mh * s_mh + o * s_o);
     }
 };
 
@@ -339,7 +353,7 @@ __global__ void __launch_bounds__(256) line_kernel(LArgs<FT> A) {
     const int nl = min(A.T, A.NXH - x0);
     for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
         int m = w / nl, t = w - m * nl;
-        s[t * G::LS + G::pos(m)] = A.in[A.lin.at(x0 + t, m, o)];
+        s[t * G::LS + G::pos(m)] = *A.lin.addr(A.in, x0 + t, m, o);
     }
     __syncthreads();
     if (MODE == LM_FWD || MODE == LM_FWD_DIV_INV) fft_fwd<LOG2N>(s, stw, nl);
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(256) line_kernel(LArgs<FT> A) {
         int m = w / nl, t = w - m * nl;
         CT v = s[t * G::LS + G::pos(m)];
         if (MODE != LM_FWD) { v.x *= A.scale; v.y *= A.scale; }
-        A.out[A.lout.at(x0 + t, m, o)] = v;
+        *A.lout.addr(A.out, x0 + t, m, o) = v;
     }
 }
 
@@ -376,6 +390,8 @@ struct FastPoisson {
     int N[3], log2[3], has_z, NXH, NXP;
     int R = 1, rank = 0, NyG = 0, KXB = 0;      // slab decomposition in y: NyG = R * N[1], KXB = NXP / R
     CT* bufA = nullptr; CT* bufB = nullptr;     // all-to-all staging (distributed only)
+    CT* peerA[8] = {}; CT* peerB[8] = {};       // the same buffers of every rank, mapped through CUDA IPC
+    bool p2p = false;
     CT* spec = nullptr;
     CT* twM = nullptr; CT* twN = nullptr; CT* twY = nullptr; CT* twZ = nullptr;
     int* kpos = nullptr;
@@ -428,6 +444,29 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
         OB_CUDA(cudaMalloc(&p->bufB, tot * sizeof(CT)));
         OB_CUDA(cudaMemset(p->bufA, 0, tot * sizeof(CT)));
         OB_CUDA(cudaMemset(p->bufB, 0, tot * sizeof(CT)));
+        if (getenv("OB200_NO_P2P") == nullptr) {
+            // exchange CUDA IPC handles of bufA / bufB so that the transform kernels can store straight into the
+            // destination rank's buffer over NVLink (the transfer is part of the kernel, not a separate collective)
+            struct H2 { cudaIpcMemHandle_t a, b; };
+            H2 mine;
+            OB_CUDA(cudaIpcGetMemHandle(&mine.a, p->bufA));
+            OB_CUDA(cudaIpcGetMemHandle(&mine.b, p->bufB));
+            H2 *dsend, *drecv;
+            OB_CUDA(cudaMalloc(&dsend, sizeof(H2)));
+            OB_CUDA(cudaMalloc(&drecv, sizeof(H2) * p->R));
+            OB_CUDA(cudaMemcpyAsync(dsend, &mine, sizeof(H2), cudaMemcpyHostToDevice, stream()));
+            cm::allgather_bytes(dsend, drecv, sizeof(H2));
+            std::vector<H2> all(p->R);
+            OB_CUDA(cudaMemcpyAsync(all.data(), drecv, sizeof(H2) * p->R, cudaMemcpyDeviceToHost, stream()));
+            OB_CUDA(cudaStreamSynchronize(stream()));
+            cudaFree(dsend); cudaFree(drecv);
+            for (int r = 0; r < p->R; ++r) {
+                if (r == p->rank) { p->peerA[r] = p->bufA; p->peerB[r] = p->bufB; continue; }
+                OB_CUDA(cudaIpcOpenMemHandle((void**)&p->peerA[r], all[r].a, cudaIpcMemLazyEnablePeerAccess));
+                OB_CUDA(cudaIpcOpenMemHandle((void**)&p->peerB[r], all[r].b, cudaIpcMemLazyEnablePeerAccess));
+            }
+            p->p2p = true;
+        }
     }
     auto twid = [&](int n, int count) {
         std::vector<CT> t(count);
@@ -462,6 +501,8 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
 template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
     if (!p) return;
     cudaFree(p->spec);
+    for (int r = 0; r < p->R; ++r)
+        if (p->p2p && r != p->rank) { cudaIpcCloseMemHandle(p->peerA[r]); cudaIpcCloseMemHandle(p->peerB[r]); }
     if (p->bufA) cudaFree(p->bufA);
     if (p->bufB) cudaFree(p->bufB);
     for (void* q : p->owned) cudaFree(q);
@@ -494,7 +535,7 @@ static size_t line_smem(int log2n, int T, size_t csize) {
 }
 
 static Lay natural_lay(int NXP, long long s_m, long long s_o) {
-    Lay l; l.kxb = 1 << 30; l.split = 1 << 30; l.s_blk = 0; l.s_ml = s_m; l.s_mh = 0; l.s_o = s_o;
+    Lay l{}; l.kxb = 1 << 30; l.split = 1 << 30; l.s_blk = 0; l.s_ml = s_m; l.s_mh = 0; l.s_o = s_o; l.pmode = 0;
     return l;
 }
 
@@ -553,23 +594,35 @@ static void distributed_middle(FastPoisson<FT>* p) {
     int NyL = p->N[1], Nz = p->N[2], KXB = p->KXB;
     long long chunk = (long long)KXB * NyL * Nz;
     Lay nat = natural_lay(p->NXP, (long long)p->NXP * NyL, p->NXP);          // z lines on [Nz][NyL][NXP]
-    Lay blk;                                                                  // [R][Nz][NyL][KXB]
+    Lay blk{};                                                                // [R][Nz][NyL][KXB]
+    blk.inv_kxb = 1.0f / KXB; blk.inv_split = 0.f;
     blk.kxb = KXB; blk.split = 1 << 30; blk.s_blk = chunk; blk.s_ml = (long long)NyL * KXB; blk.s_mh = 0; blk.s_o = KXB;
+    // y lines gathered from the R source ranks: m = s * NyL + yl, other = z, kx local to this rank
+    Lay gy{};
+    gy.inv_kxb = 0.f; gy.inv_split = 1.0f / NyL;
+    gy.kxb = 1 << 30; gy.split = NyL; gy.s_blk = 0; gy.s_ml = KXB; gy.s_mh = chunk; gy.s_o = (long long)NyL * KXB;
     LArgs<FT> A;
-    // forward z: natural -> chunk layout
+    // forward z: natural -> chunk layout.  With peer memory the chunk for rank r is stored directly into rank r's
+    // bufB (slot = this rank), so the all-to-all IS the store phase of this kernel; otherwise NCCL moves bufA -> bufB.
     A.in = p->spec; A.out = p->bufA; A.lin = nat; A.lout = blk;
+    if (p->p2p) {
+        A.lout.pmode = 1;
+        for (int r = 0; r < p->R; ++r) A.lout.ptr[r] = p->peerB[r] + (long long)p->rank * chunk;
+    }
     A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;
     A.tw = p->twZ; A.lamL = p->lamz; A.lamO = nullptr;
     launch_line_any(p, A, p->log2[2], LM_FWD);
-    all_to_all(p, p->bufA, p->bufB);
-    // y lines gathered from the R source ranks: m = s * NyL + yl, other = z, kx local to this rank
-    Lay gy;
-    gy.kxb = 1 << 30; gy.split = NyL; gy.s_blk = 0; gy.s_ml = KXB; gy.s_mh = chunk; gy.s_o = (long long)NyL * KXB;
+    if (p->p2p) cm::barrier(); else all_to_all(p, p->bufA, p->bufB);
     A.in = p->bufB; A.out = p->bufB; A.lin = A.lout = gy;
+    if (p->p2p) {      // transposed back on the fly: the part of the line that came from rank s returns to rank s's bufA
+        A.out = p->bufA;
+        A.lout.pmode = 2;
+        for (int r = 0; r < p->R; ++r) A.lout.ptr[r] = p->peerA[r] + (long long)p->rank * chunk;
+    }
     A.NXH = KXB; A.kx0 = p->rank * KXB; A.n = p->NyG; A.line_is_y = 1; A.nOther = Nz;
     A.tw = p->twY; A.lamL = p->lamy; A.lamO = p->lamz;
     launch_line_any(p, A, p->log2[1], LM_FWD_DIV_INV);
-    all_to_all(p, p->bufB, p->bufA);
+    if (p->p2p) cm::barrier(); else all_to_all(p, p->bufB, p->bufA);
     // backward z: chunk layout -> natural
     A.in = p->bufA; A.out = p->spec; A.lin = blk; A.lout = nat;
     A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;
