@@ -17,6 +17,7 @@
 //     the same rational function evaluated with ~1e-16 relative differences.
 // Parity with the oracle stays <= 1e-12 per step (tests/test_gpu_parity.py).
 #include "internal.h"
+#include "weno_fast.cuh"
 #include <cstdlib>
 
 namespace ob {
@@ -51,79 +52,10 @@ struct Ctx {
     Substep<FT> ss;
 };
 
-__device__ __forceinline__ double fast_rcp(double x) {
-    // MUFU.RCP64H seed (2^-23) + 3 Newton steps -> full double accuracy for normal positive x
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
-    return r;
-}
-
-// sum_k w_k p_k for one side, given the smoothness indicators and candidate values
-template <class FT, bool ZW>
-__device__ __forceinline__ FT weno_combine(FT C0, FT C1, FT C2, FT b0, FT b1, FT b2, FT p0, FT p1, FT p2) {
-    const FT eps = FT(1e-6);
-    if constexpr (sizeof(FT) == 8) {
-        FT D0 = b0 + eps, D1 = b1 + eps, D2 = b2 + eps;
-        FT E0 = D0 * D0, E1 = D1 * D1, E2 = D2 * D2;
-        FT g0, g1, g2;
-        if (ZW) {
-            FT tau = fabs(b2 - b0), t2 = tau * tau;
-            g0 = (C0 * (E0 + t2)) * (E1 * E2);
-            g1 = (C1 * (E1 + t2)) * (E0 * E2);
-            g2 = (C2 * (E2 + t2)) * (E0 * E1);
-        } else {
-            g0 = C0 * (E1 * E2);
-            g1 = C1 * (E0 * E2);
-            g2 = C2 * (E0 * E1);
-        }
-        FT den = (g0 + g1) + g2;
-        FT num = (g0 * p0 + g1 * p1) + g2 * p2;
-        return (FT)(num * fast_rcp((double)den));
-    } else {
-        FT a0, a1, a2;
-        if (ZW) {
-            FT tau = fabs(b2 - b0);
-            FT q0 = tau / (b0 + eps), q1 = tau / (b1 + eps), q2 = tau / (b2 + eps);
-            a0 = C0 * (1 + q0 * q0); a1 = C1 * (1 + q1 * q1); a2 = C2 * (1 + q2 * q2);
-        } else {
-            FT d0 = b0 + eps, d1 = b1 + eps, d2 = b2 + eps;
-            a0 = C0 / (d0 * d0); a1 = C1 / (d1 * d1); a2 = C2 / (d2 * d2);
-        }
-        FT sa = (a0 + a1) + a2;
-        return ((a0 * p0 + a1 * p1) + a2 * p2) / sa;
-    }
-}
-
-// One-sided reconstruction.  The upwind flux ((u+|u|) L + (u-|u|) R)/2 equals u*L for u > 0 and
-// u*R otherwise EXACTLY (one product is 0), so only the upwind side is evaluated.  The window is
-// passed towards the face: (a,b,c,d,e) = psi[f-3..f+1] for the left-biased side and
-// psi[f+2..f-2] (mirrored) for the right-biased one.  In mirrored form the right-biased candidate
-// polynomials and linear weights coincide with the left-biased ones; the smoothness slopes do not
-// (weno_fifth_order.jl:315-317 are not the mirror image of :311-313): the outer stencils use
-// (k1,-4,k3) with (k1,k3) = (1,3) on the left side and (3,1) on the right side.
-template <class FT, bool ZW>
-__device__ __forceinline__ FT weno_side(FT a, FT b, FT c, FT d, FT e, FT k1, FT k3) {
-    const FT c1312 = FT(13.0 / 12.0), c14 = FT(0.25);
-    const FT a13 = FT(1.0 / 3.0), a56 = FT(5.0 / 6.0), a16 = FT(1.0 / 6.0), a76 = FT(7.0 / 6.0), a116 = FT(11.0 / 6.0);
-    FT t2 = (a - 2 * b) + c, t1 = (b - 2 * c) + d, t0 = (c - 2 * d) + e;
-    FT s2 = (k1 * a - 4 * b) + k3 * c, s1 = b - d, s0 = (k3 * c - 4 * d) + k1 * e;
-    FT b2 = c1312 * (t2 * t2) + c14 * (s2 * s2);
-    FT b1 = c1312 * (t1 * t1) + c14 * (s1 * s1);
-    FT b0 = c1312 * (t0 * t0) + c14 * (s0 * s0);
-    FT p0 = (a13 * c + a56 * d) - a16 * e;
-    FT p1 = (-a16 * b + a56 * c) + a13 * d;
-    FT p2 = (a13 * a - a76 * b) + a116 * c;
-    return weno_combine<FT, ZW>(FT(3.0 / 10.0), FT(3.0 / 5.0), FT(1.0 / 10.0), b0, b1, b2, p0, p1, p2);
-}
-
-template <class FT, bool HASZ, int D>
-__device__ __forceinline__ FT I3f(const FT* c, long long p, long long s) {
-    if (!HASZ && D == 2) return c[p];
-    FT c0 = c[p];
-    return c0 - ((c[p + s] - c0) - (c0 - c[p - s])) * FT(1.0 / 6.0);
+// (I(p) + I(p + s))/2 along stride s (see wf::interp4)
+template <class FT>
+__device__ __forceinline__ FT I4f(const FT* c, long long p, long long s) {
+    return wf::interp4<FT>(c[p - s], c[p], c[p + s], c[p + 2 * s]);
 }
 
 // area * upwind flux of psi (component B, or tracer B = 3) in direction A at position p
@@ -136,21 +68,19 @@ __device__ __forceinline__ FT flux_at(const Ctx<FT>& c, long long p) {
     if (B == 3) {
         ut = c.U[A][p];
     } else if (A == B) {
-        ut = FT(0.5) * (I3f<FT, HASZ, A>(c.U[A], p, sA) + I3f<FT, HASZ, A>(c.U[A], p + sA, sA));
+        ut = I4f<FT>(c.U[A], p, sA);
         pf = p + sA;
     } else {
         constexpr int BB = B == 3 ? 0 : B;
         const long long sB = c.s[BB];
         if (!HASZ && BB == 2) ut = c.U[A][p];
-        else ut = FT(0.5) * (I3f<FT, HASZ, BB>(c.U[A], p - sB, sB) + I3f<FT, HASZ, BB>(c.U[A], p, sB));
+        else ut = I4f<FT>(c.U[A], p - sB, sB);
     }
     // all six loads are issued independently of ut (no dependent second memory round trip);
     // the upwind window is then selected in registers
     const FT* q = c.psi + pf;
     const FT w0 = q[-3 * sA], w1 = q[-2 * sA], w2 = q[-sA], w3 = q[0], w4 = q[sA], w5 = q[2 * sA];
-    const bool pos = ut > FT(0);
-    FT rec = weno_side<FT, ZW>(pos ? w0 : w5, pos ? w1 : w4, pos ? w2 : w3, pos ? w3 : w2, pos ? w4 : w1,
-                               pos ? FT(1) : FT(3), pos ? FT(3) : FT(1));
+    FT rec = wf::weno_upwind<FT, ZW>(ut > FT(0), w0, w1, w2, w3, w4, w5);
     return c.area[A] * (ut * rec);
 }
 

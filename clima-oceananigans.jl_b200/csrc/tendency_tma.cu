@@ -14,6 +14,7 @@
 //   * the z-direction stencil reads the ring, the x/y stencils read the level-k plane.
 // Tensor maps describe the padded internal layout (common.cuh): 3-D, box (40, 14, 1), no swizzle.
 #include "internal.h"
+#include "weno_fast.cuh"
 #include <cuda.h>
 #include <map>
 #include <mutex>
@@ -86,63 +87,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
         ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
-    return r;
-}
-
-template <class FT, bool ZW>
-__device__ __forceinline__ FT weno_combine(FT C0, FT C1, FT C2, FT b0, FT b1, FT b2, FT p0, FT p1, FT p2) {
-    const FT eps = FT(1e-6);
-    if constexpr (sizeof(FT) == 8) {
-        FT D0 = b0 + eps, D1 = b1 + eps, D2 = b2 + eps;
-        FT E0 = D0 * D0, E1 = D1 * D1, E2 = D2 * D2;
-        FT g0, g1, g2;
-        if (ZW) {
-            FT tau = fabs(b2 - b0), t2 = tau * tau;
-            g0 = (C0 * (E0 + t2)) * (E1 * E2);
-            g1 = (C1 * (E1 + t2)) * (E0 * E2);
-            g2 = (C2 * (E2 + t2)) * (E0 * E1);
-        } else {
-            g0 = C0 * (E1 * E2); g1 = C1 * (E0 * E2); g2 = C2 * (E0 * E1);
-        }
-        FT den = (g0 + g1) + g2;
-        FT num = (g0 * p0 + g1 * p1) + g2 * p2;
-        return (FT)(num * fast_rcp((double)den));
-    } else {
-        FT a0, a1, a2;
-        if (ZW) {
-            FT tau = fabs(b2 - b0);
-            FT q0 = tau / (b0 + eps), q1 = tau / (b1 + eps), q2 = tau / (b2 + eps);
-            a0 = C0 * (1 + q0 * q0); a1 = C1 * (1 + q1 * q1); a2 = C2 * (1 + q2 * q2);
-        } else {
-            FT d0 = b0 + eps, d1 = b1 + eps, d2 = b2 + eps;
-            a0 = C0 / (d0 * d0); a1 = C1 / (d1 * d1); a2 = C2 / (d2 * d2);
-        }
-        FT sa = (a0 + a1) + a2;
-        return ((a0 * p0 + a1 * p1) + a2 * p2) / sa;
-    }
-}
-// one-sided reconstruction, window ordered towards the face (see tendency_fast.cu)
-template <class FT, bool ZW>
-__device__ __forceinline__ FT weno_side(FT a, FT b, FT c, FT d, FT e, FT k1, FT k3) {
-    const FT c1312 = FT(13.0 / 12.0), c14 = FT(0.25);
-    const FT a13 = FT(1.0 / 3.0), a56 = FT(5.0 / 6.0), a16 = FT(1.0 / 6.0), a76 = FT(7.0 / 6.0), a116 = FT(11.0 / 6.0);
-    FT t2 = (a - 2 * b) + c, t1 = (b - 2 * c) + d, t0 = (c - 2 * d) + e;
-    FT s2 = (k1 * a - 4 * b) + k3 * c, s1 = b - d, s0 = (k3 * c - 4 * d) + k1 * e;
-    FT b2 = c1312 * (t2 * t2) + c14 * (s2 * s2);
-    FT b1 = c1312 * (t1 * t1) + c14 * (s1 * s1);
-    FT b0 = c1312 * (t0 * t0) + c14 * (s0 * s0);
-    FT p0 = (a13 * c + a56 * d) - a16 * e;
-    FT p1 = (-a16 * b + a56 * c) + a13 * d;
-    FT p2 = (a13 * a - a76 * b) + a116 * c;
-    return weno_combine<FT, ZW>(FT(3.0 / 10.0), FT(3.0 / 5.0), FT(1.0 / 10.0), b0, b1, b2, p0, p1, p2);
-}
-
 // position inside the staged data: level L (Julia k), tile row / column including the halo offset
 struct P3 { int L, row, col; };
 template <int D> __device__ __forceinline__ P3 shp(P3 q, int n) {
@@ -166,10 +110,11 @@ struct Rings {
     }
 };
 
+// (I(q) + I(q + 1))/2 along direction D of velocity component COMP (see wf::interp4)
 template <class FT, int B, int COMP, int D>
-__device__ __forceinline__ FT I3r(const Rings<FT, B>& r, P3 q) {
-    FT c0 = r.template V<COMP>(q);
-    return c0 - ((r.template V<COMP>(shp<D>(q, 1)) - c0) - (c0 - r.template V<COMP>(shp<D>(q, -1)))) * FT(1.0 / 6.0);
+__device__ __forceinline__ FT I4r(const Rings<FT, B>& r, P3 q) {
+    return wf::interp4<FT>(r.template V<COMP>(shp<D>(q, -1)), r.template V<COMP>(q), r.template V<COMP>(shp<D>(q, 1)),
+                           r.template V<COMP>(shp<D>(q, 2)));
 }
 
 // area * upwind flux of psi (component B or tracer) in direction A at position q
@@ -181,16 +126,14 @@ __device__ __forceinline__ FT flux_at(const Rings<FT, B>& r, const Ctx<FT>& c, P
     if constexpr (B == 3) {
         ut = r.template V<A>(q);
     } else if constexpr (A == B) {
-        ut = FT(0.5) * (I3r<FT, B, A, A>(r, q) + I3r<FT, B, A, A>(r, shp<A>(q, 1)));
+        ut = I4r<FT, B, A, A>(r, q);
         pf = shp<A>(q, 1);
     } else {
-        ut = FT(0.5) * (I3r<FT, B, A, B>(r, shp<B>(q, -1)) + I3r<FT, B, A, B>(r, q));
+        ut = I4r<FT, B, A, B>(r, shp<B>(q, -1));
     }
     const FT w0 = r.P(shp<A>(pf, -3)), w1 = r.P(shp<A>(pf, -2)), w2 = r.P(shp<A>(pf, -1)), w3 = r.P(pf),
              w4 = r.P(shp<A>(pf, 1)), w5 = r.P(shp<A>(pf, 2));
-    const bool pos = ut > FT(0);
-    FT rec = weno_side<FT, ZW>(pos ? w0 : w5, pos ? w1 : w4, pos ? w2 : w3, pos ? w3 : w2, pos ? w4 : w1,
-                               pos ? FT(1) : FT(3), pos ? FT(3) : FT(1));
+    FT rec = wf::weno_upwind<FT, ZW>(ut > FT(0), w0, w1, w2, w3, w4, w5);
     return c.area[A] * (ut * rec);
 }
 
