@@ -1,32 +1,39 @@
 // tendency_tma.cu -- TMA-staged variant of the specialised tendency (+ substep) kernel.
 //
 // Same arithmetic as tendency_fast.cu (one-sided WENO5, faces shared through registers / shared
-// memory, single-reciprocal Float64 weights).  What changes is the data path: the ncu capture of the
-// direct-load kernel (profiles/r1_tendency_v2_summary.md) shows the FP64 pipe only ~45 % busy with
-// long-scoreboard (global load latency) as the top stall.  Here every operand of the stencils is
-// staged in shared memory by the Tensor Memory Accelerator:
-//   * each block owns a 32 x 8 column tile and marches in k; for every array it reads it keeps a RING
-//     of (32+6) x (8+6) halo'd planes in shared memory (psi: levels k-3..k+3, advecting velocities:
+// memory, single-reciprocal Float64 weights: weno_fast.cuh).  What changes is the data path: every operand
+// of the stencils is staged in shared memory by the Tensor Memory Accelerator:
+//   * a block of NW warps owns a 32 x (NW-1) column tile and marches in k; for every array it reads it keeps a
+//     RING of (32+6) x (NW-1+6) halo'd planes in shared memory (psi: levels k-3..k+3, advecting velocities:
 //     the 1-4 levels their interpolation needs);
-//   * one elected thread issues `cp.async.bulk.tensor.3d` (SASS UTMALDG) for the planes of level k+1
-//     while all warps compute level k; completion is tracked with two alternating mbarriers
-//     (expect_tx / try_wait.parity), so no warp ever waits on a global load;
-//   * the z-direction stencil reads the ring, the x/y stencils read the level-k plane.
-// Tensor maps describe the padded internal layout (common.cuh): 3-D, box (40, 14, 1), no swizzle.
+//   * warps 0..NW-2 own one row of 32 cells each: three face fluxes per cell and level (x, y, z-top);
+//   * warp NW-1 is the EDGE warp: its lane 0 issues `cp.async.bulk.tensor.3d` (SASS UTMALDG) for the planes of
+//     level k+1 while all warps compute level k (completion tracked with two alternating mbarriers,
+//     expect_tx / try_wait.parity, so no warp ever waits on a global load), and its lanes compute the one extra
+//     column of x faces and the one extra row of y faces the tile needs (two flux evaluations against three in
+//     the cell warps, so the block-wide barrier that publishes the faces is not held up by it: the first
+//     version gave those edge faces to two of the cell warps, and ncu r1d showed 16 % of the stall samples
+//     at that barrier);
+//   * the z-direction stencil reads the ring, the x/y stencils read the level-k plane;
+//   * the pointwise global operands (G^-, pHY') are loaded at the top of the level, before the flux
+//     arithmetic, so their latency is hidden (36 % of the stall samples before).
+// Tensor maps describe the padded internal layout (common.cuh): 3-D, box (40, NW+5, 1), no swizzle.
 #include "internal.h"
 #include "weno_fast.cuh"
 #include <cuda.h>
 #include <map>
 #include <mutex>
+#include <tuple>
 
 namespace ob {
 namespace tma {
 
-constexpr int TX = 32, TY = 8, HALO = 3, BY = TY + 2 * HALO, COL0 = HALO + 1;
-template <class FT> struct Box {
+constexpr int TX = 32, HALO = 3, COL0 = HALO + 1;
+template <class FT, int NW> struct Box {
     // The box must START on a 16-byte boundary in x (measured on B200: an odd FP64 start coordinate raises
     // "illegal instruction", tools/tma_probe4.cu), so it starts one column left of the halo: 1 + 3 + 32 + 3 + 1.
-    static constexpr int BX = TX + 2 * HALO + 2;
+    static constexpr int R = NW - 1;                 // rows of cells
+    static constexpr int BX = TX + 2 * HALO + 2, BY = R + 2 * HALO;
     static constexpr int PLANE_BYTES = ((BX * BY * (int)sizeof(FT) + 127) / 128) * 128;
     static constexpr int PE = PLANE_BYTES / (int)sizeof(FT);
 };
@@ -59,7 +66,7 @@ struct Ctx {
     long long s[3];
     int O[3];
     FT area[3], invV, invd[3], f;
-    int fplane, Kc;
+    int fplane, Kc, Ny;
     Substep<FT> ss;
 };
 
@@ -70,6 +77,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     unsigned ok;
@@ -94,42 +104,42 @@ template <int D> __device__ __forceinline__ P3 shp(P3 q, int n) {
     return q;
 }
 
-template <class FT, int B>
+template <class FT, int B, int NW>
 struct Rings {
     const FT* psi;
     const FT* aux[3];
     __device__ __forceinline__ FT P(P3 q) const {
-        return psi[((q.L + 8) & (PSI_SL - 1)) * Box<FT>::PE + q.row * Box<FT>::BX + q.col];
+        return psi[((q.L + 8) & (PSI_SL - 1)) * Box<FT, NW>::PE + q.row * Box<FT, NW>::BX + q.col];
     }
     template <int COMP> __device__ __forceinline__ FT V(P3 q) const {
         if constexpr (COMP == B) return P(q);
         else {
             constexpr int a = Cfg<B>::comp(0) == COMP ? 0 : (Cfg<B>::comp(1) == COMP ? 1 : 2);
-            return aux[a][((q.L + 60) % Cfg<B>::sl(a)) * Box<FT>::PE + q.row * Box<FT>::BX + q.col];
+            return aux[a][((q.L + 60) % Cfg<B>::sl(a)) * Box<FT, NW>::PE + q.row * Box<FT, NW>::BX + q.col];
         }
     }
 };
 
 // (I(q) + I(q + 1))/2 along direction D of velocity component COMP (see wf::interp4)
-template <class FT, int B, int COMP, int D>
-__device__ __forceinline__ FT I4r(const Rings<FT, B>& r, P3 q) {
+template <class FT, int B, int NW, int COMP, int D>
+__device__ __forceinline__ FT I4r(const Rings<FT, B, NW>& r, P3 q) {
     return wf::interp4<FT>(r.template V<COMP>(shp<D>(q, -1)), r.template V<COMP>(q), r.template V<COMP>(shp<D>(q, 1)),
                            r.template V<COMP>(shp<D>(q, 2)));
 }
 
 // area * upwind flux of psi (component B or tracer) in direction A at position q
 // (A == B: cell-centre index; otherwise face index along A)
-template <class FT, bool ZW, int A, int B>
-__device__ __forceinline__ FT flux_at(const Rings<FT, B>& r, const Ctx<FT>& c, P3 q) {
+template <class FT, bool ZW, int A, int B, int NW>
+__device__ __forceinline__ FT flux_at(const Rings<FT, B, NW>& r, const Ctx<FT>& c, P3 q) {
     FT ut;
     P3 pf = q;
     if constexpr (B == 3) {
         ut = r.template V<A>(q);
     } else if constexpr (A == B) {
-        ut = I4r<FT, B, A, A>(r, q);
+        ut = I4r<FT, B, NW, A, A>(r, q);
         pf = shp<A>(q, 1);
     } else {
-        ut = I4r<FT, B, A, B>(r, shp<B>(q, -1));
+        ut = I4r<FT, B, NW, A, B>(r, shp<B>(q, -1));
     }
     const FT w0 = r.P(shp<A>(pf, -3)), w1 = r.P(shp<A>(pf, -2)), w2 = r.P(shp<A>(pf, -1)), w3 = r.P(pf),
              w4 = r.P(shp<A>(pf, 1)), w5 = r.P(shp<A>(pf, 2));
@@ -137,13 +147,14 @@ __device__ __forceinline__ FT flux_at(const Rings<FT, B>& r, const Ctx<FT>& c, P
     return c.area[A] * (ut * rec);
 }
 
-template <class FT, bool ZW, int B>
-__global__ void __launch_bounds__(TX* TY, 2) tendency_tma_kernel(const __grid_constant__ Ctx<FT> c) {
-    using BXs = Box<FT>;
+template <class FT, bool ZW, int B, int NW>
+__global__ void __launch_bounds__(TX* NW, NW <= 8 ? 3 : 2) tendency_tma_kernel(const __grid_constant__ Ctx<FT> c) {
+    using BXs = Box<FT, NW>;
     using CF = Cfg<B>;
+    constexpr int R = BXs::R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ FT sFx[2][TY][TX + 1];
-    __shared__ FT sFy[2][TY + 1][TX];
+    __shared__ FT sFx[2][R][TX + 1];
+    __shared__ FT sFy[2][R + 1][TX];
     __shared__ __align__(8) unsigned long long bars[2];
 
     FT* ring_psi = reinterpret_cast<FT*>(smem_raw);
@@ -153,11 +164,13 @@ __global__ void __launch_bounds__(TX* TY, 2) tendency_tma_kernel(const __grid_co
 #pragma unroll
         for (int a = 0; a < 3; ++a) { ring_aux[a] = q; q += CF::sl(a) * BXs::PE; }
     }
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
-    const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * TY, k0 = 1 + blockIdx.z * c.Kc;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const bool edge = ty == R, producer = edge && tx == 0;
+    const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * R, k0 = 1 + blockIdx.z * c.Kc;
+    const int nrows = min(R, c.Ny - j0 + 1);           // the last tile in y may be ragged
     const int cx = i0 - HALO - 2 + c.O[0], cy = j0 - HALO - 1 + c.O[1], cz0 = c.O[2] - 1;   // array coords
 
-    if (tid == 0) {
+    if (producer) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,80 +183,93 @@ __global__ void __launch_bounds__(TX* TY, 2) tendency_tma_kernel(const __grid_co
     auto load_aux = [&](int a, int L, unsigned long long* bar) {
         tma_load_3d(ring_aux[a] + ((L + 60) % CF::sl(a)) * BXs::PE, &c.tm_aux[a], cx, cy, L + cz0, bar);
     };
-    if (tid == 0) {
+    if (producer) {
         // prologue: everything iteration 0 (and the carried z face) needs
         int planes = (PSI_HI - PSI_LO + 1);
 #pragma unroll
         for (int a = 0; a < CF::NA; ++a) planes += CF::hi(a) - CF::lo(a) + 1;
-        mbar_expect_tx(&bars[0], planes * BXs::BX * BY * (unsigned)sizeof(FT));
+        mbar_expect_tx(&bars[0], planes * BXs::BX * BXs::BY * (unsigned)sizeof(FT));
         for (int L = k0 + PSI_LO; L <= k0 + PSI_HI; ++L) load_psi(L, &bars[0]);
 #pragma unroll
         for (int a = 0; a < CF::NA; ++a)
             for (int L = k0 + CF::lo(a); L <= k0 + CF::hi(a); ++L) load_aux(a, L, &bars[0]);
     }
 
-    Rings<FT, B> R;
-    R.psi = ring_psi;
-    R.aux[0] = ring_aux[0]; R.aux[1] = ring_aux[1]; R.aux[2] = ring_aux[2];
+    Rings<FT, B, NW> Rg;
+    Rg.psi = ring_psi;
+    Rg.aux[0] = ring_aux[0]; Rg.aux[1] = ring_aux[1]; Rg.aux[2] = ring_aux[2];
 
     constexpr bool XLOW = (B == 0), YLOW = (B == 1), ZLOW = (B == 2);
-    const bool xextra = tid < TY, yextra = tid >= 32 && tid < 32 + TX;
+    const bool cell = !edge && ty < nrows;
     const long long sx = c.s[0], sy = c.s[1], sz = c.s[2];
     long long p = (i0 + tx) * sx + (j0 + ty) * sy + k0 * sz;
     FT Fz_carry = FT(0);
+    const int mode = c.ss.mode;
+    const bool has_pHY = (B == 0 || B == 1) && c.pHY != nullptr, has_Gm = mode == SUB_RK3 || mode == SUB_AB2;
+    const long long sB = B == 0 ? sx : sy;
 
     for (int it = 0; it < c.Kc; ++it) {
         const int k = k0 + it, buf = it & 1;
-        if (tid == 0 && it + 1 < c.Kc) {      // prefetch the planes level k+1 adds
+        if (producer && it + 1 < c.Kc) {      // prefetch the planes level k+1 adds
             unsigned long long* nb = &bars[(it + 1) & 1];
-            mbar_expect_tx(nb, (1 + CF::NA) * BXs::BX * BY * (unsigned)sizeof(FT));
+            mbar_expect_tx(nb, (1 + CF::NA) * BXs::BX * BXs::BY * (unsigned)sizeof(FT));
             load_psi(k + 1 + PSI_HI, nb);
 #pragma unroll
             for (int a = 0; a < CF::NA; ++a) load_aux(a, k + 1 + CF::hi(a), nb);
         }
+        // pointwise global operands, in flight while the fluxes are computed
+        FT gm = FT(0), ph1 = FT(0), ph0 = FT(0);
+        if (cell) {
+            if (has_Gm) gm = c.Gm[p];
+            if (has_pHY) { ph1 = c.pHY[p]; ph0 = c.pHY[p - sB]; }
+        }
         mbar_wait(&bars[it & 1], (it >> 1) & 1);
 
-        P3 q{k, ty + HALO, tx + COL0};
-        if (it == 0) Fz_carry = flux_at<FT, ZW, 2, B>(R, c, ZLOW ? shp<2>(q, -1) : q);
-        FT Fx = flux_at<FT, ZW, 0, B>(R, c, q);
-        FT Fy = flux_at<FT, ZW, 1, B>(R, c, q);
-        sFx[buf][ty][XLOW ? tx + 1 : tx] = Fx;
-        sFy[buf][YLOW ? ty + 1 : ty][tx] = Fy;
-        if (xextra) {
-            P3 e{k, tid + HALO, (XLOW ? -1 : TX) + COL0};
-            sFx[buf][tid][XLOW ? 0 : TX] = flux_at<FT, ZW, 0, B>(R, c, e);
+        const P3 q{k, ty + HALO, tx + COL0};
+        FT Fx = FT(0), Fy = FT(0), dFz = FT(0);
+        if (cell) {
+            if (it == 0) Fz_carry = flux_at<FT, ZW, 2, B, NW>(Rg, c, ZLOW ? shp<2>(q, -1) : q);
+            Fx = flux_at<FT, ZW, 0, B, NW>(Rg, c, q);
+            Fy = flux_at<FT, ZW, 1, B, NW>(Rg, c, q);
+            sFx[buf][ty][XLOW ? tx + 1 : tx] = Fx;
+            sFy[buf][YLOW ? ty + 1 : ty][tx] = Fy;
+            FT Fz_new = flux_at<FT, ZW, 2, B, NW>(Rg, c, ZLOW ? q : shp<2>(q, 1));
+            dFz = Fz_new - Fz_carry;
+            Fz_carry = Fz_new;
+        } else if (edge) {
+            if (tx < nrows) {
+                P3 e{k, tx + HALO, (XLOW ? -1 : TX) + COL0};
+                sFx[buf][tx][XLOW ? 0 : TX] = flux_at<FT, ZW, 0, B, NW>(Rg, c, e);
+            }
+            P3 e{k, (YLOW ? -1 : nrows) + HALO, tx + COL0};
+            sFy[buf][YLOW ? 0 : nrows][tx] = flux_at<FT, ZW, 1, B, NW>(Rg, c, e);
         }
-        if (yextra) {
-            P3 e{k, (YLOW ? -1 : TY) + HALO, (tid - 32) + COL0};
-            sFy[buf][YLOW ? 0 : TY][tid - 32] = flux_at<FT, ZW, 1, B>(R, c, e);
-        }
-        FT Fz_new = flux_at<FT, ZW, 2, B>(R, c, ZLOW ? q : shp<2>(q, 1));
-        FT dFz = Fz_new - Fz_carry;
-        Fz_carry = Fz_new;
         __syncthreads();
-        FT dFx = XLOW ? (Fx - sFx[buf][ty][tx]) : (sFx[buf][ty][tx + 1] - Fx);
-        FT dFy = YLOW ? (Fy - sFy[buf][ty][tx]) : (sFy[buf][ty + 1][tx] - Fy);
-        FT G = -(c.invV * ((dFx + dFy) + dFz));
-        if (B == 0) {
-            if (c.fplane) {
-                const FT* v = c.cor;
-                FT a0 = FT(0.5) * (v[p - sx] + v[p]), a1 = FT(0.5) * (v[p - sx + sy] + v[p + sy]);
-                G = G - (-c.f * (FT(0.5) * (a0 + a1)));
+        if (cell) {
+            FT dFx = XLOW ? (Fx - sFx[buf][ty][tx]) : (sFx[buf][ty][tx + 1] - Fx);
+            FT dFy = YLOW ? (Fy - sFy[buf][ty][tx]) : (sFy[buf][ty + 1][tx] - Fy);
+            FT G = -(c.invV * ((dFx + dFy) + dFz));
+            if (B == 0) {
+                if (c.fplane) {
+                    const FT* v = c.cor;
+                    FT a0 = FT(0.5) * (v[p - sx] + v[p]), a1 = FT(0.5) * (v[p - sx + sy] + v[p + sy]);
+                    G = G - (-c.f * (FT(0.5) * (a0 + a1)));
+                }
+                if (has_pHY) G = G - (ph1 - ph0) * c.invd[0];
+            } else if (B == 1) {
+                if (c.fplane) {
+                    const FT* u = c.cor;
+                    FT a0 = FT(0.5) * (u[p - sy] + u[p + sx - sy]), a1 = FT(0.5) * (u[p] + u[p + sx]);
+                    G = G - (c.f * (FT(0.5) * (a0 + a1)));
+                }
+                if (has_pHY) G = G - (ph1 - ph0) * c.invd[1];
             }
-            if (c.pHY) G = G - (c.pHY[p] - c.pHY[p - sx]) * c.invd[0];
-        } else if (B == 1) {
-            if (c.fplane) {
-                const FT* u = c.cor;
-                FT a0 = FT(0.5) * (u[p - sy] + u[p + sx - sy]), a1 = FT(0.5) * (u[p] + u[p + sx]);
-                G = G - (c.f * (FT(0.5) * (a0 + a1)));
-            }
-            if (c.pHY) G = G - (c.pHY[p] - c.pHY[p - sy]) * c.invd[1];
+            c.Gn[p] = G;
+            const FT ps = Rg.P(q);
+            if (mode == SUB_RK3_FIRST) c.psi_new[p] = ps + c.ss.c1 * G;
+            else if (mode == SUB_RK3) c.psi_new[p] = ps + c.ss.dt * (c.ss.c1 * G + c.ss.c2 * gm);
+            else if (mode == SUB_AB2) c.psi_new[p] = ps + c.ss.dt * (c.ss.c1 * G - c.ss.c2 * gm);
         }
-        c.Gn[p] = G;
-        const FT ps = R.P(q);
-        if (c.ss.mode == SUB_RK3_FIRST) c.psi_new[p] = ps + c.ss.c1 * G;
-        else if (c.ss.mode == SUB_RK3) c.psi_new[p] = ps + c.ss.dt * (c.ss.c1 * G + c.ss.c2 * c.Gm[p]);
-        else if (c.ss.mode == SUB_AB2) c.psi_new[p] = ps + c.ss.dt * (c.ss.c1 * G - c.ss.c2 * c.Gm[p]);
         p += sz;
     }
 }
@@ -265,17 +291,17 @@ static EncodeFn get_encode() {
 }
 
 template <class FT>
-static CUtensorMap make_map(const GridD<FT>& g, const FT* base) {
-    static std::map<std::pair<const void*, long long>, CUtensorMap> cache;
+static CUtensorMap make_map(const GridD<FT>& g, const FT* base, int box_x, int box_y) {
+    static std::map<std::tuple<const void*, long long, int, int>, CUtensorMap> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    auto key = std::make_pair((const void*)base, (long long)g.total * (long long)sizeof(FT) + g.S[0]);
+    auto key = std::make_tuple((const void*)base, (long long)g.total * (long long)sizeof(FT) + g.S[0], box_x, box_y);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     CUtensorMap m;
     cuuint64_t dims[3] = {(cuuint64_t)g.S[0], (cuuint64_t)g.S[1], (cuuint64_t)g.S[2]};
     cuuint64_t strides[2] = {(cuuint64_t)g.S[0] * sizeof(FT), (cuuint64_t)g.S[0] * g.S[1] * sizeof(FT)};
-    cuuint32_t box[3] = {(cuuint32_t)Box<FT>::BX, (cuuint32_t)BY, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = get_encode()(&m, sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                               (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -286,51 +312,64 @@ static CUtensorMap make_map(const GridD<FT>& g, const FT* base) {
     return m;
 }
 
-template <class FT, bool ZW, int B>
-static void launch_one(Ctx<FT>& c, const GridD<FT>& g, const FT* const U[3]) {
+template <class FT, bool ZW, int B, int NW>
+static void launch_one(Ctx<FT>& c, const GridD<FT>& g, const FT* const U[3], const FT* psi) {
     using CF = Cfg<B>;
+    using BXs = Box<FT, NW>;
+    c.tm_psi = make_map<FT>(g, psi - g.off0, BXs::BX, BXs::BY);
     int slots = PSI_SL;
     for (int a = 0; a < CF::NA; ++a) {
         slots += CF::sl(a);
-        c.tm_aux[a] = make_map<FT>(g, U[CF::comp(a)] - g.off0);
+        c.tm_aux[a] = make_map<FT>(g, U[CF::comp(a)] - g.off0, BXs::BX, BXs::BY);
     }
-    size_t smem = (size_t)slots * Box<FT>::PLANE_BYTES;
-    auto kern = tendency_tma_kernel<FT, ZW, B>;
+    size_t smem = (size_t)slots * BXs::PLANE_BYTES;
+    auto kern = tendency_tma_kernel<FT, ZW, B, NW>;
     static bool attr_set = false;
     if (!attr_set) {
-        OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         attr_set = true;
     }
-    dim3 blk(TX, TY), grd(g.N[0] / TX, g.N[1] / TY, g.N[2] / c.Kc);
+    dim3 blk(TX, NW), grd(g.N[0] / TX, cdiv(g.N[1], BXs::R), g.N[2] / c.Kc);
     kern<<<grd, blk, smem, stream()>>>(c);
     OB_LAUNCH_CHECK();
+}
+
+static int warps_per_block() {
+    static int nw = 0;
+    if (!nw) {
+        const char* e = getenv("OB200_TMA_NW");
+        nw = e ? atoi(e) : 8;
+        if (nw != 8 && nw != 12) nw = 8;
+    }
+    return nw;
 }
 
 template <class FT>
 bool launch(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi, const FT* pHY, FT* Gn, const FT* Gm,
             FT* psi_new, const Substep<FT>& ss) {
     const GridD<FT>& g = P.g;
-    if (g.topo[2] == OB_FLAT || g.N[0] % TX || g.N[1] % TY) return false;
+    if (g.topo[2] == OB_FLAT || g.N[0] % TX) return false;
     if ((g.S[0] * sizeof(FT)) % 16) return false;
     Ctx<FT> c;
-    c.tm_psi = make_map<FT>(g, psi - g.off0);
     c.psi = psi; c.pHY = pHY; c.Gm = Gm; c.Gn = Gn; c.psi_new = psi_new; c.ss = ss;
     c.cor = comp == 0 ? U[1] : U[0];
     for (int d = 0; d < 3; ++d) { c.s[d] = g.st[d]; c.O[d] = g.O[d]; c.invd[d] = 1 / g.d[d]; }
     c.area[0] = g.d[1] * g.d[2]; c.area[1] = g.d[0] * g.d[2]; c.area[2] = g.d[0] * g.d[1];
     c.invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
     c.f = P.f; c.fplane = P.fplane;
+    c.Ny = g.N[1];
     int Kc = 32;
     while (g.N[2] % Kc) Kc >>= 1;
     c.Kc = Kc;
-#define GO(ZWV)                                                         \
-    switch (comp) {                                                     \
-        case 0: launch_one<FT, ZWV, 0>(c, g, U); break;                 \
-        case 1: launch_one<FT, ZWV, 1>(c, g, U); break;                 \
-        case 2: launch_one<FT, ZWV, 2>(c, g, U); break;                 \
-        default: launch_one<FT, ZWV, 3>(c, g, U); break;                \
+#define GO(ZWV, NWV)                                                         \
+    switch (comp) {                                                          \
+        case 0: launch_one<FT, ZWV, 0, NWV>(c, g, U, psi); break;            \
+        case 1: launch_one<FT, ZWV, 1, NWV>(c, g, U, psi); break;            \
+        case 2: launch_one<FT, ZWV, 2, NWV>(c, g, U, psi); break;            \
+        default: launch_one<FT, ZWV, 3, NWV>(c, g, U, psi); break;           \
     }
-    if (P.zweno) { GO(true) } else { GO(false) }
+    if (warps_per_block() == 8) { if (P.zweno) { GO(true, 8) } else { GO(false, 8) } }
+    else { if (P.zweno) { GO(true, 12) } else { GO(false, 12) } }
 #undef GO
     return true;
 }
