@@ -690,39 +690,52 @@ static void model_fill_state_halos(ob200_model* m, int first, int last) {
 }
 
 template <class FT>
+static void model_hydrostatic(ob200_model* m, bool periodic_images) {
+    ScopedPhase phase_timer("hydrostatic");
+    const GridD<FT>& g = gridD<FT>(m->grid);
+    Phys<FT>& P = physOf<FT>(m);
+    bool has_b = P.btr >= 0;
+    FT* b = has_b ? m->F[3 + P.btr]->template p0<FT>() : nullptr;
+    FT gz = (has_b && P.tilted) ? P.ghat[2] : FT(1);
+    launch_hydrostatic_pressure<FT>(g, b, gz, has_b, m->pHY->template p0<FT>(), periodic_images);
+}
+
+template <class FT>
 static void model_update_state(ob200_model* m, bool tracers_too = true) {
     // update_nonhydrostatic_model_state.jl:14-37
     { ScopedPhase ph("halo"); model_fill_state_halos<FT>(m, 0, tracers_too ? m->nf : 3); }
     if (m->pHY) {
-        ScopedPhase phase_timer("hydrostatic");
-        const GridD<FT>& g = gridD<FT>(m->grid);
-        Phys<FT>& P = physOf<FT>(m);
-        bool has_b = P.btr >= 0;
-        const FT* b = has_b ? m->F[3 + P.btr]->template p0<FT>() : nullptr;
-        FT gz = (has_b && P.tilted) ? P.ghat[2] : FT(1);
-        launch_hydrostatic_pressure<FT>(g, b, gz, has_b, m->pHY->template p0<FT>());
-        ob200_field* ph = m->pHY.get();
-        fill_halos<FT>(&ph, 1);
+        model_hydrostatic<FT>(m, false);
+        ScopedPhase ph("halo");
+        ob200_field* ph_ = m->pHY.get();
+        fill_halos<FT>(&ph_, 1);
     }
 }
 // update_state! as it runs inside time_step!, after model_pressure_step(..., tracers_too = true): tracer halos are
 // already valid, so pHY' is integrated first and velocities + pHY' share ONE halo fill (one neighbour exchange
 // on the slab-decomposed path instead of two).  Same values as the reference sequence.
+// fused (all non-Flat dimensions Periodic, see model_fused_periodic): the solver, the pressure correction and the
+// hydrostatic integral read their operands with periodic wrap-around, so ALL halo fills of the stage (state
+// before the solve, pNHS after it, state + pHY' here) collapse into this one single-launch shell fill.
 template <class FT>
-static void model_update_state_after_projection(ob200_model* m) {
+static void model_update_state_after_projection(ob200_model* m, bool fused) {
     std::vector<ob200_field*> v = {m->F[0].get(), m->F[1].get(), m->F[2].get()};
     if (m->pHY) {
-        ScopedPhase phase_timer("hydrostatic");
-        const GridD<FT>& g = gridD<FT>(m->grid);
-        Phys<FT>& P = physOf<FT>(m);
-        bool has_b = P.btr >= 0;
-        const FT* b = has_b ? m->F[3 + P.btr]->template p0<FT>() : nullptr;
-        FT gz = (has_b && P.tilted) ? P.ghat[2] : FT(1);
-        launch_hydrostatic_pressure<FT>(g, b, gz, has_b, m->pHY->template p0<FT>());
+        model_hydrostatic<FT>(m, fused);
         v.push_back(m->pHY.get());
+    }
+    if (fused) {
+        for (int q = 3; q < m->nf; ++q) v.push_back(m->F[q].get());
+        v.push_back(m->pNHS.get());
     }
     ScopedPhase ph("halo");
     fill_halos<FT>(v.data(), (int)v.size());
+}
+// the fused path: every non-Flat dimension Periodic (not slab-decomposed) and regular, fast FFT solver
+template <class FT>
+static bool model_fused_periodic(ob200_model* m) {
+    static const bool off = getenv("OB200_NO_FUSED_HALOS") != nullptr;
+    return !off && periodic_wrap_supported<FT>(gridD<FT>(m->grid)) && poisson_has_fast<FT>(planOf<FT>(m->solver.get()));
 }
 extern "C" int32_t ob200_model_update_state(ob200_model* m) {
     API_BEGIN
@@ -766,19 +779,21 @@ extern "C" int32_t ob200_model_calculate_tendencies(ob200_model* m) {
 }
 
 template <class FT>
-static void model_pressure_step(ob200_model* m, FT dt, bool tracers_too = false) {
+static void model_pressure_step(ob200_model* m, FT dt, bool tracers_too = false, bool fused = false) {
     // calculate_pressure_correction! + pressure_correct_velocities! (pressure_correction.jl:10-56).
     // Inside time_step! the tracers' halos are filled here as well (they do not change until the next
     // substep), which lets the update_state! that follows merge its two halo fills into one.
+    // fused: the solver reads the predictor velocities and the correction reads pNHS with periodic wrap-around,
+    // so neither fill is needed; the correction kernel stores the halo images of u, v, w and pNHS.
     const GridD<FT>& g = gridD<FT>(m->grid);
-    { ScopedPhase ph("halo"); model_fill_state_halos<FT>(m, 0, tracers_too ? m->nf : 3); }
+    if (!fused) { ScopedPhase ph("halo"); model_fill_state_halos<FT>(m, 0, tracers_too ? m->nf : 3); }
     { ScopedPhase ph("poisson");
       solve_for_pressure_T<FT>(m->solver.get(), m->pNHS.get(), (double)dt, m->F[0].get(), m->F[1].get(), m->F[2].get()); }
     ob200_field* pn = m->pNHS.get();
-    { ScopedPhase ph("halo"); fill_halos<FT>(&pn, 1); }
+    if (!fused) { ScopedPhase ph("halo"); fill_halos<FT>(&pn, 1); }
     ScopedPhase ph("pressure_correct");
     launch_pressure_correct<FT>(g, m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(),
-                                m->F[2]->template p0<FT>(), m->pNHS->template p0<FT>(), dt);
+                                m->F[2]->template p0<FT>(), m->pNHS->template p0<FT>(), dt, fused);
 }
 extern "C" int32_t ob200_model_pressure_project(ob200_model* m, double dt) {
     API_BEGIN
@@ -797,12 +812,13 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
         const FT z2 = FT(-17.0 / 60.0), z3 = FT(-5.0 / 12.0);
         FT sdt[3] = {g1 * dt, (g2 + z2) * dt, (g3 + z3) * dt};
         Substep<FT> ss[3] = {{SUB_RK3_FIRST, dt, dt * g1, 0}, {SUB_RK3, dt, g2, z2}, {SUB_RK3, dt, g3, z3}};
+        const bool fused = model_fused_periodic<FT>(m);
         for (int s = 0; s < 3; ++s) {
             model_tendencies<FT>(m, ss[s]);
-            model_pressure_step<FT>(m, sdt[s], true);
+            model_pressure_step<FT>(m, sdt[s], true, fused);
             m->time += (double)sdt[s];
             if (s < 2) for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);   // store_tendencies!
-            model_update_state_after_projection<FT>(m);
+            model_update_state_after_projection<FT>(m, fused);
         }
         m->iteration += 1;
     } else {
@@ -815,12 +831,13 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
         m->previous_dt = dt_in;
         if (m->iteration == 0) model_update_state<FT>(m);
         Substep<FT> ss{SUB_AB2, dt, FT(1.5) + chi, FT(0.5) + chi};
+        const bool fused = model_fused_periodic<FT>(m);
         model_tendencies<FT>(m, ss);
-        model_pressure_step<FT>(m, dt, true);
+        model_pressure_step<FT>(m, dt, true, fused);
         for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);
         m->time += (double)dt;
         m->iteration += 1;
-        model_update_state_after_projection<FT>(m);
+        model_update_state_after_projection<FT>(m, fused);
     }
 }
 extern "C" int32_t ob200_model_time_step(ob200_model* m, double dt, int32_t euler) {

@@ -199,6 +199,7 @@ struct XArgs {
     long long st[3];
     FT ax, ay, az, invV, dt;
     int has_z;
+    long long wrap[3];              // Periodic dims: N * stride, so that index N+1 is read as index 1 (no halo needed)
     // backward output
     FT* phi_p0;
     int Hx;
@@ -218,27 +219,53 @@ __global__ void __launch_bounds__(256) x_r2c_kernel(XArgs<FT> A) {
     const int j0 = blockIdx.x * A.T, k = blockIdx.y;
     const int nl = min(A.T, A.Ny - j0);
     const int Nx = A.Nx;
-    // stage the real source term, two consecutive reals = one complex
-    for (int w = threadIdx.x; w < nl * M; w += blockDim.x) {
-        int t = w / M, m = w - t * M;
-        int j = j0 + t;
-        FT r[2];
+    // stage the real source term, two consecutive reals = one complex.  The loads of XU work items are issued
+    // together (ncu r1d: long-scoreboard was the dominant stall with one item in flight per thread).
+    constexpr int XU = 4;
+    for (int w0 = threadIdx.x; w0 < nl * M; w0 += XU * blockDim.x) {
+        FT q[XU][2][6];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int i = 2 * m + h;
-            if (A.real_in) {
-                r[h] = A.real_in[i + (long long)Nx * (j + (long long)A.Ny * k)];
-            } else {
-                long long p = (i + 1) * A.st[0] + (j + 1) * A.st[1] + (k + 1) * A.st[2];
-                // divᶜᶜᶜ on a regular grid: 1/V (Ax δx u + Ay δy v + Az δz w); kept as in kernels.cu
-                FT tx = A.ax * A.u[p + A.st[0]] - A.ax * A.u[p];
-                FT ty = A.ay * A.v[p + A.st[1]] - A.ay * A.v[p];
-                FT tz = A.has_z ? (A.az * A.w[p + A.st[2]] - A.az * A.w[p]) : FT(0);
-                r[h] = (A.invV * ((tx + ty) + tz)) / A.dt;
+        for (int e = 0; e < XU; ++e) {
+            int w = w0 + e * blockDim.x;
+            if (w < nl * M) {
+                int t = w / M, m = w - t * M;
+                int j = j0 + t;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int i = 2 * m + h;
+                    if (A.real_in) {
+                        q[e][h][0] = A.real_in[i + (long long)Nx * (j + (long long)A.Ny * k)];
+                    } else {
+                        long long p = (i + 1) * A.st[0] + (j + 1) * A.st[1] + (k + 1) * A.st[2];
+                        q[e][h][0] = A.u[p + A.st[0] - (i + 1 == Nx ? A.wrap[0] : 0)]; q[e][h][1] = A.u[p];
+                        q[e][h][2] = A.v[p + A.st[1] - (j + 1 == A.Ny ? A.wrap[1] : 0)]; q[e][h][3] = A.v[p];
+                        if (A.has_z) { q[e][h][4] = A.w[p + A.st[2] - (k + 1 == A.Nz ? A.wrap[2] : 0)]; q[e][h][5] = A.w[p]; }
+                    }
+                }
             }
         }
-        CT c; c.x = r[0]; c.y = r[1];
-        s[t * G::LS + G::pos(m)] = c;
+#pragma unroll
+        for (int e = 0; e < XU; ++e) {
+            int w = w0 + e * blockDim.x;
+            if (w < nl * M) {
+                int t = w / M, m = w - t * M;
+                FT r[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (A.real_in) {
+                        r[h] = q[e][h][0];
+                    } else {
+                        // divᶜᶜᶜ on a regular grid: 1/V (Ax δx u + Ay δy v + Az δz w); kept as in kernels.cu
+                        FT tx = A.ax * q[e][h][0] - A.ax * q[e][h][1];
+                        FT ty = A.ay * q[e][h][2] - A.ay * q[e][h][3];
+                        FT tz = A.has_z ? (A.az * q[e][h][4] - A.az * q[e][h][5]) : FT(0);
+                        r[h] = (A.invV * ((tx + ty) + tz)) / A.dt;
+                    }
+                }
+                CT c; c.x = r[0]; c.y = r[1];
+                s[t * G::LS + G::pos(m)] = c;
+            }
+        }
     }
     __syncthreads();
     fft_fwd<LOG2M>(s, stw, nl);
@@ -269,16 +296,32 @@ __global__ void __launch_bounds__(256) x_c2r_kernel(XArgs<FT> A) {
     const int j0 = blockIdx.x * A.T, k = blockIdx.y;
     const int nl = min(A.T, A.Ny - j0);
     // tangle: Z[k] = E[k] + i O[k], E = (X[k] + conj X[M-k]) / 2, O = conj(w_N^k) (X[k] - conj X[M-k]) / 2
-    for (int w = threadIdx.x; w < nl * M; w += blockDim.x) {
-        int t = w / M, kk = w - t * M;
-        const CT* row = A.spec + (long long)A.NXP * ((j0 + t) + (long long)A.Ny * k);
-        CT a = row[kk], b = row[M - kk];
-        CT E, D;
-        E.x = FT(0.5) * (a.x + b.x); E.y = FT(0.5) * (a.y - b.y);
-        D.x = FT(0.5) * (a.x - b.x); D.y = FT(0.5) * (a.y + b.y);
-        CT O = cmulc(D, A.twN[kk]);
-        CT Z; Z.x = E.x - O.y; Z.y = E.y + O.x;
-        s[t * G::LS + G::pos(A.kpos[kk])] = Z;
+    constexpr int XU = 4;
+    for (int w0 = threadIdx.x; w0 < nl * M; w0 += XU * blockDim.x) {
+        CT av[XU], bv[XU];
+#pragma unroll
+        for (int e = 0; e < XU; ++e) {
+            int w = w0 + e * blockDim.x;
+            if (w < nl * M) {
+                int t = w / M, kk = w - t * M;
+                const CT* row = A.spec + (long long)A.NXP * ((j0 + t) + (long long)A.Ny * k);
+                av[e] = row[kk]; bv[e] = row[M - kk];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < XU; ++e) {
+            int w = w0 + e * blockDim.x;
+            if (w < nl * M) {
+                int t = w / M, kk = w - t * M;
+                CT a = av[e], b = bv[e];
+                CT E, D;
+                E.x = FT(0.5) * (a.x + b.x); E.y = FT(0.5) * (a.y - b.y);
+                D.x = FT(0.5) * (a.x - b.x); D.y = FT(0.5) * (a.y + b.y);
+                CT O = cmulc(D, A.twN[kk]);
+                CT Z; Z.x = E.x - O.y; Z.y = E.y + O.x;
+                s[t * G::LS + G::pos(A.kpos[kk])] = Z;
+            }
+        }
     }
     __syncthreads();
     fft_inv<LOG2M>(s, stw, nl);
@@ -351,6 +394,7 @@ __global__ void __launch_bounds__(256) line_kernel(LArgs<FT> A) {
     for (int w = threadIdx.x; w < N; w += blockDim.x) stw[w] = A.tw[w];
     const int x0 = blockIdx.x * A.T, o = blockIdx.y;
     const int nl = min(A.T, A.NXH - x0);
+#pragma unroll 8
     for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
         int m = w / nl, t = w - m * nl;
         s[t * G::LS + G::pos(m)] = *A.lin.addr(A.in, x0 + t, m, o);
@@ -509,11 +553,18 @@ template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
     delete p;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 template <class FT, int MODE>
 static void launch_line(const LArgs<FT>& A, int log2n, dim3 grd, size_t smem) {
+    // one radix-16 butterfly per thread and pass
+    int threads = std::min(256, std::max(64, A.T * (1 << log2n) / 16));
     auto go = [&](auto kern) {
         OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        kern<<<grd, 256, smem, stream()>>>(A);
+        kern<<<grd, threads, smem, stream()>>>(A);
         OB_LAUNCH_CHECK();
     };
     switch (log2n) {
@@ -542,7 +593,8 @@ static Lay natural_lay(int NXP, long long s_m, long long s_o) {
 template <class FT>
 static void launch_line_any(FastPoisson<FT>* p, LArgs<FT>& A, int log2n, int mode) {
     using CT = typename Cx<FT>::T;
-    int T = 16;
+    static const int T0 = env_int("OB200_FFT_TL", 8);
+    int T = T0;
     while (T > 1 && line_smem(log2n, T, sizeof(CT)) > 100 * 1024) T >>= 1;
     A.T = T;
     A.scale = (FT)(1.0 / A.n);
@@ -637,14 +689,16 @@ static void run_x(FastPoisson<FT>* p, XArgs<FT>& A) {
     A.spec = p->spec; A.Nx = p->N[0]; A.Ny = p->N[1]; A.Nz = p->N[2]; A.NXP = p->NXP;
     A.twM = p->twM; A.twN = p->twN; A.kpos = p->kpos;
     A.scale = (FT)(1.0 / (p->N[0] / 2));
-    int T = 32;
+    static const int T0 = env_int("OB200_FFT_TX", 8);
+    int T = T0;
     while (T > 1 && line_smem(lm, T, sizeof(CT)) > 100 * 1024) T >>= 1;
     A.T = T;
     dim3 grd(cdiv(A.Ny, T), A.Nz);
     size_t smem = line_smem(lm, T, sizeof(CT));
+    int threads = std::min(256, std::max(64, T * (1 << lm) / 16));
     auto go = [&](auto kern) {
         OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        kern<<<grd, 256, smem, stream()>>>(A);
+        kern<<<grd, threads, smem, stream()>>>(A);
         OB_LAUNCH_CHECK();
     };
 #define XCASE(L)                                                             \
@@ -659,7 +713,11 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
                         const FT* real_in, FT* phi_p0) {
     XArgs<FT> A{};
     A.u = u; A.v = v; A.w = w; A.real_in = real_in;
-    for (int d = 0; d < 3; ++d) A.st[d] = g.st[d];
+    for (int d = 0; d < 3; ++d) {
+        A.st[d] = g.st[d];
+        // a Periodic (not slab-decomposed) dimension is read with wrap-around: the velocities' halos need not be valid
+        A.wrap[d] = g.topo[d] == OB_PERIODIC ? (long long)g.N[d] * g.st[d] : 0;
+    }
     // divᶜᶜᶜ (divergence_operators.jl:16-19): 1/V * (δx(Ax u) + δy(Ay v) + δz(Az w)), then / Δt
     A.ax = g.d[1] * g.d[2]; A.ay = g.d[0] * g.d[2]; A.az = g.d[0] * g.d[1];
     A.invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);

@@ -45,10 +45,14 @@ bool launch_tendency_fast(const Phys<FT>& P, int comp, const FT* const U[3], con
 template <class FT, class CT>
 void launch_pressure_rhs(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,
                          bool times_dz, CT* rhs);
+// periodic_wrap (only if periodic_wrap_supported(g): all non-Flat dimensions Periodic and regular): operands are
+// read with periodic wrap-around instead of from halos, so the fills that precede these kernels in the reference
+// can be merged into one fill at the end of the stage
+template <class FT> bool periodic_wrap_supported(const GridD<FT>& g);
 template <class FT>
-void launch_pressure_correct(const GridD<FT>& g, FT* u, FT* v, FT* w, const FT* p, FT dt);
+void launch_pressure_correct(const GridD<FT>& g, FT* u, FT* v, FT* w, const FT* p, FT dt, bool periodic_wrap);
 template <class FT>
-void launch_hydrostatic_pressure(const GridD<FT>& g, const FT* b, FT gz, bool has_b, FT* pHY);
+void launch_hydrostatic_pressure(const GridD<FT>& g, const FT* b, FT gz, bool has_b, FT* pHY, bool periodic_wrap);
 template <class FT>
 void launch_to_internal(const GridD<FT>& g, const int psize[3], const int loc[3], const FT* parent, FT* base);
 template <class FT>

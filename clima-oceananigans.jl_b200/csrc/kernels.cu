@@ -1,6 +1,7 @@
 // kernels.cu -- halo fills, general tendency(+substep), pressure rhs / correction, hydrostatic
 // pressure, layout conversion and reductions.  sm_100a.
 #include "internal.h"
+#include <cstdlib>
 
 namespace ob {
 
@@ -48,6 +49,57 @@ __global__ void fill_halo_kernel(GridD<FT> g, HaloBatch<FT> hb, int d, int a, in
             }
         }
     }
+}
+
+// ---- all non-Flat dimensions Periodic: ONE launch for all dimensions and all fields ---------------------------
+// Applying the periodic copies x, then y, then z (fill_halo_regions_periodic.jl:15-105) gives every halo cell --
+// edges and corners included -- the value of the interior cell obtained by wrapping each of its indices.  The
+// shell kernel writes exactly that, reading interior cells only, so there is no ordering between dimensions.
+// The halo shell is enumerated as three groups: z-halo levels over the full (x, y) extent, y-halo rows of the
+// interior levels over the full x extent, x-halo cells of the interior rows.
+template <class FT>
+__global__ void __launch_bounds__(256) fill_halo_shell_kernel(GridD<FT> g, HaloBatch<FT> hb, long long nZ, long long nY,
+                                                               long long nX) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2], Hx = g.H[0], Hy = g.H[1], Hz = g.H[2];
+    const int Ex = Nx + 2 * Hx, Ey = Ny + 2 * Hy;       // full extents (Flat: N = 1, H = 0)
+    int i, j, k;
+    if (t < nZ) {                       // (i over Ex, j over Ey, 2 Hz levels)
+        int r = (int)(t / Ex); i = (int)(t - (long long)r * Ex) + 1 - Hx;
+        int l = r / Ey; j = r - l * Ey + 1 - Hy;
+        k = l < Hz ? l + 1 - Hz : Nz + 1 + (l - Hz);
+    } else if (t < nZ + nY) {           // (i over Ex, 2 Hy rows, k interior)
+        t -= nZ;
+        int r = (int)(t / Ex); i = (int)(t - (long long)r * Ex) + 1 - Hx;
+        int l = r % (2 * Hy); k = r / (2 * Hy) + 1;
+        j = l < Hy ? l + 1 - Hy : Ny + 1 + (l - Hy);
+    } else if (t < nZ + nY + nX) {      // (2 Hx cells, j interior, k interior)
+        t -= nZ + nY;
+        int r = (int)(t / (2 * Hx)); int l = (int)(t - (long long)r * (2 * Hx));
+        k = r / Ny + 1; j = r - (k - 1) * Ny + 1;
+        i = l < Hx ? l + 1 - Hx : Nx + 1 + (l - Hx);
+    } else return;
+    const int si = i < 1 ? i + Nx : (i > Nx ? i - Nx : i);
+    const int sj = j < 1 ? j + Ny : (j > Ny ? j - Ny : j);
+    const int sk = k < 1 ? k + Nz : (k > Nz ? k - Nz : k);
+    const long long dst = i * g.st[0] + j * g.st[1] + k * g.st[2], src = si * g.st[0] + sj * g.st[1] + sk * g.st[2];
+    FT v[MAXF];
+#pragma unroll
+    for (int n = 0; n < MAXF; ++n) if (n < hb.n) v[n] = hb.p0[n][src];
+#pragma unroll
+    for (int n = 0; n < MAXF; ++n) if (n < hb.n) hb.p0[n][dst] = v[n];
+}
+template <class FT>
+static bool shell_fill_supported(const GridD<FT>& g) {
+    static const bool off = getenv("OB200_NO_SHELL_FILL") != nullptr;
+    if (off) return false;
+    bool any = false;
+    for (int d = 0; d < 3; ++d) {
+        if (g.topo[d] == OB_FLAT) continue;
+        if (g.topo[d] != OB_PERIODIC || g.H[d] < 1 || g.N[d] < g.H[d]) return false;
+        any = true;
+    }
+    return any;
 }
 
 // ---- halo exchange for a FullyConnected (slab-decomposed) dimension ---------------------------
@@ -121,6 +173,13 @@ static void exchange_halos(const GridD<FT>& g, const HaloBatch<FT>& hb, int d) {
 template <class FT>
 void launch_fill_halos(const GridD<FT>& g, const HaloBatch<FT>& hb) {
     if (hb.n == 0) return;
+    if (shell_fill_supported(g)) {
+        const long long Ex = g.N[0] + 2 * g.H[0], Ey = g.N[1] + 2 * g.H[1];
+        const long long nZ = Ex * Ey * 2 * g.H[2], nY = Ex * 2 * g.H[1] * g.N[2], nX = 2LL * g.H[0] * g.N[1] * g.N[2];
+        fill_halo_shell_kernel<FT><<<cdiv(nZ + nY + nX, 256), 256, 0, stream()>>>(g, hb, nZ, nY, nX);
+        OB_LAUNCH_CHECK();
+        return;
+    }
     // non-periodic first, then periodic / connected dimensions in x, y, z order (fill_halo_regions.jl:56-102)
     for (int pass = 0; pass < 2; ++pass)
         for (int d = 0; d < 3; ++d) {
@@ -277,20 +336,55 @@ __global__ void pressure_correct_kernel(GridD<FT> g, FT* u, FT* v, FT* w, const 
     v[q.p] -= deriv(g, p, q, 1, OB_F) * dt;
     w[q.p] -= deriv(g, p, q, 2, OB_F) * dt;
 }
+// The same on a grid whose non-Flat dimensions are all Periodic and regular: p is read with wrap-around, so its
+// halos need not be valid (the fill_halo_regions! of pressure_correction.jl:17 is merged into the single
+// shell fill at the end of the stage).
 template <class FT>
-void launch_pressure_correct(const GridD<FT>& g, FT* u, FT* v, FT* w, const FT* p, FT dt) {
+__global__ void __launch_bounds__(256) pressure_correct_periodic_kernel(GridD<FT> g, FT* u, FT* v, FT* w, const FT* p, FT dt) {
+    int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    int k = 1 + blockIdx.z;
+    if (i > g.N[0] || j > g.N[1]) return;
+    const int id[3] = {i, j, k};
+    const long long q = i * g.st[0] + j * g.st[1] + k * g.st[2];
+    const FT pc = p[q];
+    FT* const U[3] = {u, v, w};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (g.topo[d] == OB_FLAT) { U[d][q] -= (FT(0) / g.d[d]) * dt; continue; }
+        const long long qm = q - g.st[d] + (id[d] == 1 ? (long long)g.N[d] * g.st[d] : 0);
+        U[d][q] -= ((pc - p[qm]) / g.d[d]) * dt;
+    }
+}
+template <class FT>
+bool periodic_wrap_supported(const GridD<FT>& g) {
+    bool any = false;
+    for (int d = 0; d < 3; ++d) {
+        if (g.topo[d] == OB_FLAT) continue;
+        if (g.topo[d] != OB_PERIODIC || !g.regular[d] || g.N[d] < 2 * g.H[d]) return false;
+        any = true;
+    }
+    return any;
+}
+template bool periodic_wrap_supported<float>(const GridD<float>&);
+template bool periodic_wrap_supported<double>(const GridD<double>&);
+
+template <class FT>
+void launch_pressure_correct(const GridD<FT>& g, FT* u, FT* v, FT* w, const FT* p, FT dt, bool periodic_wrap) {
     dim3 blk(64, 4, 1), grd(cdiv(g.N[0], 64), cdiv(g.N[1], 4), g.N[2]);
-    pressure_correct_kernel<FT><<<grd, blk, 0, stream()>>>(g, u, v, w, p, dt);
+    if (periodic_wrap) pressure_correct_periodic_kernel<FT><<<grd, blk, 0, stream()>>>(g, u, v, w, p, dt);
+    else pressure_correct_kernel<FT><<<grd, blk, 0, stream()>>>(g, u, v, w, p, dt);
     OB_LAUNCH_CHECK();
 }
-template void launch_pressure_correct<float>(const GridD<float>&, float*, float*, float*, const float*, float);
-template void launch_pressure_correct<double>(const GridD<double>&, double*, double*, double*, const double*, double);
+template void launch_pressure_correct<float>(const GridD<float>&, float*, float*, float*, const float*, float, bool);
+template void launch_pressure_correct<double>(const GridD<double>&, double*, double*, double*, const double*, double, bool);
 
 // _update_hydrostatic_pressure! update_hydrostatic_pressure.jl:10-18 : one column per thread, top to bottom, same
 // summation order as the reference.  The column is walked in batches of HU levels whose loads are issued
 // together (the serial k recurrence otherwise exposes one DRAM latency per level: ncu r1d showed 20 % of peak
 // DRAM throughput with long-scoreboard as the only stall).
-template <class FT>
+// WRAP (z Periodic): b[Nz+1] is read as b[1], so the tracer's halos need not be valid.
+template <class FT, bool WRAP>
 __global__ void __launch_bounds__(64) hydrostatic_kernel(GridD<FT> g, const FT* b, FT gz, bool has_b, bool tilted, FT* pHY) {
     constexpr int HU = 16;
     int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,7 +398,7 @@ __global__ void __launch_bounds__(64) hydrostatic_kernel(GridD<FT> g, const FT* 
         FT v = b[p + k * sz];
         return tilted ? gz * v : v;
     };
-    FT above = zb(Nz + 1), acc = FT(0);
+    FT above = zb(WRAP ? 1 : Nz + 1), acc = FT(0);
     for (int kt = Nz; kt >= 1; kt -= HU) {
         FT v[HU];
 #pragma unroll
@@ -322,13 +416,15 @@ __global__ void __launch_bounds__(64) hydrostatic_kernel(GridD<FT> g, const FT* 
     }
 }
 template <class FT>
-void launch_hydrostatic_pressure(const GridD<FT>& g, const FT* b, FT gz, bool has_b, FT* pHY) {
+void launch_hydrostatic_pressure(const GridD<FT>& g, const FT* b, FT gz, bool has_b, FT* pHY, bool periodic_wrap) {
     dim3 blk(32, 2), grd(cdiv(g.N[0], 32), cdiv(g.N[1], 2));
-    hydrostatic_kernel<FT><<<grd, blk, 0, stream()>>>(g, b, gz, has_b, gz != FT(1), pHY);
+    if (periodic_wrap && g.topo[2] == OB_PERIODIC)
+        hydrostatic_kernel<FT, true><<<grd, blk, 0, stream()>>>(g, b, gz, has_b, gz != FT(1), pHY);
+    else hydrostatic_kernel<FT, false><<<grd, blk, 0, stream()>>>(g, b, gz, has_b, gz != FT(1), pHY);
     OB_LAUNCH_CHECK();
 }
-template void launch_hydrostatic_pressure<float>(const GridD<float>&, const float*, float, bool, float*);
-template void launch_hydrostatic_pressure<double>(const GridD<double>&, const double*, double, bool, double*);
+template void launch_hydrostatic_pressure<float>(const GridD<float>&, const float*, float, bool, float*, bool);
+template void launch_hydrostatic_pressure<double>(const GridD<double>&, const double*, double, bool, double*, bool);
 
 // =============================================================================================
 // reference parent layout <-> internal layout

@@ -19,3 +19,19 @@ for col in cols[:2]:
 print("--- top sample lines")
 for r in sorted(data, key=lambda r: -int(r[ix['# Samples']]))[:2 * n]:
     print(f"{r[ix['# Samples']]:>6s} {r[ix['Address']][-5:]} {r[ix['Source']].strip()}")
+
+# dynamic instruction mix by opcode
+import collections
+seen, c = set(), collections.Counter()
+for r in data:
+    a = r[ix['Address']]
+    if a in seen:
+        continue
+    seen.add(a)
+    src = r[ix['Source']].strip().split()
+    op = (src[1] if src[0].startswith('@') else src[0]).split('.')[0]
+    c[op] += int(r[ix['Instructions Executed']])
+tot = sum(c.values())
+print("--- executed warp instructions", tot)
+for k, v in c.most_common(28):
+    print(f"{k:10s} {v:12d} {100 * v / tot:5.1f}%")
