@@ -383,10 +383,31 @@ struct LArgs {
 
 enum { LM_FWD = 0, LM_INV = 1, LM_FWD_DIV_INV = 2 };
 
+// pointer to element (kx, m = 0, o) and a functor for the m-th element of that line: the natural layout is an
+// affine function of m; the blocked / split / peer-memory layouts of the slab-decomposed solve go through Lay::addr
+template <class CT>
+struct LinePtr {
+    CT* p0; long long sm; const Lay* lay; CT* base; int kx, o; bool natural;
+    __device__ __forceinline__ LinePtr(const Lay& l, CT* b, int kx_, int o_) : lay(&l), base(b), kx(kx_), o(o_) {
+        natural = l.pmode == 0 && l.kxb >= (1 << 30) && l.split >= (1 << 30);
+        p0 = b + (kx_ + o_ * l.s_o); sm = l.s_ml;
+    }
+    __device__ __forceinline__ CT* at(int m) const { return natural ? p0 + m * sm : lay->addr(base, kx, m, o); }
+};
+
+__device__ __forceinline__ double rcp_full(double x) {       // 1/x to double precision: MUFU seed + one cubic step + one Newton step
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, fma(e, e, e), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
 template <class FT, int LOG2N, int MODE>
-__global__ void __launch_bounds__(256) line_kernel(LArgs<FT> A) {
+__global__ void __launch_bounds__(256) line_kernel(const __grid_constant__ LArgs<FT> A) {
     using CT = typename Cx<FT>::T;
     using G = Geo<LOG2N>;
+    using R = Rad<LOG2N>;
     constexpr int N = 1 << LOG2N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CT* s = reinterpret_cast<CT*>(smem_raw);
@@ -394,34 +415,72 @@ __global__ void __launch_bounds__(256) line_kernel(LArgs<FT> A) {
     for (int w = threadIdx.x; w < N; w += blockDim.x) stw[w] = A.tw[w];
     const int x0 = blockIdx.x * A.T, o = blockIdx.y;
     const int nl = min(A.T, A.NXH - x0);
-#pragma unroll 8
-    for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
-        int m = w / nl, t = w - m * nl;
-        s[t * G::LS + G::pos(m)] = *A.lin.addr(A.in, x0 + t, m, o);
+    // thread -> (line t, first element m0); blockDim is a multiple of T, so t is fixed and m advances by mstep:
+    // no integer division in the load / store loops (they were ~2/3 of the instructions of the first version)
+    const int t = threadIdx.x % A.T, m0 = threadIdx.x / A.T, mstep = blockDim.x / A.T;
+    CT* const sl = s + t * G::LS;
+    if (t < nl) {
+        LinePtr<const CT> in(A.lin, A.in, x0 + t, o);
+        constexpr int LU = 8;
+        for (int m = m0; m < N; m += LU * mstep) {
+            CT v[LU];
+#pragma unroll
+            for (int e = 0; e < LU; ++e) if (m + e * mstep < N) v[e] = *in.at(m + e * mstep);
+#pragma unroll
+            for (int e = 0; e < LU; ++e) if (m + e * mstep < N) sl[G::pos(m + e * mstep)] = v[e];
+        }
     }
     __syncthreads();
-    if (MODE == LM_FWD || MODE == LM_FWD_DIV_INV) fft_fwd<LOG2N>(s, stw, nl);
-    if (MODE == LM_FWD_DIV_INV) {
+    if constexpr (MODE == LM_FWD) fft_fwd<LOG2N>(s, stw, nl);
+    if constexpr (MODE == LM_INV) fft_inv<LOG2N>(s, stw, nl);
+    if constexpr (MODE == LM_FWD_DIV_INV) {
+        // all forward passes but the last one
+        constexpr int RLAST = R::R3 > 1 ? R::R3 : (R::R2 > 1 ? R::R2 : R::R1);
+        if constexpr (R::R2 > 1) { pass_fwd<R::R1, LOG2N>(s, stw, N / R::R1, nl); __syncthreads(); }
+        if constexpr (R::R3 > 1) { pass_fwd<R::R2, LOG2N>(s, stw, N / (R::R1 * R::R2), nl); __syncthreads(); }
+        // last forward pass (stride 1, no twiddles), eigenvalue divide and first backward pass, all in registers:
         // phi_hat = -b_hat / (lx + ly + lz), zero mode = 0 (fft_based_poisson_solver.jl:106-111)
-        for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
-            int m = w / nl, t = w - m * nl;
-            int kx = A.kx0 + x0 + t;
-            double lx = A.lamx[kx], lL = A.lamL[m], lO = A.lamO ? A.lamO[o] : 0.0;
-            double lam = A.line_is_y ? ((lx + lL) + lO) : ((lx + lO) + lL);
-            CT v = s[t * G::LS + G::pos(m)];
-            CT r;
-            if (kx == 0 && m == 0 && o == 0) { r.x = 0; r.y = 0; }
-            else { r.x = (FT)(-(double)v.x / lam); r.y = (FT)(-(double)v.y / lam); }
-            s[t * G::LS + G::pos(m)] = r;
+        constexpr int nb = N / RLAST, LB = ilog2c(RLAST);
+        for (int w = threadIdx.x; w < nl * nb; w += blockDim.x) {
+            const int tt = w / nb, blk = w - tt * nb, base = blk * RLAST;
+            CT* line = s + tt * G::LS;
+            CT x[RLAST], y[RLAST];
+#pragma unroll
+            for (int q = 0; q < RLAST; ++q) x[q] = line[G::pos(base + q)];
+            dft_reg<RLAST, false>(x);
+            const int kx = A.kx0 + x0 + tt;
+            const double lxo = A.line_is_y ? A.lamx[kx] : (A.lamx[kx] + (A.lamO ? A.lamO[o] : 0.0));
+            const double lO = A.lamO ? A.lamO[o] : 0.0;
+#pragma unroll
+            for (int sidx = 0; sidx < RLAST; ++sidx) {
+                const int m = base + sidx;
+                const double lL = A.lamL[m];
+                const double lam = A.line_is_y ? ((lxo + lL) + lO) : (lxo + lL);
+                const CT v = x[brev(sidx, LB)];
+                const double r = (kx == 0 && m == 0 && o == 0) ? 0.0 : -rcp_full(lam);
+                y[sidx].x = (FT)((double)v.x * r); y[sidx].y = (FT)((double)v.y * r);
+            }
+            dft_reg<RLAST, true>(y);
+#pragma unroll
+            for (int q = 0; q < RLAST; ++q) line[G::pos(base + q)] = y[brev(q, LB)];
         }
         __syncthreads();
+        if constexpr (R::R3 > 1) { pass_inv<R::R2, LOG2N>(s, stw, N / (R::R1 * R::R2), nl); __syncthreads(); }
+        if constexpr (R::R2 > 1) { pass_inv<R::R1, LOG2N>(s, stw, N / R::R1, nl); __syncthreads(); }
     }
-    if (MODE == LM_INV || MODE == LM_FWD_DIV_INV) fft_inv<LOG2N>(s, stw, nl);
-    for (int w = threadIdx.x; w < nl * N; w += blockDim.x) {
-        int m = w / nl, t = w - m * nl;
-        CT v = s[t * G::LS + G::pos(m)];
-        if (MODE != LM_FWD) { v.x *= A.scale; v.y *= A.scale; }
-        *A.lout.addr(A.out, x0 + t, m, o) = v;
+    if (t < nl) {
+        LinePtr<CT> out(A.lout, A.out, x0 + t, o);
+        constexpr int LU = 8;
+        for (int m = m0; m < N; m += LU * mstep) {
+            CT v[LU];
+#pragma unroll
+            for (int e = 0; e < LU; ++e) if (m + e * mstep < N) {
+                v[e] = sl[G::pos(m + e * mstep)];
+                if (MODE != LM_FWD) { v[e].x *= A.scale; v[e].y *= A.scale; }
+            }
+#pragma unroll
+            for (int e = 0; e < LU; ++e) if (m + e * mstep < N) *out.at(m + e * mstep) = v[e];
+        }
     }
 }
 
