@@ -22,6 +22,9 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# mean DRAM bytes per tendency launch at 256^3 from the committed ncu capture (profiles/r1_summary.md)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 9.3e8
+
 METRIC = "grid-point updates/sec (RK3 step, 256^3 WENO5+FFT)"
 UNIT = "grid-point updates/s"
 
@@ -40,22 +43,31 @@ def synthetic_state(N, seed=2):
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    """samples nvidia-smi clocks / throttle reasons every 20 ms.  It is started BEFORE the warm-up (the nvidia-smi
+    process needs ~0.1 s to deliver its first line); mark_begin()/mark_end() bracket the timed region and the
+    summary reports the samples that fall inside it (and, beside them, all samples taken under load)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 parts = [x.strip() for x in line.strip().split(",")]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
+                    self.samples.append((time.perf_counter(), parts))
                 if self.stop_flag:
                     break
             self.proc.terminate()
@@ -65,11 +77,19 @@ class ClockSampler(threading.Thread):
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+
+        def summ(samples):
+            sm = sorted(int(s[0]) for _, s in samples if s[0].isdigit())
+            reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for _, s in samples)]
+            return (sm[len(sm) // 2] if sm else None), reasons
+        inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1 + 0.02]
+        load = [x for x in self.samples if self.t0 is None or x[0] >= self.t0 - 1.0]
+        med_in, reasons_in = summ(inside) if inside else (None, [])
+        med_load, reasons_load = summ(load if load else self.samples)
+        return {"sm_mhz": med_in if med_in is not None else med_load, "sm_max_mhz": int(self.samples[0][1][1]),
+                "reasons": sorted(set(reasons_in) | set(reasons_load)), "samples": len(inside),
+                "samples_under_load": len(load), "sm_mhz_under_load": med_load}
 
 
 def cpu_reference_run(steps, warmup, sample_n=128):
@@ -156,21 +176,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(a.warmup):
         ob.time_step(model, dt)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     lib.ob200_profile_reset()
     lib.ob200_profile_enable(1)
     n0 = ob.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record(stream)
     for _ in range(a.steps):
         ob.time_step(model, dt)
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = ob.launch_count() - n0
     lib.ob200_profile_enable(0)
@@ -179,8 +201,6 @@ def main():
         t, c = C.c_double(), C.c_int64()
         lib.ob200_profile_query(ph.encode(), C.byref(t), C.byref(c))
         phases[ph] = {"ms_total": t.value, "count": c.value}
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
     if world > 1:
         tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -207,7 +227,10 @@ def main():
     avg_ms = tend["ms_total"] / max(1, tend["count"])
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "tendency+substep (per prognostic field)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if N == 256 else None,
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean of the 4 tendency "
+                                  "launches of a stage (profiles/r1_summary.md)",
+                "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "avg_launch_ms": avg_ms, "launches": tend["count"],
                 "share_of_step": tend["ms_total"] / ms if ms > 0 else None,
@@ -258,6 +281,8 @@ def main():
                "resident_state": {"value": world * N ** 3 * ksteps / el_res, "d2h_bytes_per_step": 32,
                                   "note": "state stays on the device (how run! uses the architecture); per step a scalar reduction is read back"}}
 
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, spstep, cores, sample = cpu_reference_run(2, 0)
