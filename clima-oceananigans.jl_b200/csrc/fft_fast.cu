@@ -14,6 +14,8 @@
 // passes decimation in time, so spectral data stays in digit-reversed order along y and z and no
 // reordering pass exists; eigenvalue tables are uploaded in that order.
 #include "internal.h"
+#include <cuda.h>
+#include <map>
 #include <vector>
 #include <cmath>
 #include <algorithm>
@@ -484,6 +486,8 @@ __global__ void __launch_bounds__(256) line_kernel(const __grid_constant__ LArgs
     }
 }
 
+#include "fft_tma.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
@@ -500,6 +504,8 @@ struct FastPoisson {
     int* kpos = nullptr;
     double *lamx = nullptr, *lamy = nullptr, *lamz = nullptr;
     std::vector<void*> owned;
+    bool tma_ok = false;                        // persistent TMA-pipelined y / z passes (fft_tma.cuh)
+    CUtensorMap tm_y, tm_z;
 };
 
 namespace cm = ::ob::comm;
@@ -524,6 +530,8 @@ bool fast_poisson_supported(const GridD<FT>& g) {
     for (int d = 0; d < 3; ++d) if (!g.regular[d]) return false;
     return true;
 }
+
+template <class FT> static void setup_tma(FastPoisson<FT>* p);
 
 template <class FT>
 FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
@@ -599,6 +607,7 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
     for (int P = 0; P < p->NyG; ++P) ly[P] = lam(1, freq_of_pos(p->log2[1], P));
     if (p->has_z) for (int P = 0; P < g.N[2]; ++P) lz[P] = lam(2, freq_of_pos(p->log2[2], P));
     p->lamx = up(lx, p->owned); p->lamy = up(ly, p->owned); p->lamz = up(lz, p->owned);
+    setup_tma(p);
     return p;
 }
 template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
@@ -665,9 +674,93 @@ static void launch_line_any(FastPoisson<FT>* p, LArgs<FT>& A, int log2n, int mod
     else launch_line<FT, LM_FWD_DIV_INV>(A, log2n, grd, smem);
 }
 
+// ---- TMA-pipelined y / z passes (fft_tma.cuh) --------------------------------------------------------------
+constexpr int TMA_TK = 8;
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+template <class FT>
+static bool make_spec_map(FastPoisson<FT>* p, bool along_y, CUtensorMap* out) {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) != cudaSuccess || !q) return false;
+        fn = (EncodeFn)q;
+    }
+    const int Ny = p->N[1], Nz = p->N[2];
+    cuuint64_t dims[3] = {(cuuint64_t)2 * p->NXP, (cuuint64_t)Ny, (cuuint64_t)Nz};
+    cuuint64_t strides[2] = {(cuuint64_t)2 * p->NXP * sizeof(FT), (cuuint64_t)2 * p->NXP * Ny * sizeof(FT)};
+    cuuint32_t box[3] = {2 * TMA_TK, (cuuint32_t)(along_y ? Ny : 1), (cuuint32_t)(along_y ? 1 : Nz)};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(out, sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p->spec,
+                    dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+template <class FT>
+static void setup_tma(FastPoisson<FT>* p) {
+    p->tma_ok = false;
+    if (getenv("OB200_NO_FFT_TMA") != nullptr || p->R != 1 || p->NXP % TMA_TK) return;
+    if (p->log2[1] < 4 || p->log2[1] > 8 || (p->has_z && (p->log2[2] < 4 || p->log2[2] > 8))) return;
+    if (!make_spec_map(p, true, &p->tm_y)) return;
+    if (p->has_z && !make_spec_map(p, false, &p->tm_z)) return;
+    p->tma_ok = true;
+}
+
+template <class FT, int MODE, int STAGES>
+static void launch_line_tma(const tl::TArgs<FT>& A, int log2n) {
+    using CT = typename Cx<FT>::T;
+    const int n = 1 << log2n;
+    const size_t smem = (size_t)STAGES * n * TMA_TK * sizeof(CT) + (size_t)n * sizeof(CT);
+    const int threads = std::min(256, std::max(64, TMA_TK * n / 16));
+    auto go = [&](auto kern) {
+        // all instantiations share one function-pointer type: key the per-kernel set-up on the pointer
+        static std::map<const void*, int> occ;
+        int& blocks_per_sm = occ[(const void*)kern];
+        if (!blocks_per_sm) {
+            OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            OB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem));
+            blocks_per_sm = std::max(1, blocks_per_sm);
+        }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = std::min(A.nkx * A.nOther, sms * blocks_per_sm);
+        kern<<<grid, threads, smem, stream()>>>(A);
+        OB_LAUNCH_CHECK();
+    };
+    switch (log2n) {
+        case 4: go(tl::line_tma_kernel<FT, 4, MODE, TMA_TK, STAGES>); break;
+        case 5: go(tl::line_tma_kernel<FT, 5, MODE, TMA_TK, STAGES>); break;
+        case 6: go(tl::line_tma_kernel<FT, 6, MODE, TMA_TK, STAGES>); break;
+        case 7: go(tl::line_tma_kernel<FT, 7, MODE, TMA_TK, STAGES>); break;
+        default: go(tl::line_tma_kernel<FT, 8, MODE, TMA_TK, STAGES>); break;
+    }
+}
+template <class FT>
+static void run_line_tma(FastPoisson<FT>* p, int dim, int mode) {
+    tl::TArgs<FT> A;
+    A.tm = dim == 1 ? p->tm_y : p->tm_z;
+    A.line_is_y = dim == 1;
+    A.nkx = p->NXP / TMA_TK;
+    A.nOther = dim == 1 ? p->N[2] : p->N[1];
+    A.tw = dim == 1 ? p->twY : p->twZ;
+    A.scale = (FT)(1.0 / p->N[dim]);
+    A.lamx = p->lamx;
+    A.lamL = dim == 1 ? p->lamy : p->lamz;
+    A.lamO = dim == 1 ? p->lamz : p->lamy;
+    static const int stages = env_int("OB200_FFT_STAGES", 3);
+    const int l = p->log2[dim];
+#define GO(M)  { if (stages == 2) launch_line_tma<FT, M, 2>(A, l); else launch_line_tma<FT, M, 3>(A, l); }
+    if (mode == LM_FWD) GO(LM_FWD) else if (mode == LM_INV) GO(LM_INV) else GO(LM_FWD_DIV_INV)
+#undef GO
+}
+
 // single-GPU passes on the natural [Nz][Ny][NXP] layout, in place
 template <class FT>
 static void run_line(FastPoisson<FT>* p, int dim, int mode) {
+    if (p->tma_ok) { run_line_tma(p, dim, mode); return; }
     LArgs<FT> A;
     int Ny = p->N[1], Nz = p->N[2];
     A.in = p->spec; A.out = p->spec;
