@@ -208,10 +208,19 @@ struct XArgs {
     FT scale;
 };
 
-// forward x: real line -> half spectrum (natural kx order)
+// two consecutive reals as one aligned vector load / store (interior rows start 32-byte aligned, common.cuh)
+template <class FT> struct Pair;
+template <> struct Pair<double> { using T = double2; };
+template <> struct Pair<float> { using T = float2; };
+
+// forward x: real line -> half spectrum (natural kx order).
+// Thread -> (line t = tid / tpl, lane l = tid % tpl): the row pointers of a thread are fixed and the x loops advance
+// by tpl pairs, so the loops carry no index arithmetic (the first version spent half of its instructions on it:
+// ncu r1g, IMAD + LEA + IADD3 + SHF = 43 % of 75 M warp instructions).
 template <class FT, int LOG2M>
-__global__ void __launch_bounds__(256) x_r2c_kernel(XArgs<FT> A) {
+__global__ void __launch_bounds__(256) x_r2c_kernel(const __grid_constant__ XArgs<FT> A) {
     using CT = typename Cx<FT>::T;
+    using P2 = typename Pair<FT>::T;
     using G = Geo<LOG2M>;
     constexpr int M = 1 << LOG2M;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -221,74 +230,82 @@ __global__ void __launch_bounds__(256) x_r2c_kernel(XArgs<FT> A) {
     const int j0 = blockIdx.x * A.T, k = blockIdx.y;
     const int nl = min(A.T, A.Ny - j0);
     const int Nx = A.Nx;
-    // stage the real source term, two consecutive reals = one complex.  The loads of XU work items are issued
-    // together (ncu r1d: long-scoreboard was the dominant stall with one item in flight per thread).
-    constexpr int XU = 4;
-    for (int w0 = threadIdx.x; w0 < nl * M; w0 += XU * blockDim.x) {
-        FT q[XU][2][6];
-#pragma unroll
-        for (int e = 0; e < XU; ++e) {
-            int w = w0 + e * blockDim.x;
-            if (w < nl * M) {
-                int t = w / M, m = w - t * M;
-                int j = j0 + t;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    int i = 2 * m + h;
-                    if (A.real_in) {
-                        q[e][h][0] = A.real_in[i + (long long)Nx * (j + (long long)A.Ny * k)];
-                    } else {
-                        long long p = (i + 1) * A.st[0] + (j + 1) * A.st[1] + (k + 1) * A.st[2];
-                        q[e][h][0] = A.u[p + A.st[0] - (i + 1 == Nx ? A.wrap[0] : 0)]; q[e][h][1] = A.u[p];
-                        q[e][h][2] = A.v[p + A.st[1] - (j + 1 == A.Ny ? A.wrap[1] : 0)]; q[e][h][3] = A.v[p];
-                        if (A.has_z) { q[e][h][4] = A.w[p + A.st[2] - (k + 1 == A.Nz ? A.wrap[2] : 0)]; q[e][h][5] = A.w[p]; }
-                    }
-                }
+    const int tpl = blockDim.x / A.T, t = threadIdx.x / tpl, l = threadIdx.x - t * tpl;
+    CT* const sl = s + t * G::LS;
+    if (t < nl) {
+        const int j = j0 + t;
+        if (A.real_in) {
+            const FT* row = A.real_in + (long long)Nx * (j + (long long)A.Ny * k);
+            for (int m = l; m < M; m += tpl) {
+                CT c; c.x = row[2 * m]; c.y = row[2 * m + 1];
+                sl[G::pos(m)] = c;
             }
-        }
+        } else {
+            // divᶜᶜᶜ on a regular grid: 1/V (Ax δx u + Ay δy v + Az δz w), then / Δt (solve_for_pressure.jl:15-18);
+            // index N+1 of a Periodic dimension is read as index 1 (A.wrap), so the velocities' halos need not be valid
+            const long long p = A.st[0] + (j + 1) * A.st[1] + (k + 1) * A.st[2];     // Julia (1, j+1, k+1)
+            const FT* u0 = A.u + p;
+            const FT* v0 = A.v + p;
+            const FT* v1 = v0 + A.st[1] - (j + 1 == A.Ny ? A.wrap[1] : 0);
+            const FT* w0 = A.w + p;
+            const FT* w1 = w0 + A.st[2] - (k + 1 == A.Nz ? A.wrap[2] : 0);
+            const FT inv_dt = FT(1) / A.dt;
+            constexpr int XU = 4;
+            for (int mb = l; mb < M; mb += XU * tpl) {
+                P2 ua[XU], va[XU], vb[XU], wa[XU], wb[XU];
+                FT un[XU];
 #pragma unroll
-        for (int e = 0; e < XU; ++e) {
-            int w = w0 + e * blockDim.x;
-            if (w < nl * M) {
-                int t = w / M, m = w - t * M;
-                FT r[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (A.real_in) {
-                        r[h] = q[e][h][0];
-                    } else {
-                        // divᶜᶜᶜ on a regular grid: 1/V (Ax δx u + Ay δy v + Az δz w); kept as in kernels.cu
-                        FT tx = A.ax * q[e][h][0] - A.ax * q[e][h][1];
-                        FT ty = A.ay * q[e][h][2] - A.ay * q[e][h][3];
-                        FT tz = A.has_z ? (A.az * q[e][h][4] - A.az * q[e][h][5]) : FT(0);
-                        r[h] = (A.invV * ((tx + ty) + tz)) / A.dt;
+                for (int e = 0; e < XU; ++e) {
+                    const int m = mb + e * tpl;
+                    if (m < M) {
+                        ua[e] = *reinterpret_cast<const P2*>(u0 + 2 * m);
+                        un[e] = u0[2 * m + 2 - (2 * m + 2 == Nx ? A.wrap[0] : 0)];
+                        va[e] = *reinterpret_cast<const P2*>(v0 + 2 * m);
+                        vb[e] = *reinterpret_cast<const P2*>(v1 + 2 * m);
+                        if (A.has_z) {
+                            wa[e] = *reinterpret_cast<const P2*>(w0 + 2 * m);
+                            wb[e] = *reinterpret_cast<const P2*>(w1 + 2 * m);
+                        }
                     }
                 }
-                CT c; c.x = r[0]; c.y = r[1];
-                s[t * G::LS + G::pos(m)] = c;
+#pragma unroll
+                for (int e = 0; e < XU; ++e) {
+                    const int m = mb + e * tpl;
+                    if (m < M) {
+                        FT tx0 = A.ax * ua[e].y - A.ax * ua[e].x, tx1 = A.ax * un[e] - A.ax * ua[e].y;
+                        FT ty0 = A.ay * vb[e].x - A.ay * va[e].x, ty1 = A.ay * vb[e].y - A.ay * va[e].y;
+                        FT tz0 = FT(0), tz1 = FT(0);
+                        if (A.has_z) { tz0 = A.az * wb[e].x - A.az * wa[e].x; tz1 = A.az * wb[e].y - A.az * wa[e].y; }
+                        CT c;
+                        c.x = (A.invV * ((tx0 + ty0) + tz0)) * inv_dt;
+                        c.y = (A.invV * ((tx1 + ty1) + tz1)) * inv_dt;
+                        sl[G::pos(m)] = c;
+                    }
+                }
             }
         }
     }
     __syncthreads();
     fft_fwd<LOG2M>(s, stw, nl);
     // untangle: X[k] = E[k] + w_N^k O[k], E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / (2i)
-    for (int w = threadIdx.x; w < nl * (M + 1); w += blockDim.x) {
-        int t = w / (M + 1), kk = w - t * (M + 1);
-        const CT* line = s + t * G::LS;
-        CT a = line[G::pos(A.kpos[kk & (M - 1)])];
-        CT b = line[G::pos(A.kpos[(M - kk) & (M - 1)])];
-        CT E, O;
-        E.x = FT(0.5) * (a.x + b.x); E.y = FT(0.5) * (a.y - b.y);
-        O.x = FT(0.5) * (a.y + b.y); O.y = FT(-0.5) * (a.x - b.x);
-        CT X = cadd(E, cmul(O, A.twN[kk]));
-        A.spec[kk + (long long)A.NXP * ((j0 + t) + (long long)A.Ny * k)] = X;
+    if (t < nl) {
+        CT* out = A.spec + (long long)A.NXP * ((j0 + t) + (long long)A.Ny * k);
+        for (int kk = l; kk <= M; kk += tpl) {
+            CT a = sl[G::pos(A.kpos[kk & (M - 1)])];
+            CT b = sl[G::pos(A.kpos[(M - kk) & (M - 1)])];
+            CT E, O;
+            E.x = FT(0.5) * (a.x + b.x); E.y = FT(0.5) * (a.y - b.y);
+            O.x = FT(0.5) * (a.y + b.y); O.y = FT(-0.5) * (a.x - b.x);
+            out[kk] = cadd(E, cmul(O, A.twN[kk]));
+        }
     }
 }
 
 // backward x: half spectrum -> real line, written into the haloed field (+ periodic x halos)
 template <class FT, int LOG2M>
-__global__ void __launch_bounds__(256) x_c2r_kernel(XArgs<FT> A) {
+__global__ void __launch_bounds__(256) x_c2r_kernel(const __grid_constant__ XArgs<FT> A) {
     using CT = typename Cx<FT>::T;
+    using P2 = typename Pair<FT>::T;
     using G = Geo<LOG2M>;
     constexpr int M = 1 << LOG2M;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -297,50 +314,50 @@ __global__ void __launch_bounds__(256) x_c2r_kernel(XArgs<FT> A) {
     for (int w = threadIdx.x; w < M; w += blockDim.x) stw[w] = A.twM[w];
     const int j0 = blockIdx.x * A.T, k = blockIdx.y;
     const int nl = min(A.T, A.Ny - j0);
+    const int tpl = blockDim.x / A.T, t = threadIdx.x / tpl, l = threadIdx.x - t * tpl;
+    CT* const sl = s + t * G::LS;
     // tangle: Z[k] = E[k] + i O[k], E = (X[k] + conj X[M-k]) / 2, O = conj(w_N^k) (X[k] - conj X[M-k]) / 2
-    constexpr int XU = 4;
-    for (int w0 = threadIdx.x; w0 < nl * M; w0 += XU * blockDim.x) {
-        CT av[XU], bv[XU];
+    if (t < nl) {
+        const CT* row = A.spec + (long long)A.NXP * ((j0 + t) + (long long)A.Ny * k);
+        constexpr int XU = 4;
+        for (int kb = l; kb < M; kb += XU * tpl) {
+            CT av[XU], bv[XU];
 #pragma unroll
-        for (int e = 0; e < XU; ++e) {
-            int w = w0 + e * blockDim.x;
-            if (w < nl * M) {
-                int t = w / M, kk = w - t * M;
-                const CT* row = A.spec + (long long)A.NXP * ((j0 + t) + (long long)A.Ny * k);
-                av[e] = row[kk]; bv[e] = row[M - kk];
+            for (int e = 0; e < XU; ++e) {
+                const int kk = kb + e * tpl;
+                if (kk < M) { av[e] = row[kk]; bv[e] = row[M - kk]; }
             }
-        }
 #pragma unroll
-        for (int e = 0; e < XU; ++e) {
-            int w = w0 + e * blockDim.x;
-            if (w < nl * M) {
-                int t = w / M, kk = w - t * M;
-                CT a = av[e], b = bv[e];
-                CT E, D;
-                E.x = FT(0.5) * (a.x + b.x); E.y = FT(0.5) * (a.y - b.y);
-                D.x = FT(0.5) * (a.x - b.x); D.y = FT(0.5) * (a.y + b.y);
-                CT O = cmulc(D, A.twN[kk]);
-                CT Z; Z.x = E.x - O.y; Z.y = E.y + O.x;
-                s[t * G::LS + G::pos(A.kpos[kk])] = Z;
+            for (int e = 0; e < XU; ++e) {
+                const int kk = kb + e * tpl;
+                if (kk < M) {
+                    CT a = av[e], b = bv[e];
+                    CT E, D;
+                    E.x = FT(0.5) * (a.x + b.x); E.y = FT(0.5) * (a.y - b.y);
+                    D.x = FT(0.5) * (a.x - b.x); D.y = FT(0.5) * (a.y + b.y);
+                    CT O = cmulc(D, A.twN[kk]);
+                    CT Z; Z.x = E.x - O.y; Z.y = E.y + O.x;
+                    sl[G::pos(A.kpos[kk])] = Z;
+                }
             }
         }
     }
     __syncthreads();
     fft_inv<LOG2M>(s, stw, nl);
     const int Nx = A.Nx, H = A.Hx;
-    for (int w = threadIdx.x; w < nl * M; w += blockDim.x) {
-        int t = w / M, m = w - t * M;
-        CT z = s[t * G::LS + G::pos(m)];
-        FT r0 = z.x * A.scale, r1 = z.y * A.scale;
-        FT* row = A.phi_p0 + (j0 + t + 1) * A.st[1] + (k + 1) * A.st[2];
-        int i = 2 * m + 1;                       // Julia index of the first of the two reals
-        row[i * A.st[0]] = r0;
-        row[(i + 1) * A.st[0]] = r1;
-        // periodic halos in x (fill_halo_regions_periodic.jl:37-46)
-        if (i > Nx - H) row[(i - Nx) * A.st[0]] = r0;
-        if (i + 1 > Nx - H) row[(i + 1 - Nx) * A.st[0]] = r1;
-        if (i <= H) row[(i + Nx) * A.st[0]] = r0;
-        if (i + 1 <= H) row[(i + 1 + Nx) * A.st[0]] = r1;
+    if (t < nl) {
+        FT* row = A.phi_p0 + (j0 + t + 1) * A.st[1] + (k + 1) * A.st[2];      // Julia (0, j, k)
+        for (int m = l; m < M; m += tpl) {
+            CT z = sl[G::pos(m)];
+            P2 r; r.x = z.x * A.scale; r.y = z.y * A.scale;
+            const int i = 2 * m + 1;                 // Julia index of the first of the two reals
+            *reinterpret_cast<P2*>(row + i) = r;
+            // periodic halos in x (fill_halo_regions_periodic.jl:37-46)
+            if (i > Nx - H) row[i - Nx] = r.x;
+            if (i + 1 > Nx - H) row[i + 1 - Nx] = r.y;
+            if (i <= H) row[i + Nx] = r.x;
+            if (i + 1 <= H) row[i + 1 + Nx] = r.y;
+        }
     }
 }
 

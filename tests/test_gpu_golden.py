@@ -1,0 +1,116 @@
+"""GPU: the CUDA path (through the C ABI) against the committed golden vectors (tests/golden/*.npz) and, at sizes that
+take the SPECIALISED kernels of the headline path (TMA-staged tendency kernels, fast FFT solver, fused periodic
+stage), against the live oracle.  Float64 <= 1e-12, Float32 <= 1e-5 per step (BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from golden_cases import MODEL_CASES, POISSON_CASES, build_model, build_oracle_model, model_initial_values, poisson_rhs
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import ocean_b200 as ob
+    ob.arch = ob.B200()
+    return ob
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("name", list(MODEL_CASES))
+def test_cuda_path_reproduces_golden_model_steps(ob, name):
+    cfg = MODEL_CASES[name]
+    gold = np.load(os.path.join(GOLD, f"model_{name}.npz"))
+    mo = build_oracle_model(O, cfg)                       # only for the seeded initial values
+    vals = model_initial_values(mo, cfg["seed"])
+    mb = build_model(ob, ob.RectilinearGrid(ob.arch, np.float64, **cfg["grid"]), cfg)
+    ob.set_model(mb, **vals)
+    for step in range(cfg["steps"]):
+        ob.time_step(mb, cfg["dt"])
+        if step == 0:
+            for n in mb.names:
+                assert rel(mb.fields[n].interior(), gold[f"step1_{n}"]) < 1e-12, (name, n)
+    for n in mb.names:
+        assert rel(mb.fields[n].interior(), gold[f"final_{n}"]) < 1e-12, (name, n)
+    ke = mb.diagnostics()["kinetic_energy"]
+    assert abs(ke - float(gold["kinetic_energy"])) <= 1e-11 * abs(float(gold["kinetic_energy"]))
+
+
+@pytest.mark.parametrize("name", list(POISSON_CASES))
+def test_cuda_path_reproduces_golden_poisson(ob, name):
+    cfg = POISSON_CASES[name]
+    gold = np.load(os.path.join(GOLD, f"poisson_{name}.npz"))["phi"]
+    go = O.RectilinearGrid(np.float64, **cfg["grid"])
+    gb = ob.RectilinearGrid(ob.arch, np.float64, **cfg["grid"])
+    rhs = poisson_rhs(go, cfg["seed"])
+    phi = ob.CenterField(gb)
+    solver = (ob.FourierTridiagonalPoissonSolver if cfg["solver"] == "ft" else ob.FFTBasedPoissonSolver)(gb)
+    ob.solve(phi, solver, rhs)
+    assert rel(phi.interior(), gold) < 1e-11
+
+
+# ---- the specialised kernels of the headline path, at sizes the oracle finishes in seconds ---------------------
+# (Nx multiple of 32 -> tendency_tma_kernel; power-of-two sizes -> fast FFT + TMA line passes; all Periodic -> fused
+# stage with wrap-around reads and the shell fill).  Ny = 20 and 9 give ragged last tiles in y.
+FAST_CASES = {
+    "rk3_zweno": dict(size=(32, 16, 16), ts="RungeKutta3", zweno=True, f=None, steps=3),
+    "rk3_zweno_ragged": dict(size=(64, 20, 8), ts="RungeKutta3", zweno=True, f=None, steps=2),
+    "ab2_fplane": dict(size=(32, 9, 16), ts="QuasiAdamsBashforth2", zweno=True, f=0.7, steps=3),
+    "rk3_js": dict(size=(32, 8, 32), ts="RungeKutta3", zweno=False, f=None, steps=2),
+}
+
+
+def _fast_pair(ob, cfg, FT):
+    kw = dict(size=cfg["size"], extent=(1.0, 1.5, 0.75), topology=("Periodic",) * 3)
+    go, gb = O.RectilinearGrid(FT, **kw), ob.RectilinearGrid(ob.arch, FT, **kw)
+    mk = lambda M, g: M.NonhydrostaticModel(
+        g, advection=M.WENO5(FT, zweno=cfg["zweno"]), tracers=("b",), buoyancy=M.Buoyancy(M.BuoyancyTracer(), None),
+        coriolis=M.FPlane(cfg["f"]) if cfg["f"] else None, timestepper=cfg["ts"])
+    return mk(O, go), mk(ob, gb)
+
+
+@pytest.mark.parametrize("FT,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+@pytest.mark.parametrize("name", list(FAST_CASES))
+def test_specialised_kernels_match_oracle(ob, name, FT, tol):
+    cfg = FAST_CASES[name]
+    mo, mb = _fast_pair(ob, cfg, FT)
+    vals = {n: v.astype(FT) for n, v in model_initial_values(mo, 77).items()}
+    mo.set(**vals)
+    ob.set_model(mb, **vals)
+    dt = 2e-3
+    for step in range(cfg["steps"]):
+        mo.time_step(dt)
+        ob.time_step(mb, dt)
+        for n in mo.names:
+            assert rel(mb.fields[n].interior(), mo.fields[n].interior) < tol, (name, step, n)
+    # halos after the step are the periodic images (shell fill), bit for bit
+    for n in mo.names:
+        p = mb.fields[n].parent()
+        Nx, Ny, Nz = cfg["size"]
+        H = 3
+        assert np.array_equal(p[:H], p[Nx:Nx + H]) and np.array_equal(p[Nx + H:], p[H:2 * H])
+        assert np.array_equal(p[:, :H], p[:, Ny:Ny + H]) and np.array_equal(p[:, :, Nz + H:], p[:, :, H:2 * H])
+
+
+def test_specialised_and_general_kernels_agree(ob):
+    """same state through the specialised kernels and through the general ones (use_fast_kernels(False))"""
+    cfg = FAST_CASES["rk3_zweno_ragged"]
+    mo, m1 = _fast_pair(ob, cfg, np.float64)
+    _, m2 = _fast_pair(ob, cfg, np.float64)
+    m2.use_fast_kernels(False)
+    vals = model_initial_values(mo, 78)
+    ob.set_model(m1, **vals)
+    ob.set_model(m2, **vals)
+    for _ in range(2):
+        ob.time_step(m1, 2e-3)
+        ob.time_step(m2, 2e-3)
+    for n in m1.names:
+        assert rel(m1.fields[n].interior(), m2.fields[n].interior()) < 1e-13
