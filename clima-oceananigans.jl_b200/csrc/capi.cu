@@ -12,6 +12,7 @@
 #include <vector>
 
 namespace ob {
+namespace comm { bool peer_halo_error(); }
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 static cudaStream_t g_stream = nullptr;
@@ -160,6 +161,7 @@ extern "C" int32_t ob200_sync(void) {
     API_BEGIN
     ensure_device();
     OB_CUDA(cudaStreamSynchronize(stream()));
+    if (ob::comm::peer_halo_error()) throw ob::Error("halo exchange: a neighbour's boundary planes did not arrive (peer-memory flag wait timed out)");
     API_END
 }
 extern "C" size_t ob200_last_error(char* buf, size_t len) {
@@ -786,11 +788,24 @@ static void model_pressure_step(ob200_model* m, FT dt, bool tracers_too = false,
     // fused: the solver reads the predictor velocities and the correction reads pNHS with periodic wrap-around,
     // so neither fill is needed; the correction kernel stores the halo images of u, v, w and pNHS.
     const GridD<FT>& g = gridD<FT>(m->grid);
+    const int dc = fused ? single_comm_dim(g) : -1;      // slab-decomposed dimension of a fused stage, if any
+    auto exchange_one = [&](ob200_field* f, bool need_lo, bool need_hi) {
+        ScopedPhase ph("halo");
+        HaloBatch<FT> hb;
+        hb.n = 1; hb.p0[0] = f->template p0<FT>();
+        for (int d = 0; d < 3; ++d) hb.loc[0][d] = f->loc[d];
+        for (int s = 0; s < 6; ++s) { hb.bc_kind[0][s] = f->bcs[s].kind; hb.bc_val[0][s] = (FT)f->bcs[s].value; }
+        launch_exchange_planes<FT>(g, hb, dc, 1, need_lo, need_hi);
+    };
     if (!fused) { ScopedPhase ph("halo"); model_fill_state_halos<FT>(m, 0, tracers_too ? m->nf : 3); }
+    // the divergence needs the velocity normal to the slab boundary one plane beyond it: the neighbour's first plane
+    else if (dc >= 0) exchange_one(m->F[dc].get(), false, true);
     { ScopedPhase ph("poisson");
       solve_for_pressure_T<FT>(m->solver.get(), m->pNHS.get(), (double)dt, m->F[0].get(), m->F[1].get(), m->F[2].get()); }
     ob200_field* pn = m->pNHS.get();
     if (!fused) { ScopedPhase ph("halo"); fill_halos<FT>(&pn, 1); }
+    // the pressure gradient at the first face of the slab needs the neighbour's last plane of pNHS
+    else if (dc >= 0) exchange_one(pn, true, false);
     ScopedPhase ph("pressure_correct");
     launch_pressure_correct<FT>(g, m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(),
                                 m->F[2]->template p0<FT>(), m->pNHS->template p0<FT>(), dt, fused);

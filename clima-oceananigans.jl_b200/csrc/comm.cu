@@ -5,6 +5,7 @@
 #include "internal.h"
 #include <dlfcn.h>
 #include <cstring>
+#include <vector>
 
 namespace ob {
 namespace comm {
@@ -71,7 +72,9 @@ void init(int nranks, int rank, const char id_bytes[128]) {
     ck(api.CommInitRank(&g_comm, nranks, id, rank), "ncclCommInitRank");
     g_rank = rank; g_size = nranks;
 }
+static void link_release();
 void destroy() {
+    if (g_comm) link_release();
     if (g_comm) { api.CommDestroy(g_comm); g_comm = nullptr; g_size = 1; g_rank = 0; }
 }
 int rank() { return g_rank; }
@@ -98,6 +101,132 @@ void barrier() {
     if (!tok) { OB_CUDA(cudaMalloc(&tok, 8)); OB_CUDA(cudaMemset(tok, 0, 8)); }
     ck(api.AllReduce(tok, tok, 1, ncclFloat64, ncclSum, g_comm, stream()), "ncclAllReduce(barrier)");
     count_launch(1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer-memory halo link (ring neighbours of the slab decomposition).
+// Reference: Distributed/halo_communication.jl:62-183 posts MPI.Isend / Irecv per field and side.  Here every rank
+// owns receive buffers that its two ring neighbours map through CUDA IPC: the pack kernel of the SENDER stores the
+// boundary planes straight into the receiver's buffer over NVLink, a one-thread kernel then publishes an epoch
+// number in the receiver's flag word (system-scope fence + store), and the receiver's unpack kernel is preceded by a
+// one-thread kernel that spins on its own flag words.  No collective call and no host synchronisation is involved;
+// buffers and flags are double-buffered by epoch parity, which makes reuse safe: a rank packs exchange e+2 only
+// after it has unpacked exchange e+1, i.e. after its neighbour packed e+1, which the neighbour did after unpacking e.
+// ---------------------------------------------------------------------------------------------------------------
+struct PeerLink {
+    size_t cap = 0;                       // bytes per (parity, side) buffer
+    unsigned char* block = nullptr;       // mine: [256 B flags][2 parities][2 sides][cap]
+    unsigned char* above = nullptr;       // the same block of the rank above / below (IPC mappings; may coincide)
+    unsigned char* below = nullptr;
+    unsigned long long epoch = 0;
+    int* err = nullptr;                   // device flag: a wait timed out
+};
+static PeerLink g_link;
+static const size_t LINK_HDR = 256;
+
+static void link_release() {
+    PeerLink& L = g_link;
+    if (!L.block) return;
+    cudaStreamSynchronize(stream());
+    barrier();
+    cudaStreamSynchronize(stream());
+    if (L.above && L.above != L.block) cudaIpcCloseMemHandle(L.above);
+    if (L.below && L.below != L.block && L.below != L.above) cudaIpcCloseMemHandle(L.below);
+    cudaFree(L.block);
+    L.block = L.above = L.below = nullptr;
+    L.cap = 0;
+}
+
+// collective: every rank calls it with the same size
+void peer_halo_prepare(size_t bytes_per_side) {
+    PeerLink& L = g_link;
+    if (!active()) throw Error("peer halo link without an initialised communicator");
+    if (bytes_per_side <= L.cap) return;
+    link_release();
+    size_t cap = ((bytes_per_side * 5 / 4 + 4095) / 4096) * 4096;       // head room: the field list may grow
+    size_t total = LINK_HDR + 4 * cap;
+    OB_CUDA(cudaMalloc(&L.block, total));
+    OB_CUDA(cudaMemsetAsync(L.block, 0, LINK_HDR, stream()));
+    if (!L.err) { OB_CUDA(cudaMalloc(&L.err, sizeof(int))); OB_CUDA(cudaMemsetAsync(L.err, 0, sizeof(int), stream())); }
+    cudaIpcMemHandle_t mine;
+    OB_CUDA(cudaIpcGetMemHandle(&mine, L.block));
+    cudaIpcMemHandle_t *dsend, *drecv;
+    OB_CUDA(cudaMalloc(&dsend, sizeof(mine)));
+    OB_CUDA(cudaMalloc(&drecv, sizeof(mine) * g_size));
+    OB_CUDA(cudaMemcpyAsync(dsend, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream()));
+    allgather_bytes(dsend, drecv, sizeof(mine));
+    std::vector<cudaIpcMemHandle_t> all(g_size);
+    OB_CUDA(cudaMemcpyAsync(all.data(), drecv, sizeof(mine) * g_size, cudaMemcpyDeviceToHost, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    cudaFree(dsend); cudaFree(drecv);
+    const int up = (g_rank + 1) % g_size, dn = (g_rank - 1 + g_size) % g_size;
+    auto open = [&](int r) -> unsigned char* {
+        if (r == g_rank) return L.block;
+        void* q = nullptr;
+        OB_CUDA(cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess));
+        return (unsigned char*)q;
+    };
+    L.above = open(up);
+    L.below = dn == up ? L.above : open(dn);
+    L.cap = cap;
+    L.epoch = 0;
+    barrier();                 // every rank has zeroed its flags before anybody publishes
+    OB_CUDA(cudaStreamSynchronize(stream()));
+}
+
+static unsigned char* link_buf(unsigned char* block, size_t cap, int parity, int side) {
+    return block + LINK_HDR + (size_t)(2 * parity + side) * cap;
+}
+static unsigned long long* link_flag(unsigned char* block, int parity, int side) {
+    return reinterpret_cast<unsigned long long*>(block) + (2 * parity + side);
+}
+
+__global__ void link_signal_kernel(unsigned long long* f0, unsigned long long* f1, unsigned long long epoch) {
+    __threadfence_system();
+    unsigned long long* f = threadIdx.x == 0 ? f0 : f1;
+    if (f) *reinterpret_cast<volatile unsigned long long*>(f) = epoch;
+}
+__global__ void link_wait_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long epoch, int* err) {
+    const volatile unsigned long long* f = threadIdx.x == 0 ? f0 : f1;
+    if (f) {
+        long long spins = 0;
+        while (*f < epoch) {
+            __nanosleep(64);
+            if (++spins > 40000000LL) { *err = 1; break; }      // a few seconds: report instead of hanging the GPU
+        }
+    }
+    __threadfence_system();
+}
+
+// side 0 = low halo, 1 = high halo.  begin(): next epoch; send_ptr(side): where MY boundary planes for the neighbour's
+// halo `side` go (side 1: my bottom planes -> the rank below's high halo; side 0: my top planes -> the rank above's low halo);
+// recv_ptr(side): my own buffer for my halo `side`.
+void peer_halo_begin() { g_link.epoch += 1; }
+void* peer_halo_send_ptr(int side) {
+    PeerLink& L = g_link;
+    return link_buf(side == 1 ? L.below : L.above, L.cap, (int)(L.epoch & 1), side);
+}
+void* peer_halo_recv_ptr(int side) {
+    PeerLink& L = g_link;
+    return link_buf(L.block, L.cap, (int)(L.epoch & 1), side);
+}
+void peer_halo_signal(bool lo, bool hi) {
+    PeerLink& L = g_link;
+    const int par = (int)(L.epoch & 1);
+    link_signal_kernel<<<1, 2, 0, stream()>>>(lo ? link_flag(L.above, par, 0) : nullptr, hi ? link_flag(L.below, par, 1) : nullptr, L.epoch);
+    count_launch(1);
+}
+void peer_halo_wait(bool lo, bool hi) {
+    PeerLink& L = g_link;
+    const int par = (int)(L.epoch & 1);
+    link_wait_kernel<<<1, 2, 0, stream()>>>(lo ? link_flag(L.block, par, 0) : nullptr, hi ? link_flag(L.block, par, 1) : nullptr, L.epoch, L.err);
+    count_launch(1);
+}
+bool peer_halo_error() {
+    if (!g_link.err) return false;
+    int e = 0;
+    cudaMemcpy(&e, g_link.err, sizeof(int), cudaMemcpyDeviceToHost);
+    return e != 0;
 }
 }  // namespace comm
 }  // namespace ob

@@ -17,6 +17,11 @@ struct HaloBatch {
     FT bc_val[MAXF][6];
 };
 template <class FT> void launch_fill_halos(const GridD<FT>& g, const HaloBatch<FT>& hb);
+// slab-decomposed dimension d: exchange `np` boundary planes (interior extent of the other dimensions) with the ring
+// neighbours through peer memory; need_lo / need_hi select which of this rank's halos are filled
+template <class FT>
+void launch_exchange_planes(const GridD<FT>& g, const HaloBatch<FT>& hb, int d, int np, bool need_lo, bool need_hi);
+template <class FT> int single_comm_dim(const GridD<FT>& g);
 
 // substep modes for the fused tendency kernels
 enum { SUB_NONE = 0, SUB_RK3_FIRST = 1, SUB_RK3 = 2, SUB_AB2 = 3 };

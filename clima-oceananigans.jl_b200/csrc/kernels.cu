@@ -1,6 +1,7 @@
 // kernels.cu -- halo fills, general tendency(+substep), pressure rhs / correction, hydrostatic
 // pressure, layout conversion and reductions.  sm_100a.
 #include "internal.h"
+#include <algorithm>
 #include <cstdlib>
 
 namespace ob {
@@ -51,55 +52,86 @@ __global__ void fill_halo_kernel(GridD<FT> g, HaloBatch<FT> hb, int d, int a, in
     }
 }
 
-// ---- all non-Flat dimensions Periodic: ONE launch for all dimensions and all fields ---------------------------
+// ---- all non-Flat dimensions Periodic (or slab-decomposed): ONE launch for all dimensions and all fields --------
 // Applying the periodic copies x, then y, then z (fill_halo_regions_periodic.jl:15-105) gives every halo cell --
 // edges and corners included -- the value of the interior cell obtained by wrapping each of its indices.  The
-// shell kernel writes exactly that, reading interior cells only, so there is no ordering between dimensions.
-// The halo shell is enumerated as three groups: z-halo levels over the full (x, y) extent, y-halo rows of the
-// interior levels over the full x extent, x-halo cells of the interior rows.
+// shell kernel writes exactly that, reading cells that no thread of the launch writes, so there is no ordering
+// between dimensions.  The shell is enumerated as up to three groups, one per Periodic dimension D (z, y, x in
+// that order): index along D in the 2H halo planes; the dimensions enumerated before D over their interior (their
+// halo cells belong to the earlier group), the others over their full extent.  A slab-decomposed (FullyConnected)
+// dimension has no group of its own -- its halos come from the neighbour exchange, done BEFORE this launch on the
+// interior extent of the other dimensions -- but it is always walked over its full extent and never wrapped, so
+// the corner cells pick up the exchanged values.
+struct ShellGroup { int D, lo[3], n[3]; long long count; };
+struct ShellPlan { ShellGroup g[3]; int ng; long long total; };
+
 template <class FT>
-__global__ void __launch_bounds__(256) fill_halo_shell_kernel(GridD<FT> g, HaloBatch<FT> hb, long long nZ, long long nY,
-                                                               long long nX) {
+__global__ void __launch_bounds__(256) fill_halo_shell_kernel(GridD<FT> g, HaloBatch<FT> hb, ShellPlan P) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2], Hx = g.H[0], Hy = g.H[1], Hz = g.H[2];
-    const int Ex = Nx + 2 * Hx, Ey = Ny + 2 * Hy;       // full extents (Flat: N = 1, H = 0)
-    int i, j, k;
-    if (t < nZ) {                       // (i over Ex, j over Ey, 2 Hz levels)
-        int r = (int)(t / Ex); i = (int)(t - (long long)r * Ex) + 1 - Hx;
-        int l = r / Ey; j = r - l * Ey + 1 - Hy;
-        k = l < Hz ? l + 1 - Hz : Nz + 1 + (l - Hz);
-    } else if (t < nZ + nY) {           // (i over Ex, 2 Hy rows, k interior)
-        t -= nZ;
-        int r = (int)(t / Ex); i = (int)(t - (long long)r * Ex) + 1 - Hx;
-        int l = r % (2 * Hy); k = r / (2 * Hy) + 1;
-        j = l < Hy ? l + 1 - Hy : Ny + 1 + (l - Hy);
-    } else if (t < nZ + nY + nX) {      // (2 Hx cells, j interior, k interior)
-        t -= nZ + nY;
-        int r = (int)(t / (2 * Hx)); int l = (int)(t - (long long)r * (2 * Hx));
-        k = r / Ny + 1; j = r - (k - 1) * Ny + 1;
-        i = l < Hx ? l + 1 - Hx : Nx + 1 + (l - Hx);
-    } else return;
-    const int si = i < 1 ? i + Nx : (i > Nx ? i - Nx : i);
-    const int sj = j < 1 ? j + Ny : (j > Ny ? j - Ny : j);
-    const int sk = k < 1 ? k + Nz : (k > Nz ? k - Nz : k);
-    const long long dst = i * g.st[0] + j * g.st[1] + k * g.st[2], src = si * g.st[0] + sj * g.st[1] + sk * g.st[2];
+    if (t >= P.total) return;
+    int q = 0;
+    while (q + 1 < P.ng && t >= P.g[q].count) { t -= P.g[q].count; ++q; }
+    const ShellGroup& G = P.g[q];
+    int id[3];
+    {   // x fastest
+        long long r = t / G.n[0];
+        id[0] = (int)(t - r * G.n[0]);
+        long long r2 = r / G.n[1];
+        id[1] = (int)(r - r2 * G.n[1]);
+        id[2] = (int)r2;
+    }
+    long long dst = 0, src = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int v;
+        if (d == G.D) v = id[d] < g.H[d] ? id[d] + 1 - g.H[d] : g.N[d] + 1 + (id[d] - g.H[d]);
+        else v = G.lo[d] + id[d];
+        int sv = v;
+        if (g.topo[d] == OB_PERIODIC) sv = v < 1 ? v + g.N[d] : (v > g.N[d] ? v - g.N[d] : v);
+        dst += v * g.st[d];
+        src += sv * g.st[d];
+    }
     FT v[MAXF];
 #pragma unroll
     for (int n = 0; n < MAXF; ++n) if (n < hb.n) v[n] = hb.p0[n][src];
 #pragma unroll
     for (int n = 0; n < MAXF; ++n) if (n < hb.n) hb.p0[n][dst] = v[n];
 }
+// `with_comm`: a FullyConnected dimension is allowed (the caller exchanges it first)
 template <class FT>
-static bool shell_fill_supported(const GridD<FT>& g) {
+static bool shell_fill_supported(const GridD<FT>& g, bool with_comm) {
     static const bool off = getenv("OB200_NO_SHELL_FILL") != nullptr;
     if (off) return false;
     bool any = false;
     for (int d = 0; d < 3; ++d) {
         if (g.topo[d] == OB_FLAT) continue;
+        if (g.topo[d] == OB_COMM) { if (!with_comm) return false; continue; }
         if (g.topo[d] != OB_PERIODIC || g.H[d] < 1 || g.N[d] < g.H[d]) return false;
         any = true;
     }
     return any;
+}
+template <class FT>
+static void launch_shell(const GridD<FT>& g, const HaloBatch<FT>& hb) {
+    ShellPlan P{};
+    bool done[3] = {false, false, false};
+    for (int D = 2; D >= 0; --D) {
+        if (g.topo[D] != OB_PERIODIC) continue;
+        ShellGroup& G = P.g[P.ng++];
+        G.D = D;
+        G.count = 1;
+        for (int d = 0; d < 3; ++d) {
+            if (d == D) { G.lo[d] = 0; G.n[d] = 2 * g.H[d]; }
+            else if (g.topo[d] == OB_FLAT || (g.topo[d] == OB_PERIODIC && done[d])) { G.lo[d] = 1; G.n[d] = g.N[d]; }
+            else { G.lo[d] = 1 - g.H[d]; G.n[d] = g.N[d] + 2 * g.H[d]; }
+            G.count *= G.n[d];
+        }
+        done[D] = true;
+        P.total += G.count;
+    }
+    if (P.total == 0) return;
+    fill_halo_shell_kernel<FT><<<cdiv(P.total, 256), 256, 0, stream()>>>(g, hb, P);
+    OB_LAUNCH_CHECK();
 }
 
 // ---- halo exchange for a FullyConnected (slab-decomposed) dimension ---------------------------
@@ -170,14 +202,82 @@ static void exchange_halos(const GridD<FT>& g, const HaloBatch<FT>& hb, int d) {
     OB_LAUNCH_CHECK();
 }
 
+// ---- the same exchange through peer memory (comm.cu: PeerLink) ------------------------------------------------
+// The pack kernel stores the boundary planes straight into the neighbour's receive buffer over NVLink; flag words
+// published / awaited by one-thread kernels order it with the neighbour's unpack.  `np` planes per side (np <= H);
+// need_lo / need_hi: which of MY halos must be filled (every rank passes the same values, so need_hi means that
+// every rank sends its bottom planes down).  The planes span the INTERIOR of the other dimensions: their halos are
+// either not needed (wrap-around readers) or written afterwards by the shell fill.
+namespace comm {
+void peer_halo_prepare(size_t); void peer_halo_begin();
+void* peer_halo_send_ptr(int); void* peer_halo_recv_ptr(int);
+void peer_halo_signal(bool, bool); void peer_halo_wait(bool, bool);
+}
+template <class FT, bool PACK>
+__global__ void halo_planes_kernel(GridD<FT> g, HaloBatch<FT> hb, int d, int a, int b, int nA, int nB, int np,
+                                   FT* buf_lo, FT* buf_hi) {
+    int ia = blockIdx.x * blockDim.x + threadIdx.x;
+    int ib = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ia >= nA || ib >= nB) return;
+    long long base = (1 + ia) * g.st[a] + (1 + ib) * g.st[b];
+    long long s = g.st[d];
+    int N = g.N[d];
+    for (int n = 0; n < hb.n; ++n) {
+        FT* f = hb.p0[n] + base;
+        for (int h = 0; h < np; ++h) {
+            long long q = (((long long)n * np + h) * nB + ib) * nA + ia;
+            if (PACK) {
+                if (buf_hi) buf_hi[q] = f[(1 + h) * s];              // my planes 1..np      -> the rank below's high halo
+                if (buf_lo) buf_lo[q] = f[(N - np + 1 + h) * s];     // my planes N-np+1..N  -> the rank above's low halo
+            } else {
+                if (buf_lo) f[(1 - np + h) * s] = buf_lo[q];         // low halo  <- planes N-np+1..N of the rank below
+                if (buf_hi) f[(N + 1 + h) * s] = buf_hi[q];          // high halo <- planes 1..np of the rank above
+            }
+        }
+    }
+}
+static bool peer_halo_enabled() {
+    static const bool off = getenv("OB200_NO_PEER_HALO") != nullptr;
+    return !off && comm::active();
+}
+template <class FT>
+void launch_exchange_planes(const GridD<FT>& g, const HaloBatch<FT>& hb, int d, int np, bool need_lo, bool need_hi) {
+    if (hb.n == 0 || (!need_lo && !need_hi)) return;
+    int a = d == 0 ? 1 : 0, b = d == 2 ? 1 : 2;
+    int nA = g.N[a], nB = g.N[b];
+    size_t bytes = (size_t)hb.n * np * nA * nB * sizeof(FT);
+    // capacity for the largest exchange of this grid (MAXF fields, H planes) so that the link is set up once
+    comm::peer_halo_prepare(std::max(bytes, (size_t)MAXF * g.H[d] * nA * nB * sizeof(FT)));
+    comm::peer_halo_begin();
+    dim3 blk(a == 0 ? 64 : 16, a == 0 ? 4 : 16), grd(cdiv(nA, blk.x), cdiv(nB, blk.y));
+    halo_planes_kernel<FT, true><<<grd, blk, 0, stream()>>>(g, hb, d, a, b, nA, nB, np,
+        need_lo ? (FT*)comm::peer_halo_send_ptr(0) : nullptr, need_hi ? (FT*)comm::peer_halo_send_ptr(1) : nullptr);
+    OB_LAUNCH_CHECK();
+    comm::peer_halo_signal(need_lo, need_hi);
+    comm::peer_halo_wait(need_lo, need_hi);
+    halo_planes_kernel<FT, false><<<grd, blk, 0, stream()>>>(g, hb, d, a, b, nA, nB, np,
+        need_lo ? (FT*)comm::peer_halo_recv_ptr(0) : nullptr, need_hi ? (FT*)comm::peer_halo_recv_ptr(1) : nullptr);
+    OB_LAUNCH_CHECK();
+}
+template void launch_exchange_planes<float>(const GridD<float>&, const HaloBatch<float>&, int, int, bool, bool);
+template void launch_exchange_planes<double>(const GridD<double>&, const HaloBatch<double>&, int, int, bool, bool);
+template <class FT>
+int single_comm_dim(const GridD<FT>& g) {       // the slab-decomposed dimension if there is exactly one, else -1
+    int dc = -1;
+    for (int d = 0; d < 3; ++d) if (g.topo[d] == OB_COMM) { if (dc >= 0) return -1; dc = d; }
+    return dc;
+}
+template int single_comm_dim<float>(const GridD<float>&);
+template int single_comm_dim<double>(const GridD<double>&);
+
 template <class FT>
 void launch_fill_halos(const GridD<FT>& g, const HaloBatch<FT>& hb) {
     if (hb.n == 0) return;
-    if (shell_fill_supported(g)) {
-        const long long Ex = g.N[0] + 2 * g.H[0], Ey = g.N[1] + 2 * g.H[1];
-        const long long nZ = Ex * Ey * 2 * g.H[2], nY = Ex * 2 * g.H[1] * g.N[2], nX = 2LL * g.H[0] * g.N[1] * g.N[2];
-        fill_halo_shell_kernel<FT><<<cdiv(nZ + nY + nX, 256), 256, 0, stream()>>>(g, hb, nZ, nY, nX);
-        OB_LAUNCH_CHECK();
+    if (shell_fill_supported(g, false)) { launch_shell<FT>(g, hb); return; }
+    const int dc = single_comm_dim(g);
+    if (dc >= 0 && peer_halo_enabled() && shell_fill_supported(g, true) && g.N[dc] >= g.H[dc]) {
+        launch_exchange_planes<FT>(g, hb, dc, g.H[dc], true, true);
+        launch_shell<FT>(g, hb);
         return;
     }
     // non-periodic first, then periodic / connected dimensions in x, y, z order (fill_halo_regions.jl:56-102)
@@ -352,7 +452,8 @@ __global__ void __launch_bounds__(256) pressure_correct_periodic_kernel(GridD<FT
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         if (g.topo[d] == OB_FLAT) { U[d][q] -= (FT(0) / g.d[d]) * dt; continue; }
-        const long long qm = q - g.st[d] + (id[d] == 1 ? (long long)g.N[d] * g.st[d] : 0);
+        // Periodic: wrap; slab-decomposed: the low halo plane (exchanged by the caller)
+        const long long qm = q - g.st[d] + (id[d] == 1 && g.topo[d] == OB_PERIODIC ? (long long)g.N[d] * g.st[d] : 0);
         U[d][q] -= ((pc - p[qm]) / g.d[d]) * dt;
     }
 }
@@ -361,6 +462,10 @@ bool periodic_wrap_supported(const GridD<FT>& g) {
     bool any = false;
     for (int d = 0; d < 3; ++d) {
         if (g.topo[d] == OB_FLAT) continue;
+        if (g.topo[d] == OB_COMM) {       // one slab-decomposed dimension, exchanged through peer memory
+            if (single_comm_dim(g) != d || !peer_halo_enabled() || !g.regular[d] || g.N[d] < 2 * g.H[d]) return false;
+            continue;
+        }
         if (g.topo[d] != OB_PERIODIC || !g.regular[d] || g.N[d] < 2 * g.H[d]) return false;
         any = true;
     }
