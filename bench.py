@@ -197,10 +197,12 @@ def main():
     launches = ob.launch_count() - n0
     lib.ob200_profile_enable(0)
     phases = {}
-    for ph in ("tendency", "poisson", "halo", "pressure_correct", "hydrostatic"):
+    fft_names = ("fft_x_fwd", "fft_y", "fft_z", "fft_z_fwd", "fft_z_inv", "fft_sync", "fft_x_inv")
+    for ph in ("tendency", "poisson", "halo", "pressure_correct", "hydrostatic") + fft_names:
         t, c = C.c_double(), C.c_int64()
         lib.ob200_profile_query(ph.encode(), C.byref(t), C.byref(c))
         phases[ph] = {"ms_total": t.value, "count": c.value}
+    fft_phases = {k: phases.pop(k) for k in fft_names}
     if world > 1:
         tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -237,7 +239,8 @@ def main():
                 "whole_step": {"algorithmic_GB_per_step": 880.0 * N ** 3 / 1e9,
                                "achieved_GBps": 880.0 * N ** 3 * a.steps / (ms * 1e-3) / 1e9,
                                "frac": 880.0 * N ** 3 * a.steps / (ms * 1e-3) / 1e9 / peak},
-                "phases_ms_per_step": {k: v["ms_total"] / a.steps for k, v in phases.items()}}
+                "phases_ms_per_step": {k: v["ms_total"] / a.steps for k, v in phases.items()},
+                "poisson_ms_per_step": {k: v["ms_total"] / a.steps for k, v in fft_phases.items() if v["count"]}}
 
     # ---- e2e: host buffers in, host buffers out, every step (pinned; copies inside the timed region) ----
     e2e = None

@@ -61,6 +61,8 @@ struct ScopedPhase {
         ph->pending.emplace_back(a, b);
     }
 };
+PhaseScope::PhaseScope(const char* name) : impl(g_profile ? new ScopedPhase(name) : nullptr) {}
+PhaseScope::~PhaseScope() { delete static_cast<ScopedPhase*>(impl); }
 static void resolve_phases() {
     cudaStreamSynchronize(g_stream);
     for (auto& kv : g_phases) {

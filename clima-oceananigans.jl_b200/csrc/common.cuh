@@ -47,6 +47,14 @@ struct Error : std::runtime_error {
 
 void count_launch(int n = 1);
 cudaStream_t stream();
+// CUDA-event phase timer (capi.cu: ob200_profile_*); a no-op unless profiling is enabled
+struct PhaseScope {
+    void* impl;
+    explicit PhaseScope(const char* name);
+    ~PhaseScope();
+    PhaseScope(const PhaseScope&) = delete;
+    PhaseScope& operator=(const PhaseScope&) = delete;
+};
 
 #define OB_CUDA(x)                                                                        \
     do {                                                                                  \

@@ -832,8 +832,8 @@ static void distributed_middle(FastPoisson<FT>* p) {
     }
     A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;
     A.tw = p->twZ; A.lamL = p->lamz; A.lamO = nullptr;
-    launch_line_any(p, A, p->log2[2], LM_FWD);
-    if (p->p2p) cm::barrier(); else all_to_all(p, p->bufA, p->bufB);
+    { PhaseScope ph("fft_z_fwd"); launch_line_any(p, A, p->log2[2], LM_FWD); }
+    { PhaseScope ph("fft_sync"); if (p->p2p) cm::barrier(); else all_to_all(p, p->bufA, p->bufB); }
     A.in = p->bufB; A.out = p->bufB; A.lin = A.lout = gy;
     if (p->p2p) {      // transposed back on the fly: the part of the line that came from rank s returns to rank s's bufA
         A.out = p->bufA;
@@ -842,13 +842,13 @@ static void distributed_middle(FastPoisson<FT>* p) {
     }
     A.NXH = KXB; A.kx0 = p->rank * KXB; A.n = p->NyG; A.line_is_y = 1; A.nOther = Nz;
     A.tw = p->twY; A.lamL = p->lamy; A.lamO = p->lamz;
-    launch_line_any(p, A, p->log2[1], LM_FWD_DIV_INV);
-    if (p->p2p) cm::barrier(); else all_to_all(p, p->bufB, p->bufA);
+    { PhaseScope ph("fft_y"); launch_line_any(p, A, p->log2[1], LM_FWD_DIV_INV); }
+    { PhaseScope ph("fft_sync"); if (p->p2p) cm::barrier(); else all_to_all(p, p->bufB, p->bufA); }
     // backward z: chunk layout -> natural
     A.in = p->bufA; A.out = p->spec; A.lin = blk; A.lout = nat;
     A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;
     A.tw = p->twZ; A.lamL = p->lamz; A.lamO = nullptr;
-    launch_line_any(p, A, p->log2[2], LM_INV);
+    { PhaseScope ph("fft_z_inv"); launch_line_any(p, A, p->log2[2], LM_INV); }
 }
 
 template <class FT, bool FWD>
@@ -893,17 +893,18 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
     A.dt = dt;
     A.has_z = p->has_z;
     A.phi_p0 = phi_p0; A.Hx = g.H[0];
-    run_x<FT, true>(p, A);
+    { PhaseScope ph("fft_x_fwd"); run_x<FT, true>(p, A); }
     if (p->R > 1) {
         distributed_middle(p);
     } else if (p->has_z) {
-        run_line(p, 1, LM_FWD);
-        run_line(p, 2, LM_FWD_DIV_INV);
-        run_line(p, 1, LM_INV);
+        { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
+        { PhaseScope ph("fft_z"); run_line(p, 2, LM_FWD_DIV_INV); }
+        { PhaseScope ph("fft_y"); run_line(p, 1, LM_INV); }
     } else {
+        PhaseScope ph("fft_y");
         run_line(p, 1, LM_FWD_DIV_INV);
     }
-    run_x<FT, false>(p, A);
+    { PhaseScope ph("fft_x_inv"); run_x<FT, false>(p, A); }
 }
 
 #define INST(FT)                                                                                   \

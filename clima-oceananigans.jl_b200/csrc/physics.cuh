@@ -116,6 +116,34 @@ OBD FT weno5_core(int side, int zweno, FT a, FT b, FT c, FT d, FT e, const FT* c
         s2 = (3 * a - 4 * b) + c;       // psi2: 3ψ1 - 4ψ2 + ψ3
         C0 = FT(1.0 / 10.0); C1 = FT(3.0 / 5.0); C2 = FT(3.0 / 10.0);
     }
+    FT p0 = (cf[0] * c + cf[1] * d) + cf[2] * e;
+    FT p1 = (cf[3] * b + cf[4] * c) + cf[5] * d;
+    FT p2 = (cf[6] * a + cf[7] * b) + cf[8] * c;
+#ifndef OB200_STRICT
+    if constexpr (sizeof(FT) == 8) {
+        // Same rational function with ONE reciprocal instead of six divisions (see weno_fast.cuh):
+        // sum_k w_k p_k = (sum_k g_k p_k) / (sum_k g_k), g_k = C_k (E_k + tau^2) prod_{j != k} E_j, E_k = (beta_k + eps)^2,
+        // evaluated with 4 beta and 4 eps (everything is homogeneous in beta); differences ~1e-16 relative.
+        const FT k133 = FT(13.0 / 3.0), eps4 = FT(4.0e-6);
+        FT B0 = fma(s0, s0, k133 * (t0 * t0)), B1 = fma(s1, s1, k133 * (t1 * t1)), B2 = fma(s2, s2, k133 * (t2 * t2));
+        FT D0 = B0 + eps4, D1 = B1 + eps4, D2 = B2 + eps4;
+        FT E0 = D0 * D0, E1 = D1 * D1, E2 = D2 * D2;
+        FT P12 = E1 * E2, P02 = E0 * E2, P01 = E0 * E1;
+        FT g0, g1, g2;
+        if (zweno) {
+            FT tau = B2 - B0, tt = tau * tau, PI = E0 * P12;
+            g0 = C0 * fma(tt, P12, PI); g1 = C1 * fma(tt, P02, PI); g2 = C2 * fma(tt, P01, PI);
+        } else {
+            g0 = C0 * P12; g1 = C1 * P02; g2 = C2 * P01;
+        }
+        FT den = (g0 + g1) + g2;
+        FT num = fma(g0, p0, fma(g1, p1, g2 * p2));
+        double r0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"((double)den));
+        double er = fma(-(double)den, r0, 1.0), q0 = (double)num * r0;
+        return (FT)fma(q0, fma(er, er, er), q0);
+    }
+#endif
     FT b0 = c1312 * (t0 * t0) + c14 * (s0 * s0);
     FT b1 = c1312 * (t1 * t1) + c14 * (s1 * s1);
     FT b2 = c1312 * (t2 * t2) + c14 * (s2 * s2);
@@ -135,9 +163,6 @@ OBD FT weno5_core(int side, int zweno, FT a, FT b, FT c, FT d, FT e, const FT* c
     }
     FT sa = (a0 + a1) + a2;
     FT w0 = a0 / sa, w1 = a1 / sa, w2 = a2 / sa;
-    FT p0 = (cf[0] * c + cf[1] * d) + cf[2] * e;
-    FT p1 = (cf[3] * b + cf[4] * c) + cf[5] * d;
-    FT p2 = (cf[6] * a + cf[7] * b) + cf[8] * c;
     return (w0 * p0 + w1 * p1) + w2 * p2;
 }
 
@@ -254,9 +279,15 @@ OBD FT momentum_flux(const Phys<FT>& P, int A, int B, const FT* Ua, const FT* ps
     FT Ar = areaA(g, A, q, fl[0], fl[1], fl[2]);
     FT ut = sym_c(P, Ua, q, ud, ul);
     if (P.scheme >= ADV_U1) {          // upwind_biased_advective_fluxes.jl:18-97
+#ifdef OB200_STRICT
         FT L = biased_c(P, SIDE_LEFT, psi, q, A, pl);
         FT R = biased_c(P, SIDE_RIGHT, psi, q, A, pl);
         return Ar * upwind_product(ut, L, R);
+#else
+        // ((u + |u|) L + (u - |u|) R) / 2 is EXACTLY u L for u > 0 and u R otherwise (one coefficient is 0, the
+        // other 2u): only the upwind side is reconstructed, chosen per thread (no divergence: `side` is data)
+        return Ar * (ut * biased_c(P, ut > FT(0) ? SIDE_LEFT : SIDE_RIGHT, psi, q, A, pl));
+#endif
     }
     return (Ar * ut) * sym_c(P, psi, q, A, pl);     // centered_advective_fluxes.jl:15-27
 }
@@ -269,9 +300,14 @@ OBD FT tracer_flux(const Phys<FT>& P, int A, const FT* Ua, const FT* c, Pt q) {
     FT Ar = areaA(g, A, q, fl[0], fl[1], fl[2]);
     if (P.scheme == ADV_C2) return (Ar * Ua[q.p]) * IF(g, c, q, A);
     if (P.scheme >= ADV_U1) {          // :103-128
+#ifdef OB200_STRICT
         FT L = biased_c(P, SIDE_LEFT, c, q, A, OB_F);
         FT R = biased_c(P, SIDE_RIGHT, c, q, A, OB_F);
         return Ar * upwind_product(Ua[q.p], L, R);
+#else
+        const FT ua = Ua[q.p];
+        return Ar * (ua * biased_c(P, ua > FT(0) ? SIDE_LEFT : SIDE_RIGHT, c, q, A, OB_F));
+#endif
     }
     return (Ar * Ua[q.p]) * sym_c(P, c, q, A, OB_F);
 }
