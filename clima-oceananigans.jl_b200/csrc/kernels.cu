@@ -322,8 +322,10 @@ struct TendArgs {
     int comp;
 };
 
-template <class FT>
-__global__ void __launch_bounds__(128) tendency_general_kernel(Phys<FT> P, TendArgs<FT> A) {
+// COMP (0, 1, 2 = u, v, w; 3 = any tracer) is a template parameter so that the staggering flags of every operator in
+// the inlined call tree (locations, which spacings and areas, which directions interpolate) are compile-time constants
+template <class FT, int COMP>
+__global__ void __launch_bounds__(128) tendency_general_kernel(const __grid_constant__ Phys<FT> P, const __grid_constant__ TendArgs<FT> A) {
     const GridD<FT>& g = P.g;
     int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -333,10 +335,10 @@ __global__ void __launch_bounds__(128) tendency_general_kernel(Phys<FT> P, TendA
     q.i[0] = i; q.i[1] = j; q.i[2] = k;
     q.p = i * g.st[0] + j * g.st[1] + k * g.st[2];
     const FT* U[3] = {A.U[0], A.U[1], A.U[2]};
-    FT G = tendency(P, A.comp, U, A.psi, A.pHY, A.b, q);
+    FT G = tendency(P, COMP == 3 ? A.comp : COMP, U, A.psi, A.pHY, A.b, q);
     // apply_x/y/z_bcs! (apply_flux_bcs.jl:35-160): constant Flux BCs of this field
     int l[3] = {OB_C, OB_C, OB_C};
-    if (A.comp < 3) l[A.comp] = OB_F;
+    if (COMP < 3) l[COMP] = OB_F;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         if (g.topo[d] != OB_BOUNDED) continue;
@@ -365,7 +367,12 @@ void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], 
     A.ss = ss; A.fbc = fbc; A.comp = comp;
     dim3 blk(32, 4, 1);
     dim3 grd(cdiv(P.g.N[0], 32), cdiv(P.g.N[1], 4), P.g.N[2]);
-    tendency_general_kernel<FT><<<grd, blk, 0, stream()>>>(P, A);
+    switch (comp) {
+        case 0: tendency_general_kernel<FT, 0><<<grd, blk, 0, stream()>>>(P, A); break;
+        case 1: tendency_general_kernel<FT, 1><<<grd, blk, 0, stream()>>>(P, A); break;
+        case 2: tendency_general_kernel<FT, 2><<<grd, blk, 0, stream()>>>(P, A); break;
+        default: tendency_general_kernel<FT, 3><<<grd, blk, 0, stream()>>>(P, A); break;
+    }
     OB_LAUNCH_CHECK();
 }
 template void launch_tendency_general<float>(const Phys<float>&, int, const float* const[3], const float*,
