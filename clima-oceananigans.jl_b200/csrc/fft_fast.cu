@@ -202,6 +202,7 @@ struct XArgs {
     FT ax, ay, az, invV, dt;
     int has_z;
     long long wrap[3];              // Periodic dims: N * stride, so that index N+1 is read as index 1 (no halo needed)
+    long long x0;                   // offset of the first element of a padded row from its Julia index 0 (1 - Ox)
     // backward output
     FT* phi_p0;
     int Hx;
@@ -504,6 +505,7 @@ __global__ void __launch_bounds__(256) line_kernel(const __grid_constant__ LArgs
 }
 
 #include "fft_tma.cuh"
+#include "fft_xtma.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // plan
@@ -851,6 +853,60 @@ static void distributed_middle(FastPoisson<FT>* p) {
     { PhaseScope ph("fft_z_inv"); launch_line_any(p, A, p->log2[2], LM_INV); }
 }
 
+// persistent bulk-copy-pipelined x passes (fft_xtma.cuh); false if the configuration is not covered
+template <class FT, bool FWD>
+static bool run_x_tma(FastPoisson<FT>* p, XArgs<FT>& A) {
+    using CT = typename Cx<FT>::T;
+    static const bool off = getenv("OB200_NO_FFT_XTMA") != nullptr;
+    const int lm = p->log2[0] - 1;
+    if (off || !p->tma_ok || lm < 4 || lm > 9) return false;
+    // measured at 256^3 (profiles/r1_summary.md): the staged backward pass is faster than the direct-load one
+    // (84 vs 93 us), the staged forward pass is not (194 vs 156 us: one 160 KB block per SM leaves 8 warps for the
+    // divergence + transform + untangle chain), so the forward pass keeps the direct-load kernel by default
+    static const bool fwd_on = env_int("OB200_FFT_XTMA_FWD", 0) != 0;
+    if (FWD && (!fwd_on || A.real_in)) return false;
+    static const int T0 = env_int("OB200_FFT_TXT", 8);
+    int T = T0;
+    while (T > 1 && (A.Ny % T)) T >>= 1;
+    if (T < 2) return false;
+    if (((size_t)A.st[1] * sizeof(FT)) % 16 || ((size_t)T * A.NXP * sizeof(CT)) % 16) return false;
+    A.T = T;
+    const int M = 1 << lm;
+    const int RL = lm == 4 ? 16 : (lm == 5 ? 4 : (lm == 8 ? 16 : 8));
+    const size_t work = ((size_t)T * (M + M / RL + 1) + M) * sizeof(CT);
+    static const int stages_f = env_int("OB200_FFT_XSTAGES_F", 2), stages_b = env_int("OB200_FFT_XSTAGES_B", 3);
+    const int stages = FWD ? stages_f : stages_b;
+    const int nrows = A.has_z ? 4 * T + 1 : 2 * T + 1;
+    const size_t stage = FWD ? ((size_t)nrows * A.st[1] * sizeof(FT) + 127) / 128 * 128
+                             : ((size_t)T * A.NXP * sizeof(CT) + 127) / 128 * 128;
+    const size_t smem = stages * stage + work;
+    if (smem > 200 * 1024) return false;
+    static const int threads = env_int("OB200_FFT_XTHREADS", 256);
+    auto go = [&](auto kern) {
+        static std::map<const void*, int> occ;
+        int& bps = occ[(const void*)kern];
+        if (!bps) {
+            OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            OB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, threads, smem));
+            bps = std::max(1, bps);
+        }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = std::min((A.Ny / T) * A.Nz, sms * bps);
+        kern<<<grid, threads, smem, stream()>>>(A);
+        OB_LAUNCH_CHECK();
+    };
+#define XT(L)                                                                                        \
+    case L:                                                                                          \
+        if (FWD) { if (stages == 2) go(tx::x_r2c_tma_kernel<FT, L, 2>); else go(tx::x_r2c_tma_kernel<FT, L, 3>); } \
+        else { if (stages == 2) go(tx::x_c2r_tma_kernel<FT, L, 2>); else go(tx::x_c2r_tma_kernel<FT, L, 3>); }     \
+        break;
+    switch (lm) { XT(4) XT(5) XT(6) XT(7) XT(8) default: XT(9) }
+#undef XT
+    return true;
+}
+
 template <class FT, bool FWD>
 static void run_x(FastPoisson<FT>* p, XArgs<FT>& A) {
     using CT = typename Cx<FT>::T;
@@ -858,6 +914,7 @@ static void run_x(FastPoisson<FT>* p, XArgs<FT>& A) {
     A.spec = p->spec; A.Nx = p->N[0]; A.Ny = p->N[1]; A.Nz = p->N[2]; A.NXP = p->NXP;
     A.twM = p->twM; A.twN = p->twN; A.kpos = p->kpos;
     A.scale = (FT)(1.0 / (p->N[0] / 2));
+    if (run_x_tma<FT, FWD>(p, A)) return;
     static const int T0 = env_int("OB200_FFT_TX", 8);
     int T = T0;
     while (T > 1 && line_smem(lm, T, sizeof(CT)) > 100 * 1024) T >>= 1;
@@ -887,6 +944,7 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
         // a Periodic (not slab-decomposed) dimension is read with wrap-around: the velocities' halos need not be valid
         A.wrap[d] = g.topo[d] == OB_PERIODIC ? (long long)g.N[d] * g.st[d] : 0;
     }
+    A.x0 = 1 - g.O[0];
     // divᶜᶜᶜ (divergence_operators.jl:16-19): 1/V * (δx(Ax u) + δy(Ay v) + δz(Az w)), then / Δt
     A.ax = g.d[1] * g.d[2]; A.ay = g.d[0] * g.d[2]; A.az = g.d[0] * g.d[1];
     A.invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
