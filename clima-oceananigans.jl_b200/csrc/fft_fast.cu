@@ -525,6 +525,10 @@ struct FastPoisson {
     std::vector<void*> owned;
     bool tma_ok = false;                        // persistent TMA-pipelined y / z passes (fft_tma.cuh)
     CUtensorMap tm_y, tm_z;
+    // slab-decomposed solve through TMA (peer-memory tensor maps): see distributed_middle_tma
+    bool dtma_ok = false;
+    int dtk_y = 8;                              // columns per y tile (8, 4, 2 for gathered lines of <= 512, 1024, 2048)
+    CUtensorMap tm4_zi, tm4_y, tmr_zf[8], tmr_zi[8], tmr_y[8];
 };
 
 namespace cm = ::ob::comm;
@@ -717,22 +721,68 @@ static bool make_spec_map(FastPoisson<FT>* p, bool along_y, CUtensorMap* out) {
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
+// tensor map over `base` viewed as reals: rank-nd dims / strides (strides in BYTES for dims 1..), box
+template <class FT>
+static bool encode_map(CUtensorMap* out, void* base, int nd, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                       const cuuint32_t* box) {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) != cudaSuccess || !q) return false;
+        fn = (EncodeFn)q;
+    }
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return fn(out, sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, nd, base, dims,
+              strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// maps of the slab-decomposed solve: chunk layout [R][Nz][NyL][KXB] in bufA / bufB of every rank (peer mapped)
+template <class FT>
+static void setup_dist_tma(FastPoisson<FT>* p) {
+    using CT = typename Cx<FT>::T;
+    p->dtma_ok = false;
+    if (getenv("OB200_NO_FFT_TMA") != nullptr || getenv("OB200_NO_FFT_DTMA") != nullptr) return;
+    if (p->R < 2 || !p->p2p || !p->has_z) return;
+    const int NyL = p->N[1], Nz = p->N[2], KXB = p->KXB, R = p->R;
+    if (NyL > 256 || Nz > 256 || p->log2[2] < 4 || p->log2[2] > 8 || p->log2[1] < 4 || p->log2[1] > 11) return;
+    p->dtk_y = p->log2[1] <= 9 ? 8 : (p->log2[1] == 10 ? 4 : 2);
+    const size_t W = sizeof(FT);
+    const long long chunk = (long long)KXB * NyL * Nz;
+    if (!make_spec_map(p, false, &p->tm_z)) return;                       // natural half spectrum, z lines
+    cuuint64_t d3[3] = {(cuuint64_t)2 * KXB, (cuuint64_t)NyL, (cuuint64_t)Nz};
+    cuuint64_t sc[2] = {(cuuint64_t)2 * KXB * W, (cuuint64_t)2 * KXB * NyL * W};                  // chunk strides
+    cuuint64_t sn[2] = {(cuuint64_t)2 * p->NXP * W, (cuuint64_t)2 * p->NXP * NyL * W};           // natural strides
+    cuuint32_t bz[3] = {2 * TMA_TK, 1, (cuuint32_t)Nz}, by[3] = {(cuuint32_t)(2 * p->dtk_y), (cuuint32_t)NyL, 1};
+    for (int r = 0; r < R; ++r) {
+        if (!encode_map<FT>(&p->tmr_zf[r], p->peerB[r] + (long long)p->rank * chunk, 3, d3, sc, bz)) return;
+        if (!encode_map<FT>(&p->tmr_zi[r], p->spec + (long long)r * KXB, 3, d3, sn, bz)) return;
+        if (!encode_map<FT>(&p->tmr_y[r], p->peerA[r] + (long long)p->rank * chunk, 3, d3, sc, by)) return;
+    }
+    cuuint64_t d4[4] = {(cuuint64_t)2 * KXB, (cuuint64_t)NyL, (cuuint64_t)Nz, (cuuint64_t)R};
+    cuuint64_t s4[3] = {sc[0], sc[1], (cuuint64_t)2 * chunk * W};
+    cuuint32_t b4z[4] = {2 * TMA_TK, 1, (cuuint32_t)Nz, 1}, b4y[4] = {(cuuint32_t)(2 * p->dtk_y), (cuuint32_t)NyL, 1, (cuuint32_t)R};
+    if (!encode_map<FT>(&p->tm4_zi, p->bufA, 4, d4, s4, b4z)) return;
+    if (!encode_map<FT>(&p->tm4_y, p->bufB, 4, d4, s4, b4y)) return;
+    p->dtma_ok = true;
+}
 template <class FT>
 static void setup_tma(FastPoisson<FT>* p) {
     p->tma_ok = false;
-    if (getenv("OB200_NO_FFT_TMA") != nullptr || p->R != 1 || p->NXP % TMA_TK) return;
+    if (p->R > 1) { setup_dist_tma(p); return; }
+    if (getenv("OB200_NO_FFT_TMA") != nullptr || p->NXP % TMA_TK) return;
     if (p->log2[1] < 4 || p->log2[1] > 8 || (p->has_z && (p->log2[2] < 4 || p->log2[2] > 8))) return;
     if (!make_spec_map(p, true, &p->tm_y)) return;
     if (p->has_z && !make_spec_map(p, false, &p->tm_z)) return;
     p->tma_ok = true;
 }
 
-template <class FT, int MODE, int STAGES>
+template <class FT, int MODE, int STAGES, int TK = TMA_TK>
 static void launch_line_tma(const tl::TArgs<FT>& A, int log2n) {
     using CT = typename Cx<FT>::T;
     const int n = 1 << log2n;
-    const size_t smem = (size_t)STAGES * n * TMA_TK * sizeof(CT) + (size_t)n * sizeof(CT);
-    const int threads = std::min(256, std::max(64, TMA_TK * n / 16));
+    const size_t smem = (size_t)STAGES * n * TK * sizeof(CT) + (size_t)n * sizeof(CT);
+    const int threads = std::min(256, std::max(64, TK * n / 16));
     auto go = [&](auto kern) {
         // all instantiations share one function-pointer type: key the per-kernel set-up on the pointer
         static std::map<const void*, int> occ;
@@ -749,18 +799,29 @@ static void launch_line_tma(const tl::TArgs<FT>& A, int log2n) {
         kern<<<grid, threads, smem, stream()>>>(A);
         OB_LAUNCH_CHECK();
     };
-    switch (log2n) {
-        case 4: go(tl::line_tma_kernel<FT, 4, MODE, TMA_TK, STAGES>); break;
-        case 5: go(tl::line_tma_kernel<FT, 5, MODE, TMA_TK, STAGES>); break;
-        case 6: go(tl::line_tma_kernel<FT, 6, MODE, TMA_TK, STAGES>); break;
-        case 7: go(tl::line_tma_kernel<FT, 7, MODE, TMA_TK, STAGES>); break;
-        default: go(tl::line_tma_kernel<FT, 8, MODE, TMA_TK, STAGES>); break;
+    if constexpr (TK == TMA_TK) {
+        switch (log2n) {
+            case 4: go(tl::line_tma_kernel<FT, 4, MODE, TK, STAGES>); break;
+            case 5: go(tl::line_tma_kernel<FT, 5, MODE, TK, STAGES>); break;
+            case 6: go(tl::line_tma_kernel<FT, 6, MODE, TK, STAGES>); break;
+            case 7: go(tl::line_tma_kernel<FT, 7, MODE, TK, STAGES>); break;
+            case 8: go(tl::line_tma_kernel<FT, 8, MODE, TK, STAGES>); break;
+            default:
+                if constexpr (MODE == LM_FWD_DIV_INV && STAGES == 2) go(tl::line_tma_kernel<FT, 9, MODE, TK, STAGES>);
+                else throw Error("line_tma: unsupported length");
+                break;
+        }
+    } else if constexpr (TK == 4) {
+        go(tl::line_tma_kernel<FT, 10, MODE, TK, STAGES>);
+    } else {
+        go(tl::line_tma_kernel<FT, 11, MODE, TK, STAGES>);
     }
 }
 template <class FT>
 static void run_line_tma(FastPoisson<FT>* p, int dim, int mode) {
     tl::TArgs<FT> A;
     A.tm = dim == 1 ? p->tm_y : p->tm_z;
+    A.addr = tl::ADDR_NAT; A.R = 1; A.KXB = p->NXP; A.tpc = p->NXP / TMA_TK; A.NyL = p->N[1]; A.kx_base = 0; A.NXP = p->NXP;
     A.line_is_y = dim == 1;
     A.nkx = p->NXP / TMA_TK;
     A.nOther = dim == 1 ? p->N[2] : p->N[1];
@@ -810,6 +871,43 @@ static void all_to_all(FastPoisson<FT>* p, const typename Cx<FT>::T* src, typena
         cm::recv(dst + r * chunk, chunk * sizeof(CT), r);
     }
     cm::group_end();
+}
+
+// the slab-decomposed middle of the solve through the TMA-pipelined kernel: z forward (stores into the peers' bufB),
+// gathered y lines forward / divide / backward (stores back into the peers' bufA), z backward
+template <class FT>
+static void distributed_middle_tma(FastPoisson<FT>* p) {
+    const int R = p->R, KXB = p->KXB, NyL = p->N[1], Nz = p->N[2];
+    tl::TArgs<FT> A;
+    A.R = R; A.KXB = KXB; A.NyL = NyL; A.NXP = p->NXP; A.kx_base = 0;
+    A.lamx = p->lamx;
+    // z forward
+    A.addr = tl::ADDR_ZF; A.tm = p->tm_z;
+    for (int r = 0; r < R; ++r) A.tmr[r] = p->tmr_zf[r];
+    A.tpc = cdiv(KXB, TMA_TK); A.nkx = R * A.tpc; A.nOther = NyL; A.line_is_y = 0;
+    A.tw = p->twZ; A.scale = (FT)(1.0 / Nz); A.lamL = p->lamz; A.lamO = nullptr;
+    { PhaseScope ph("fft_z_fwd"); launch_line_tma<FT, LM_FWD, 3>(A, p->log2[2]); }
+    { PhaseScope ph("fft_sync"); cm::barrier(); }
+    // gathered y lines: forward, eigenvalue divide, backward
+    A.addr = tl::ADDR_Y; A.tm4 = p->tm4_y;
+    for (int r = 0; r < R; ++r) A.tmr[r] = p->tmr_y[r];
+    A.tpc = cdiv(KXB, p->dtk_y); A.nkx = A.tpc; A.nOther = Nz; A.line_is_y = 1; A.kx_base = p->rank * KXB;
+    A.tw = p->twY; A.scale = (FT)(1.0 / p->NyG); A.lamL = p->lamy; A.lamO = p->lamz;
+    {
+        PhaseScope ph("fft_y");
+        const int l = p->log2[1];
+        if (l <= 8) launch_line_tma<FT, LM_FWD_DIV_INV, 3>(A, l);
+        else if (l == 9) launch_line_tma<FT, LM_FWD_DIV_INV, 2>(A, l);
+        else if (l == 10) launch_line_tma<FT, LM_FWD_DIV_INV, 2, 4>(A, l);
+        else launch_line_tma<FT, LM_FWD_DIV_INV, 2, 2>(A, l);
+    }
+    { PhaseScope ph("fft_sync"); cm::barrier(); }
+    // z backward
+    A.addr = tl::ADDR_ZI; A.tm4 = p->tm4_zi; A.kx_base = 0;
+    for (int r = 0; r < R; ++r) A.tmr[r] = p->tmr_zi[r];
+    A.tpc = cdiv(KXB, TMA_TK); A.nkx = R * A.tpc; A.nOther = NyL; A.line_is_y = 0;
+    A.tw = p->twZ; A.scale = (FT)(1.0 / Nz); A.lamL = p->lamz; A.lamO = nullptr;
+    { PhaseScope ph("fft_z_inv"); launch_line_tma<FT, LM_INV, 3>(A, p->log2[2]); }
 }
 
 template <class FT>
@@ -953,7 +1051,7 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
     A.phi_p0 = phi_p0; A.Hx = g.H[0];
     { PhaseScope ph("fft_x_fwd"); run_x<FT, true>(p, A); }
     if (p->R > 1) {
-        distributed_middle(p);
+        if (p->dtma_ok) distributed_middle_tma(p); else distributed_middle(p);
     } else if (p->has_z) {
         { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
         { PhaseScope ph("fft_z"); run_line(p, 2, LM_FWD_DIV_INV); }

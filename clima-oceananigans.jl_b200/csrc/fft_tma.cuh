@@ -41,6 +41,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int x, int y, int z, int w, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(w), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int x, int y, int z, const void* src) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
                  ::"l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(src)) : "memory");
@@ -49,11 +54,26 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// addressing of a tile (which tensor maps, which coordinates):
+//   ADDR_NAT  in place on the natural half spectrum [Nz][Ny][NXP] (single GPU)
+// and, for the slab-decomposed solve (y split over R ranks, chunk layout [R][Nz][NyL][KXB], see fft_fast.cu):
+//   ADDR_ZF   z lines: load natural, STORE the KXB columns that belong to rank r into rank r's receive buffer
+//             (tensor map over PEER memory: the all-to-all transpose is the store phase of the transform);
+//   ADDR_ZI   z lines: load from the chunk layout (4-D map), store natural;
+//   ADDR_Y    gathered y lines (m = s NyL + yl): load all R chunks of a column block with one 4-D box, transform,
+//             store the part that came from rank s back into rank s's buffer (peer memory).
+// Tiles of the distributed modes are aligned to chunk boundaries; a tile that sticks out of its chunk is clipped
+// by the tensor-map bounds on store and zero-filled on load.
+enum { ADDR_NAT = 0, ADDR_ZF = 1, ADDR_ZI = 2, ADDR_Y = 3 };
 template <class FT>
 struct TArgs {
-    CUtensorMap tm;                 // view of the half spectrum as doubles / floats: dims (2 NXP, Ny, Nz)
+    CUtensorMap tm;                 // ADDR_NAT / ZF load, ZI store base..., view as reals: dims (2 NXP, Ny, Nz)
+    CUtensorMap tm4;                // ADDR_ZI / ADDR_Y: 4-D view of the local chunk buffer (2 KXB, NyL, Nz, R)
+    CUtensorMap tmr[8];             // per-rank 3-D chunk views (peer buffers, or chunk r of the local spectrum)
+    int addr, R, KXB, tpc, NyL, kx_base, NXP;
     int line_is_y;                  // 1: lines along y, other = z ; 0: lines along z, other = y
     int nkx, nOther;                // tiles: nkx = NXP / TK columns blocks x nOther lines sets
     const typename Cx<FT>::T* tw;   // exp(-2 pi i t / N)
@@ -134,19 +154,28 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
     const int ntiles = A.nkx * A.nOther;
     const int first = blockIdx.x, step = gridDim.x;
     const int mine = first < ntiles ? (ntiles - first + step - 1) / step : 0;
-    auto coords = [&](int n, int& cx, int& cy, int& cz, int& kxb, int& o) {
+    // tile -> (column block kxb [in units of TK columns; within chunk r for the distributed modes], other index o,
+    // chunk r); kx0 = first global kx of the tile
+    auto coords = [&](int n, int& kxb, int& o, int& r, int& kx0) {
         const int tile = first + n * step;
         o = tile / A.nkx; kxb = tile - o * A.nkx;
-        cx = 2 * TK * kxb; cy = A.line_is_y ? 0 : o; cz = A.line_is_y ? o : 0;
+        r = 0;
+        if (A.addr == ADDR_ZF || A.addr == ADDR_ZI) { r = kxb / A.tpc; kxb -= r * A.tpc; kx0 = r * A.KXB + TK * kxb; }
+        else kx0 = A.kx_base + TK * kxb;
     };
     auto issue_load = [&](int n) {
-        int cx, cy, cz, kxb, o;
-        coords(n, cx, cy, cz, kxb, o);
+        int kxb, o, r, kx0;
+        coords(n, kxb, o, r, kx0);
         unsigned long long* bar = &full[n % STAGES];
         mbar_expect_tx(bar, TILE_BYTES);
-        tma_load_3d(buf(n % STAGES), &A.tm, cx, cy, cz, bar);
+        void* dst = buf(n % STAGES);
+        if (A.addr == ADDR_NAT) tma_load_3d(dst, &A.tm, 2 * kx0, A.line_is_y ? 0 : o, A.line_is_y ? o : 0, bar);
+        else if (A.addr == ADDR_ZF) tma_load_3d(dst, &A.tm, 2 * kx0, o, 0, bar);
+        else if (A.addr == ADDR_ZI) tma_load_4d(dst, &A.tm4, 2 * TK * kxb, o, 0, r, bar);
+        else tma_load_4d(dst, &A.tm4, 2 * TK * kxb, 0, o, 0, bar);
     };
     if (lead && mine > 0) issue_load(0);
+    (void)0;
 
     for (int n = 0; n < mine; ++n) {
         const int slot = n % STAGES;
@@ -157,8 +186,8 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
         }
         mbar_wait(&full[slot], (n / STAGES) & 1);
         CT* s = buf(slot);
-        int cx, cy, cz, kxb, o;
-        coords(n, cx, cy, cz, kxb, o);
+        int kxb, o, r, kx0;
+        coords(n, kxb, o, r, kx0);
 
         if constexpr (MODE == LM_FWD) {
             pass_fwd_t<R::R1, LOG2N, TK>(s, stw, N / R::R1);
@@ -184,7 +213,7 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
 #pragma unroll
                 for (int q = 0; q < RLAST; ++q) x[q] = col[(base + q) * TK];
                 dft_reg<RLAST, false>(x);
-                const int kx = kxb * TK + t;
+                const int kx = min(kx0 + t, A.NXP - 1);       // columns clipped out of a chunk carry zeros
                 const double lO = A.lamO ? A.lamO[o] : 0.0;
                 const double lxo = A.line_is_y ? A.lamx[kx] : (A.lamx[kx] + lO);
 #pragma unroll
@@ -210,11 +239,13 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
         fence_async_smem();           // generic-proxy writes of the tile -> visible to the bulk store
         __syncthreads();
         if (lead) {
-            tma_store_3d(&A.tm, cx, cy, cz, s);
+            if (A.addr == ADDR_NAT) tma_store_3d(&A.tm, 2 * kx0, A.line_is_y ? 0 : o, A.line_is_y ? o : 0, s);
+            else if (A.addr == ADDR_ZF || A.addr == ADDR_ZI) tma_store_3d(&A.tmr[r], 2 * TK * kxb, o, 0, s);
+            else for (int q = 0; q < A.R; ++q) tma_store_3d(&A.tmr[q], 2 * TK * kxb, 0, o, s + (size_t)q * A.NyL * TK);
             bulk_commit();
         }
     }
-    if (lead) bulk_wait_read<0>();    // shared memory must outlive the last stores
+    if (lead) bulk_wait_all();        // shared memory must outlive the last stores; peer writes are complete at exit
 }
 
 }  // namespace tl
