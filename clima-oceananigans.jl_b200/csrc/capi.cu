@@ -16,6 +16,7 @@ namespace comm { bool peer_halo_error(); }
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_h2d = nullptr, g_d2h = nullptr;     // copy streams of the asynchronous parent transfers
 static bool g_inited = false;
 
 void count_launch(int n) { g_launches += n; }
@@ -115,10 +116,14 @@ struct ob200_field {
     void* alt = nullptr;                    // second buffer (prognostic fields of a model)
     bool owns = true;
     int psize[3];
-    void* staging = nullptr;                // device copy in the reference's parent layout
+    void* staging = nullptr;                // device copy in the reference's parent layout (uploads)
+    void* staging_out = nullptr;            // ... and a second one for asynchronous downloads
+    cudaEvent_t ev_in_ready = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_free = nullptr;
     ~ob200_field() {
         if (owns) { if (base) cudaFree(base); if (alt) cudaFree(alt); }
         if (staging) cudaFree(staging);
+        if (staging_out) cudaFree(staging_out);
+        for (cudaEvent_t e : {ev_in_ready, ev_in_free, ev_out_ready, ev_out_free}) if (e) cudaEventDestroy(e);
     }
     template <class FT> FT* p0() const {
         return (FT*)base + (grid->ftype == OB200_F32 ? grid->g32.off0 : grid->g64.off0);
@@ -163,7 +168,31 @@ extern "C" int32_t ob200_sync(void) {
     API_BEGIN
     ensure_device();
     OB_CUDA(cudaStreamSynchronize(stream()));
+    if (ob::g_h2d) OB_CUDA(cudaStreamSynchronize(ob::g_h2d));
+    if (ob::g_d2h) OB_CUDA(cudaStreamSynchronize(ob::g_d2h));
     if (ob::comm::peer_halo_error()) throw ob::Error("halo exchange: a neighbour's boundary planes did not arrive (peer-memory flag wait timed out)");
+    API_END
+}
+// blocks until every download (ob200_field_get_parent_async) enqueued so far EXCEPT those of the most recent
+// `keep_in_flight` ob200_mark_download_batch() batches has been delivered to host memory
+static std::vector<cudaEvent_t> g_batch_events;
+extern "C" int32_t ob200_mark_download_batch(void) {
+    API_BEGIN
+    if (!ob::g_d2h) return 0;
+    cudaEvent_t e;
+    OB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    OB_CUDA(cudaEventRecord(e, ob::g_d2h));
+    g_batch_events.push_back(e);
+    API_END
+}
+extern "C" int32_t ob200_sync_downloads(int32_t keep_in_flight) {
+    API_BEGIN
+    while ((int)g_batch_events.size() > std::max(0, keep_in_flight)) {
+        cudaEvent_t e = g_batch_events.front();
+        OB_CUDA(cudaEventSynchronize(e));
+        cudaEventDestroy(e);
+        g_batch_events.erase(g_batch_events.begin());
+    }
     API_END
 }
 extern "C" size_t ob200_last_error(char* buf, size_t len) {
@@ -332,24 +361,60 @@ extern "C" int32_t ob200_field_parent_size(const ob200_field* f, int32_t out[3])
     return 0;
 }
 
+// Transfers of the reference's parent arrays.  The asynchronous variants run the DMA on two dedicated copy streams
+// (one per direction: PCIe is full duplex) with their own staging buffers, ordered against the compute stream by
+// events only, so that -- for a caller that streams host buffers through successive steps -- the upload of step
+// n+1 and the download of step n overlap the kernels of the step in between.  ob200_sync() drains all three.
+static void ensure_copy_streams() {
+    if (!g_h2d) OB_CUDA(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
+    if (!g_d2h) OB_CUDA(cudaStreamCreateWithFlags(&g_d2h, cudaStreamNonBlocking));
+}
+static void ensure_event(cudaEvent_t& e) {
+    if (!e) OB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
 template <class FT>
 static void field_set_parent(ob200_field* f, const void* host, bool sync) {
     const GridD<FT>& g = gridD<FT>(f->grid);
     size_t n = (size_t)f->psize[0] * f->psize[1] * f->psize[2];
     if (!f->staging) OB_CUDA(cudaMalloc(&f->staging, n * sizeof(FT)));
-    OB_CUDA(cudaMemcpyAsync(f->staging, host, n * sizeof(FT), cudaMemcpyHostToDevice, stream()));
+    if (sync) {
+        if (f->ev_in_free) OB_CUDA(cudaEventSynchronize(f->ev_in_free));
+        OB_CUDA(cudaMemcpyAsync(f->staging, host, n * sizeof(FT), cudaMemcpyHostToDevice, stream()));
+    } else {
+        ensure_copy_streams();
+        ensure_event(f->ev_in_ready);
+        if (f->ev_in_free) OB_CUDA(cudaStreamWaitEvent(g_h2d, f->ev_in_free, 0));     // previous conversion has read the staging
+        OB_CUDA(cudaMemcpyAsync(f->staging, host, n * sizeof(FT), cudaMemcpyHostToDevice, g_h2d));
+        OB_CUDA(cudaEventRecord(f->ev_in_ready, g_h2d));
+        OB_CUDA(cudaStreamWaitEvent(stream(), f->ev_in_ready, 0));
+    }
     launch_to_internal<FT>(g, f->psize, f->loc, (const FT*)f->staging, (FT*)f->base);
     if (f->alt) launch_to_internal<FT>(g, f->psize, f->loc, (const FT*)f->staging, (FT*)f->alt);
+    if (!sync) { ensure_event(f->ev_in_free); OB_CUDA(cudaEventRecord(f->ev_in_free, stream())); }
     if (sync) OB_CUDA(cudaStreamSynchronize(stream()));
 }
 template <class FT>
 static void field_get_parent(ob200_field* f, void* host, bool sync) {
     const GridD<FT>& g = gridD<FT>(f->grid);
     size_t n = (size_t)f->psize[0] * f->psize[1] * f->psize[2];
-    if (!f->staging) OB_CUDA(cudaMalloc(&f->staging, n * sizeof(FT)));
-    launch_from_internal<FT>(g, f->psize, f->loc, (const FT*)f->base, (FT*)f->staging);
-    OB_CUDA(cudaMemcpyAsync(host, f->staging, n * sizeof(FT), cudaMemcpyDeviceToHost, stream()));
-    if (sync) OB_CUDA(cudaStreamSynchronize(stream()));
+    if (sync) {
+        if (!f->staging) OB_CUDA(cudaMalloc(&f->staging, n * sizeof(FT)));
+        if (f->ev_in_free) OB_CUDA(cudaEventSynchronize(f->ev_in_free));
+        launch_from_internal<FT>(g, f->psize, f->loc, (const FT*)f->base, (FT*)f->staging);
+        OB_CUDA(cudaMemcpyAsync(host, f->staging, n * sizeof(FT), cudaMemcpyDeviceToHost, stream()));
+        OB_CUDA(cudaStreamSynchronize(stream()));
+        return;
+    }
+    ensure_copy_streams();
+    if (!f->staging_out) OB_CUDA(cudaMalloc(&f->staging_out, n * sizeof(FT)));
+    ensure_event(f->ev_out_ready);
+    if (f->ev_out_free) OB_CUDA(cudaStreamWaitEvent(stream(), f->ev_out_free, 0));     // previous DMA has drained the staging
+    launch_from_internal<FT>(g, f->psize, f->loc, (const FT*)f->base, (FT*)f->staging_out);
+    OB_CUDA(cudaEventRecord(f->ev_out_ready, stream()));
+    OB_CUDA(cudaStreamWaitEvent(g_d2h, f->ev_out_ready, 0));
+    OB_CUDA(cudaMemcpyAsync(host, f->staging_out, n * sizeof(FT), cudaMemcpyDeviceToHost, g_d2h));
+    ensure_event(f->ev_out_free);
+    OB_CUDA(cudaEventRecord(f->ev_out_free, g_d2h));
 }
 extern "C" int32_t ob200_field_set_parent(ob200_field* f, const void* host) {
     API_BEGIN

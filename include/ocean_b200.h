@@ -134,10 +134,16 @@ int32_t ob200_field_parent_size(const ob200_field* f, int32_t out[3]);
 /* parent(field) .= host array  /  Array(parent(field)); element type = grid ftype */
 int32_t ob200_field_set_parent(ob200_field* f, const void* host_parent);
 int32_t ob200_field_get_parent(const ob200_field* f, void* host_parent);
-/* same, enqueued on the stream without a final synchronisation: the host buffer (pinned for a
- * truly asynchronous copy) must stay valid until ob200_sync() */
+/* same, without a final synchronisation: the DMA runs on the library's upload / download copy streams (one per
+ * direction), ordered against the compute stream by events, so that the transfers of successive steps overlap the
+ * kernels.  The host buffer (pinned for a truly asynchronous copy) must stay valid until ob200_sync() or, for
+ * downloads, until ob200_sync_downloads() has passed the batch it belongs to. */
 int32_t ob200_field_set_parent_async(ob200_field* f, const void* host_parent);
 int32_t ob200_field_get_parent_async(const ob200_field* f, void* host_parent);
+/* marks the downloads enqueued so far as one batch / blocks until all batches except the `keep_in_flight` most
+ * recent ones have been delivered to host memory (OutputWriters/fetch_output.jl:24-36 is the synchronous analogue) */
+int32_t ob200_mark_download_batch(void);
+int32_t ob200_sync_downloads(int32_t keep_in_flight);
 /* internal device storage: base pointer, index of Julia (1,1,1), strides in elements */
 int32_t ob200_field_device_view(const ob200_field* f, void** base, int64_t offset111[1],
                                 int64_t strides[3]);
