@@ -386,6 +386,18 @@ PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double*
     p->kind = kind;
     if (kind == 1 && ff::fast_poisson_supported<FT>(g) && getenv("OB200_NO_FAST_FFT") == nullptr)
         p->fast = ff::fast_poisson_create<FT>(g);
+    if (kind == 2 && ff::fast_ft_supported<FT>(g) && getenv("OB200_NO_FAST_FFT") == nullptr && getenv("OB200_NO_FAST_FT") == nullptr) {
+        // half-spectrum x / y passes + Thomas sweep on the half spectrum (fft_fast.cu); none of the general path's
+        // full-spectrum arrays is needed
+        int Nz = g.N[2];
+        p->fast = ff::fast_poisson_create<FT>(g);
+        std::vector<double> f(dzF_host, dzF_host + Nz + 2), c(dzC_host, dzC_host + Nz + 2);
+        p->dzF = dev_upload(f, p->owned);
+        p->dzC = dev_upload(c, p->owned);
+        ff::fast_poisson_set_tridiagonal<FT>(p->fast, p->dzF, p->dzC);
+        for (int d = 0; d < 3; ++d) { p->N[d] = g.N[d]; p->topo[d] = g.topo[d]; }
+        return p;
+    }
     if (g.topo[0] == OB_COMM || g.topo[1] == OB_COMM || g.topo[2] == OB_COMM) {
         if (!p->fast) {
             delete p;

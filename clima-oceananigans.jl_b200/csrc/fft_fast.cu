@@ -203,6 +203,11 @@ struct XArgs {
     int has_z;
     long long wrap[3];              // Periodic dims: N * stride, so that index N+1 is read as index 1 (no halo needed)
     long long x0;                   // offset of the first element of a padded row from its Julia index 0 (1 - Ox)
+    // Fourier-tridiagonal solve (Bounded, possibly stretched z): the source term is Δzᶜ_k div(U*) / Δt
+    // (solve_for_pressure.jl:28-33) with the level's own areas and volume; dzC is indexed by the Julia level
+    int tri;
+    const FT* dzC;                  // nullptr: regular z (spacing dz)
+    FT dx, dy, dz;
     // backward output
     FT* phi_p0;
     int Hx;
@@ -237,8 +242,10 @@ __global__ void __launch_bounds__(256) x_r2c_kernel(const __grid_constant__ XArg
         const int j = j0 + t;
         if (A.real_in) {
             const FT* row = A.real_in + (long long)Nx * (j + (long long)A.Ny * k);
+            const FT lev = A.tri ? (A.dzC ? A.dzC[k + 1] : A.dz) : FT(1);       // set_source_term!: times Δzᶜ
             for (int m = l; m < M; m += tpl) {
                 CT c; c.x = row[2 * m]; c.y = row[2 * m + 1];
+                if (A.tri) { c.x *= lev; c.y *= lev; }
                 sl[G::pos(m)] = c;
             }
         } else {
@@ -251,6 +258,12 @@ __global__ void __launch_bounds__(256) x_r2c_kernel(const __grid_constant__ XArg
             const FT* w0 = A.w + p;
             const FT* w1 = w0 + A.st[2] - (k + 1 == A.Nz ? A.wrap[2] : 0);
             const FT inv_dt = FT(1) / A.dt;
+            // level metrics (regular solve: the constants of the plan; tridiagonal solve: this level's Δzᶜ)
+            FT ax = A.ax, ay = A.ay, invV = A.invV, lev = FT(1);
+            if (A.tri) {
+                const FT dzk = A.dzC ? A.dzC[k + 1] : A.dz;
+                ax = A.dy * dzk; ay = A.dx * dzk; invV = 1 / ((A.dx * A.dy) * dzk); lev = dzk;
+            }
             constexpr int XU = 4;
             for (int mb = l; mb < M; mb += XU * tpl) {
                 P2 ua[XU], va[XU], vb[XU], wa[XU], wb[XU];
@@ -273,13 +286,13 @@ __global__ void __launch_bounds__(256) x_r2c_kernel(const __grid_constant__ XArg
                 for (int e = 0; e < XU; ++e) {
                     const int m = mb + e * tpl;
                     if (m < M) {
-                        FT tx0 = A.ax * ua[e].y - A.ax * ua[e].x, tx1 = A.ax * un[e] - A.ax * ua[e].y;
-                        FT ty0 = A.ay * vb[e].x - A.ay * va[e].x, ty1 = A.ay * vb[e].y - A.ay * va[e].y;
+                        FT tx0 = ax * ua[e].y - ax * ua[e].x, tx1 = ax * un[e] - ax * ua[e].y;
+                        FT ty0 = ay * vb[e].x - ay * va[e].x, ty1 = ay * vb[e].y - ay * va[e].y;
                         FT tz0 = FT(0), tz1 = FT(0);
                         if (A.has_z) { tz0 = A.az * wb[e].x - A.az * wa[e].x; tz1 = A.az * wb[e].y - A.az * wa[e].y; }
                         CT c;
-                        c.x = (A.invV * ((tx0 + ty0) + tz0)) * inv_dt;
-                        c.y = (A.invV * ((tx1 + ty1) + tz1)) * inv_dt;
+                        c.x = (lev * (invV * ((tx0 + ty0) + tz0))) * inv_dt;
+                        c.y = (lev * (invV * ((tx1 + ty1) + tz1))) * inv_dt;
                         sl[G::pos(m)] = c;
                     }
                 }
@@ -523,6 +536,9 @@ struct FastPoisson {
     int* kpos = nullptr;
     double *lamx = nullptr, *lamy = nullptr, *lamz = nullptr;
     std::vector<void*> owned;
+    int tri = 0;                                // Fourier-tridiagonal solve: z is Bounded and solved by Thomas
+    const double *dzF = nullptr, *dzC = nullptr; // device, Julia-indexed 0..Nz+1 (owned by the PoissonPlan)
+    FT* tsc = nullptr;                          // Thomas scratch t, [Nz][Ny][NXP]
     bool tma_ok = false;                        // persistent TMA-pipelined y / z passes (fft_tma.cuh)
     CUtensorMap tm_y, tm_z;
     // slab-decomposed solve through TMA (peer-memory tensor maps): see distributed_middle_tma
@@ -556,6 +572,16 @@ bool fast_poisson_supported(const GridD<FT>& g) {
 
 template <class FT> static void setup_tma(FastPoisson<FT>* p);
 
+// Fourier-tridiagonal fast path: x, y Periodic power-of-two regular; z Bounded with any spacing; single GPU
+template <class FT>
+bool fast_ft_supported(const GridD<FT>& g) {
+    if (g.topo[0] != OB_PERIODIC || g.topo[1] != OB_PERIODIC || g.topo[2] != OB_BOUNDED) return false;
+    if (!pow2(g.N[0]) || g.N[0] < 32 || g.N[0] > 2048) return false;
+    if (!pow2(g.N[1]) || g.N[1] < 16 || g.N[1] > 2048) return false;
+    if (!g.regular[0] || !g.regular[1] || g.N[2] < 2) return false;
+    return true;
+}
+
 template <class FT>
 FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
     using CT = typename Cx<FT>::T;
@@ -563,6 +589,7 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
     const long double PI = 3.14159265358979323846264338327950288L;
     for (int d = 0; d < 3; ++d) { p->N[d] = g.N[d]; p->log2[d] = ilog2c(g.N[d]); }
     p->has_z = g.topo[2] != OB_FLAT;
+    p->tri = g.topo[2] == OB_BOUNDED;           // only reached through fast_ft_supported
     if (g.topo[1] == OB_COMM) { p->R = cm::size(); p->rank = cm::rank(); }
     p->NyG = p->R * g.N[1];
     p->log2[1] = ilog2c(p->NyG);
@@ -613,7 +640,11 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
     p->twM = up(twid(M, M), p->owned);
     p->twN = up(twid(Nx, M + 1), p->owned);
     p->twY = up(twid(p->NyG, p->NyG), p->owned);
-    if (p->has_z) p->twZ = up(twid(g.N[2], g.N[2]), p->owned);
+    if (p->has_z && !p->tri) p->twZ = up(twid(g.N[2], g.N[2]), p->owned);
+    if (p->tri) {
+        OB_CUDA(cudaMalloc(&p->tsc, tot * sizeof(FT)));
+        p->owned.push_back(p->tsc);
+    }
     std::vector<int> kp(M);
     for (int P = 0; P < M; ++P) kp[freq_of_pos(lm, P)] = P;
     p->kpos = up(kp, p->owned);
@@ -628,10 +659,14 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
     std::vector<double> lx(p->NXP, 1.0), ly(p->NyG), lz(std::max(1, g.N[2]), 0.0);
     for (int k = 0; k <= M; ++k) lx[k] = lam(0, k);
     for (int P = 0; P < p->NyG; ++P) ly[P] = lam(1, freq_of_pos(p->log2[1], P));
-    if (p->has_z) for (int P = 0; P < g.N[2]; ++P) lz[P] = lam(2, freq_of_pos(p->log2[2], P));
+    if (p->has_z && !p->tri) for (int P = 0; P < g.N[2]; ++P) lz[P] = lam(2, freq_of_pos(p->log2[2], P));
     p->lamx = up(lx, p->owned); p->lamy = up(ly, p->owned); p->lamz = up(lz, p->owned);
     setup_tma(p);
     return p;
+}
+// the Δzᶠ / Δzᶜ tables of the tridiagonal solve (device, Julia-indexed; owned by the caller's plan)
+template <class FT> void fast_poisson_set_tridiagonal(FastPoisson<FT>* p, const double* dzF_dev, const double* dzC_dev) {
+    p->dzF = dzF_dev; p->dzC = dzC_dev;
 }
 template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
     if (!p) return;
@@ -771,9 +806,10 @@ static void setup_tma(FastPoisson<FT>* p) {
     p->tma_ok = false;
     if (p->R > 1) { setup_dist_tma(p); return; }
     if (getenv("OB200_NO_FFT_TMA") != nullptr || p->NXP % TMA_TK) return;
-    if (p->log2[1] < 4 || p->log2[1] > 8 || (p->has_z && (p->log2[2] < 4 || p->log2[2] > 8))) return;
+    const bool zfft = p->has_z && !p->tri;
+    if (p->log2[1] < 4 || p->log2[1] > 8 || (zfft && (p->log2[2] < 4 || p->log2[2] > 8))) return;
     if (!make_spec_map(p, true, &p->tm_y)) return;
-    if (p->has_z && !make_spec_map(p, false, &p->tm_z)) return;
+    if (zfft && !make_spec_map(p, false, &p->tm_z)) return;
     p->tma_ok = true;
 }
 
@@ -962,7 +998,7 @@ static bool run_x_tma(FastPoisson<FT>* p, XArgs<FT>& A) {
     // (84 vs 93 us), the staged forward pass is not (194 vs 156 us: one 160 KB block per SM leaves 8 warps for the
     // divergence + transform + untangle chain), so the forward pass keeps the direct-load kernel by default
     static const bool fwd_on = env_int("OB200_FFT_XTMA_FWD", 0) != 0;
-    if (FWD && (!fwd_on || A.real_in)) return false;
+    if (FWD && (!fwd_on || A.real_in || A.tri)) return false;
     static const int T0 = env_int("OB200_FFT_TXT", 8);
     int T = T0;
     while (T > 1 && (A.Ny % T)) T >>= 1;
@@ -1031,6 +1067,66 @@ static void run_x(FastPoisson<FT>* p, XArgs<FT>& A) {
 #undef XCASE
 }
 
+// Thomas sweep of the Fourier-tridiagonal solver on the half spectrum [Nz][Ny][NXP]: one (kx, y) column per thread,
+// coalesced in kx; same arithmetic as thomas_kernel (fft.cu) -- batched_tridiagonal_solver.jl:91-122 with the main
+// diagonal of fourier_tridiagonal_poisson_solver.jl:16-28 generated on the fly and the `|beta| <= 10 eps` break.
+// The column (kx, ky) = (0, 0) carries the horizontal means: removing ITS vertical mean afterwards is the
+// `phi .-= mean(phi)` of :93-99 done in spectral space.
+template <class FT>
+__global__ void __launch_bounds__(128) thomas_half_kernel(typename Cx<FT>::T* spec, FT* tsc, int NXH, int NXP, int Ny, int Nz,
+                                                           const double* lamx, const double* lamy, const double* dzF,
+                                                           const double* dzC) {
+    using CT = typename Cx<FT>::T;
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (kx >= NXH) return;
+    const long long col = kx + (long long)NXP * y, pl = (long long)NXP * Ny;
+    const double lam = lamx[kx] + lamy[y];
+    auto diag = [&](int k) -> double {     // k is 1-based
+        if (k == 1) return -1 / dzF[2] - dzC[1] * lam;
+        if (k == Nz) return -1 / dzF[Nz] - dzC[Nz] * lam;
+        return -(1 / dzF[k + 1] + 1 / dzF[k]) - dzC[k] * lam;
+    };
+    const double eps10 = 10 * (sizeof(FT) == 4 ? 1.1920928955078125e-07 : 2.220446049250313e-16);
+    double beta = diag(1);
+    CT f1 = spec[col], prev;
+    prev.x = (FT)((double)f1.x / beta); prev.y = (FT)((double)f1.y / beta);
+    spec[col] = prev;
+    for (int k = 2; k <= Nz; ++k) {
+        const double ak = 1 / dzF[k];            // lower = upper diagonal: 1/Δzᶠ_k
+        const FT t = (FT)(ak / beta);
+        tsc[col + (k - 1) * pl] = t;
+        beta = diag(k) - ak * (double)t;
+        if (!(fabs(beta) > eps10)) break;
+        const CT fk = spec[col + (k - 1) * pl];
+        CT r;
+        r.x = (FT)(((double)fk.x - ak * (double)prev.x) / beta);
+        r.y = (FT)(((double)fk.y - ak * (double)prev.y) / beta);
+        spec[col + (k - 1) * pl] = r;
+        prev = r;
+    }
+    CT nxt = spec[col + (long long)(Nz - 1) * pl];
+    for (int k = Nz - 1; k >= 1; --k) {
+        const FT t = tsc[col + k * pl];
+        CT v = spec[col + (k - 1) * pl];
+        v.x -= t * nxt.x; v.y -= t * nxt.y;
+        spec[col + (k - 1) * pl] = v;
+        nxt = v;
+    }
+    if (kx == 0 && y == 0) {
+        double sum = 0;
+        for (int k = 0; k < Nz; ++k) sum += (double)spec[col + k * pl].x;
+        const FT mean = (FT)(sum / Nz);
+        for (int k = 0; k < Nz; ++k) { CT v = spec[col + k * pl]; v.x -= mean; v.y = 0; spec[col + k * pl] = v; }
+    }
+}
+template <class FT>
+static void run_thomas(FastPoisson<FT>* p) {
+    dim3 blk(64), grd(cdiv(p->NXH, 64), p->N[1]);
+    thomas_half_kernel<FT><<<grd, blk, 0, stream()>>>(p->spec, p->tsc, p->NXH, p->NXP, p->N[1], p->N[2], p->lamx, p->lamy,
+                                                      p->dzF, p->dzC);
+    OB_LAUNCH_CHECK();
+}
+
 // source term from the velocities (u, v, w Julia-(0,0,0) pointers) or from a real array; result in phi
 template <class FT>
 void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,
@@ -1043,6 +1139,7 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
         A.wrap[d] = g.topo[d] == OB_PERIODIC ? (long long)g.N[d] * g.st[d] : 0;
     }
     A.x0 = 1 - g.O[0];
+    A.tri = p->tri; A.dzC = g.regular[2] ? nullptr : g.dC[2]; A.dx = g.d[0]; A.dy = g.d[1]; A.dz = g.d[2];
     // divᶜᶜᶜ (divergence_operators.jl:16-19): 1/V * (δx(Ax u) + δy(Ay v) + δz(Az w)), then / Δt
     A.ax = g.d[1] * g.d[2]; A.ay = g.d[0] * g.d[2]; A.az = g.d[0] * g.d[1];
     A.invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
@@ -1052,6 +1149,10 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
     { PhaseScope ph("fft_x_fwd"); run_x<FT, true>(p, A); }
     if (p->R > 1) {
         if (p->dtma_ok) distributed_middle_tma(p); else distributed_middle(p);
+    } else if (p->tri) {
+        { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
+        { PhaseScope ph("fft_z"); run_thomas(p); }
+        { PhaseScope ph("fft_y"); run_line(p, 1, LM_INV); }
     } else if (p->has_z) {
         { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
         { PhaseScope ph("fft_z"); run_line(p, 2, LM_FWD_DIV_INV); }
@@ -1064,6 +1165,8 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
 }
 
 #define INST(FT)                                                                                   \
+    template bool fast_ft_supported<FT>(const GridD<FT>&);                                          \
+    template void fast_poisson_set_tridiagonal<FT>(FastPoisson<FT>*, const double*, const double*); \
     template bool fast_poisson_supported<FT>(const GridD<FT>&);                                     \
     template FastPoisson<FT>* fast_poisson_create<FT>(const GridD<FT>&);                            \
     template void fast_poisson_destroy<FT>(FastPoisson<FT>*);                                       \

@@ -82,6 +82,9 @@ template <class FT> void poisson_solve(PoissonPlan<FT>* p, const GridD<FT>& g, F
 namespace ff {
 template <class FT> struct FastPoisson;
 template <class FT> bool fast_poisson_supported(const GridD<FT>& g);
+// Fourier-tridiagonal variant (Bounded z solved by a Thomas sweep on the half spectrum)
+template <class FT> bool fast_ft_supported(const GridD<FT>& g);
+template <class FT> void fast_poisson_set_tridiagonal(FastPoisson<FT>* p, const double* dzF_dev, const double* dzC_dev);
 template <class FT> FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g);
 template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p);
 // source term = div(u,v,w)/dt computed on the fly, or a real Nx*Ny*Nz device array `real_in`

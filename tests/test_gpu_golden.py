@@ -114,3 +114,39 @@ def test_specialised_and_general_kernels_agree(ob):
         ob.time_step(m2, 2e-3)
     for n in m1.names:
         assert rel(m1.fields[n].interior(), m2.fields[n].interior()) < 1e-13
+
+
+# ---- fast Fourier-tridiagonal solve (half-spectrum x / y passes + Thomas sweep on the half spectrum) ------------
+def _zf(n, p=1.5):
+    return -np.linspace(1, 0, n + 1) ** p
+
+
+@pytest.mark.parametrize("size", [(32, 16, 12), (64, 32, 20)])
+def test_fast_fourier_tridiagonal_matches_oracle(ob, size):
+    kw = dict(size=size, x=(0, 1), y=(0, 2), z=_zf(size[2]), topology=("Periodic", "Periodic", "Bounded"))
+    go, gb = O.RectilinearGrid(np.float64, **kw), ob.RectilinearGrid(ob.arch, np.float64, **kw)
+    rhs = poisson_rhs(go, 301)
+    po = O.Field(go, auxiliary=True)
+    O.FourierTridiagonalPoissonSolver(go).solve(po, rhs)
+    pb = ob.CenterField(gb)
+    ob.solve(pb, ob.FourierTridiagonalPoissonSolver(gb), rhs)
+    assert rel(pb.interior(), po.interior) < 1e-11
+
+
+@pytest.mark.parametrize("FT,tol", [(np.float64, 1e-12), (np.float32, 2e-5)])
+def test_c3_physics_with_fast_tridiagonal_solver(ob, FT, tol):
+    """config 3 physics (stretched Bounded z, WENO5(grid), closure, FPlane, flux / gradient BCs) at a size whose pressure
+    solve takes the fast Fourier-tridiagonal path (Nx >= 32, Ny >= 16 powers of two)"""
+    cfg = dict(MODEL_CASES["c3_stretched_weno_rk3"])
+    cfg["grid"] = dict(size=(32, 16, 14), x=(0, 1), y=(0, 1), z=_zf(14), topology=("Periodic", "Periodic", "Bounded"))
+    go, gb = O.RectilinearGrid(FT, **cfg["grid"]), ob.RectilinearGrid(ob.arch, FT, **cfg["grid"])
+    mo, mb = build_model(O, go, cfg), build_model(ob, gb, cfg)
+    vals = {n: v.astype(FT) for n, v in model_initial_values(mo, 104).items()}
+    mo.set(**vals)
+    ob.set_model(mb, **vals)
+    for step in range(3):
+        mo.time_step(cfg["dt"])
+        ob.time_step(mb, cfg["dt"])
+        for n in mo.names:
+            assert rel(mb.fields[n].interior(), mo.fields[n].interior) < tol, (step, n)
+    assert mb.diagnostics()["max_abs_div"] < (1e-12 if FT == np.float64 else 1e-4)
