@@ -23,7 +23,7 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 # mean DRAM bytes per tendency launch at 256^3 from the committed ncu capture (profiles/r1_summary.md)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 9.3e8
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 8.93e8
 
 METRIC = "grid-point updates/sec (RK3 step, 256^3 WENO5+FFT)"
 UNIT = "grid-point updates/s"
