@@ -226,7 +226,9 @@ def main():
     # algorithmic words per point per launch: (4F+1)/F for stages 2,3 and (3F+1)/F for stage 1
     words = ((3 * F + 1) + 2 * (4 * F + 1)) / 3.0 / F
     alg_bytes = words * 8 * N ** 3
-    avg_ms = tend["ms_total"] / max(1, tend["count"])
+    # the "tendency" phase brackets the F launches of a stage (they run on forked streams so that their tails overlap)
+    tend_launches = tend["count"] * F
+    avg_ms = tend["ms_total"] / max(1, tend_launches)
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "tendency+substep (per prognostic field)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if N == 256 else None,
@@ -234,7 +236,7 @@ def main():
                                   "launches of a stage (profiles/r1_summary.md)",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "avg_launch_ms": avg_ms, "launches": tend["count"],
+                "avg_launch_ms": avg_ms, "launches": tend_launches,
                 "share_of_step": tend["ms_total"] / ms if ms > 0 else None,
                 "whole_step": {"algorithmic_GB_per_step": 880.0 * N ** 3 / 1e9,
                                "achieved_GBps": 880.0 * N ** 3 * a.steps / (ms * 1e-3) / 1e9,

@@ -20,7 +20,8 @@ static cudaStream_t g_h2d = nullptr, g_d2h = nullptr;     // copy streams of the
 static bool g_inited = false;
 
 void count_launch(int n) { g_launches += n; }
-cudaStream_t stream() { return g_stream; }
+static cudaStream_t g_override = nullptr;     // set while independent launches are spread over the side streams
+cudaStream_t stream() { return g_override ? g_override : g_stream; }
 
 static void ensure_device() {
     if (g_inited) return;
@@ -819,20 +820,48 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
     const FT* U[3] = {m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(), m->F[2]->template p0<FT>()};
     const FT* pHY = m->pHY ? m->pHY->template p0<FT>() : nullptr;
     const FT* b = P.btr >= 0 ? m->F[3 + P.btr]->template p0<FT>() : nullptr;
+    // The launches of the prognostic fields are independent (each reads the old state and writes its own G^n and
+    // new-state buffer), so they go to side streams forked from the library stream: the tail of one launch (its last,
+    // partly filled wave of blocks) overlaps the head of the next instead of leaving SMs idle four times per stage.
+    static const bool spread = getenv("OB200_NO_STREAM_SPREAD") == nullptr;
+    static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    const bool fork = spread && m->use_fast && m->nf > 1;
+    if (fork && !ev_fork) {
+        OB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        for (int q = 0; q < 3; ++q) {
+            OB_CUDA(cudaStreamCreateWithFlags(&side[q], cudaStreamNonBlocking));
+            OB_CUDA(cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming));
+        }
+    }
+    ScopedPhase ph("tendency");
+    if (fork) OB_CUDA(cudaEventRecord(ev_fork, g_stream));
     for (int q = 0; q < m->nf; ++q) {
         ob200_field* f = m->F[q].get();
         FluxBC<FT> fbc;
         for (int s = 0; s < 6; ++s) { fbc.kind[s] = f->bcs[s].kind; fbc.val[s] = (FT)f->bcs[s].value; }
         FT* newp = ss.mode == SUB_NONE ? nullptr : f->template alt0<FT>();
         bool done = false;
-        ScopedPhase ph("tendency");
-        if (m->use_fast)
-            done = launch_tendency_fast<FT>(P, q, U, f->template p0<FT>(), pHY, m->Gn[q]->template p0<FT>(),
+        const int lane = fork ? q % 4 : 0;               // lane 0 = the library stream itself
+        if (lane > 0) {
+            if (q < 4) OB_CUDA(cudaStreamWaitEvent(side[lane - 1], ev_fork, 0));
+            g_override = side[lane - 1];
+        }
+        try {
+            if (m->use_fast)
+                done = launch_tendency_fast<FT>(P, q, U, f->template p0<FT>(), pHY, m->Gn[q]->template p0<FT>(),
+                                                m->Gm[q]->template p0<FT>(), newp, ss);
+            if (!done)
+                launch_tendency_general<FT>(P, q, U, f->template p0<FT>(), pHY, b, fbc, m->Gn[q]->template p0<FT>(),
                                             m->Gm[q]->template p0<FT>(), newp, ss);
-        if (!done)
-            launch_tendency_general<FT>(P, q, U, f->template p0<FT>(), pHY, b, fbc, m->Gn[q]->template p0<FT>(),
-                                        m->Gm[q]->template p0<FT>(), newp, ss);
+        } catch (...) { g_override = nullptr; throw; }
+        g_override = nullptr;
     }
+    if (fork)
+        for (int q = 0; q < 3 && q + 1 < m->nf; ++q) {
+            OB_CUDA(cudaEventRecord(ev_join[q], side[q]));
+            OB_CUDA(cudaStreamWaitEvent(g_stream, ev_join[q], 0));
+        }
     if (ss.mode != SUB_NONE) {
         // the out-of-place substep wrote the new state into the second buffer: swap.  Cells the
         // kernels never write (wall faces, outer halos of Bounded dims) are refreshed by the halo
