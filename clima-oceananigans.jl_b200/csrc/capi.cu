@@ -51,15 +51,17 @@ static cudaEvent_t get_event() {
 struct ScopedPhase {
     Phase* ph = nullptr;
     cudaEvent_t a, b;
+    cudaStream_t st = nullptr;
     explicit ScopedPhase(const char* name) {
         if (!g_profile) return;
         ph = &g_phases[name];
         a = get_event(); b = get_event();
-        cudaEventRecord(a, g_stream);
+        st = stream();
+        cudaEventRecord(a, st);
     }
     ~ScopedPhase() {
         if (!ph) return;
-        cudaEventRecord(b, g_stream);
+        cudaEventRecord(b, st);
         ph->pending.emplace_back(a, b);
     }
 };
@@ -788,10 +790,10 @@ static void model_update_state(ob200_model* m, bool tracers_too = true) {
 // hydrostatic integral read their operands with periodic wrap-around, so ALL halo fills of the stage (state
 // before the solve, pNHS after it, state + pHY' here) collapse into this one single-launch shell fill.
 template <class FT>
-static void model_update_state_after_projection(ob200_model* m, bool fused) {
+static void model_update_state_after_projection(ob200_model* m, bool fused, bool hydrostatic_done = false) {
     std::vector<ob200_field*> v = {m->F[0].get(), m->F[1].get(), m->F[2].get()};
     if (m->pHY) {
-        model_hydrostatic<FT>(m, fused);
+        if (!hydrostatic_done) model_hydrostatic<FT>(m, fused);
         v.push_back(m->pHY.get());
     }
     if (fused) {
@@ -801,6 +803,30 @@ static void model_update_state_after_projection(ob200_model* m, bool fused) {
     ScopedPhase ph("halo");
     fill_halos<FT>(v.data(), (int)v.size());
 }
+// Fused stage: the hydrostatic integral depends only on the buoyancy tracer, which is final once the tendency kernels
+// have run, so it is enqueued on a side stream and overlaps the pressure solve and the correction (it is a
+// latency-bound column walk that leaves most of the machine idle).  Returns true if it was started.
+static cudaStream_t g_hy_stream = nullptr;
+static cudaEvent_t g_hy_fork = nullptr, g_hy_done = nullptr;
+template <class FT>
+static bool model_hydrostatic_async_begin(ob200_model* m) {
+    static const bool off = getenv("OB200_NO_STREAM_SPREAD") != nullptr;
+    if (off || !m->pHY) return false;
+    if (!g_hy_stream) {
+        OB_CUDA(cudaStreamCreateWithFlags(&g_hy_stream, cudaStreamNonBlocking));
+        OB_CUDA(cudaEventCreateWithFlags(&g_hy_fork, cudaEventDisableTiming));
+        OB_CUDA(cudaEventCreateWithFlags(&g_hy_done, cudaEventDisableTiming));
+    }
+    OB_CUDA(cudaEventRecord(g_hy_fork, g_stream));
+    OB_CUDA(cudaStreamWaitEvent(g_hy_stream, g_hy_fork, 0));
+    g_override = g_hy_stream;
+    try { model_hydrostatic<FT>(m, true); } catch (...) { g_override = nullptr; throw; }
+    g_override = nullptr;
+    OB_CUDA(cudaEventRecord(g_hy_done, g_hy_stream));
+    return true;
+}
+static void model_hydrostatic_async_end() { OB_CUDA(cudaStreamWaitEvent(g_stream, g_hy_done, 0)); }
+
 // the fused path: every non-Flat dimension Periodic (not slab-decomposed) and regular, fast FFT solver
 template <class FT>
 static bool model_fused_periodic(ob200_model* m) {
@@ -926,10 +952,12 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
         const bool fused = model_fused_periodic<FT>(m);
         for (int s = 0; s < 3; ++s) {
             model_tendencies<FT>(m, ss[s]);
+            const bool hy = fused && model_hydrostatic_async_begin<FT>(m);
             model_pressure_step<FT>(m, sdt[s], true, fused);
             m->time += (double)sdt[s];
             if (s < 2) for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);   // store_tendencies!
-            model_update_state_after_projection<FT>(m, fused);
+            if (hy) model_hydrostatic_async_end();
+            model_update_state_after_projection<FT>(m, fused, hy);
         }
         m->iteration += 1;
     } else {
@@ -944,11 +972,13 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
         Substep<FT> ss{SUB_AB2, dt, FT(1.5) + chi, FT(0.5) + chi};
         const bool fused = model_fused_periodic<FT>(m);
         model_tendencies<FT>(m, ss);
+        const bool hy = fused && model_hydrostatic_async_begin<FT>(m);
         model_pressure_step<FT>(m, dt, true, fused);
         for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);
         m->time += (double)dt;
         m->iteration += 1;
-        model_update_state_after_projection<FT>(m, fused);
+        if (hy) model_hydrostatic_async_end();
+        model_update_state_after_projection<FT>(m, fused, hy);
     }
 }
 extern "C" int32_t ob200_model_time_step(ob200_model* m, double dt, int32_t euler) {
