@@ -749,7 +749,7 @@ static bool make_spec_map(FastPoisson<FT>* p, bool along_y, CUtensorMap* out) {
     const int Ny = p->N[1], Nz = p->N[2];
     cuuint64_t dims[3] = {(cuuint64_t)2 * p->NXP, (cuuint64_t)Ny, (cuuint64_t)Nz};
     cuuint64_t strides[2] = {(cuuint64_t)2 * p->NXP * sizeof(FT), (cuuint64_t)2 * p->NXP * Ny * sizeof(FT)};
-    cuuint32_t box[3] = {2 * TMA_TK, (cuuint32_t)(along_y ? Ny : 1), (cuuint32_t)(along_y ? 1 : Nz)};
+    cuuint32_t box[3] = {2 * TMA_TK, (cuuint32_t)(along_y ? std::min(Ny, 256) : 1), (cuuint32_t)(along_y ? 1 : std::min(Nz, 256))};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = fn(out, sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p->spec,
                     dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -807,7 +807,7 @@ static void setup_tma(FastPoisson<FT>* p) {
     if (p->R > 1) { setup_dist_tma(p); return; }
     if (getenv("OB200_NO_FFT_TMA") != nullptr || p->NXP % TMA_TK) return;
     const bool zfft = p->has_z && !p->tri;
-    if (p->log2[1] < 4 || p->log2[1] > 8 || (zfft && (p->log2[2] < 4 || p->log2[2] > 8))) return;
+    if (p->log2[1] < 4 || p->log2[1] > 9 || (zfft && (p->log2[2] < 4 || p->log2[2] > 9))) return;
     if (!make_spec_map(p, true, &p->tm_y)) return;
     if (zfft && !make_spec_map(p, false, &p->tm_z)) return;
     p->tma_ok = true;
@@ -842,8 +842,8 @@ static void launch_line_tma(const tl::TArgs<FT>& A, int log2n) {
             case 6: go(tl::line_tma_kernel<FT, 6, MODE, TK, STAGES>); break;
             case 7: go(tl::line_tma_kernel<FT, 7, MODE, TK, STAGES>); break;
             case 8: go(tl::line_tma_kernel<FT, 8, MODE, TK, STAGES>); break;
-            default:
-                if constexpr (MODE == LM_FWD_DIV_INV && STAGES == 2) go(tl::line_tma_kernel<FT, 9, MODE, TK, STAGES>);
+            default:       // 512-point lines: 64 KB tiles, two stages
+                if constexpr (STAGES == 2) go(tl::line_tma_kernel<FT, 9, MODE, TK, STAGES>);
                 else throw Error("line_tma: unsupported length");
                 break;
         }
@@ -868,7 +868,7 @@ static void run_line_tma(FastPoisson<FT>* p, int dim, int mode) {
     A.lamO = dim == 1 ? p->lamz : p->lamy;
     static const int stages = env_int("OB200_FFT_STAGES", 3);
     const int l = p->log2[dim];
-#define GO(M)  { if (stages == 2) launch_line_tma<FT, M, 2>(A, l); else launch_line_tma<FT, M, 3>(A, l); }
+#define GO(M)  { if (stages == 2 || l >= 9) launch_line_tma<FT, M, 2>(A, l); else launch_line_tma<FT, M, 3>(A, l); }
     if (mode == LM_FWD) GO(LM_FWD) else if (mode == LM_INV) GO(LM_INV) else GO(LM_FWD_DIV_INV)
 #undef GO
 }

@@ -169,7 +169,14 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
         unsigned long long* bar = &full[n % STAGES];
         mbar_expect_tx(bar, TILE_BYTES);
         void* dst = buf(n % STAGES);
-        if (A.addr == ADDR_NAT) tma_load_3d(dst, &A.tm, 2 * kx0, A.line_is_y ? 0 : o, A.line_is_y ? o : 0, bar);
+        if (A.addr == ADDR_NAT) {
+            // a box holds at most 256 rows: lines of 512 points are staged as two boxes
+            constexpr int ROWS = N > 256 ? 256 : N;
+#pragma unroll
+            for (int b = 0; b < N / ROWS; ++b)
+                tma_load_3d(reinterpret_cast<CT*>(dst) + (size_t)b * ROWS * TK, &A.tm, 2 * kx0, A.line_is_y ? b * ROWS : o,
+                            A.line_is_y ? o : b * ROWS, bar);
+        }
         else if (A.addr == ADDR_ZF) tma_load_3d(dst, &A.tm, 2 * kx0, o, 0, bar);
         else if (A.addr == ADDR_ZI) tma_load_4d(dst, &A.tm4, 2 * TK * kxb, o, 0, r, bar);
         else tma_load_4d(dst, &A.tm4, 2 * TK * kxb, 0, o, 0, bar);
@@ -239,7 +246,12 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
         fence_async_smem();           // generic-proxy writes of the tile -> visible to the bulk store
         __syncthreads();
         if (lead) {
-            if (A.addr == ADDR_NAT) tma_store_3d(&A.tm, 2 * kx0, A.line_is_y ? 0 : o, A.line_is_y ? o : 0, s);
+            if (A.addr == ADDR_NAT) {
+                constexpr int ROWS = N > 256 ? 256 : N;
+#pragma unroll
+                for (int b = 0; b < N / ROWS; ++b)
+                    tma_store_3d(&A.tm, 2 * kx0, A.line_is_y ? b * ROWS : o, A.line_is_y ? o : b * ROWS, s + (size_t)b * ROWS * TK);
+            }
             else if (A.addr == ADDR_ZF || A.addr == ADDR_ZI) tma_store_3d(&A.tmr[r], 2 * TK * kxb, o, 0, s);
             else for (int q = 0; q < A.R; ++q) tma_store_3d(&A.tmr[q], 2 * TK * kxb, 0, o, s + (size_t)q * A.NyL * TK);
             bulk_commit();

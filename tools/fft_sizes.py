@@ -7,7 +7,7 @@ for p in (ROOT, os.path.join(ROOT, "clima-oceananigans.jl_b200")):
     sys.path.insert(0, p)
 import ocean_b200 as ob
 arch = ob.B200(0)
-sizes = [(32, 16, 16), (64, 32, 128), (64, 64, 64), (128, 64, 32), (32, 256, 16), (128, 128, 128), (256, 256, 256)]
+sizes = [(32, 16, 16), (64, 32, 128), (64, 64, 64), (128, 64, 32), (32, 256, 16), (64, 512, 16), (64, 16, 512), (128, 128, 128), (256, 256, 256)]
 for N in sizes:
     try:
         g = ob.RectilinearGrid(arch, np.float64, size=N, extent=(1, 1, 1), topology=("Periodic",) * 3)
