@@ -357,6 +357,112 @@ __global__ void __launch_bounds__(128) tendency_general_kernel(const __grid_cons
     else if (s.mode == SUB_AB2) A.psi_new[q.p] = A.psi[q.p] + s.dt * (s.c1 * G - s.c2 * A.Gm[q.p]);
 }
 
+// =============================================================================================
+// general tendency kernel with SHARED faces (any scheme / closure / BCs on a 3-D grid)
+// The kernel above evaluates both faces of every cell in every direction (as the reference does,
+// momentum_advection_operators.jl:52-56): each face flux is computed twice.  Here a block of 32 x 8 threads walks
+// up in k and every thread evaluates ONE face per direction -- advective + viscous / diffusive flux summed -- of
+// its own position; the other face of a cell comes from the neighbouring thread: along x by a warp shuffle, along y
+// through shared memory, along z from the previous level kept in a register.  Tiles overlap by one column and one
+// row (31 x 7 cells are finished per block), which replaces every special case at tile edges.  Same operator
+// functions (physics.cuh) as the kernel above; the divergence of the summed fluxes differs from the sum of the two
+// divergences by rounding only.
+// =============================================================================================
+template <class FT, int COMP>
+__global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_constant__ Phys<FT> P, const __grid_constant__ TendArgs<FT> A, int Kc) {
+    const GridD<FT>& g = P.g;
+    constexpr int TXS = 32, TYS = 8;
+    constexpr int B = COMP < 3 ? COMP : 3;
+    // pairing along direction d: LOW = the cell needs f(q) - f(q-1) (its own face and the previous thread's),
+    // HIGH = f(q+1) - f(q).  Momentum: LOW along its own direction, HIGH otherwise; tracers: HIGH everywhere.
+    constexpr bool XLOW = B == 0, YLOW = B == 1, ZLOW = B == 2;
+    __shared__ FT sF[2][TYS][TXS];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = (XLOW ? 0 : 1) + blockIdx.x * (TXS - 1) + tx;
+    const int j = (YLOW ? 0 : 1) + blockIdx.y * (TYS - 1) + ty;
+    const int k0 = 1 + blockIdx.z * Kc, k1 = min(g.N[2], k0 + Kc - 1);
+    const bool outx = (XLOW ? tx >= 1 : tx <= TXS - 2) && i >= 1 && i <= g.N[0];
+    const bool outy = (YLOW ? ty >= 1 : ty <= TYS - 2) && j >= 1 && j <= g.N[1];
+    const bool cell = outx && outy;
+    const bool need_x = outy && i <= g.N[0] + 1, need_y = outx && j <= g.N[1] + 1;
+    const FT* U[3] = {A.U[0], A.U[1], A.U[2]};
+    const int comp = COMP == 3 ? A.comp : COMP;
+    const bool visc = P.closure != CLO_NONE;
+    const FT kappa = COMP == 3 ? P.kappa[comp - 3] : FT(0);
+    auto face = [&](int d, Pt q) -> FT {       // area-weighted advective + viscous / diffusive flux at q along d
+        FT f = FT(0);
+        if (COMP < 3) {
+            if (P.scheme != ADV_NONE) f = momentum_flux(P, d, B, U[d], A.psi, q);
+            if (visc) f = f + viscous_Aflux(P, B, d, U, q);
+        } else {
+            if (P.scheme != ADV_NONE) f = tracer_flux(P, d, U[d], A.psi, q);
+            if (visc) f = f + diffusive_Aflux(P, d, kappa, A.psi, q);
+        }
+        return f;
+    };
+    Pt q;
+    q.i[0] = i; q.i[1] = j; q.i[2] = k0;
+    q.p = i * g.st[0] + j * g.st[1] + k0 * g.st[2];
+    FT Fz_carry = FT(0);
+    if (cell) Fz_carry = face(2, ZLOW ? sh(g, q, 2, -1) : q);
+    for (int k = k0; k <= k1; ++k) {
+        const int buf = (k - k0) & 1;
+        FT Fx = FT(0), Fy = FT(0), dFz = FT(0);
+        if (need_x) Fx = face(0, q);
+        if (need_y) Fy = face(1, q);
+        sF[buf][ty][tx] = Fy;
+        if (cell) {
+            FT Fz_new = face(2, ZLOW ? q : sh(g, q, 2, 1));
+            dFz = Fz_new - Fz_carry;
+            Fz_carry = Fz_new;
+        }
+        const FT Fxn = XLOW ? __shfl_up_sync(0xffffffffu, Fx, 1) : __shfl_down_sync(0xffffffffu, Fx, 1);
+        __syncthreads();
+        if (cell) {
+            const FT dFx = XLOW ? (Fx - Fxn) : (Fxn - Fx);
+            const FT Fyn = sF[buf][YLOW ? ty - 1 : ty + 1][tx];
+            const FT dFy = YLOW ? (Fy - Fyn) : (Fyn - Fy);
+            int l[3] = {OB_C, OB_C, OB_C};
+            if (COMP < 3) l[COMP] = OB_F;
+            FT G = -((1 / volume(g, q, l[0], l[1], l[2])) * ((dFx + dFy) + dFz));
+            if (COMP == 0) {
+                if (P.fplane) {          // x_f_cross_U = -f ℑxyᶠᶜᵃ(v)   (f_plane.jl:42)
+                    FT a0 = IF(g, U[1], q, 0);
+                    FT v = g.topo[1] == OB_FLAT ? a0 : FT(0.5) * (a0 + IF(g, U[1], sh(g, q, 1, 1), 0));
+                    G = G - (-P.f * v);
+                }
+                if (A.pHY) G = G - deriv(g, A.pHY, q, 0, OB_F);
+            } else if (COMP == 1) {
+                if (P.fplane) {          // y_f_cross_U = f ℑxyᶜᶠᵃ(u)    (f_plane.jl:43)
+                    FT a1 = IC(g, U[0], q, 0);
+                    FT u = g.topo[1] == OB_FLAT ? a1 : FT(0.5) * (IC(g, U[0], sh(g, q, 1, -1), 0) + a1);
+                    G = G - (P.f * u);
+                }
+                if (A.pHY) G = G - deriv(g, A.pHY, q, 1, OB_F);
+            }
+            if (COMP < 2 && P.tilted && A.b) G = G + P.ghat[COMP] * A.b[q.p];      // x/y_dot_g_b (g_dot_b.jl:1-3)
+            // apply_x/y/z_bcs! (apply_flux_bcs.jl:35-160): constant Flux BCs of this field
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (g.topo[d] != OB_BOUNDED) continue;
+                int lf[3] = {l[0], l[1], l[2]};
+                lf[d] = l[d] == OB_C ? OB_F : OB_C;
+                if (A.fbc.kind[2 * d] == 2 && q.i[d] == 1 && A.fbc.val[2 * d] != FT(0))
+                    G += A.fbc.val[2 * d] * areaA(g, d, q, lf[0], lf[1], lf[2]) / volume(g, q, l[0], l[1], l[2]);
+                if (A.fbc.kind[2 * d + 1] == 2 && q.i[d] == g.N[d] && A.fbc.val[2 * d + 1] != FT(0))
+                    G -= A.fbc.val[2 * d + 1] * areaA(g, d, sh(g, q, d, 1), lf[0], lf[1], lf[2]) /
+                         volume(g, q, l[0], l[1], l[2]);
+            }
+            A.Gn[q.p] = G;
+            const Substep<FT>& ss = A.ss;
+            if (ss.mode == SUB_RK3_FIRST) A.psi_new[q.p] = A.psi[q.p] + ss.c1 * G;
+            else if (ss.mode == SUB_RK3) A.psi_new[q.p] = A.psi[q.p] + ss.dt * (ss.c1 * G + ss.c2 * A.Gm[q.p]);
+            else if (ss.mode == SUB_AB2) A.psi_new[q.p] = A.psi[q.p] + ss.dt * (ss.c1 * G - ss.c2 * A.Gm[q.p]);
+        }
+        q = sh(g, q, 2, 1);
+    }
+}
+
 template <class FT>
 void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi,
                              const FT* pHY, const FT* b, const FluxBC<FT>& fbc, FT* Gn,
@@ -365,6 +471,23 @@ void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], 
     for (int d = 0; d < 3; ++d) A.U[d] = U[d];
     A.psi = psi; A.pHY = pHY; A.b = b; A.Gn = Gn; A.Gm = Gm; A.psi_new = psi_new;
     A.ss = ss; A.fbc = fbc; A.comp = comp;
+    // shared-face variant: 3-D grids (every direction has two faces to pair) with a halo wide enough for the one
+    // extra face position per direction
+    static const bool no_shared = getenv("OB200_NO_SHARED_GENERAL") != nullptr;
+    bool shared = !no_shared && (P.scheme != ADV_NONE || P.closure != CLO_NONE);
+    for (int d = 0; d < 3; ++d) shared = shared && P.g.topo[d] != OB_FLAT && P.g.N[d] >= 2;
+    if (shared) {
+        const int Kc = 32;
+        dim3 bs(32, 8, 1), gs(cdiv(P.g.N[0], 31), cdiv(P.g.N[1], 7), cdiv(P.g.N[2], Kc));
+        switch (comp) {
+            case 0: tendency_shared_kernel<FT, 0><<<gs, bs, 0, stream()>>>(P, A, Kc); break;
+            case 1: tendency_shared_kernel<FT, 1><<<gs, bs, 0, stream()>>>(P, A, Kc); break;
+            case 2: tendency_shared_kernel<FT, 2><<<gs, bs, 0, stream()>>>(P, A, Kc); break;
+            default: tendency_shared_kernel<FT, 3><<<gs, bs, 0, stream()>>>(P, A, Kc); break;
+        }
+        OB_LAUNCH_CHECK();
+        return;
+    }
     dim3 blk(32, 4, 1);
     dim3 grd(cdiv(P.g.N[0], 32), cdiv(P.g.N[1], 4), P.g.N[2]);
     switch (comp) {
