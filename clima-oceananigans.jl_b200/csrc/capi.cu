@@ -255,6 +255,7 @@ static void build_gridD(ob200_grid* G, GridD<FT>& g) {
             if (d == 0) g.S[d] = ((g.S[d] + align - 1) / align) * align;
         }
     }
+    for (int d = 0; d < 3; ++d) g.invd[d] = g.regular[d] ? FT(1) / g.d[d] : FT(0);
     g.st[0] = 1; g.st[1] = g.S[0]; g.st[2] = (long long)g.S[0] * g.S[1];
     g.total = (long long)g.S[0] * g.S[1] * g.S[2];
     g.off0 = (g.O[0] - 1) * g.st[0] + (g.O[1] - 1) * g.st[1] + (g.O[2] - 1) * g.st[2];

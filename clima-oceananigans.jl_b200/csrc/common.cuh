@@ -29,6 +29,7 @@ struct GridD {
     long long total;        // allocated elements per field
     int regular[3];
     FT d[3];                // spacing of regular (and Flat: 1) dimensions
+    FT invd[3];             // 1 / d[] (regular dimensions: derivatives multiply instead of dividing)
     const FT* dC[3];        // stretched: Δ at centers, pre-offset: dC[d][i] with Julia index i
     const FT* dF[3];        // stretched: Δ at faces
     FT L[3];

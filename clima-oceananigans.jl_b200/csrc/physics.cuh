@@ -69,6 +69,9 @@ template <class FT> OBD FT I2(const GridD<FT>& g, const FT* f, Pt q, int d, int 
 // ∂ at result location loc along d: δ / Δ (derivative_operators.jl:6-29)
 template <class FT> OBD FT deriv(const GridD<FT>& g, const FT* f, Pt q, int d, int loc) {
     FT del = loc == OB_C ? dC(g, f, q, d) : dFc(g, f, q, d);
+#ifndef OB200_STRICT
+    if (g.regular[d]) return del * g.invd[d];       // one rounding instead of a Float64 division (~20 instructions)
+#endif
     return del / spacing(g, d, loc, q.i[d]);
 }
 
