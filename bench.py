@@ -124,6 +124,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ftype", default="f64", choices=["f64", "f32"],
+                    help="arithmetic type of the run (the headline configuration is Float64; f32 is reported for reference)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,9 +165,10 @@ def main():
         arch = ob.MultiArch.from_torch_distributed(local_rank)
     else:
         arch = ob.B200(local_rank)
-    grid = ob.RectilinearGrid(arch, np.float64, size=(N, N * world, N), extent=(1, world, 1),
+    FTYPE = np.float64 if a.ftype == "f64" else np.float32
+    grid = ob.RectilinearGrid(arch, FTYPE, size=(N, N * world, N), extent=(1, world, 1),
                               topology=("Periodic",) * 3)
-    model = ob.NonhydrostaticModel(grid, advection=ob.WENO5(), tracers=("b",), buoyancy=ob.BuoyancyTracer(),
+    model = ob.NonhydrostaticModel(grid, advection=ob.WENO5(FTYPE), tracers=("b",), buoyancy=ob.BuoyancyTracer(),
                                    timestepper="RungeKutta3")
     vals = synthetic_state(N, seed=2 + rank)
     ob.set_model(model, **vals)
@@ -212,7 +215,7 @@ def main():
     if world > 1:
         d["max_abs_div"] = arch.allreduce([d["max_abs_div"]], "max")[0]
         d["kinetic_energy"] = arch.allreduce([d["kinetic_energy"]], "sum")[0]
-    assert np.isfinite(d["kinetic_energy"]) and d["max_abs_div"] < 1e-8, d
+    assert np.isfinite(d["kinetic_energy"]) and d["max_abs_div"] < (1e-8 if a.ftype == "f64" else 1e-1), d
 
     # ---- roofline of the dominant kernel: the fused tendency+substep kernel (one launch per field) ----
     peaks = {}
@@ -225,7 +228,8 @@ def main():
     tend = phases["tendency"]
     # algorithmic words per point per launch: (4F+1)/F for stages 2,3 and (3F+1)/F for stage 1
     words = ((3 * F + 1) + 2 * (4 * F + 1)) / 3.0 / F
-    alg_bytes = words * 8 * N ** 3
+    W = 8 if a.ftype == "f64" else 4
+    alg_bytes = words * W * N ** 3
     # the "tendency" phase brackets the F launches of a stage (they run on forked streams so that their tails overlap)
     tend_launches = tend["count"] * F
     avg_ms = tend["ms_total"] / max(1, tend_launches)
@@ -238,9 +242,9 @@ def main():
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "avg_launch_ms": avg_ms, "launches": tend_launches,
                 "share_of_step": tend["ms_total"] / ms if ms > 0 else None,
-                "whole_step": {"algorithmic_GB_per_step": 880.0 * N ** 3 / 1e9,
-                               "achieved_GBps": 880.0 * N ** 3 * a.steps / (ms * 1e-3) / 1e9,
-                               "frac": 880.0 * N ** 3 * a.steps / (ms * 1e-3) / 1e9 / peak},
+                "whole_step": {"algorithmic_GB_per_step": 110.0 * W * N ** 3 / 1e9,
+                               "achieved_GBps": 110.0 * W * N ** 3 * a.steps / (ms * 1e-3) / 1e9,
+                               "frac": 110.0 * W * N ** 3 * a.steps / (ms * 1e-3) / 1e9 / peak},
                 "phases_ms_per_step": {k: v["ms_total"] / a.steps for k, v in phases.items()},
                 "poisson_ms_per_step": {k: v["ms_total"] / a.steps for k, v in fft_phases.items() if v["count"]}}
 
@@ -253,7 +257,7 @@ def main():
         # two sets of pinned output buffers: step n writes set n % 2 and the host "consumes" (checksums one value of)
         # set (n - 1) % 2 while the GPU works, as a streaming caller would
         hout = [{n: torch.empty_like(hin[n]).pin_memory() for n in names} for _ in range(2)]
-        nbytes = sum(t.numel() * 8 for t in hin.values())
+        nbytes = sum(t.numel() * t.element_size() for t in hin.values())
         ksteps = max(4, min(a.steps, 10))
         done_events = [torch.cuda.Event() for _ in range(2)]
 
@@ -321,8 +325,8 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "grid": [N, N, N], "timestepper": "RungeKutta3", "advection": "WENO5 (Z)",
+            "dtype": a.ftype, "data": "synthetic",
+            "config": {"workload": workload if a.ftype == "f64" else workload.replace("Float64", "Float32"), "grid": [N, N, N], "timestepper": "RungeKutta3", "advection": "WENO5 (Z)",
                        "fields": F, "dt": dt, "l2": "inputs larger than L2 (14 fields x 144 MB)",
                        "parallelism": "single GPU" if world == 1 else
                        f"slab decomposition in y, ranks=(1,{world},1): global grid {N}x{N * world}x{N}, {N}^3 per GPU; "

@@ -70,17 +70,19 @@ __device__ __forceinline__ FT weno_face(FT a, FT b, FT c, FT d, FT e, FT x2, FT 
         const FT q = fma(q0, fma(er, er, er), q0);     // S / den
         return fma(q, K<FT>(2), m);
     } else {
+        // Float32: the product form above would overflow for large-amplitude fields, so the weights keep the
+        // reference's quotient form, with fast (2 ulp) divisions -- the tolerance of this precision is 1e-5
         const FT D0 = B0 + eps4, D1 = B1 + eps4, D2 = B2 + eps4;
         FT a0, a1, a2;
         if (ZW) {
             const FT tau = B2 - B0;
-            const FT q0 = tau / D0, q1 = tau / D1, q2 = tau / D2;
+            const FT q0 = __fdividef(tau, D0), q1 = __fdividef(tau, D1), q2 = __fdividef(tau, D2);
             a0 = FT(3) * fma(q0, q0, FT(1)); a1 = FT(6) * fma(q1, q1, FT(1)); a2 = fma(q2, q2, FT(1));
         } else {
-            a0 = FT(3) / (D0 * D0); a1 = FT(6) / (D1 * D1); a2 = FT(1) / (D2 * D2);
+            a0 = __fdividef(FT(3), D0 * D0); a1 = __fdividef(FT(6), D1 * D1); a2 = __fdividef(FT(1), D2 * D2);
         }
         const FT S = fma(a0, t0, fma(a1, t1, a2 * r2));
-        return fma(S / ((a0 + a1) + a2), K<FT>(2), m);
+        return fma(__fdividef(S, (a0 + a1) + a2), K<FT>(2), m);
     }
 }
 
