@@ -231,7 +231,7 @@ def main():
     W = 8 if a.ftype == "f64" else 4
     alg_bytes = words * W * N ** 3
     # the "tendency" phase brackets the F launches of a stage (they run on forked streams so that their tails overlap)
-    tend_launches = tend["count"] * F
+    tend_launches = a.steps * 3 * F
     avg_ms = tend["ms_total"] / max(1, tend_launches)
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "tendency+substep (per prognostic field)", "achieved": achieved, "peak": peak,
