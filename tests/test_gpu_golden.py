@@ -150,3 +150,29 @@ def test_c3_physics_with_fast_tridiagonal_solver(ob, FT, tol):
         for n in mo.names:
             assert rel(mb.fields[n].interior(), mo.fields[n].interior) < tol, (step, n)
     assert mb.diagnostics()["max_abs_div"] < (1e-12 if FT == np.float64 else 1e-4)
+
+
+def test_async_parent_transfers_round_trip_and_pipeline(ob):
+    """ob200_field_{set,get}_parent_async + ob200_mark_download_batch / ob200_sync_downloads: uploads and downloads on
+    the copy streams deliver exactly what the synchronous calls deliver, also when several batches are in flight"""
+    import ctypes as C
+    from ocean_b200._lib import lib
+    g = ob.RectilinearGrid(ob.arch, np.float64, size=(32, 16, 8), extent=(1, 1, 1), topology=("Periodic",) * 3)
+    f = ob.CenterField(g)
+    rng = np.random.default_rng(9)
+    shape = f.parent_size
+    outs = []
+    for step in range(4):
+        a = np.asfortranarray(rng.random(shape))
+        out = np.zeros(shape, order="F")
+        assert lib.ob200_field_set_parent_async(f.handle, a.ctypes.data_as(C.c_void_p)) == 0
+        assert lib.ob200_field_get_parent_async(f.handle, out.ctypes.data_as(C.c_void_p)) == 0
+        assert lib.ob200_mark_download_batch() == 0
+        outs.append((a, out))
+        if step >= 2:
+            assert lib.ob200_sync_downloads(1) == 0            # everything but the newest batch has arrived
+            assert np.array_equal(outs[step - 1][0], outs[step - 1][1])
+    assert lib.ob200_sync() == 0
+    for a, out in outs:
+        assert np.array_equal(a, out)
+    assert np.array_equal(f.parent(), outs[-1][0])
