@@ -102,14 +102,15 @@ def cpu_reference_run(steps, warmup, sample_n=128):
     N = sample_n
     vals = synthetic_state(N)
     dt = 0.1 / N
-    cores = cpu_twin.max_threads()
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    cores = max(cpu_twin.max_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     args = ((N, N, N), (1.0, 1.0, 1.0), vals["u"], vals["v"], vals["w"], vals["b"])
     # the set-up (halo allocation, copies) is inside the call; time two run lengths and difference them
     t0 = time.perf_counter()
-    cpu_twin.rk3_run(*args, 0, dt, project=False)
+    cpu_twin.rk3_run(*args, 0, dt, project=False, nthreads=cores)
     t_setup = time.perf_counter() - t0
     t0 = time.perf_counter()
-    cpu_twin.rk3_run(*args, steps, dt, project=False)
+    cpu_twin.rk3_run(*args, steps, dt, project=False, nthreads=cores)
     el = max(time.perf_counter() - t0 - t_setup, 1e-9)
     return (N ** 3 * steps / el, el / steps, cores,
             f"{steps} RK3 step(s) of the same model at {N}^3 (compiled OpenMP twin of the oracle, {cores} threads)")
