@@ -295,10 +295,12 @@ static EncodeFn get_encode() {
 
 template <class FT>
 static CUtensorMap make_map(const GridD<FT>& g, const FT* base, int box_x, int box_y) {
-    static std::map<std::tuple<const void*, long long, int, int>, CUtensorMap> cache;
+    // keyed on everything the encoding depends on: the same address can come back from the allocator for a field of
+    // another grid with the same element count but different extents
+    static std::map<std::tuple<const void*, int, int, int, int, int, int>, CUtensorMap> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    auto key = std::make_tuple((const void*)base, (long long)g.total * (long long)sizeof(FT) + g.S[0], box_x, box_y);
+    auto key = std::make_tuple((const void*)base, g.S[0], g.S[1], g.S[2], (int)sizeof(FT), box_x, box_y);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     CUtensorMap m;
