@@ -176,3 +176,28 @@ def test_async_parent_transfers_round_trip_and_pipeline(ob):
     for a, out in outs:
         assert np.array_equal(a, out)
     assert np.array_equal(f.parent(), outs[-1][0])
+
+
+def test_full_size_256_step_matches_compiled_oracle(ob):
+    """BASELINE.json configs[1] AT ITS FULL SIZE (256^3, triply periodic, WENO5 + b, FFT solve, RK3, Float64): one full
+    time step of the CUDA path against the compiled OpenMP twin of the oracle (oracle/oracle_cpu.c, itself pinned to
+    the NumPy oracle and the golden vectors by tests/test_golden_oracle.py), every prognostic field <= 1e-12."""
+    from oracle import cpu_twin
+    N = 256
+    rng = np.random.default_rng(2)
+    vals = {}
+    for n in "uvw":
+        a = rng.uniform(-1, 1, (N, N, N))
+        vals[n] = a - a.mean()
+    z = (np.arange(N) + 0.5) / N
+    vals["b"] = 1e-5 * z.reshape(1, 1, N) + 1e-3 * rng.uniform(-1, 1, (N, N, N))
+    gb = ob.RectilinearGrid(ob.arch, np.float64, size=(N, N, N), extent=(1, 1, 1), topology=("Periodic",) * 3)
+    mb = ob.NonhydrostaticModel(gb, advection=ob.WENO5(), tracers=("b",), buoyancy=ob.BuoyancyTracer(),
+                                timestepper="RungeKutta3")
+    ob.set_model(mb, **vals)
+    dt = 0.1 / N
+    ob.time_step(mb, dt)
+    ref = cpu_twin.rk3_run((N, N, N), (1.0, 1.0, 1.0), vals["u"], vals["v"], vals["w"], vals["b"], 1, dt, project=True,
+                           nthreads=len(__import__("os").sched_getaffinity(0)))
+    for n, r in zip("uvwb", ref):
+        assert rel(mb.fields[n].interior(), r) < 1e-12, n
