@@ -543,6 +543,10 @@ struct FastPoisson {
     CUtensorMap tm_y, tm_z;
     // slab-decomposed solve through TMA (peer-memory tensor maps): see distributed_middle_tma
     bool dtma_ok = false;
+    // bulk = true: the transform kernels store into LOCAL chunk buffers and the chunks travel to their ranks as large
+    // contiguous copies (copy engines over NVLink); false: the kernels store straight into the peers' buffers
+    bool bulk_a2a = false;
+    CT* bufC = nullptr;
     int dtk_y = 8;                              // columns per y tile (8, 4, 2 for gathered lines of <= 512, 1024, 2048)
     CUtensorMap tm4_zi, tm4_y, tmr_zf[8], tmr_zi[8], tmr_y[8];
 };
@@ -789,10 +793,21 @@ static void setup_dist_tma(FastPoisson<FT>* p) {
     cuuint64_t sc[2] = {(cuuint64_t)2 * KXB * W, (cuuint64_t)2 * KXB * NyL * W};                  // chunk strides
     cuuint64_t sn[2] = {(cuuint64_t)2 * p->NXP * W, (cuuint64_t)2 * p->NXP * NyL * W};           // natural strides
     cuuint32_t bz[3] = {2 * TMA_TK, 1, (cuuint32_t)Nz}, by[3] = {(cuuint32_t)(2 * p->dtk_y), (cuuint32_t)NyL, 1};
+    // default: peer stores for 2 ranks (half of the data stays local and the rest overlaps the transform), bulk
+    // copies beyond (measured: the 128-byte rows of the fused stores reach ~440 GB/s of NVLink, contiguous copies more)
+    const char* eb = getenv("OB200_FFT_BULK_A2A");
+    p->bulk_a2a = eb ? atoi(eb) != 0 : R > 2;
+    if (p->bulk_a2a && !p->bufC) {
+        OB_CUDA(cudaMalloc(&p->bufC, (size_t)R * chunk * sizeof(CT)));
+        p->owned.push_back(p->bufC);
+    }
     for (int r = 0; r < R; ++r) {
-        if (!encode_map<FT>(&p->tmr_zf[r], p->peerB[r] + (long long)p->rank * chunk, 3, d3, sc, bz)) return;
+        // own chunk: always straight into its final place; other ranks: peer buffer, or local staging (bufA / bufC)
+        CT* zf = (!p->bulk_a2a || r == p->rank) ? p->peerB[r] + (long long)p->rank * chunk : p->bufA + (long long)r * chunk;
+        CT* yy = (!p->bulk_a2a || r == p->rank) ? p->peerA[r] + (long long)p->rank * chunk : p->bufC + (long long)r * chunk;
+        if (!encode_map<FT>(&p->tmr_zf[r], zf, 3, d3, sc, bz)) return;
         if (!encode_map<FT>(&p->tmr_zi[r], p->spec + (long long)r * KXB, 3, d3, sn, bz)) return;
-        if (!encode_map<FT>(&p->tmr_y[r], p->peerA[r] + (long long)p->rank * chunk, 3, d3, sc, by)) return;
+        if (!encode_map<FT>(&p->tmr_y[r], yy, 3, d3, sc, by)) return;
     }
     cuuint64_t d4[4] = {(cuuint64_t)2 * KXB, (cuuint64_t)NyL, (cuuint64_t)Nz, (cuuint64_t)R};
     cuuint64_t s4[3] = {sc[0], sc[1], (cuuint64_t)2 * chunk * W};
@@ -922,7 +937,18 @@ static void distributed_middle_tma(FastPoisson<FT>* p) {
     for (int r = 0; r < R; ++r) A.tmr[r] = p->tmr_zf[r];
     A.tpc = cdiv(KXB, TMA_TK); A.nkx = R * A.tpc; A.nOther = NyL; A.line_is_y = 0;
     A.tw = p->twZ; A.scale = (FT)(1.0 / Nz); A.lamL = p->lamz; A.lamO = nullptr;
-    { PhaseScope ph("fft_z_fwd"); launch_line_tma<FT, LM_FWD, 3>(A, p->log2[2]); }
+    const size_t chunk_bytes = (size_t)KXB * NyL * Nz * sizeof(typename Cx<FT>::T);
+    const long long chunk_el = (long long)KXB * NyL * Nz;
+    {
+        PhaseScope ph("fft_z_fwd");
+        launch_line_tma<FT, LM_FWD, 3>(A, p->log2[2]);
+        if (p->bulk_a2a)       // chunk r of my staging -> slot `rank` of rank r's bufB, one contiguous copy each
+            for (int q = 1; q < R; ++q) {
+                const int r = (p->rank + q) % R;
+                OB_CUDA(cudaMemcpyAsync(p->peerB[r] + (long long)p->rank * chunk_el, p->bufA + (long long)r * chunk_el,
+                                        chunk_bytes, cudaMemcpyDefault, stream()));
+            }
+    }
     { PhaseScope ph("fft_sync"); cm::barrier(); }
     // gathered y lines: forward, eigenvalue divide, backward
     A.addr = tl::ADDR_Y; A.tm4 = p->tm4_y;
@@ -936,6 +962,12 @@ static void distributed_middle_tma(FastPoisson<FT>* p) {
         else if (l == 9) launch_line_tma<FT, LM_FWD_DIV_INV, 2>(A, l);
         else if (l == 10) launch_line_tma<FT, LM_FWD_DIV_INV, 2, 4>(A, l);
         else launch_line_tma<FT, LM_FWD_DIV_INV, 2, 2>(A, l);
+        if (p->bulk_a2a)
+            for (int q = 1; q < R; ++q) {
+                const int r = (p->rank + q) % R;
+                OB_CUDA(cudaMemcpyAsync(p->peerA[r] + (long long)p->rank * chunk_el, p->bufC + (long long)r * chunk_el,
+                                        chunk_bytes, cudaMemcpyDefault, stream()));
+            }
     }
     { PhaseScope ph("fft_sync"); cm::barrier(); }
     // z backward
