@@ -796,7 +796,7 @@ static void setup_dist_tma(FastPoisson<FT>* p) {
     // default: peer stores for 2 ranks (half of the data stays local and the rest overlaps the transform), bulk
     // copies beyond (measured: the 128-byte rows of the fused stores reach ~440 GB/s of NVLink, contiguous copies more)
     const char* eb = getenv("OB200_FFT_BULK_A2A");
-    p->bulk_a2a = eb ? atoi(eb) != 0 : R > 2;
+    p->bulk_a2a = eb ? atoi(eb) != 0 : true;
     if (p->bulk_a2a && !p->bufC) {
         OB_CUDA(cudaMalloc(&p->bufC, (size_t)R * chunk * sizeof(CT)));
         p->owned.push_back(p->bufC);
@@ -873,6 +873,7 @@ static void run_line_tma(FastPoisson<FT>* p, int dim, int mode) {
     tl::TArgs<FT> A;
     A.tm = dim == 1 ? p->tm_y : p->tm_z;
     A.addr = tl::ADDR_NAT; A.R = 1; A.KXB = p->NXP; A.tpc = p->NXP / TMA_TK; A.NyL = p->N[1]; A.kx_base = 0; A.NXP = p->NXP;
+    A.r_only = -1; A.o_first = 0;
     A.line_is_y = dim == 1;
     A.nkx = p->NXP / TMA_TK;
     A.nOther = dim == 1 ? p->N[2] : p->N[1];
@@ -937,17 +938,40 @@ static void distributed_middle_tma(FastPoisson<FT>* p) {
     for (int r = 0; r < R; ++r) A.tmr[r] = p->tmr_zf[r];
     A.tpc = cdiv(KXB, TMA_TK); A.nkx = R * A.tpc; A.nOther = NyL; A.line_is_y = 0;
     A.tw = p->twZ; A.scale = (FT)(1.0 / Nz); A.lamL = p->lamz; A.lamO = nullptr;
-    const size_t chunk_bytes = (size_t)KXB * NyL * Nz * sizeof(typename Cx<FT>::T);
+    using CTt = typename Cx<FT>::T;
+    const size_t chunk_bytes = (size_t)KXB * NyL * Nz * sizeof(CTt);
     const long long chunk_el = (long long)KXB * NyL * Nz;
+    // bulk transposes are pipelined with the transform: the launch is split (z forward: one launch per destination
+    // chunk; y lines: one launch per block of z levels, whose slice of every chunk is contiguous) and each finished
+    // piece is copied on a second stream while the next piece is transformed
+    static cudaStream_t cpy = nullptr;
+    static cudaEvent_t ev_piece[16] = {}, ev_done = nullptr;
+    if (p->bulk_a2a && !cpy) {
+        OB_CUDA(cudaStreamCreateWithFlags(&cpy, cudaStreamNonBlocking));
+        for (auto& e : ev_piece) OB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        OB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    }
+    A.r_only = -1; A.o_first = 0;
     {
         PhaseScope ph("fft_z_fwd");
-        launch_line_tma<FT, LM_FWD, 3>(A, p->log2[2]);
-        if (p->bulk_a2a)       // chunk r of my staging -> slot `rank` of rank r's bufB, one contiguous copy each
-            for (int q = 1; q < R; ++q) {
+        if (!p->bulk_a2a) {
+            launch_line_tma<FT, LM_FWD, 3>(A, p->log2[2]);
+        } else {
+            A.nkx = A.tpc;
+            for (int q = 1; q <= R; ++q) {          // the other ranks' chunks first, the own chunk (no copy) last
                 const int r = (p->rank + q) % R;
+                A.r_only = r;
+                launch_line_tma<FT, LM_FWD, 3>(A, p->log2[2]);
+                if (r == p->rank) continue;
+                OB_CUDA(cudaEventRecord(ev_piece[q], stream()));
+                OB_CUDA(cudaStreamWaitEvent(cpy, ev_piece[q], 0));
                 OB_CUDA(cudaMemcpyAsync(p->peerB[r] + (long long)p->rank * chunk_el, p->bufA + (long long)r * chunk_el,
-                                        chunk_bytes, cudaMemcpyDefault, stream()));
+                                        chunk_bytes, cudaMemcpyDefault, cpy));
             }
+            A.r_only = -1;
+            OB_CUDA(cudaEventRecord(ev_done, cpy));
+            OB_CUDA(cudaStreamWaitEvent(stream(), ev_done, 0));
+        }
     }
     { PhaseScope ph("fft_sync"); cm::barrier(); }
     // gathered y lines: forward, eigenvalue divide, backward
@@ -958,20 +982,40 @@ static void distributed_middle_tma(FastPoisson<FT>* p) {
     {
         PhaseScope ph("fft_y");
         const int l = p->log2[1];
-        if (l <= 8) launch_line_tma<FT, LM_FWD_DIV_INV, 3>(A, l);
-        else if (l == 9) launch_line_tma<FT, LM_FWD_DIV_INV, 2>(A, l);
-        else if (l == 10) launch_line_tma<FT, LM_FWD_DIV_INV, 2, 4>(A, l);
-        else launch_line_tma<FT, LM_FWD_DIV_INV, 2, 2>(A, l);
-        if (p->bulk_a2a)
-            for (int q = 1; q < R; ++q) {
-                const int r = (p->rank + q) % R;
-                OB_CUDA(cudaMemcpyAsync(p->peerA[r] + (long long)p->rank * chunk_el, p->bufC + (long long)r * chunk_el,
-                                        chunk_bytes, cudaMemcpyDefault, stream()));
+        auto launch_y = [&]() {
+            if (l <= 8) launch_line_tma<FT, LM_FWD_DIV_INV, 3>(A, l);
+            else if (l == 9) launch_line_tma<FT, LM_FWD_DIV_INV, 2>(A, l);
+            else if (l == 10) launch_line_tma<FT, LM_FWD_DIV_INV, 2, 4>(A, l);
+            else launch_line_tma<FT, LM_FWD_DIV_INV, 2, 2>(A, l);
+        };
+        if (!p->bulk_a2a) {
+            launch_y();
+        } else {
+            const int NB = Nz >= 64 ? 4 : 1;                 // blocks of z levels
+            const int zb = cdiv(Nz, NB);
+            for (int b = 0; b < NB; ++b) {
+                const int z0 = b * zb, nz = std::min(zb, Nz - z0);
+                if (nz <= 0) break;
+                A.o_first = z0; A.nOther = nz;
+                launch_y();
+                OB_CUDA(cudaEventRecord(ev_piece[b], stream()));
+                OB_CUDA(cudaStreamWaitEvent(cpy, ev_piece[b], 0));
+                const long long off = (long long)z0 * NyL * KXB;       // chunk layout [z][yl][kx]: a z block is contiguous
+                const size_t bytes = (size_t)nz * NyL * KXB * sizeof(CTt);
+                for (int q = 1; q < R; ++q) {
+                    const int r = (p->rank + q) % R;
+                    OB_CUDA(cudaMemcpyAsync(p->peerA[r] + (long long)p->rank * chunk_el + off, p->bufC + (long long)r * chunk_el + off,
+                                            bytes, cudaMemcpyDefault, cpy));
+                }
             }
+            A.o_first = 0; A.nOther = Nz;
+            OB_CUDA(cudaEventRecord(ev_done, cpy));
+            OB_CUDA(cudaStreamWaitEvent(stream(), ev_done, 0));
+        }
     }
     { PhaseScope ph("fft_sync"); cm::barrier(); }
     // z backward
-    A.addr = tl::ADDR_ZI; A.tm4 = p->tm4_zi; A.kx_base = 0;
+    A.addr = tl::ADDR_ZI; A.tm4 = p->tm4_zi; A.kx_base = 0; A.r_only = -1; A.o_first = 0;
     for (int r = 0; r < R; ++r) A.tmr[r] = p->tmr_zi[r];
     A.tpc = cdiv(KXB, TMA_TK); A.nkx = R * A.tpc; A.nOther = NyL; A.line_is_y = 0;
     A.tw = p->twZ; A.scale = (FT)(1.0 / Nz); A.lamL = p->lamz; A.lamO = nullptr;

@@ -74,6 +74,8 @@ struct TArgs {
     CUtensorMap tm4;                // ADDR_ZI / ADDR_Y: 4-D view of the local chunk buffer (2 KXB, NyL, Nz, R)
     CUtensorMap tmr[8];             // per-rank 3-D chunk views (peer buffers, or chunk r of the local spectrum)
     int addr, R, KXB, tpc, NyL, kx_base, NXP;
+    int r_only;                     // ADDR_ZF: >= 0 restricts the launch to the tiles of destination chunk r_only (nkx = tpc)
+    int o_first;                    // first value of the other index handled by this launch (split launches)
     int line_is_y;                  // 1: lines along y, other = z ; 0: lines along z, other = y
     int nkx, nOther;                // tiles: nkx = NXP / TK columns blocks x nOther lines sets
     const typename Cx<FT>::T* tw;   // exp(-2 pi i t / N)
@@ -159,8 +161,10 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
     auto coords = [&](int n, int& kxb, int& o, int& r, int& kx0) {
         const int tile = first + n * step;
         o = tile / A.nkx; kxb = tile - o * A.nkx;
+        o += A.o_first;
         r = 0;
-        if (A.addr == ADDR_ZF || A.addr == ADDR_ZI) { r = kxb / A.tpc; kxb -= r * A.tpc; kx0 = r * A.KXB + TK * kxb; }
+        if (A.addr == ADDR_ZF && A.r_only >= 0) { r = A.r_only; kx0 = r * A.KXB + TK * kxb; }
+        else if (A.addr == ADDR_ZF || A.addr == ADDR_ZI) { r = kxb / A.tpc; kxb -= r * A.tpc; kx0 = r * A.KXB + TK * kxb; }
         else kx0 = A.kx_base + TK * kxb;
     };
     auto issue_load = [&](int n) {
