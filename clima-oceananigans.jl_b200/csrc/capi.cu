@@ -2,6 +2,7 @@
 // NonhydrostaticModel time step.  No torch types, no CPU fallback.
 #include "../../include/ocean_b200.h"
 #include "internal.h"
+#include "tma_util.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -123,7 +124,13 @@ struct ob200_field {
     void* staging_out = nullptr;            // ... and a second one for asynchronous downloads
     cudaEvent_t ev_in_ready = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_free = nullptr;
     ~ob200_field() {
-        if (owns) { if (base) cudaFree(base); if (alt) cudaFree(alt); }
+        if (owns) {
+            // tensor maps over these buffers (tendency kernels) must not outlive them: the allocator may hand the same
+            // address to a field of another grid
+            const size_t bytes = grid ? (size_t)(grid->ftype == OB200_F32 ? grid->g32.total * 4 : grid->g64.total * 8) : 0;
+            if (base) { ob::tmau::evict_maps(base, bytes); cudaFree(base); }
+            if (alt) { ob::tmau::evict_maps(alt, bytes); cudaFree(alt); }
+        }
         if (staging) cudaFree(staging);
         if (staging_out) cudaFree(staging_out);
         for (cudaEvent_t e : {ev_in_ready, ev_in_free, ev_out_ready, ev_out_free}) if (e) cudaEventDestroy(e);
@@ -862,8 +869,22 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
         }
     }
     ScopedPhase ph("tendency");
+    // all fields in one persistent launch (tendency_fused.cu) when the configuration allows; `first` = fields it handled
+    int first = 0;
+    if (m->use_fast && m->nf >= 3) {
+        FusedFields<FT> ff;
+        ff.nf = m->nf; ff.pHY = pHY; ff.ss = ss;
+        for (int q = 0; q < m->nf && q < FUSED_MAXF; ++q) {
+            ob200_field* f = m->F[q].get();
+            ff.state[q] = f->template p0<FT>();
+            ff.Gm[q] = m->Gm[q]->template p0<FT>();
+            ff.Gn[q] = m->Gn[q]->template p0<FT>();
+            ff.nw[q] = ss.mode == SUB_NONE ? nullptr : f->template alt0<FT>();
+        }
+        first = fz::launch<FT>(P, ff);
+    }
     if (fork) OB_CUDA(cudaEventRecord(ev_fork, g_stream));
-    for (int q = 0; q < m->nf; ++q) {
+    for (int q = first; q < m->nf; ++q) {
         ob200_field* f = m->F[q].get();
         FluxBC<FT> fbc;
         for (int s = 0; s < 6; ++s) { fbc.kind[s] = f->bcs[s].kind; fbc.val[s] = (FT)f->bcs[s].value; }

@@ -47,6 +47,22 @@ template <class FT>
 bool launch_tendency_fast(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi,
                           const FT* pHY, FT* Gn, const FT* Gm, FT* psi_new, const Substep<FT>& ss);
 
+// tendency_fused.cu: all prognostic fields of the specialised configuration in ONE launch.  Returns how many leading
+// fields (u, v, w, first tracers) it handled: 0 if the configuration is not covered, otherwise 3 + min(ntracers, 2);
+// the caller steps the remaining tracers with the per-field kernels.
+constexpr int FUSED_MAXF = 5;
+template <class FT>
+struct FusedFields {
+    int nf;
+    const FT* state[FUSED_MAXF];     // Julia-(0,0,0) pointers: u, v, w, tracers
+    const FT* Gm[FUSED_MAXF];
+    FT* Gn[FUSED_MAXF];
+    FT* nw[FUSED_MAXF];              // out-of-place new state (null: tendencies only)
+    const FT* pHY;
+    Substep<FT> ss;
+};
+namespace fz { template <class FT> int launch(const Phys<FT>& P, const FusedFields<FT>& a); }
+
 template <class FT, class CT>
 void launch_pressure_rhs(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,
                          bool times_dz, CT* rhs);

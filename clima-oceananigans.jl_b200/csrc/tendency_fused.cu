@@ -1,0 +1,493 @@
+// tendency_fused.cu -- ONE launch per stage for the tendencies + substep of u, v, w and the first tracer of the headline
+// configuration (every non-Flat dimension Periodic or slab-decomposed, regular spacing, WENO5 with uniform
+// coefficients, closure = nothing, optional FPlane / hydrostatic pressure).
+//
+// Replaces calculate_Gu!/Gv!/Gw!/Gc! (calculate_nonhydrostatic_tendencies.jl:155-180), rk3_substep_field!
+// (runge_kutta_3.jl:204-218) / ab2_step_field! (quasi_adams_bashforth_2.jl:158-166) and store_field_tendencies!.
+//
+// Design (B200: 227 KB of shared memory per SM, TMA, 64 FP64 lanes and one 128 B/clk shared-memory port per SM):
+//   * one PERSISTENT block per SM owns a 32 x R column tile and marches up in k.  Every state array is staged ONCE
+//     per level by the Tensor Memory Accelerator (cp.async.bulk.tensor.3d, SASS UTMALDG) into an 8-slot ring of
+//     (32+8) x (R+6) halo'd planes (levels k-3 .. k+3 live, k+4 in flight); the rings of u, v, w serve both as the
+//     advected quantity of their own momentum equation and as the advecting velocities of all the others, so a
+//     stage reads each state plane from HBM once instead of 3-4 times (one launch per field before);
+//   * the warps form NG independent GROUPS that share the staged planes but own different FIELDS ((u, v) and
+//     (w, c) with a tracer; u / v / w without): twice the warps on the same shared memory, each group with its own
+//     named barrier, so one group's barrier drain is covered by the other's arithmetic.  In a group, warps 0..R-1
+//     own one row of 32 cells (per level and field three face fluxes: x, y, z-top; the z face is carried in a
+//     register along k, x / y faces are exchanged through shared memory) and warp R computes the extra column / row
+//     of faces of the tile;
+//   * a dedicated producer warp issues the TMA loads: `full` mbarriers (transaction counts) publish a level to the
+//     groups, `done` mbarriers (one arrival per group and level) return the slot, so the groups may drift apart by
+//     a level without a block-wide barrier;
+//   * tiles are scheduled in LOCKSTEP (block b owns tiles b, b + G, ...; all blocks are at the same level at the same
+//     time, so the halo rows / columns two neighbouring tiles share are read from HBM once and hit in L2 the second
+//     time); the tiles left over after the last full round are split evenly over all blocks along z, so there is no
+//     tail and no wave quantisation;
+//   * shared-memory traffic is the second scarce resource (a warp-wide LDS.64 takes 2 cycles of the port, an FP64
+//     instruction 0.5 cycles of the SM's FP64 lanes): faces whose advecting velocity is interpolated from the
+//     advected field itself (u in x, v in y, w in z) take it from the six window values they load anyway; windows in
+//     x and z are selected by ADDRESS (five loads, conflict-free in z, nearly so in x), windows in y by register
+//     selects (the row pitch of 40 would make address selection a two-way bank conflict);
+//   * constant factors (1/2 of the two-point averages, 1/12 of the fourth-order interpolant, face areas / volume) are
+//     folded into three coefficients applied to the flux DIFFERENCES, and 4 eps into the smoothness-indicator FMA
+//     (weno_fast.cuh: weno_face2): 170 FP64 instructions per cell and field against 193.
+// Same rational functions of the same inputs as the reference (differences ~1e-16 relative); parity <= 1e-12 per
+// step is tested against the oracle (tests/test_gpu_parity.py, tests/test_gpu_golden.py).
+#include "internal.h"
+#include "weno_fast.cuh"
+#include "tma_util.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+namespace ob {
+namespace fz {
+
+constexpr int TX = 32, HALO = 3, COL0 = HALO + 1, BX = TX + 2 * HALO + 2, SLOTS = 8;
+
+template <int NT, bool ONE> struct Groups {          // field -> group map (ONE: one field per group)
+    static constexpr int NF = 3 + NT;
+    static constexpr int NG = (NT == 0 || ONE) ? NF : 2;
+    static constexpr int FPG = (NT == 0 || ONE) ? 1 : 2;      // fields per group
+};
+
+template <class FT, int R, int NF> struct Geo {
+    static constexpr int BY = R + 2 * HALO;
+    static constexpr int BOX_BYTES = BX * BY * (int)sizeof(FT);
+    static constexpr int PLANE_BYTES = ((BOX_BYTES + 127) / 128) * 128;
+    static constexpr int PE = PLANE_BYTES / (int)sizeof(FT);
+    // exchange buffers per field: the tile-edge column of x faces (the others travel by warp shuffle) and the y faces
+    static constexpr int FXE = ((R + 1) / 2) * 2, FYE = (R + 1) * TX;
+    static constexpr int XE = NF * (FXE + FYE);                        // one set of exchange buffers
+    static constexpr size_t SMEM = (size_t)NF * SLOTS * PLANE_BYTES + (size_t)XE * sizeof(FT);
+};
+
+template <class FT, int NF>
+struct Args {
+    CUtensorMap tm[NF];
+    const FT* Gm[NF];
+    FT* Gn[NF];
+    FT* nw[NF];
+    const FT* pHY;
+    long long sy, sz;
+    int O[3];
+    int Ny, Nz, ntx, ntiles, chunk;
+    FT cf[3];              // area[A] / V (further scaled per field class in the kernel)
+    FT invdx, invdy, f;
+    int fplane, do_sub;
+    FT ca, cb;             // psi_new = psi + ca * G + cb * G^-
+};
+
+// ---- work decomposition: whole tiles in lockstep rounds, then the leftover tiles split along z ----------------
+// (all 32-bit and a pure function of blockIdx / gridDim / kernel parameters, so that the level index and the ring-slot
+// offsets derived from it stay in UNIFORM registers)
+struct Work {
+    int Nz, G, b, full, round, pos, end;
+    __device__ __forceinline__ Work(int ntiles, int Nz_, int chunk) : Nz(Nz_), G(gridDim.x), b(blockIdx.x), round(0) {
+        full = ntiles / G;
+        const int T2 = (ntiles - full * G) * Nz;        // leftover levels; `chunk` = ceil(T2 / G) from the host
+        pos = min(T2, b * chunk);
+        end = min(T2, pos + chunk);
+    }
+    __device__ __forceinline__ bool next(int& tile, int& kfirst, int& len) {
+        if (round < full) {
+            tile = round * G + b; kfirst = 0; len = Nz;
+            ++round;
+            return true;
+        }
+        if (pos >= end) return false;
+        const int t2 = pos / Nz;
+        tile = full * G + t2;
+        kfirst = pos - t2 * Nz;
+        len = min(Nz - kfirst, end - pos);
+        pos += len;
+        return true;
+    }
+};
+
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// wait of the producer warp: it is idle most of the time, so it sleeps between polls instead of taking issue slots
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(tmau::smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(100);
+    }
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmau::smem_u32(bar)) : "memory");
+}
+
+template <class FT>
+__device__ __forceinline__ FT interp12(FT cm, FT c0, FT c1, FT c2) {      // 12 x wf::interp4
+    return fma(FT(7), c0 + c1, -(cm + c2));
+}
+// twice the upwind reconstruction from the six values around the face, selected in registers
+template <class FT, bool ZW>
+__device__ __forceinline__ FT weno_sel6(bool pos, FT w0, FT w1, FT w2, FT w3, FT w4, FT w5) {
+    const FT c = pos ? w2 : w3;
+    return wf::weno_face2<FT, ZW>(pos ? w0 : w5, pos ? w1 : w4, c, pos ? w3 : w2, pos ? w4 : w1, pos ? c : w5, pos ? c : w1);
+}
+
+// 24 x (momentum) or 2 x (tracers) the upwind flux ut * psi_face of field ring FB (component B, 3 = tracer) in
+// direction A at plane element e, relative level NQ (A == B: cell-centre index; otherwise face index along A)
+template <class FT, bool ZW, int A, int B, int NQ, int PE>
+__device__ __forceinline__ FT flux(const FT* __restrict__ S, const int (&so)[SLOTS], int FB, int e) {
+    constexpr int sA = A == 0 ? 1 : BX;
+    if constexpr (B != 3 && A == B) {
+        // the advecting velocity is the fourth-order interpolant of the advected component itself: values 1..4 of the window
+        FT w[6];
+        if constexpr (A < 2) {
+            const FT* q = S + FB * SLOTS * PE + so[NQ + 3] + e + sA;
+#pragma unroll
+            for (int n = 0; n < 6; ++n) w[n] = q[(n - 3) * sA];
+        } else {
+            const FT* q = S + FB * SLOTS * PE + e;
+#pragma unroll
+            for (int n = 0; n < 6; ++n) w[n] = q[so[NQ + 1 + n]];          // levels NQ+1-3 .. NQ+1+2
+        }
+        const FT ut = interp12<FT>(w[1], w[2], w[3], w[4]);
+        return ut * weno_sel6<FT, ZW>(ut > FT(0), w[0], w[1], w[2], w[3], w[4], w[5]);
+    } else {
+        FT ut;
+        if constexpr (B == 3) {
+            ut = S[A * SLOTS * PE + so[NQ + 3] + e];
+        } else if constexpr (B < 2) {
+            constexpr int sB = B == 0 ? 1 : BX;
+            const FT* q = S + A * SLOTS * PE + so[NQ + 3] + e;
+            ut = interp12<FT>(q[-2 * sB], q[-sB], q[0], q[sB]);
+        } else {
+            const FT* q = S + A * SLOTS * PE + e;
+            ut = interp12<FT>(q[so[NQ + 1]], q[so[NQ + 2]], q[so[NQ + 3]], q[so[NQ + 4]]);
+        }
+        const bool pos = ut > FT(0);
+        if constexpr (A == 1) {
+            const FT* q = S + FB * SLOTS * PE + so[NQ + 3] + e;
+            return ut * weno_sel6<FT, ZW>(pos, q[-3 * BX], q[-2 * BX], q[-BX], q[0], q[BX], q[2 * BX]);
+        } else {
+            FT a, b, c, d, g;
+            if constexpr (A == 0) {
+                const int base = FB * SLOTS * PE + so[NQ + 3] + e;
+                const int A0 = pos ? base : base - 1, t = pos ? 1 : -1;
+                a = S[A0 - 3 * t]; b = S[A0 - 2 * t]; c = S[A0 - t]; d = S[A0]; g = S[A0 + t];
+            } else {
+                const FT* q = S + FB * SLOTS * PE + e;
+                const int oa = pos ? so[NQ] : so[NQ + 5], ob_ = pos ? so[NQ + 1] : so[NQ + 4],
+                          oc = pos ? so[NQ + 2] : so[NQ + 3], od = pos ? so[NQ + 3] : so[NQ + 2],
+                          og = pos ? so[NQ + 4] : so[NQ + 1];
+                a = q[oa]; b = q[ob_]; c = q[oc]; d = q[od]; g = q[og];
+            }
+            return ut * wf::weno_face2<FT, ZW>(a, b, c, d, g, pos ? c : a, pos ? c : g);
+        }
+    }
+}
+
+// one field of one level for a cell thread: first the faces that are exchanged (x, y), then the z-top face
+template <class FT, bool ZW, int B, int PE>
+__device__ __forceinline__ void cell_fluxes_xy(const FT* S, const int (&so)[SLOTS], int FB, int e, bool first, FT& Fx, FT& Fy,
+                                               FT& Fz) {
+    constexpr int NQL = B == 2 ? -1 : 0;
+    if (first) Fz = flux<FT, ZW, 2, B, NQL, PE>(S, so, FB, e);
+    Fx = flux<FT, ZW, 0, B, 0, PE>(S, so, FB, e);
+    Fy = flux<FT, ZW, 1, B, 0, PE>(S, so, FB, e);
+}
+template <class FT, bool ZW, int B, int PE>
+__device__ __forceinline__ void cell_flux_z(const FT* S, const int (&so)[SLOTS], int FB, int e, FT& Fz, FT& dFz) {
+    constexpr int NQH = B == 2 ? 0 : 1;
+    const FT Fn = flux<FT, ZW, 2, B, NQH, PE>(S, so, FB, e);
+    dFz = Fn - Fz;
+    Fz = Fn;
+}
+
+template <class FT, bool ZW, int NT, bool HAS_GM, int R, bool ONE, int GRP>
+__device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT* sX, unsigned long long* full,
+                                           unsigned long long* done) {
+    using GR = Groups<NT, ONE>;
+    constexpr int NF = GR::NF, FPG = GR::FPG;
+    using G_ = Geo<FT, R, NF>;
+    constexpr int PE = G_::PE;
+    constexpr int F0 = GRP * FPG;                 // first field of this group
+    constexpr int GT = TX * (R + 1);              // threads of the group
+    const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) - GRP * (R + 1);
+    const bool edge = ty == R;
+    const unsigned sy = (unsigned)c.sy, sz = (unsigned)c.sz;
+    const FT cmx = c.cf[0] * FT(1.0 / 24.0), cmy = c.cf[1] * FT(1.0 / 24.0), cmz = c.cf[2] * FT(1.0 / 24.0);
+    const FT ctx_ = c.cf[0] * FT(0.5), cty = c.cf[1] * FT(0.5), ctz = c.cf[2] * FT(0.5);
+    const int e = (ty + HALO) * BX + tx + COL0;
+    unsigned git = 0;
+    Work wk(c.ntiles, c.Nz, c.chunk);
+    int tile, kfirst, len;
+    while (wk.next(tile, kfirst, len)) {
+        const int bx = tile % c.ntx, by = tile / c.ntx;
+        const int i0 = 1 + bx * TX, j0 = 1 + by * R, k0 = 1 + kfirst;
+        const int nrows = min(R, c.Ny - j0 + 1);
+        const bool cell = !edge && ty < nrows;
+        __syncthreads();                          // (all roles) the rings are refilled from scratch
+        unsigned p = (unsigned)(i0 + tx) + (unsigned)(j0 + ty) * sy + (unsigned)k0 * sz;      // < 2^31 elements per field
+        FT Fz[FPG];
+#pragma unroll
+        for (int s = 0; s < FPG; ++s) Fz[s] = FT(0);
+        for (int it = 0; it < len; ++it, ++git) {
+            const int k = k0 + it;
+            int so[SLOTS];                        // element offset of the slot of level k + n, n = -3 .. 4
+#pragma unroll
+            for (int n = 0; n < SLOTS; ++n) so[n] = ((k + n - 3) & (SLOTS - 1)) * PE;
+            FT* const sFx = sX;                               // [NF][R]: x face of the tile-edge column
+            FT* const sFy = sFx + NF * G_::FXE;               // [NF][R + 1][TX]
+            // pointwise global operands, in flight while the fluxes are computed
+            FT gm[FPG], ph = FT(0), phx = FT(0), phy = FT(0);
+            if (cell) {
+                if (HAS_GM) {
+#pragma unroll
+                    for (int s = 0; s < FPG; ++s) gm[s] = c.Gm[F0 + s][p];
+                }
+                if (F0 < 2 && c.pHY) {
+                    ph = c.pHY[p];
+                    if (F0 == 0) phx = c.pHY[p - 1];
+                    if (F0 + FPG > 1) phy = c.pHY[p - sy];
+                }
+            }
+            // the edge warp observes the arrival of the level, the named barrier publishes it to the group (warps parked at
+            // bar.sync cost no issue slots; polling an mbarrier from every warp did); the same barrier orders the reads of
+            // the previous level's exchange buffers before this level's writes
+            if (edge) tmau::mbar_wait(&full[git & 3], (git >> 2) & 1);
+            named_sync(1 + GRP, GT);
+
+            FT Fx[FPG], Fy[FPG], dFz[FPG];
+            if (cell) {
+#pragma unroll
+                for (int s = 0; s < FPG; ++s) {
+                    const int f = F0 + s;
+                    if (f == 0) cell_fluxes_xy<FT, ZW, 0, PE>(S, so, 0, e, it == 0, Fx[s], Fy[s], Fz[s]);
+                    else if (f == 1) cell_fluxes_xy<FT, ZW, 1, PE>(S, so, 1, e, it == 0, Fx[s], Fy[s], Fz[s]);
+                    else if (f == 2) cell_fluxes_xy<FT, ZW, 2, PE>(S, so, 2, e, it == 0, Fx[s], Fy[s], Fz[s]);
+                    else cell_fluxes_xy<FT, ZW, 3, PE>(S, so, f, e, it == 0, Fx[s], Fy[s], Fz[s]);
+                    sFy[f * G_::FYE + (f == 1 ? ty + 1 : ty) * TX + tx] = Fy[s];
+                }
+            } else if (edge) {
+                // x faces of column -1 (u) / TX (others), rows 0 .. nrows-1; y faces of row -1 (v) / nrows (others)
+                const int rx = (min(tx, nrows - 1) + HALO) * BX + COL0;
+                const int ey = HALO * BX + tx + COL0;
+#pragma unroll
+                for (int s = 0; s < FPG; ++s) {
+                    const int f = F0 + s;
+                    FT ex, ey_;
+                    if (f == 0) {
+                        ex = flux<FT, ZW, 0, 0, 0, PE>(S, so, 0, rx - 1);
+                        ey_ = flux<FT, ZW, 1, 0, 0, PE>(S, so, 0, ey + nrows * BX);
+                    } else if (f == 1) {
+                        ex = flux<FT, ZW, 0, 1, 0, PE>(S, so, 1, rx + TX);
+                        ey_ = flux<FT, ZW, 1, 1, 0, PE>(S, so, 1, ey - BX);
+                    } else if (f == 2) {
+                        ex = flux<FT, ZW, 0, 2, 0, PE>(S, so, 2, rx + TX);
+                        ey_ = flux<FT, ZW, 1, 2, 0, PE>(S, so, 2, ey + nrows * BX);
+                    } else {
+                        ex = flux<FT, ZW, 0, 3, 0, PE>(S, so, f, rx + TX);
+                        ey_ = flux<FT, ZW, 1, 3, 0, PE>(S, so, f, ey + nrows * BX);
+                    }
+                    if (tx < nrows) sFx[f * G_::FXE + tx] = ex;
+                    sFy[f * G_::FYE + (f == 1 ? 0 : nrows) * TX + tx] = ey_;
+                }
+            }
+            if (cell) {
+#pragma unroll
+                for (int s = 0; s < FPG; ++s) {
+                    const int f = F0 + s;
+                    if (f == 0) cell_flux_z<FT, ZW, 0, PE>(S, so, 0, e, Fz[s], dFz[s]);
+                    else if (f == 1) cell_flux_z<FT, ZW, 1, PE>(S, so, 1, e, Fz[s], dFz[s]);
+                    else if (f == 2) cell_flux_z<FT, ZW, 2, PE>(S, so, 2, e, Fz[s], dFz[s]);
+                    else cell_flux_z<FT, ZW, 3, PE>(S, so, f, e, Fz[s], dFz[s]);
+                }
+            }
+            named_sync(1 + GRP, GT);              // faces published; this group's stencil reads of the level are finished:
+            if (edge && tx == 0) mbar_arrive(&done[git & 3]);     // the producer may refill the slot of level k-2 two levels on
+            if (cell) {
+#pragma unroll
+                for (int s = 0; s < FPG; ++s) {
+                    const int f = F0 + s;
+                    // the other x face of the cell: the neighbouring lane's (u: lower neighbour), the edge warp's at the tile edge
+                    FT ox = f == 0 ? __shfl_up_sync(0xffffffffu, Fx[s], 1) : __shfl_down_sync(0xffffffffu, Fx[s], 1);
+                    if (tx == (f == 0 ? 0 : TX - 1)) ox = sFx[f * G_::FXE + ty];
+                    const FT oy = sFy[f * G_::FYE + (f == 1 ? ty : ty + 1) * TX + tx];
+                    const FT dFx = f == 0 ? Fx[s] - ox : ox - Fx[s];
+                    const FT dFy = f == 1 ? Fy[s] - oy : oy - Fy[s];
+                    FT Gv = f < 3 ? -fma(cmx, dFx, fma(cmy, dFy, cmz * dFz[s]))
+                                  : -fma(ctx_, dFx, fma(cty, dFy, ctz * dFz[s]));
+                    if (f == 0) {
+                        if (c.fplane) {           // - x_f_cross_U = + f * ℑxyᶠᶜᵃ(v)   (f_plane.jl:42)
+                            const FT* v = S + 1 * SLOTS * PE + so[3] + e;
+                            FT a0 = FT(0.5) * (v[-1] + v[0]), a1 = FT(0.5) * (v[BX - 1] + v[BX]);
+                            Gv = Gv - (-c.f * (FT(0.5) * (a0 + a1)));
+                        }
+                        if (c.pHY) Gv = Gv - (ph - phx) * c.invdx;
+                    } else if (f == 1) {
+                        if (c.fplane) {           // - y_f_cross_U = - f * ℑxyᶜᶠᵃ(u)   (f_plane.jl:43)
+                            const FT* u = S + so[3] + e;
+                            FT a0 = FT(0.5) * (u[-BX] + u[1 - BX]), a1 = FT(0.5) * (u[0] + u[1]);
+                            Gv = Gv - (c.f * (FT(0.5) * (a0 + a1)));
+                        }
+                        if (c.pHY) Gv = Gv - (ph - phy) * c.invdy;
+                    }
+                    c.Gn[f][p] = Gv;
+                    if (c.do_sub) {
+                        const FT ps = S[f * SLOTS * PE + so[3] + e];
+                        FT nv = fma(c.ca, Gv, ps);
+                        if (HAS_GM) nv = fma(c.cb, gm[s], nv);
+                        c.nw[f][p] = nv;
+                    }
+                }
+            }
+            p += sz;
+        }
+    }
+}
+
+template <class FT, bool ZW, int NT, bool HAS_GM, int R, bool ONE>
+__global__ void __launch_bounds__(TX*(Groups<NT, ONE>::NG*(R + 1) + 1), 1)
+tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
+    using GR = Groups<NT, ONE>;
+    constexpr int NF = GR::NF, NG = GR::NG;
+    using G_ = Geo<FT, R, NF>;
+    constexpr int PE = G_::PE;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full[4], done[4];
+    FT* const S = reinterpret_cast<FT*>(smem_raw);                  // rings: field f, slot s at (f * SLOTS + s) * PE
+    FT* const sX = S + NF * SLOTS * PE;                             // exchange buffers
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 4; ++q) { tmau::mbar_init(&full[q], 1); tmau::mbar_init(&done[q], NG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == NG * (R + 1)) {
+        // ---- producer warp -------------------------------------------------------------------------------
+        unsigned git = 0;
+        Work wk(c.ntiles, c.Nz, c.chunk);
+        int tile, kfirst, len;
+        const bool lead = (threadIdx.x & 31) == 0;
+        while (wk.next(tile, kfirst, len)) {
+            const int bx = tile % c.ntx, by = tile / c.ntx;
+            const int i0 = 1 + bx * TX, j0 = 1 + by * R, k0 = 1 + kfirst;
+            const int cx = i0 - HALO - 2 + c.O[0], cy = j0 - HALO - 1 + c.O[1], cz0 = c.O[2] - 1;
+            __syncthreads();
+            if (lead) {
+                unsigned long long* pb = &full[git & 3];
+                tmau::mbar_expect_tx(pb, 7u * NF * G_::BOX_BYTES);
+                for (int L = k0 - 3; L <= k0 + 3; ++L)
+#pragma unroll
+                    for (int f = 0; f < NF; ++f)
+                        tmau::tma_load_3d(S + (f * SLOTS + (L & (SLOTS - 1))) * PE, &c.tm[f], cx, cy, L + cz0, pb);
+            }
+            for (int it = 0; it < len; ++it, ++git) {
+                if (lead && it + 1 < len) {       // the planes level k+1 adds: level k+4 into the slot of level k-4
+                    const int k = k0 + it;
+                    // its slot held level k-4: last read in iteration it-2 (it-1 for the bottom face of the first level)
+                    if (it >= 1) { const unsigned w = it == 1 ? git - 1 : git - 2; mbar_wait_sleep(&done[w & 3], (w >> 2) & 1); }
+                    unsigned long long* nb = &full[(git + 1) & 3];
+                    tmau::mbar_expect_tx(nb, (unsigned)NF * G_::BOX_BYTES);
+#pragma unroll
+                    for (int f = 0; f < NF; ++f)
+                        tmau::tma_load_3d(S + (f * SLOTS + ((k + 4) & (SLOTS - 1))) * PE, &c.tm[f], cx, cy, k + 4 + cz0, nb);
+                }
+            }
+        }
+        return;
+    }
+    const int grp = warp / (R + 1);
+    if (grp == 0) group_main<FT, ZW, NT, HAS_GM, R, ONE, 0>(c, S, sX, full, done);
+    else if (grp == 1) group_main<FT, ZW, NT, HAS_GM, R, ONE, 1>(c, S, sX, full, done);
+    else if (NG > 2 && grp == 2) group_main<FT, ZW, NT, HAS_GM, R, ONE, (NG > 2 ? 2 : 0)>(c, S, sX, full, done);
+    else if (NG > 3) group_main<FT, ZW, NT, HAS_GM, R, ONE, (NG > 3 ? 3 : 0)>(c, S, sX, full, done);
+}
+
+// ---- host side --------------------------------------------------------------------------------
+template <class FT, bool ZW, int NT, bool HAS_GM, int R, bool ONE>
+static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
+    using GR = Groups<NT, ONE>;
+    constexpr int NF = GR::NF;
+    using G_ = Geo<FT, R, NF>;
+    static_assert(G_::SMEM <= 227 * 1024 - 64, "shared memory budget");
+    const GridD<FT>& g = P.g;
+    Args<FT, NF> c;
+    for (int f = 0; f < NF; ++f) {
+        c.tm[f] = tmau::make_map<FT>(g, a.state[f] - g.off0, BX, G_::BY);
+        c.Gm[f] = a.Gm[f]; c.Gn[f] = a.Gn[f]; c.nw[f] = a.nw[f];
+    }
+    c.pHY = a.pHY;
+    c.sy = g.st[1]; c.sz = g.st[2];
+    for (int d = 0; d < 3; ++d) c.O[d] = g.O[d];
+    c.Ny = g.N[1]; c.Nz = g.N[2];
+    c.ntx = g.N[0] / TX;
+    c.ntiles = c.ntx * cdiv(g.N[1], R);
+    const FT invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
+    c.cf[0] = (g.d[1] * g.d[2]) * invV; c.cf[1] = (g.d[0] * g.d[2]) * invV; c.cf[2] = (g.d[0] * g.d[1]) * invV;
+    c.invdx = 1 / g.d[0]; c.invdy = 1 / g.d[1];
+    c.f = P.f; c.fplane = P.fplane;
+    const Substep<FT>& ss = a.ss;
+    c.do_sub = ss.mode != SUB_NONE;
+    c.ca = ss.mode == SUB_RK3_FIRST ? ss.c1 : ss.dt * ss.c1;
+    c.cb = ss.mode == SUB_RK3 ? ss.dt * ss.c2 : (ss.mode == SUB_AB2 ? -(ss.dt * ss.c2) : FT(0));
+    auto kern = tendency_fused_kernel<FT, ZW, NT, HAS_GM, R, ONE>;
+    static bool attr_set = false;      // per instantiation
+    if (!attr_set) {
+        OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
+        attr_set = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        OB_CUDA(cudaGetDevice(&dev));
+        OB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long T = (long long)c.ntiles * c.Nz;
+    if (T >= (1LL << 30)) throw Error("tendency_fused: grid too large for the 32-bit work decomposition");
+    static const int forced = getenv("OB200_FUSED_GRID") ? atoi(getenv("OB200_FUSED_GRID")) : 0;
+    int grid = forced > 0 ? forced : sms;
+    grid = (int)std::max(1LL, std::min((long long)grid, T / 8));
+    c.chunk = cdiv((long long)(c.ntiles - (c.ntiles / grid) * grid) * c.Nz, grid);
+    kern<<<grid, TX * (GR::NG * (R + 1) + 1), G_::SMEM, stream()>>>(c);
+    OB_LAUNCH_CHECK();
+}
+
+template <class FT, bool ZW, int NT, int R, bool ONE>
+static void launch_gm(const Phys<FT>& P, const FusedFields<FT>& a) {
+    const bool has_gm = a.ss.mode == SUB_RK3 || a.ss.mode == SUB_AB2;
+    if (has_gm) launch_variant<FT, ZW, NT, true, R, ONE>(P, a);
+    else launch_variant<FT, ZW, NT, false, R, ONE>(P, a);
+}
+
+template <class FT>
+int launch(const Phys<FT>& P, const FusedFields<FT>& a) {
+    const GridD<FT>& g = P.g;
+    static const bool off = getenv("OB200_NO_FUSED_TENDENCY") != nullptr;
+    if (off) return 0;
+    if (P.scheme != ADV_WENO5 || P.closure != CLO_NONE || P.tilted) return 0;
+    if (g.topo[0] != OB_PERIODIC || (g.topo[1] != OB_PERIODIC && g.topo[1] != OB_COMM) || g.topo[2] != OB_PERIODIC) return 0;
+    for (int d = 0; d < 3; ++d) {
+        if (!g.regular[d] || P.wc[d][0] || P.wc[d][1] || g.H[d] < 3) return 0;
+    }
+    if (g.N[0] % TX || (g.S[0] * sizeof(FT)) % 16 || g.total >= (1LL << 31)) return 0;
+    if (a.nf < 3) return 0;
+    const int nt = std::min(a.nf - 3, 1);
+    static const int var = getenv("OB200_FUSED_VAR") ? atoi(getenv("OB200_FUSED_VAR")) : 0;
+#define GO(NTV, RV, ONEV)                                                                  \
+    { if (P.zweno) launch_gm<FT, true, NTV, RV, ONEV>(P, a); else launch_gm<FT, false, NTV, RV, ONEV>(P, a); }
+    if (nt == 0) GO(0, 8, true)
+    else if (var == 1) GO(1, 6, true)
+    else if (var == 2) GO(1, 11, false)
+    else GO(1, 12, false)
+#undef GO
+    return 3 + nt;
+}
+template int launch<float>(const Phys<float>&, const FusedFields<float>&);
+template int launch<double>(const Phys<double>&, const FusedFields<double>&);
+
+}  // namespace fz
+}  // namespace ob

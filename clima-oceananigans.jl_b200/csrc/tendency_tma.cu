@@ -20,12 +20,77 @@
 // Tensor maps describe the padded internal layout (common.cuh): 3-D, box (40, NW+5, 1), no swizzle.
 #include "internal.h"
 #include "weno_fast.cuh"
+#include "tma_util.cuh"
 #include <cuda.h>
 #include <cmath>
 #include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
+
+
+namespace ob {
+namespace tmau {
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        OB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+        if (!p || qr != cudaDriverEntryPointSuccess) throw Error("cuTensorMapEncodeTiled not available");
+        fn = (EncodeFn)p;
+    }
+    return fn;
+}
+
+typedef std::tuple<const void*, int, int, int, int, int, int> MapKey;
+static std::map<MapKey, CUtensorMap>& map_cache() { static std::map<MapKey, CUtensorMap> c; return c; }
+static std::mutex& map_mutex() { static std::mutex m; return m; }
+
+template <class FT>
+CUtensorMap make_map(const GridD<FT>& g, const FT* base, int box_x, int box_y) {
+    std::lock_guard<std::mutex> lk(map_mutex());
+    auto& cache = map_cache();
+    auto key = std::make_tuple((const void*)base, g.S[0], g.S[1], g.S[2], (int)sizeof(FT), box_x, box_y);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)g.S[0], (cuuint64_t)g.S[1], (cuuint64_t)g.S[2]};
+    cuuint64_t strides[2] = {(cuuint64_t)g.S[0] * sizeof(FT), (cuuint64_t)g.S[0] * g.S[1] * sizeof(FT)};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = get_encode()(&m, sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                              (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    cache[key] = m;
+    return m;
+}
+template CUtensorMap make_map<float>(const GridD<float>&, const float*, int, int);
+template CUtensorMap make_map<double>(const GridD<double>&, const double*, int, int);
+
+void evict_maps(const void* base, size_t bytes) {
+    std::lock_guard<std::mutex> lk(map_mutex());
+    auto& cache = map_cache();
+    const char* lo = (const char*)base;
+    const char* hi = lo + bytes;
+    for (auto it = cache.begin(); it != cache.end();) {
+        const char* p = (const char*)std::get<0>(it->first);
+        if (p >= lo && p < hi) it = cache.erase(it); else ++it;
+    }
+}
+size_t cached_maps() {
+    std::lock_guard<std::mutex> lk(map_mutex());
+    return map_cache().size();
+}
+
+}  // namespace tmau
+}  // namespace ob
 
 namespace ob {
 namespace tma {
@@ -72,32 +137,7 @@ struct Ctx {
     Substep<FT> ss;
 };
 
-// ---- PTX helpers ------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, unsigned long long* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
-}
+using tmau::smem_u32; using tmau::mbar_init; using tmau::mbar_expect_tx; using tmau::mbar_wait; using tmau::tma_load_3d;
 
 // position inside the staged data: level L (Julia k), tile row / column including the halo offset
 struct P3 { int L, row, col; };
@@ -278,44 +318,7 @@ __global__ void __launch_bounds__(TX* NW, NW <= 8 ? 3 : 2) tendency_tma_kernel(c
 }
 
 // ---- host side --------------------------------------------------------------------------------
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeFn get_encode() {
-    static EncodeFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        OB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
-        if (!p || qr != cudaDriverEntryPointSuccess) throw Error("cuTensorMapEncodeTiled not available");
-        fn = (EncodeFn)p;
-    }
-    return fn;
-}
-
-template <class FT>
-static CUtensorMap make_map(const GridD<FT>& g, const FT* base, int box_x, int box_y) {
-    // keyed on everything the encoding depends on: the same address can come back from the allocator for a field of
-    // another grid with the same element count but different extents
-    static std::map<std::tuple<const void*, int, int, int, int, int, int>, CUtensorMap> cache;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    auto key = std::make_tuple((const void*)base, g.S[0], g.S[1], g.S[2], (int)sizeof(FT), box_x, box_y);
-    auto it = cache.find(key);
-    if (it != cache.end()) return it->second;
-    CUtensorMap m;
-    cuuint64_t dims[3] = {(cuuint64_t)g.S[0], (cuuint64_t)g.S[1], (cuuint64_t)g.S[2]};
-    cuuint64_t strides[2] = {(cuuint64_t)g.S[0] * sizeof(FT), (cuuint64_t)g.S[0] * g.S[1] * sizeof(FT)};
-    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = get_encode()(&m, sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                              (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-    cache[key] = m;
-    return m;
-}
+using tmau::make_map;
 
 template <class FT, bool ZW, int B, int NW>
 static void launch_one(Ctx<FT>& c, const GridD<FT>& g, const FT* const U[3], const FT* psi) {
@@ -329,7 +332,7 @@ static void launch_one(Ctx<FT>& c, const GridD<FT>& g, const FT* const U[3], con
     }
     size_t smem = (size_t)slots * BXs::PLANE_BYTES;
     auto kern = tendency_tma_kernel<FT, ZW, B, NW>;
-    static bool attr_set = false;
+    static bool attr_set = false;      // one flag per kernel instantiation (function-local static of a template)
     if (!attr_set) {
         OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         attr_set = true;

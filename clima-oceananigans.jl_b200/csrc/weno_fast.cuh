@@ -23,9 +23,9 @@
 namespace ob {
 namespace wf {
 
-// 0: 13/3   1: 4 eps   2: -1/6   3: 7/12   4: -1/12
-__constant__ double kd[5] = {13.0 / 3.0, 4.0e-6, -1.0 / 6.0, 7.0 / 12.0, -1.0 / 12.0};
-__constant__ float kf[5] = {(float)(13.0 / 3.0), 4.0e-6f, (float)(-1.0 / 6.0), (float)(7.0 / 12.0), (float)(-1.0 / 12.0)};
+// 0: 13/3   1: 4 eps   2: -1/6   3: 7/12   4: -1/12   5: -1/3
+__constant__ double kd[6] = {13.0 / 3.0, 4.0e-6, -1.0 / 6.0, 7.0 / 12.0, -1.0 / 12.0, -1.0 / 3.0};
+__constant__ float kf[6] = {(float)(13.0 / 3.0), 4.0e-6f, (float)(-1.0 / 6.0), (float)(7.0 / 12.0), (float)(-1.0 / 12.0), (float)(-1.0 / 3.0)};
 template <class FT> __device__ __forceinline__ FT K(int i) {
     if constexpr (sizeof(FT) == 8) return kd[i]; else return kf[i];
 }
@@ -83,6 +83,52 @@ __device__ __forceinline__ FT weno_face(FT a, FT b, FT c, FT d, FT e, FT x2, FT 
         }
         const FT S = fma(a0, t0, fma(a1, t1, a2 * r2));
         return fma(__fdividef(S, (a0 + a1) + a2), K<FT>(2), m);
+    }
+}
+
+// weno_face with the constant factors folded out (tendency_fused.cu): returns TWICE the reconstruction,
+// (c + d) - S / (3 den), and folds 4 eps into the smoothness-indicator FMA (D_k = s_k^2 + (13/3 t_k) t_k + 4 eps):
+// 47 FP64 instructions against 51.
+template <class FT, bool ZW>
+__device__ __forceinline__ FT weno_face2(FT a, FT b, FT c, FT d, FT e, FT x2, FT x0) {
+    const FT t2 = fma(FT(-2), b, a) + c, t1 = fma(FT(-2), c, b) + d, t0 = fma(FT(-2), d, c) + e;
+    const FT s2 = fma(FT(2), x2 - b, t2), s1 = b - d, s0 = fma(FT(2), x0 - d, t0);
+    const FT k133 = K<FT>(0), eps4 = K<FT>(1);
+    const FT D2 = fma(s2, s2, fma(k133 * t2, t2, eps4));      // 4 (beta_k + eps)
+    const FT D1 = fma(s1, s1, fma(k133 * t1, t1, eps4));
+    const FT D0 = fma(s0, s0, fma(k133 * t0, t0, eps4));
+    const FT r2 = fma(FT(3), t1, FT(-2) * t2);
+    const FT m2 = c + d;
+    if constexpr (sizeof(FT) == 8) {
+        const FT E0 = D0 * D0, E1 = D1 * D1, E2 = D2 * D2;
+        const FT P12 = E1 * E2, P02 = E0 * E2, P01 = E0 * E1;
+        FT g0, g1, g2;       // 10 x the unnormalised weights
+        if (ZW) {
+            const FT tau = D2 - D0, tt = tau * tau, PI = E0 * P12;
+            g0 = FT(3) * fma(tt, P12, PI);
+            g1 = FT(6) * fma(tt, P02, PI);
+            g2 = fma(tt, P01, PI);
+        } else {
+            g0 = FT(3) * P12; g1 = FT(6) * P02; g2 = P01;
+        }
+        const FT den = (g0 + g1) + g2;
+        const FT S = fma(g0, t0, fma(g1, t1, g2 * r2));
+        const FT r0 = rcp_seed(den);
+        const FT er = fma(-den, r0, FT(1));
+        const FT q0 = S * r0;
+        const FT q = fma(q0, fma(er, er, er), q0);     // S / den
+        return fma(q, K<FT>(5), m2);
+    } else {
+        FT a0, a1, a2;
+        if (ZW) {
+            const FT tau = D2 - D0;
+            const FT q0 = __fdividef(tau, D0), q1 = __fdividef(tau, D1), q2 = __fdividef(tau, D2);
+            a0 = FT(3) * fma(q0, q0, FT(1)); a1 = FT(6) * fma(q1, q1, FT(1)); a2 = fma(q2, q2, FT(1));
+        } else {
+            a0 = __fdividef(FT(3), D0 * D0); a1 = __fdividef(FT(6), D1 * D1); a2 = __fdividef(FT(1), D2 * D2);
+        }
+        const FT S = fma(a0, t0, fma(a1, t1, a2 * r2));
+        return fma(__fdividef(S, (a0 + a1) + a2), K<FT>(5), m2);
     }
 }
 

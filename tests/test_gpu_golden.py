@@ -65,14 +65,21 @@ FAST_CASES = {
     "rk3_zweno_ragged": dict(size=(64, 20, 8), ts="RungeKutta3", zweno=True, f=None, steps=2),
     "ab2_fplane": dict(size=(32, 9, 16), ts="QuasiAdamsBashforth2", zweno=True, f=0.7, steps=3),
     "rk3_js": dict(size=(32, 8, 32), ts="RungeKutta3", zweno=False, f=None, steps=2),
+    # field counts of the fused tendency kernel: no tracer, two tracers, and a third one (stepped by the per-field kernel)
+    "rk3_no_tracer": dict(size=(32, 20, 16), ts="RungeKutta3", zweno=True, f=0.3, steps=2, tracers=()),
+    "rk3_two_tracers": dict(size=(32, 12, 16), ts="RungeKutta3", zweno=True, f=None, steps=2, tracers=("b", "c")),
+    "ab2_three_tracers": dict(size=(64, 9, 8), ts="QuasiAdamsBashforth2", zweno=True, f=0.5, steps=2,
+                              tracers=("b", "c", "d")),
 }
 
 
 def _fast_pair(ob, cfg, FT):
     kw = dict(size=cfg["size"], extent=(1.0, 1.5, 0.75), topology=("Periodic",) * 3)
     go, gb = O.RectilinearGrid(FT, **kw), ob.RectilinearGrid(ob.arch, FT, **kw)
+    tracers = cfg.get("tracers", ("b",))
     mk = lambda M, g: M.NonhydrostaticModel(
-        g, advection=M.WENO5(FT, zweno=cfg["zweno"]), tracers=("b",), buoyancy=M.Buoyancy(M.BuoyancyTracer(), None),
+        g, advection=M.WENO5(FT, zweno=cfg["zweno"]), tracers=tracers,
+        buoyancy=M.Buoyancy(M.BuoyancyTracer(), None) if "b" in tracers else None,
         coriolis=M.FPlane(cfg["f"]) if cfg["f"] else None, timestepper=cfg["ts"])
     return mk(O, go), mk(ob, gb)
 
