@@ -45,10 +45,10 @@ namespace fz {
 
 constexpr int TX = 32, HALO = 3, COL0 = HALO + 1, BX = TX + 2 * HALO + 2, SLOTS = 8;
 
-template <int NT, bool ONE> struct Groups {          // field -> group map (ONE: one field per group)
+template <int NT> struct Groups {          // field -> group map
     static constexpr int NF = 3 + NT;
-    static constexpr int NG = (NT == 0 || ONE) ? NF : 2;
-    static constexpr int FPG = (NT == 0 || ONE) ? 1 : 2;      // fields per group
+    static constexpr int NG = NT == 0 ? 3 : 2;
+    static constexpr int FPG = NT == 0 ? 1 : 2;      // fields per group
 };
 
 template <class FT, int R, int NF> struct Geo {
@@ -56,8 +56,7 @@ template <class FT, int R, int NF> struct Geo {
     static constexpr int BOX_BYTES = BX * BY * (int)sizeof(FT);
     static constexpr int PLANE_BYTES = ((BOX_BYTES + 127) / 128) * 128;
     static constexpr int PE = PLANE_BYTES / (int)sizeof(FT);
-    // exchange buffers per field: the tile-edge column of x faces (the others travel by warp shuffle) and the y faces
-    static constexpr int FXE = ((R + 1) / 2) * 2, FYE = (R + 1) * TX;
+    static constexpr int FXE = R * (TX + 1), FYE = (R + 1) * TX;       // exchange buffers per field (x faces, y faces)
     static constexpr int XE = NF * (FXE + FYE);                        // one set of exchange buffers
     static constexpr size_t SMEM = (size_t)NF * SLOTS * PLANE_BYTES + (size_t)XE * sizeof(FT);
 };
@@ -206,10 +205,10 @@ __device__ __forceinline__ void cell_flux_z(const FT* S, const int (&so)[SLOTS],
     Fz = Fn;
 }
 
-template <class FT, bool ZW, int NT, bool HAS_GM, int R, bool ONE, int GRP>
+template <class FT, bool ZW, int NT, bool HAS_GM, int R, int V, int GRP>
 __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT* sX, unsigned long long* full,
                                            unsigned long long* done) {
-    using GR = Groups<NT, ONE>;
+    using GR = Groups<NT>;
     constexpr int NF = GR::NF, FPG = GR::FPG;
     using G_ = Geo<FT, R, NF>;
     constexpr int PE = G_::PE;
@@ -239,7 +238,7 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
             int so[SLOTS];                        // element offset of the slot of level k + n, n = -3 .. 4
 #pragma unroll
             for (int n = 0; n < SLOTS; ++n) so[n] = ((k + n - 3) & (SLOTS - 1)) * PE;
-            FT* const sFx = sX;                               // [NF][R]: x face of the tile-edge column
+            FT* const sFx = sX;                               // [NF][R][TX + 1]
             FT* const sFy = sFx + NF * G_::FXE;               // [NF][R + 1][TX]
             // pointwise global operands, in flight while the fluxes are computed
             FT gm[FPG], ph = FT(0), phx = FT(0), phy = FT(0);
@@ -257,8 +256,13 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
             // the edge warp observes the arrival of the level, the named barrier publishes it to the group (warps parked at
             // bar.sync cost no issue slots; polling an mbarrier from every warp did); the same barrier orders the reads of
             // the previous level's exchange buffers before this level's writes
-            if (edge) tmau::mbar_wait(&full[git & 3], (git >> 2) & 1);
-            named_sync(1 + GRP, GT);
+            if (V & 1) {
+                if (edge) tmau::mbar_wait(&full[git & 3], (git >> 2) & 1);
+                named_sync(1 + GRP, GT);
+            } else {
+                named_sync(1 + GRP, GT);
+                tmau::mbar_wait(&full[git & 3], (git >> 2) & 1);
+            }
 
             FT Fx[FPG], Fy[FPG], dFz[FPG];
             if (cell) {
@@ -269,7 +273,14 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
                     else if (f == 1) cell_fluxes_xy<FT, ZW, 1, PE>(S, so, 1, e, it == 0, Fx[s], Fy[s], Fz[s]);
                     else if (f == 2) cell_fluxes_xy<FT, ZW, 2, PE>(S, so, 2, e, it == 0, Fx[s], Fy[s], Fz[s]);
                     else cell_fluxes_xy<FT, ZW, 3, PE>(S, so, f, e, it == 0, Fx[s], Fy[s], Fz[s]);
+                    sFx[f * G_::FXE + ty * (TX + 1) + (f == 0 ? tx + 1 : tx)] = Fx[s];
                     sFy[f * G_::FYE + (f == 1 ? ty + 1 : ty) * TX + tx] = Fy[s];
+                    if (!(V & 2)) {
+                        if (f == 0) cell_flux_z<FT, ZW, 0, PE>(S, so, 0, e, Fz[s], dFz[s]);
+                        else if (f == 1) cell_flux_z<FT, ZW, 1, PE>(S, so, 1, e, Fz[s], dFz[s]);
+                        else if (f == 2) cell_flux_z<FT, ZW, 2, PE>(S, so, 2, e, Fz[s], dFz[s]);
+                        else cell_flux_z<FT, ZW, 3, PE>(S, so, f, e, Fz[s], dFz[s]);
+                    }
                 }
             } else if (edge) {
                 // x faces of column -1 (u) / TX (others), rows 0 .. nrows-1; y faces of row -1 (v) / nrows (others)
@@ -292,11 +303,11 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
                         ex = flux<FT, ZW, 0, 3, 0, PE>(S, so, f, rx + TX);
                         ey_ = flux<FT, ZW, 1, 3, 0, PE>(S, so, f, ey + nrows * BX);
                     }
-                    if (tx < nrows) sFx[f * G_::FXE + tx] = ex;
+                    if (tx < nrows) sFx[f * G_::FXE + tx * (TX + 1) + (f == 0 ? 0 : TX)] = ex;
                     sFy[f * G_::FYE + (f == 1 ? 0 : nrows) * TX + tx] = ey_;
                 }
             }
-            if (cell) {
+            if (cell && (V & 2)) {
 #pragma unroll
                 for (int s = 0; s < FPG; ++s) {
                     const int f = F0 + s;
@@ -312,9 +323,7 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
 #pragma unroll
                 for (int s = 0; s < FPG; ++s) {
                     const int f = F0 + s;
-                    // the other x face of the cell: the neighbouring lane's (u: lower neighbour), the edge warp's at the tile edge
-                    FT ox = f == 0 ? __shfl_up_sync(0xffffffffu, Fx[s], 1) : __shfl_down_sync(0xffffffffu, Fx[s], 1);
-                    if (tx == (f == 0 ? 0 : TX - 1)) ox = sFx[f * G_::FXE + ty];
+                    const FT ox = sFx[f * G_::FXE + ty * (TX + 1) + (f == 0 ? tx : tx + 1)];
                     const FT oy = sFy[f * G_::FYE + (f == 1 ? ty : ty + 1) * TX + tx];
                     const FT dFx = f == 0 ? Fx[s] - ox : ox - Fx[s];
                     const FT dFy = f == 1 ? Fy[s] - oy : oy - Fy[s];
@@ -349,10 +358,10 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
     }
 }
 
-template <class FT, bool ZW, int NT, bool HAS_GM, int R, bool ONE>
-__global__ void __launch_bounds__(TX*(Groups<NT, ONE>::NG*(R + 1) + 1), 1)
+template <class FT, bool ZW, int NT, bool HAS_GM, int R, int V>
+__global__ void __launch_bounds__(TX*(Groups<NT>::NG*(R + 1) + 1), 1)
 tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
-    using GR = Groups<NT, ONE>;
+    using GR = Groups<NT>;
     constexpr int NF = GR::NF, NG = GR::NG;
     using G_ = Geo<FT, R, NF>;
     constexpr int PE = G_::PE;
@@ -389,7 +398,7 @@ tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
                 if (lead && it + 1 < len) {       // the planes level k+1 adds: level k+4 into the slot of level k-4
                     const int k = k0 + it;
                     // its slot held level k-4: last read in iteration it-2 (it-1 for the bottom face of the first level)
-                    if (it >= 1) { const unsigned w = it == 1 ? git - 1 : git - 2; mbar_wait_sleep(&done[w & 3], (w >> 2) & 1); }
+                    if (it >= 1) { const unsigned w = it == 1 ? git - 1 : git - 2; if (V & 4) mbar_wait_sleep(&done[w & 3], (w >> 2) & 1); else tmau::mbar_wait(&done[w & 3], (w >> 2) & 1); }
                     unsigned long long* nb = &full[(git + 1) & 3];
                     tmau::mbar_expect_tx(nb, (unsigned)NF * G_::BOX_BYTES);
 #pragma unroll
@@ -401,16 +410,15 @@ tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
         return;
     }
     const int grp = warp / (R + 1);
-    if (grp == 0) group_main<FT, ZW, NT, HAS_GM, R, ONE, 0>(c, S, sX, full, done);
-    else if (grp == 1) group_main<FT, ZW, NT, HAS_GM, R, ONE, 1>(c, S, sX, full, done);
-    else if (NG > 2 && grp == 2) group_main<FT, ZW, NT, HAS_GM, R, ONE, (NG > 2 ? 2 : 0)>(c, S, sX, full, done);
-    else if (NG > 3) group_main<FT, ZW, NT, HAS_GM, R, ONE, (NG > 3 ? 3 : 0)>(c, S, sX, full, done);
+    if (grp == 0) group_main<FT, ZW, NT, HAS_GM, R, V, 0>(c, S, sX, full, done);
+    else if (grp == 1) group_main<FT, ZW, NT, HAS_GM, R, V, 1>(c, S, sX, full, done);
+    else if (NG > 2) group_main<FT, ZW, NT, HAS_GM, R, V, (NG > 2 ? 2 : 0)>(c, S, sX, full, done);
 }
 
 // ---- host side --------------------------------------------------------------------------------
-template <class FT, bool ZW, int NT, bool HAS_GM, int R, bool ONE>
+template <class FT, bool ZW, int NT, bool HAS_GM, int R, int V>
 static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
-    using GR = Groups<NT, ONE>;
+    using GR = Groups<NT>;
     constexpr int NF = GR::NF;
     using G_ = Geo<FT, R, NF>;
     static_assert(G_::SMEM <= 227 * 1024 - 64, "shared memory budget");
@@ -434,7 +442,7 @@ static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     c.do_sub = ss.mode != SUB_NONE;
     c.ca = ss.mode == SUB_RK3_FIRST ? ss.c1 : ss.dt * ss.c1;
     c.cb = ss.mode == SUB_RK3 ? ss.dt * ss.c2 : (ss.mode == SUB_AB2 ? -(ss.dt * ss.c2) : FT(0));
-    auto kern = tendency_fused_kernel<FT, ZW, NT, HAS_GM, R, ONE>;
+    auto kern = tendency_fused_kernel<FT, ZW, NT, HAS_GM, R, V>;
     static bool attr_set = false;      // per instantiation
     if (!attr_set) {
         OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
@@ -456,11 +464,11 @@ static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     OB_LAUNCH_CHECK();
 }
 
-template <class FT, bool ZW, int NT, int R, bool ONE>
+template <class FT, bool ZW, int NT, int R, int V>
 static void launch_gm(const Phys<FT>& P, const FusedFields<FT>& a) {
     const bool has_gm = a.ss.mode == SUB_RK3 || a.ss.mode == SUB_AB2;
-    if (has_gm) launch_variant<FT, ZW, NT, true, R, ONE>(P, a);
-    else launch_variant<FT, ZW, NT, false, R, ONE>(P, a);
+    if (has_gm) launch_variant<FT, ZW, NT, true, R, V>(P, a);
+    else launch_variant<FT, ZW, NT, false, R, V>(P, a);
 }
 
 template <class FT>
@@ -477,12 +485,12 @@ int launch(const Phys<FT>& P, const FusedFields<FT>& a) {
     if (a.nf < 3) return 0;
     const int nt = std::min(a.nf - 3, 1);
     static const int var = getenv("OB200_FUSED_VAR") ? atoi(getenv("OB200_FUSED_VAR")) : 0;
-#define GO(NTV, RV, ONEV)                                                                  \
-    { if (P.zweno) launch_gm<FT, true, NTV, RV, ONEV>(P, a); else launch_gm<FT, false, NTV, RV, ONEV>(P, a); }
-    if (nt == 0) GO(0, 8, true)
-    else if (var == 1) GO(1, 6, true)
-    else if (var == 2) GO(1, 11, false)
-    else GO(1, 12, false)
+#define GO(NTV, RV, VV)                                                                    \
+    { if (P.zweno) launch_gm<FT, true, NTV, RV, VV>(P, a); else launch_gm<FT, false, NTV, RV, VV>(P, a); }
+    if (nt == 0) GO(0, 8, 0)
+    else if (var == 1) GO(1, 10, 0)
+    else if (var == 2) GO(1, 9, 0)
+    else GO(1, 12, 0)
 #undef GO
     return 3 + nt;
 }
