@@ -107,19 +107,6 @@ struct Work {
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// wait of the producer warp: it is idle most of the time, so it sleeps between polls instead of taking issue slots
-__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    for (;;) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(tmau::smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) break;
-        __nanosleep(100);
-    }
-}
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmau::smem_u32(bar)) : "memory");
 }
@@ -205,7 +192,7 @@ __device__ __forceinline__ void cell_flux_z(const FT* S, const int (&so)[SLOTS],
     Fz = Fn;
 }
 
-template <class FT, bool ZW, int NT, bool HAS_GM, int R, int V, int GRP>
+template <class FT, bool ZW, int NT, bool HAS_GM, int R, int GRP>
 __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT* sX, unsigned long long* full,
                                            unsigned long long* done) {
     using GR = Groups<NT>;
@@ -253,16 +240,10 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
                     if (F0 + FPG > 1) phy = c.pHY[p - sy];
                 }
             }
-            // the edge warp observes the arrival of the level, the named barrier publishes it to the group (warps parked at
-            // bar.sync cost no issue slots; polling an mbarrier from every warp did); the same barrier orders the reads of
-            // the previous level's exchange buffers before this level's writes
-            if (V & 1) {
-                if (edge) tmau::mbar_wait(&full[git & 3], (git >> 2) & 1);
-                named_sync(1 + GRP, GT);
-            } else {
-                named_sync(1 + GRP, GT);
-                tmau::mbar_wait(&full[git & 3], (git >> 2) & 1);
-            }
+            // the reads of the previous level's exchange buffers are ordered before this level's writes (warps parked at
+            // bar.sync cost no issue slots: an mbarrier-polled exchange with early arrive / late wait measured 10 % slower)
+            named_sync(1 + GRP, GT);
+            tmau::mbar_wait(&full[git & 3], (git >> 2) & 1);
 
             FT Fx[FPG], Fy[FPG], dFz[FPG];
             if (cell) {
@@ -275,7 +256,7 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
                     else cell_fluxes_xy<FT, ZW, 3, PE>(S, so, f, e, it == 0, Fx[s], Fy[s], Fz[s]);
                     sFx[f * G_::FXE + ty * (TX + 1) + (f == 0 ? tx + 1 : tx)] = Fx[s];
                     sFy[f * G_::FYE + (f == 1 ? ty + 1 : ty) * TX + tx] = Fy[s];
-                    if (!(V & 2)) {
+                    {
                         if (f == 0) cell_flux_z<FT, ZW, 0, PE>(S, so, 0, e, Fz[s], dFz[s]);
                         else if (f == 1) cell_flux_z<FT, ZW, 1, PE>(S, so, 1, e, Fz[s], dFz[s]);
                         else if (f == 2) cell_flux_z<FT, ZW, 2, PE>(S, so, 2, e, Fz[s], dFz[s]);
@@ -305,16 +286,6 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
                     }
                     if (tx < nrows) sFx[f * G_::FXE + tx * (TX + 1) + (f == 0 ? 0 : TX)] = ex;
                     sFy[f * G_::FYE + (f == 1 ? 0 : nrows) * TX + tx] = ey_;
-                }
-            }
-            if (cell && (V & 2)) {
-#pragma unroll
-                for (int s = 0; s < FPG; ++s) {
-                    const int f = F0 + s;
-                    if (f == 0) cell_flux_z<FT, ZW, 0, PE>(S, so, 0, e, Fz[s], dFz[s]);
-                    else if (f == 1) cell_flux_z<FT, ZW, 1, PE>(S, so, 1, e, Fz[s], dFz[s]);
-                    else if (f == 2) cell_flux_z<FT, ZW, 2, PE>(S, so, 2, e, Fz[s], dFz[s]);
-                    else cell_flux_z<FT, ZW, 3, PE>(S, so, f, e, Fz[s], dFz[s]);
                 }
             }
             named_sync(1 + GRP, GT);              // faces published; this group's stencil reads of the level are finished:
@@ -358,7 +329,7 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
     }
 }
 
-template <class FT, bool ZW, int NT, bool HAS_GM, int R, int V>
+template <class FT, bool ZW, int NT, bool HAS_GM, int R>
 __global__ void __launch_bounds__(TX*(Groups<NT>::NG*(R + 1) + 1), 1)
 tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
     using GR = Groups<NT>;
@@ -398,7 +369,7 @@ tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
                 if (lead && it + 1 < len) {       // the planes level k+1 adds: level k+4 into the slot of level k-4
                     const int k = k0 + it;
                     // its slot held level k-4: last read in iteration it-2 (it-1 for the bottom face of the first level)
-                    if (it >= 1) { const unsigned w = it == 1 ? git - 1 : git - 2; if (V & 4) mbar_wait_sleep(&done[w & 3], (w >> 2) & 1); else tmau::mbar_wait(&done[w & 3], (w >> 2) & 1); }
+                    if (it >= 1) { const unsigned w = it == 1 ? git - 1 : git - 2; tmau::mbar_wait(&done[w & 3], (w >> 2) & 1); }
                     unsigned long long* nb = &full[(git + 1) & 3];
                     tmau::mbar_expect_tx(nb, (unsigned)NF * G_::BOX_BYTES);
 #pragma unroll
@@ -410,13 +381,13 @@ tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
         return;
     }
     const int grp = warp / (R + 1);
-    if (grp == 0) group_main<FT, ZW, NT, HAS_GM, R, V, 0>(c, S, sX, full, done);
-    else if (grp == 1) group_main<FT, ZW, NT, HAS_GM, R, V, 1>(c, S, sX, full, done);
-    else if (NG > 2) group_main<FT, ZW, NT, HAS_GM, R, V, (NG > 2 ? 2 : 0)>(c, S, sX, full, done);
+    if (grp == 0) group_main<FT, ZW, NT, HAS_GM, R, 0>(c, S, sX, full, done);
+    else if (grp == 1) group_main<FT, ZW, NT, HAS_GM, R, 1>(c, S, sX, full, done);
+    else if (NG > 2) group_main<FT, ZW, NT, HAS_GM, R, (NG > 2 ? 2 : 0)>(c, S, sX, full, done);
 }
 
 // ---- host side --------------------------------------------------------------------------------
-template <class FT, bool ZW, int NT, bool HAS_GM, int R, int V>
+template <class FT, bool ZW, int NT, bool HAS_GM, int R>
 static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     using GR = Groups<NT>;
     constexpr int NF = GR::NF;
@@ -442,7 +413,7 @@ static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     c.do_sub = ss.mode != SUB_NONE;
     c.ca = ss.mode == SUB_RK3_FIRST ? ss.c1 : ss.dt * ss.c1;
     c.cb = ss.mode == SUB_RK3 ? ss.dt * ss.c2 : (ss.mode == SUB_AB2 ? -(ss.dt * ss.c2) : FT(0));
-    auto kern = tendency_fused_kernel<FT, ZW, NT, HAS_GM, R, V>;
+    auto kern = tendency_fused_kernel<FT, ZW, NT, HAS_GM, R>;
     static bool attr_set = false;      // per instantiation
     if (!attr_set) {
         OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
@@ -464,11 +435,11 @@ static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     OB_LAUNCH_CHECK();
 }
 
-template <class FT, bool ZW, int NT, int R, int V>
+template <class FT, bool ZW, int NT, int R>
 static void launch_gm(const Phys<FT>& P, const FusedFields<FT>& a) {
     const bool has_gm = a.ss.mode == SUB_RK3 || a.ss.mode == SUB_AB2;
-    if (has_gm) launch_variant<FT, ZW, NT, true, R, V>(P, a);
-    else launch_variant<FT, ZW, NT, false, R, V>(P, a);
+    if (has_gm) launch_variant<FT, ZW, NT, true, R>(P, a);
+    else launch_variant<FT, ZW, NT, false, R>(P, a);
 }
 
 template <class FT>
@@ -484,13 +455,12 @@ int launch(const Phys<FT>& P, const FusedFields<FT>& a) {
     if (g.N[0] % TX || (g.S[0] * sizeof(FT)) % 16 || g.total >= (1LL << 31)) return 0;
     if (a.nf < 3) return 0;
     const int nt = std::min(a.nf - 3, 1);
-    static const int var = getenv("OB200_FUSED_VAR") ? atoi(getenv("OB200_FUSED_VAR")) : 0;
-#define GO(NTV, RV, VV)                                                                    \
-    { if (P.zweno) launch_gm<FT, true, NTV, RV, VV>(P, a); else launch_gm<FT, false, NTV, RV, VV>(P, a); }
-    if (nt == 0) GO(0, 8, 0)
-    else if (var == 1) GO(1, 10, 0)
-    else if (var == 2) GO(1, 9, 0)
-    else GO(1, 12, 0)
+#define GO(NTV, RV)                                                                        \
+    { if (P.zweno) launch_gm<FT, true, NTV, RV>(P, a); else launch_gm<FT, false, NTV, RV>(P, a); }
+    // rows per tile: the largest for which the block (NG (R + 1) + 1 warps) keeps 72 registers per thread and the rings
+    // + exchange buffers fit 227 KB; measured at 256^3: R = 12 3.13 ms per step, 11: 3.16, 10: 3.26, 9: 3.19
+    if (nt == 0) GO(0, 8)
+    else GO(1, 12)
 #undef GO
     return 3 + nt;
 }
