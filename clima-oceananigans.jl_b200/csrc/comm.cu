@@ -4,6 +4,9 @@
 // process that already loaded torch's bundled NCCL the same library instance is reused.
 #include "internal.h"
 #include <dlfcn.h>
+#include <unistd.h>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -104,6 +107,58 @@ void barrier() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Can the ranks reach each other's memory?  Collective, evaluated once: all ranks on one host (hash of the host name),
+// and every rank can open a CUDA IPC handle of every other rank's probe allocation (fails on GPUs without peer access, on
+// multi-node communicators and in containers with IPC disabled).  If any rank says no, ALL ranks use the NCCL paths
+// (grouped send / recv halo exchange, all_to_all transposes) -- the decision is global so that the two sides of an
+// exchange never disagree.  OB200_NO_P2P=1 forces the NCCL paths.
+// ---------------------------------------------------------------------------------------------------------------
+bool peer_access_ok() {
+    static int state = -1;
+    if (state >= 0) return state != 0;
+    if (!active() || getenv("OB200_NO_P2P") != nullptr) { state = 0; return false; }
+    struct Probe { unsigned long long host; int ok; int pad; cudaIpcMemHandle_t h; };
+    Probe mine{};
+    char name[256] = {0};
+    gethostname(name, sizeof(name) - 1);
+    unsigned long long hsh = 1469598103934665603ULL;
+    for (const char* q = name; *q; ++q) hsh = (hsh ^ (unsigned char)*q) * 1099511628211ULL;
+    mine.host = hsh;
+    void* probe = nullptr;
+    mine.ok = cudaMalloc(&probe, 4096) == cudaSuccess && cudaIpcGetMemHandle(&mine.h, probe) == cudaSuccess;
+    cudaGetLastError();
+    Probe *dsend = nullptr, *drecv = nullptr;
+    OB_CUDA(cudaMalloc(&dsend, sizeof(Probe)));
+    OB_CUDA(cudaMalloc(&drecv, sizeof(Probe) * g_size));
+    OB_CUDA(cudaMemcpyAsync(dsend, &mine, sizeof(Probe), cudaMemcpyHostToDevice, stream()));
+    allgather_bytes(dsend, drecv, sizeof(Probe));
+    std::vector<Probe> all(g_size);
+    OB_CUDA(cudaMemcpyAsync(all.data(), drecv, sizeof(Probe) * g_size, cudaMemcpyDeviceToHost, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    int ok = mine.ok;
+    for (int r = 0; r < g_size && ok; ++r) {
+        if (r == g_rank) continue;
+        if (!all[r].ok || all[r].host != mine.host) { ok = 0; break; }
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+        cudaIpcCloseMemHandle(q);
+    }
+    double bad = ok ? 0.0 : 1.0;
+    double* dflag = reinterpret_cast<double*>(dsend);
+    OB_CUDA(cudaMemcpyAsync(dflag, &bad, sizeof(double), cudaMemcpyHostToDevice, stream()));
+    allreduce_f64(dflag, 1, true);              // max of the failure flags; also: nobody frees its probe before all have closed it
+    OB_CUDA(cudaMemcpyAsync(&bad, dflag, sizeof(double), cudaMemcpyDeviceToHost, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    cudaFree(dsend); cudaFree(drecv);
+    if (probe) cudaFree(probe);
+    state = bad == 0.0 ? 1 : 0;
+    if (!state && g_rank == 0 && getenv("OB200_QUIET") == nullptr)
+        fprintf(stderr, "libocean_b200: no peer memory access between the ranks (other host, no P2P or CUDA IPC disabled): "
+                        "using the NCCL send/recv and all-to-all paths\n");
+    return state != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Peer-memory halo link (ring neighbours of the slab decomposition).
 // Reference: Distributed/halo_communication.jl:62-183 posts MPI.Isend / Irecv per field and side.  Here every rank
 // owns receive buffers that its two ring neighbours map through CUDA IPC: the pack kernel of the SENDER stores the
@@ -186,22 +241,55 @@ __global__ void link_signal_kernel(unsigned long long* f0, unsigned long long* f
     unsigned long long* f = threadIdx.x == 0 ? f0 : f1;
     if (f) *reinterpret_cast<volatile unsigned long long*>(f) = epoch;
 }
-__global__ void link_wait_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long epoch, int* err) {
+// The wait gives up only after `timeout_ns` (OB200_LINK_TIMEOUT_S, default 600 s: a rank may legitimately be seconds
+// late -- output, plan creation, a debugger) and then it is FATAL: the error word is set and the kernel traps, so the
+// unpack kernel behind it never copies stale halo planes into a field and every later call on this context fails
+// (cudaErrorLaunchFailure -> status != 0 from every entry point that touches the stream) instead of carrying on.
+__global__ void link_wait_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long epoch, int* err,
+                                 unsigned long long timeout_ns) {
     const volatile unsigned long long* f = threadIdx.x == 0 ? f0 : f1;
     if (f) {
-        long long spins = 0;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         while (*f < epoch) {
-            __nanosleep(64);
-            if (++spins > 40000000LL) { *err = 1; break; }      // a few seconds: report instead of hanging the GPU
+            __nanosleep(128);
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                *err = 1;
+                __threadfence_system();
+                __trap();
+            }
         }
     }
     __threadfence_system();
+}
+static unsigned long long link_timeout_ns() {
+    static unsigned long long ns = 0;
+    if (!ns) {
+        const char* e = getenv("OB200_LINK_TIMEOUT_S");
+        double s = e ? atof(e) : 600.0;
+        if (!(s > 0)) s = 600.0;
+        ns = (unsigned long long)(s * 1e9);
+    }
+    return ns;
 }
 
 // side 0 = low halo, 1 = high halo.  begin(): next epoch; send_ptr(side): where MY boundary planes for the neighbour's
 // halo `side` go (side 1: my bottom planes -> the rank below's high halo; side 0: my top planes -> the rank above's low halo);
 // recv_ptr(side): my own buffer for my halo `side`.
 void peer_halo_begin() { g_link.epoch += 1; }
+// The parity double buffering is safe as long as a rank never packs exchange e+2 into a neighbour that has not unpacked
+// exchange e.  Two-sided exchanges wait on both neighbours, so that holds by construction; ONE-sided exchanges (the single
+// planes around the pressure solve) are only safe in alternation with a collective in between (the distributed solve), which
+// is how model_pressure_step issues them.  Two one-sided exchanges of the same side in a row would break it: refuse them.
+static int g_last_one_sided = -1;
+void peer_halo_check_pattern(bool need_lo, bool need_hi) {
+    const int kind = (need_lo && need_hi) ? -1 : (need_lo ? 0 : 1);
+    if (kind >= 0 && kind == g_last_one_sided)
+        throw Error("peer halo link: two one-sided exchanges of the same side in a row (unsafe buffer reuse)");
+    g_last_one_sided = kind;
+}
 void* peer_halo_send_ptr(int side) {
     PeerLink& L = g_link;
     return link_buf(side == 1 ? L.below : L.above, L.cap, (int)(L.epoch & 1), side);
@@ -219,7 +307,7 @@ void peer_halo_signal(bool lo, bool hi) {
 void peer_halo_wait(bool lo, bool hi) {
     PeerLink& L = g_link;
     const int par = (int)(L.epoch & 1);
-    link_wait_kernel<<<1, 2, 0, stream()>>>(lo ? link_flag(L.block, par, 0) : nullptr, hi ? link_flag(L.block, par, 1) : nullptr, L.epoch, L.err);
+    link_wait_kernel<<<1, 2, 0, stream()>>>(lo ? link_flag(L.block, par, 0) : nullptr, hi ? link_flag(L.block, par, 1) : nullptr, L.epoch, L.err, link_timeout_ns());
     count_launch(1);
 }
 bool peer_halo_error() {

@@ -516,6 +516,11 @@ static void run_pass(PoissonPlan<FT>* p, typename Cx<FT>::T* data, int d, int mo
 template <class FT>
 void poisson_solve(PoissonPlan<FT>* p, const GridD<FT>& g, FT* phi_p0) {
     using CT = typename Cx<FT>::T;
+    // plans that own only the half-spectrum fast path (and slab-decomposed plans) have no complex general storage:
+    // they are driven through poisson_solve_velocities / poisson_solve_real
+    if (poisson_storage<FT>(p) == nullptr)
+        throw Error("this Poisson plan has no general complex storage: pass a right-hand side (ob200_poisson_solve with rhs != NULL) "
+                    "or use ob200_solve_for_pressure");
     int dims[3], nd = 0;
     for (int d = 0; d < 3; ++d)
         if (p->topo[d] != OB_FLAT && !(p->kind == 2 && d == 2)) dims[nd++] = d;

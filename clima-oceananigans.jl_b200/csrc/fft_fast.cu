@@ -23,7 +23,7 @@
 
 namespace ob {
 namespace comm {
-bool active(); int rank(); int size();
+bool active(); int rank(); int size(); bool peer_access_ok();
 void group_start(); void group_end();
 void send(const void*, size_t, int); void recv(void*, size_t, int);
 void allgather_bytes(const void*, void*, size_t); void barrier();
@@ -609,7 +609,7 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
         OB_CUDA(cudaMalloc(&p->bufB, tot * sizeof(CT)));
         OB_CUDA(cudaMemset(p->bufA, 0, tot * sizeof(CT)));
         OB_CUDA(cudaMemset(p->bufB, 0, tot * sizeof(CT)));
-        if (getenv("OB200_NO_P2P") == nullptr) {
+        if (cm::peer_access_ok()) {            // collective probe (comm.cu); otherwise NCCL all-to-all
             // exchange CUDA IPC handles of bufA / bufB so that the transform kernels can store straight into the
             // destination rank's buffer over NVLink (the transfer is part of the kernel, not a separate collective)
             struct H2 { cudaIpcMemHandle_t a, b; };

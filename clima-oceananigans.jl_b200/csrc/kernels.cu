@@ -165,7 +165,7 @@ __global__ void halo_pack_kernel(GridD<FT> g, HaloBatch<FT> hb, int d, int a, in
 }
 
 namespace comm {
-bool active(); int rank(); int size();
+bool active(); int rank(); int size(); bool peer_access_ok();
 void group_start(); void group_end();
 void send(const void*, size_t, int); void recv(void*, size_t, int);
 }
@@ -209,7 +209,7 @@ static void exchange_halos(const GridD<FT>& g, const HaloBatch<FT>& hb, int d) {
 // every rank sends its bottom planes down).  The planes span the INTERIOR of the other dimensions: their halos are
 // either not needed (wrap-around readers) or written afterwards by the shell fill.
 namespace comm {
-void peer_halo_prepare(size_t); void peer_halo_begin();
+void peer_halo_prepare(size_t); void peer_halo_begin(); void peer_halo_check_pattern(bool, bool);
 void* peer_halo_send_ptr(int); void* peer_halo_recv_ptr(int);
 void peer_halo_signal(bool, bool); void peer_halo_wait(bool, bool);
 }
@@ -238,7 +238,7 @@ __global__ void halo_planes_kernel(GridD<FT> g, HaloBatch<FT> hb, int d, int a, 
 }
 static bool peer_halo_enabled() {
     static const bool off = getenv("OB200_NO_PEER_HALO") != nullptr;
-    return !off && comm::active();
+    return !off && comm::active() && comm::peer_access_ok();
 }
 template <class FT>
 void launch_exchange_planes(const GridD<FT>& g, const HaloBatch<FT>& hb, int d, int np, bool need_lo, bool need_hi) {
@@ -248,6 +248,7 @@ void launch_exchange_planes(const GridD<FT>& g, const HaloBatch<FT>& hb, int d, 
     size_t bytes = (size_t)hb.n * np * nA * nB * sizeof(FT);
     // capacity for the largest exchange of this grid (MAXF fields, H planes) so that the link is set up once
     comm::peer_halo_prepare(std::max(bytes, (size_t)MAXF * g.H[d] * nA * nB * sizeof(FT)));
+    comm::peer_halo_check_pattern(need_lo, need_hi);
     comm::peer_halo_begin();
     dim3 blk(a == 0 ? 64 : 16, a == 0 ? 4 : 16), grd(cdiv(nA, blk.x), cdiv(nB, blk.y));
     halo_planes_kernel<FT, true><<<grd, blk, 0, stream()>>>(g, hb, d, a, b, nA, nB, np,
