@@ -705,6 +705,13 @@ extern "C" int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model*
     if (desc->advection < 0 || desc->advection > OB200_ADV_WENO5) throw Error("unsupported advection scheme");
     if (desc->closure < 0 || desc->closure > OB200_CLOSURE_VERTICAL) throw Error("unsupported closure");
     if (desc->buoyancy_tracer >= desc->ntracers) throw Error("buoyancy tracer index out of range");
+    if (desc->buoyancy_kind < 0 || desc->buoyancy_kind > 1) throw Error("unsupported buoyancy model");
+    if (desc->buoyancy_kind == 1) {
+        if (desc->temperature_tracer >= desc->ntracers || desc->salinity_tracer >= desc->ntracers)
+            throw Error("temperature / salinity tracer index out of range");
+        if (desc->temperature_tracer < 0 && desc->salinity_tracer < 0)
+            throw Error("SeawaterBuoyancy needs an active temperature or salinity tracer");
+    }
     const ob200_grid_desc& GD = desc->grid->desc;
     // required halo: Advection.jl:40 (buffer + 1), closures need 1
     static const int need[7] = {1, 1, 2, 2, 2, 3, 3};
@@ -769,15 +776,33 @@ static void model_fill_state_halos(ob200_model* m, int first, int last) {
     fill_halos<FT>(v.data(), (int)v.size());
 }
 
+// the buoyancy model with the CURRENT state pointers (the state buffers swap every substep)
+template <class FT>
+static Buoy<FT> model_buoyancy(ob200_model* m) {
+    const ob200_model_desc& D = m->desc;
+    Buoy<FT> b{};
+    b.mode = BUOY_NONE;
+    auto tr = [&](int idx) -> const FT* { return m->F[3 + idx]->template p0<FT>(); };
+    if (D.buoyancy_kind == 1) {
+        b.g = (FT)D.gravitational_acceleration; b.alpha = (FT)D.thermal_expansion; b.beta = (FT)D.haline_contraction;
+        b.ga = b.g * b.alpha; b.ngb = (-b.g) * b.beta;
+        if (D.temperature_tracer >= 0 && D.salinity_tracer >= 0) { b.mode = BUOY_TS; b.T = tr(D.temperature_tracer); b.S = tr(D.salinity_tracer); }
+        else if (D.temperature_tracer >= 0) { b.mode = BUOY_T; b.T = tr(D.temperature_tracer); }
+        else if (D.salinity_tracer >= 0) { b.mode = BUOY_S; b.S = tr(D.salinity_tracer); }
+    } else if (D.buoyancy_tracer >= 0) {
+        b.mode = BUOY_TRACER; b.T = tr(D.buoyancy_tracer);
+    }
+    return b;
+}
+
 template <class FT>
 static void model_hydrostatic(ob200_model* m, bool periodic_images) {
     ScopedPhase phase_timer("hydrostatic");
     const GridD<FT>& g = gridD<FT>(m->grid);
     Phys<FT>& P = physOf<FT>(m);
-    bool has_b = P.btr >= 0;
-    FT* b = has_b ? m->F[3 + P.btr]->template p0<FT>() : nullptr;
-    FT gz = (has_b && P.tilted) ? P.ghat[2] : FT(1);
-    launch_hydrostatic_pressure<FT>(g, b, gz, has_b, m->pHY->template p0<FT>(), periodic_images);
+    const Buoy<FT> b = model_buoyancy<FT>(m);
+    FT gz = (b.mode && P.tilted) ? P.ghat[2] : FT(1);
+    launch_hydrostatic_pressure<FT>(g, b, gz, m->pHY->template p0<FT>(), periodic_images);
 }
 
 template <class FT>
@@ -853,7 +878,7 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
     Phys<FT>& P = physOf<FT>(m);
     const FT* U[3] = {m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(), m->F[2]->template p0<FT>()};
     const FT* pHY = m->pHY ? m->pHY->template p0<FT>() : nullptr;
-    const FT* b = P.btr >= 0 ? m->F[3 + P.btr]->template p0<FT>() : nullptr;
+    const Buoy<FT> b = model_buoyancy<FT>(m);
     // The launches of the prognostic fields are independent (each reads the old state and writes its own G^n and
     // new-state buffer), so they go to side streams forked from the library stream: the tail of one launch (its last,
     // partly filled wave of blocks) overlaps the head of the next instead of leaving SMs idle four times per stage.
@@ -1042,6 +1067,32 @@ extern "C" int32_t ob200_model_diagnostics(ob200_model* m, double* maxdiv, doubl
         }
         *ke = 0.5 * acc;
     }
+    API_END
+}
+
+// maximum(abs, parent(u)), maximum(abs, parent(v)), maximum(abs, parent(w)): the three device reductions of
+// cell_advection_timescale (Utils/cell_advection_timescale.jl:4-21; the reference reduces over the PARENT arrays, halos
+// included).  The host divides the grid's minimum spacings by them (TimeStepWizard, Simulations/time_step_wizard.jl:78-95).
+extern "C" int32_t ob200_model_max_abs_velocities(ob200_model* m, double out[3]) {
+    API_BEGIN
+    static double* buf = nullptr;
+    if (!buf) OB_CUDA(cudaMalloc(&buf, 12 * sizeof(double)));
+    const ob200_grid_desc& D = m->grid->desc;
+    for (int q = 0; q < 3; ++q) {
+        const ob200_field* f = m->F[q].get();
+        int lo[3], n[3];
+        for (int d = 0; d < 3; ++d) {
+            const bool flat = D.topology[d] == OB200_FLAT;
+            lo[d] = flat ? 1 : 1 - D.H[d];
+            n[d] = flat ? 1 : D.N[d] + 2 * D.H[d] + ((f->loc[d] == OB200_FACE && D.topology[d] == OB200_BOUNDED) ? 1 : 0);
+        }
+        if (m->grid->ftype == OB200_F32) launch_reduce_box<float>(m->grid->g32, f->p0<float>(), lo, n, buf + 4 * q);
+        else launch_reduce_box<double>(m->grid->g64, f->p0<double>(), lo, n, buf + 4 * q);
+    }
+    double h[12];
+    OB_CUDA(cudaMemcpyAsync(h, buf, sizeof(h), cudaMemcpyDeviceToHost, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    for (int q = 0; q < 3; ++q) out[q] = h[4 * q + 3] > 0 ? (0.0 / 0.0) : h[4 * q + 2];
     API_END
 }
 

@@ -39,7 +39,7 @@ struct FluxBC {            // constant Flux boundary conditions of the field bei
 // general tendency (+ optional fused substep) for prognostic field `comp`
 template <class FT>
 void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi,
-                             const FT* pHY, const FT* b, const FluxBC<FT>& fbc, FT* Gn,
+                             const FT* pHY, const Buoy<FT>& b, const FluxBC<FT>& fbc, FT* Gn,
                              const FT* Gm, FT* psi_new, const Substep<FT>& ss);
 // fast path (triply periodic, regular, WENO5 uniform, no closure/coriolis); returns false if
 // the configuration is not covered
@@ -73,7 +73,7 @@ template <class FT> bool periodic_wrap_supported(const GridD<FT>& g);
 template <class FT>
 void launch_pressure_correct(const GridD<FT>& g, FT* u, FT* v, FT* w, const FT* p, FT dt, bool periodic_wrap);
 template <class FT>
-void launch_hydrostatic_pressure(const GridD<FT>& g, const FT* b, FT gz, bool has_b, FT* pHY, bool periodic_wrap);
+void launch_hydrostatic_pressure(const GridD<FT>& g, const Buoy<FT>& b, FT gz, FT* pHY, bool periodic_wrap);
 template <class FT>
 void launch_to_internal(const GridD<FT>& g, const int psize[3], const int loc[3], const FT* parent, FT* base);
 template <class FT>
@@ -81,6 +81,9 @@ void launch_from_internal(const GridD<FT>& g, const int psize[3], const int loc[
 // reductions over Julia box [1..n0]x[1..n1]x[1..n2]; out (device, 4 doubles): sum, sumsq, maxabs, nan
 template <class FT>
 void launch_reduce(const GridD<FT>& g, const FT* p0, const int n[3], double* out4);
+// same over the Julia box [lo, lo + n) (e.g. the whole parent array, halos included)
+template <class FT>
+void launch_reduce_box(const GridD<FT>& g, const FT* p0, const int lo[3], const int n[3], double* out4);
 template <class FT>
 void launch_max_divergence(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, double* out4);
 

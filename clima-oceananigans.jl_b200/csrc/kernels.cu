@@ -314,7 +314,7 @@ struct TendArgs {
     const FT* U[3];
     const FT* psi;
     const FT* pHY;
-    const FT* b;
+    Buoy<FT> b;
     FT* Gn;
     const FT* Gm;
     FT* psi_new;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
                 }
                 if (A.pHY) G = G - deriv(g, A.pHY, q, 1, OB_F);
             }
-            if (COMP < 2 && P.tilted && A.b) G = G + P.ghat[COMP] * A.b[q.p];      // x/y_dot_g_b (g_dot_b.jl:1-3)
+            if (COMP < 2 && P.tilted && A.b.mode) G = G + P.ghat[COMP] * buoyancy_at(A.b, q.p);      // x/y_dot_g_b (g_dot_b.jl:1-3)
             // apply_x/y/z_bcs! (apply_flux_bcs.jl:35-160): constant Flux BCs of this field
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
 
 template <class FT>
 void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi,
-                             const FT* pHY, const FT* b, const FluxBC<FT>& fbc, FT* Gn,
+                             const FT* pHY, const Buoy<FT>& b, const FluxBC<FT>& fbc, FT* Gn,
                              const FT* Gm, FT* psi_new, const Substep<FT>& ss) {
     TendArgs<FT> A;
     for (int d = 0; d < 3; ++d) A.U[d] = U[d];
@@ -500,10 +500,10 @@ void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], 
     OB_LAUNCH_CHECK();
 }
 template void launch_tendency_general<float>(const Phys<float>&, int, const float* const[3], const float*,
-                                             const float*, const float*, const FluxBC<float>&, float*,
+                                             const float*, const Buoy<float>&, const FluxBC<float>&, float*,
                                              const float*, float*, const Substep<float>&);
 template void launch_tendency_general<double>(const Phys<double>&, int, const double* const[3], const double*,
-                                              const double*, const double*, const FluxBC<double>&, double*,
+                                              const double*, const Buoy<double>&, const FluxBC<double>&, double*,
                                               const double*, double*, const Substep<double>&);
 
 // =============================================================================================
@@ -670,7 +670,7 @@ template void launch_pressure_correct<double>(const GridD<double>&, double*, dou
 // DRAM throughput with long-scoreboard as the only stall).
 // WRAP (z Periodic): b[Nz+1] is read as b[1], so the tracer's halos need not be valid.
 template <class FT, bool WRAP>
-__global__ void __launch_bounds__(64) hydrostatic_kernel(GridD<FT> g, const FT* b, FT gz, bool has_b, bool tilted, FT* pHY) {
+__global__ void __launch_bounds__(64) hydrostatic_kernel(GridD<FT> g, const Buoy<FT> b, FT gz, bool tilted, FT* pHY) {
     constexpr int HU = 16;
     int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -679,8 +679,8 @@ __global__ void __launch_bounds__(64) hydrostatic_kernel(GridD<FT> g, const FT* 
     long long sz = g.st[2];
     int Nz = g.N[2];
     auto zb = [&](int k) -> FT {
-        if (!has_b) return FT(0);
-        FT v = b[p + k * sz];
+        if (!b.mode) return FT(0);
+        FT v = buoyancy_at(b, p + k * sz);
         return tilted ? gz * v : v;
     };
     FT above = zb(WRAP ? 1 : Nz + 1), acc = FT(0);
@@ -701,15 +701,15 @@ __global__ void __launch_bounds__(64) hydrostatic_kernel(GridD<FT> g, const FT* 
     }
 }
 template <class FT>
-void launch_hydrostatic_pressure(const GridD<FT>& g, const FT* b, FT gz, bool has_b, FT* pHY, bool periodic_wrap) {
+void launch_hydrostatic_pressure(const GridD<FT>& g, const Buoy<FT>& b, FT gz, FT* pHY, bool periodic_wrap) {
     dim3 blk(32, 2), grd(cdiv(g.N[0], 32), cdiv(g.N[1], 2));
     if (periodic_wrap && g.topo[2] == OB_PERIODIC)
-        hydrostatic_kernel<FT, true><<<grd, blk, 0, stream()>>>(g, b, gz, has_b, gz != FT(1), pHY);
-    else hydrostatic_kernel<FT, false><<<grd, blk, 0, stream()>>>(g, b, gz, has_b, gz != FT(1), pHY);
+        hydrostatic_kernel<FT, true><<<grd, blk, 0, stream()>>>(g, b, gz, gz != FT(1), pHY);
+    else hydrostatic_kernel<FT, false><<<grd, blk, 0, stream()>>>(g, b, gz, gz != FT(1), pHY);
     OB_LAUNCH_CHECK();
 }
-template void launch_hydrostatic_pressure<float>(const GridD<float>&, const float*, float, bool, float*, bool);
-template void launch_hydrostatic_pressure<double>(const GridD<double>&, const double*, double, bool, double*, bool);
+template void launch_hydrostatic_pressure<float>(const GridD<float>&, const Buoy<float>&, float, float*, bool);
+template void launch_hydrostatic_pressure<double>(const GridD<double>&, const Buoy<double>&, double, double*, bool);
 
 // =============================================================================================
 // reference parent layout <-> internal layout
@@ -777,15 +777,15 @@ __device__ __forceinline__ void block_reduce_store(double s, double s2, double m
 }
 
 template <class FT>
-__global__ void reduce_kernel(GridD<FT> g, const FT* p0, int n0, int n1, int n2, double* out4) {
+__global__ void reduce_kernel(GridD<FT> g, const FT* p0, int l0, int l1, int l2, int n0, int n1, int n2, double* out4) {
     long long total = (long long)n0 * n1 * n2;
     double s = 0, s2 = 0, mx = 0;
     int nan = 0;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
-        int i = 1 + (int)(t % n0);
-        int j = 1 + (int)((t / n0) % n1);
-        int k = 1 + (int)(t / ((long long)n0 * n1));
+        int i = l0 + (int)(t % n0);
+        int j = l1 + (int)((t / n0) % n1);
+        int k = l2 + (int)(t / ((long long)n0 * n1));
         double v = (double)p0[i * g.st[0] + j * g.st[1] + k * g.st[2]];
         if (v != v) nan = 1;
         else { s += v; s2 += v * v; mx = fmax(mx, fabs(v)); }
@@ -793,15 +793,22 @@ __global__ void reduce_kernel(GridD<FT> g, const FT* p0, int n0, int n1, int n2,
     block_reduce_store(s, s2, mx, nan, out4);
 }
 template <class FT>
-void launch_reduce(const GridD<FT>& g, const FT* p0, const int n[3], double* out4) {
+void launch_reduce_box(const GridD<FT>& g, const FT* p0, const int lo[3], const int n[3], double* out4) {
     OB_CUDA(cudaMemsetAsync(out4, 0, 4 * sizeof(double), stream()));
     long long total = (long long)n[0] * n[1] * n[2];
     int blocks = (int)std::min<long long>(148 * 8, (total + 255) / 256);
-    reduce_kernel<FT><<<blocks, 256, 0, stream()>>>(g, p0, n[0], n[1], n[2], out4);
+    reduce_kernel<FT><<<blocks, 256, 0, stream()>>>(g, p0, lo[0], lo[1], lo[2], n[0], n[1], n[2], out4);
     OB_LAUNCH_CHECK();
+}
+template <class FT>
+void launch_reduce(const GridD<FT>& g, const FT* p0, const int n[3], double* out4) {
+    const int lo[3] = {1, 1, 1};
+    launch_reduce_box<FT>(g, p0, lo, n, out4);
 }
 template void launch_reduce<float>(const GridD<float>&, const float*, const int[3], double*);
 template void launch_reduce<double>(const GridD<double>&, const double*, const int[3], double*);
+template void launch_reduce_box<float>(const GridD<float>&, const float*, const int[3], const int[3], double*);
+template void launch_reduce_box<double>(const GridD<double>&, const double*, const int[3], const int[3], double*);
 
 template <class FT>
 __global__ void maxdiv_kernel(GridD<FT> g, const FT* u, const FT* v, const FT* w, double* out4) {

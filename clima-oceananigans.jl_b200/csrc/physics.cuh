@@ -16,6 +16,28 @@ enum { ADV_NONE = 0, ADV_C2 = 1, ADV_C4 = 2, ADV_U1 = 3, ADV_U3 = 4, ADV_U5 = 5,
 enum { CLO_NONE = 0, CLO_3D = 1, CLO_H = 2, CLO_V = 3 };
 enum { SIDE_LEFT = 0, SIDE_RIGHT = 1 };
 
+// buoyancy_perturbation(i, j, k, grid, b, C): BuoyancyTracer (buoyancy_tracer.jl:12) or SeawaterBuoyancy with the linear
+// equation of state (linear_equation_of_state.jl:69-77; the reference's evaluation order is kept)
+enum { BUOY_NONE = 0, BUOY_TRACER = 1, BUOY_TS = 2, BUOY_T = 3, BUOY_S = 4 };
+template <class FT>
+struct Buoy {
+    int mode;
+    const FT* T;            // the buoyancy tracer (BUOY_TRACER) or temperature
+    const FT* S;            // salinity
+    FT g, alpha, beta;      // g, thermal expansion, haline contraction
+    FT ga, ngb;             // g * alpha, (-g) * beta
+};
+template <class FT>
+OBD FT buoyancy_at(const Buoy<FT>& B, long long p) {
+    switch (B.mode) {
+        case BUOY_TRACER: return B.T[p];
+        case BUOY_TS: return B.g * (B.alpha * B.T[p] - B.beta * B.S[p]);
+        case BUOY_T: return B.ga * B.T[p];
+        case BUOY_S: return B.ngb * B.S[p];
+        default: return FT(0);
+    }
+}
+
 template <class FT>
 struct Phys {
     GridD<FT> g;
@@ -438,7 +460,7 @@ OBD FT div_q(const Phys<FT>& P, FT kappa, const FT* c, Pt q) {
 // comp 0,1,2 = u,v,w ; comp >= 3 = tracer (comp-3)
 template <class FT>
 OBD FT tendency(const Phys<FT>& P, int comp, const FT* const* U, const FT* psi, const FT* pHY,
-                const FT* b, Pt q) {
+                const Buoy<FT>& b, Pt q) {
     const GridD<FT>& g = P.g;
     if (comp >= 3) {
         FT G = -div_Uc(P, U, psi, q);
@@ -462,7 +484,7 @@ OBD FT tendency(const Phys<FT>& P, int comp, const FT* const* U, const FT* psi, 
         if (pHY) G = G - deriv(g, pHY, q, 1, OB_F);
     }
     G = G - div_tau(P, comp, U, q);
-    if (comp < 2 && P.tilted && b) G = G + P.ghat[comp] * b[q.p];      // x/y_dot_g_b (g_dot_b.jl:1-3)
+    if (comp < 2 && P.tilted && b.mode) G = G + P.ghat[comp] * buoyancy_at(b, q.p);      // x/y_dot_g_b (g_dot_b.jl:1-3)
     return G;
 }
 

@@ -25,7 +25,7 @@ using Oceananigans.Advection: CenteredSecondOrder, CenteredFourthOrder, UpwindBi
 using Oceananigans.TurbulenceClosures: ScalarDiffusivity, ThreeDimensionalFormulation, HorizontalFormulation,
                                        VerticalFormulation, ExplicitTimeDiscretization
 using Oceananigans.Coriolis: FPlane
-using Oceananigans.BuoyancyModels: Buoyancy, BuoyancyTracer, ZDirection
+using Oceananigans.BuoyancyModels: Buoyancy, BuoyancyTracer, SeawaterBuoyancy, LinearEquationOfState, ZDirection, required_tracers
 using Oceananigans.TimeSteppers: RungeKutta3TimeStepper, QuasiAdamsBashforth2TimeStepper, Clock
 using Oceananigans.Solvers: FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver, BatchedTridiagonalSolver
 using Oceananigans.Models.NonhydrostaticModels: NonhydrostaticModel
@@ -136,6 +136,8 @@ struct ModelDesc
     closure::Int32; nu::Float64; kappa::NTuple{MAX_TRACERS,Float64}
     coriolis_fplane::Int32; f::Float64; buoyancy_tracer::Int32; gravity_tilted::Int32; g_hat::NTuple{3,Float64}
     ntracers::Int32; bcs::NTuple{6 * (3 + MAX_TRACERS), BC}; pressure_solver::Int32
+    buoyancy_kind::Int32; temperature_tracer::Int32; salinity_tracer::Int32
+    gravitational_acceleration::Float64; thermal_expansion::Float64; haline_contraction::Float64
 end
 
 topo_code(::Type{Periodic}) = Int32(0); topo_code(::Type{Bounded}) = Int32(1); topo_code(::Type{Flat}) = Int32(2)
@@ -301,9 +303,21 @@ function model_desc(grid, gh; advection, buoyancy, coriolis, closure, tracers, t
     fplane, f = coriolis === nothing ? (0, 0.0) : coriolis isa FPlane ? (1, Float64(coriolis.f)) :
                 throw(ArgumentError("B200(): coriolis must be nothing or FPlane"))
     btr, tilted, ĝ = -1, 0, (0.0, 0.0, 1.0)
+    bkind, iT, iS, grav, α, β = 0, -1, -1, 0.0, 0.0, 0.0
     if buoyancy !== nothing
-        buoyancy.model isa BuoyancyTracer || throw(ArgumentError("B200(): buoyancy must be nothing or BuoyancyTracer()"))
-        btr = findfirst(==(:b), tracers) - 1
+        bm = buoyancy.model
+        if bm isa BuoyancyTracer
+            btr = findfirst(==(:b), tracers) - 1
+        elseif bm isa SeawaterBuoyancy{<:Any, <:LinearEquationOfState}      # linear_equation_of_state.jl:69-77
+            bkind = 1
+            req = required_tracers(bm)
+            iT = :T in req ? findfirst(==(:T), tracers) - 1 : -1
+            iS = :S in req ? findfirst(==(:S), tracers) - 1 : -1
+            grav = Float64(bm.gravitational_acceleration)
+            α, β = Float64(bm.equation_of_state.thermal_expansion), Float64(bm.equation_of_state.haline_contraction)
+        else
+            throw(ArgumentError("B200(): buoyancy must be nothing, BuoyancyTracer() or SeawaterBuoyancy with LinearEquationOfState"))
+        end
         if !(buoyancy.gravity_unit_vector isa ZDirection)
             tilted = 1; ĝ = Float64.(Tuple(buoyancy.gravity_unit_vector))
         end
@@ -316,7 +330,8 @@ function model_desc(grid, gh; advection, buoyancy, coriolis, closure, tracers, t
     end
     ptr(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
     desc = ModelDesc(gh, ts, χ, adv_code(advection), advection isa WENO5 ? Int32(advection.zweno) : Int32(1),
-                     map(ptr, tabs), clo, ν, κ, fplane, f, btr, tilted, ĝ, length(tracers), bcs, 0)
+                     map(ptr, tabs), clo, ν, κ, fplane, f, btr, tilted, ĝ, length(tracers), bcs, 0,
+                     bkind, iT, iS, grav, α, β)
     return desc, tabs           # `tabs` must be GC.@preserve'd across ob200_model_create (host pointers are borrowed)
 end
 
@@ -413,6 +428,18 @@ function reduce_field(f::B200Field)
                 field_handle(f), s, s2, m, nan))
     return (sum = s[], sumsq = s2[], maxabs = m[], has_nan = nan[] != 0)
 end
+
+# cell_advection_timescale(model) (Utils/cell_advection_timescale.jl:4-21) without downloading the velocities: the three
+# maximum(abs, parent(.)) reductions run on the device, the division by the minimum spacings stays host logic
+import Oceananigans.Utils: cell_advection_timescale
+function cell_advection_timescale(model::B200Model)
+    m = Ref{NTuple{3, Float64}}()
+    check(ccall((:ob200_model_max_abs_velocities, lib), Int32, (Ptr{Cvoid}, Ref{NTuple{3, Float64}}), handle(model), m))
+    umax, vmax, wmax = m[]
+    g = model.grid
+    return min(Oceananigans.Grids.min_Δx(g) / umax, Oceananigans.Grids.min_Δy(g) / vmax, Oceananigans.Grids.min_Δz(g) / wmax)
+end
+Oceananigans.Simulations.hasnan(model::B200Model) = reduce_field(model.velocities.u).has_nan      # nan_checker.jl:33-36
 
 # ---- several GPUs: MultiArch(B200(); ranks=(1, R, 1)) (Distributed/multi_architectures.jl:64-113) --------------------------
 "Called once per process after MPI.Init, before any grid on a MultiArch{B200} is created: distributes the NCCL id with MPI."

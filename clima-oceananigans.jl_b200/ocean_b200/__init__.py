@@ -10,10 +10,12 @@ from .model import (Field, CenterField, XFaceField, YFaceField, ZFaceField, fill
                     solve, solve_for_pressure, NonhydrostaticModel, WENO5, CenteredSecondOrder,
                     CenteredFourthOrder, UpwindBiasedFirstOrder, UpwindBiasedThirdOrder,
                     UpwindBiasedFifthOrder, ScalarDiffusivity, VerticalScalarDiffusivity,
-                    HorizontalScalarDiffusivity, FPlane, BuoyancyTracer, Buoyancy, BoundaryCondition,
+                    HorizontalScalarDiffusivity, FPlane, BuoyancyTracer, Buoyancy, SeawaterBuoyancy,
+                    LinearEquationOfState, BoundaryCondition,
                     FluxBoundaryCondition, ValueBoundaryCondition, GradientBoundaryCondition,
                     update_state, calculate_tendencies, set_model, time_step, sync)
-from .simulations import Simulation, run  # noqa: F401
+from .simulations import (Simulation, run, TimeStepWizard, cell_advection_timescale,  # noqa: F401
+                          cell_diffusion_timescale, max_abs_velocities)
 
 
 def launch_count():

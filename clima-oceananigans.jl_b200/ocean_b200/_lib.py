@@ -38,7 +38,10 @@ class ModelDesc(C.Structure):
                 ("coriolis_fplane", C.c_int32), ("f", C.c_double),
                 ("buoyancy_tracer", C.c_int32), ("gravity_tilted", C.c_int32), ("g_hat", C.c_double * 3),
                 ("ntracers", C.c_int32), ("bcs", (BC * 6) * (3 + MAX_TRACERS)),
-                ("pressure_solver", C.c_int32)]
+                ("pressure_solver", C.c_int32),
+                ("buoyancy_kind", C.c_int32), ("temperature_tracer", C.c_int32), ("salinity_tracer", C.c_int32),
+                ("gravitational_acceleration", C.c_double), ("thermal_expansion", C.c_double),
+                ("haline_contraction", C.c_double)]
 
 
 #: every symbol include/ocean_b200.h declares: name -> (restype, argtypes)
@@ -85,6 +88,7 @@ SYMBOLS = {
     "ob200_model_clock": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ob200_model_set_clock": (C.c_int32, [C.c_void_p, C.c_double, C.c_int64, C.c_double]),
     "ob200_model_diagnostics": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ob200_model_max_abs_velocities": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     "ob200_comm_unique_id": (C.c_int32, [C.c_char_p]),
     "ob200_comm_init": (C.c_int32, [C.c_int32, C.c_int32, C.c_char_p]),
     "ob200_comm_destroy": (C.c_int32, []),

@@ -326,11 +326,44 @@ class BuoyancyTracer:
     pass
 
 
+class LinearEquationOfState:
+    """LinearEquationOfState(FT; thermal_expansion=1.67e-4, haline_contraction=7.80e-4)
+    (src/BuoyancyModels/linear_equation_of_state.jl:6-30)"""
+
+    def __init__(self, thermal_expansion=1.67e-4, haline_contraction=7.80e-4):
+        self.thermal_expansion, self.haline_contraction = thermal_expansion, haline_contraction
+
+
+class SeawaterBuoyancy:
+    """SeawaterBuoyancy(FT; gravitational_acceleration=g_Earth, equation_of_state=LinearEquationOfState(FT),
+    constant_temperature=nothing, constant_salinity=nothing) (src/BuoyancyModels/seawater_buoyancy.jl:61-73).
+    Only the linear equation of state crosses the C ABI."""
+    g_Earth = 9.80665            # BuoyancyModels.jl:20
+
+    def __init__(self, gravitational_acceleration=None, equation_of_state=None, constant_temperature=None,
+                 constant_salinity=None):
+        self.gravitational_acceleration = self.g_Earth if gravitational_acceleration is None else gravitational_acceleration
+        self.equation_of_state = equation_of_state or LinearEquationOfState()
+        if not isinstance(self.equation_of_state, LinearEquationOfState):
+            raise ValueError("only LinearEquationOfState is supported on the B200 architecture")
+        self.constant_temperature = 0.0 if constant_temperature is True else constant_temperature
+        self.constant_salinity = 0.0 if constant_salinity is True else constant_salinity
+        if self.constant_temperature is not None and self.constant_salinity is not None:
+            raise ValueError("temperature and salinity cannot both be constant")
+
+    def required_tracers(self):
+        if self.constant_salinity is not None:
+            return ("T",)
+        if self.constant_temperature is not None:
+            return ("S",)
+        return ("T", "S")
+
+
 class Buoyancy:
     def __init__(self, model=None, gravity_unit_vector=None):
         self.model = model or BuoyancyTracer()
-        if not isinstance(self.model, BuoyancyTracer):
-            raise ValueError("only BuoyancyTracer is supported on the B200 architecture")
+        if not isinstance(self.model, (BuoyancyTracer, SeawaterBuoyancy)):
+            raise ValueError("only BuoyancyTracer and SeawaterBuoyancy(LinearEquationOfState) are supported on the B200 architecture")
         self.g = gravity_unit_vector
 
 
@@ -372,11 +405,14 @@ class NonhydrostaticModel:
             advection = CenteredSecondOrder()
         if timestepper not in L.TS:
             raise ValueError(f"unknown timestepper {timestepper}")
-        if isinstance(buoyancy, BuoyancyTracer):
+        if isinstance(buoyancy, (BuoyancyTracer, SeawaterBuoyancy)):
             buoyancy = Buoyancy(buoyancy)
         tracers = (tracers,) if isinstance(tracers, str) else tuple(tracers or ())
-        if buoyancy is not None and "b" not in tracers:
-            raise ValueError("BuoyancyTracer requires a tracer named :b")
+        if buoyancy is not None:          # validate_buoyancy (BuoyancyModels.jl:37-46)
+            req = ("b",) if isinstance(buoyancy.model, BuoyancyTracer) else buoyancy.model.required_tracers()
+            for n in req:
+                if n not in tracers:
+                    raise ValueError(f"{type(buoyancy.model).__name__} requires a tracer named :{n}")
         if len(tracers) > L.MAX_TRACERS:
             raise ValueError("too many tracers")
         if isinstance(advection, WENO5) and advection.FT != grid.FT:
@@ -411,7 +447,18 @@ class NonhydrostaticModel:
             if not isinstance(coriolis, FPlane):
                 raise ValueError("only FPlane is supported on the B200 architecture")
             d.f = float(coriolis.f)
-        d.buoyancy_tracer = tracers.index("b") if buoyancy is not None else -1
+        d.buoyancy_tracer, d.buoyancy_kind, d.temperature_tracer, d.salinity_tracer = -1, 0, -1, -1
+        if buoyancy is not None and isinstance(buoyancy.model, SeawaterBuoyancy):
+            sw = buoyancy.model
+            d.buoyancy_kind = 1
+            req = sw.required_tracers()
+            d.temperature_tracer = tracers.index("T") if "T" in req else -1
+            d.salinity_tracer = tracers.index("S") if "S" in req else -1
+            d.gravitational_acceleration = float(sw.gravitational_acceleration)
+            d.thermal_expansion = float(sw.equation_of_state.thermal_expansion)
+            d.haline_contraction = float(sw.equation_of_state.haline_contraction)
+        elif buoyancy is not None:
+            d.buoyancy_tracer = tracers.index("b")
         d.gravity_tilted = int(buoyancy is not None and buoyancy.g is not None)
         g_hat = buoyancy.g if (buoyancy is not None and buoyancy.g is not None) else (0.0, 0.0, 1.0)
         for k in range(3):

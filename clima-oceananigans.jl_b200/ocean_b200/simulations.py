@@ -1,9 +1,77 @@
 """Simulation / run! (reference src/Simulations/simulation.jl:44-85, run.jl:42-140): unchanged
 host logic driving `time_step!` on the B200 model; NaNChecker (nan_checker.jl:33-52) uses the
 library's device reduction."""
+import ctypes as C
 import math
 
+import numpy as np
+
+from ._lib import lib, check
+from .grids import Flat
 from .model import time_step, sync
+
+
+def min_spacings(grid):
+    """min_Δx, min_Δy, min_Δz (src/Grids/rectilinear_grid.jl:429-454): Inf along Flat dimensions, the scalar spacing of a
+    regular dimension, the minimum of the Δᶜ vector (halos included) of a stretched one."""
+    out = []
+    for d in range(3):
+        if grid.topology[d] == Flat:
+            out.append(math.inf)
+        elif grid.regular[d]:
+            out.append(float(grid.dC[d]))
+        else:
+            out.append(float(np.min(grid.dC[d].a)))
+    return tuple(out)
+
+
+def max_abs_velocities(model):
+    """maximum(abs, parent(u / v / w)) by three device reductions in one library call"""
+    out = (C.c_double * 3)()
+    check(lib.ob200_model_max_abs_velocities(model.handle, out))
+    return tuple(out)
+
+
+def cell_advection_timescale(model):
+    """cell_advection_timescale(model) (src/Utils/cell_advection_timescale.jl:4-21): min(Δx/umax, Δy/vmax, Δz/wmax)"""
+    umax, vmax, wmax = max_abs_velocities(model)
+    dx, dy, dz = min_spacings(model.grid)
+    div = lambda a, b: (math.inf if b == 0 else a / b) if math.isfinite(a) else math.inf
+    return min(div(dx, umax), div(dy, vmax), div(dz, wmax))
+
+
+def cell_diffusion_timescale(model):
+    """cell_diffusion_timescale (src/TurbulenceClosures/turbulence_closure_diagnostics.jl:23-39) for nothing / ScalarDiffusivity"""
+    clo = model.closure
+    if clo is None:
+        return math.inf
+    dx, dy, dz = min_spacings(model.grid)
+    Δ = {"ThreeDimensional": min(dx, dy, dz), "Horizontal": min(dx, dy), "Vertical": dz}[clo.formulation]
+    κs = list(clo.κ.values()) if isinstance(clo.κ, dict) else [clo.κ]
+    max_κ = max(κs) if κs else 0
+    div = lambda a, b: math.inf if b == 0 else a / b
+    return min(div(Δ ** 2, clo.ν), div(Δ ** 2, max_κ))
+
+
+class TimeStepWizard:
+    """TimeStepWizard(; cfl=0.2, diffusive_cfl=Inf, max_change=1.1, min_change=0.5, max_Δt=Inf, min_Δt=0)
+    (src/Simulations/time_step_wizard.jl:17-95): a callback that resets simulation.Δt from the CFL numbers; the only device
+    work is the velocity max-reduction."""
+
+    def __init__(self, cfl=0.2, diffusive_cfl=math.inf, max_change=1.1, min_change=0.5, max_Δt=math.inf, min_Δt=0.0):
+        self.cfl, self.diffusive_cfl = cfl, diffusive_cfl
+        self.max_change, self.min_change, self.max_Δt, self.min_Δt = max_change, min_change, max_Δt, min_Δt
+
+    def new_time_step(self, old_Δt, model):
+        advective = self.cfl * cell_advection_timescale(model)
+        diffusive = self.diffusive_cfl * cell_diffusion_timescale(model) if math.isfinite(self.diffusive_cfl) else math.inf
+        new = min(advective, diffusive)
+        new = min(self.max_change * old_Δt, new)
+        new = max(self.min_change * old_Δt, new)
+        return min(max(new, self.min_Δt), self.max_Δt)
+
+    def __call__(self, simulation):
+        simulation.Δt = self.new_time_step(simulation.Δt, simulation.model)
 
 
 class Simulation:

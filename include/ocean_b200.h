@@ -101,6 +101,13 @@ typedef struct {
     int32_t ntracers;
     ob200_bc bcs[3 + OB200_MAX_TRACERS][6];   /* per prognostic field (u,v,w,tracers...), per side */
     int32_t pressure_solver;        /* OB200_SOLVER_AUTO picks as NonhydrostaticModels.jl:18-27 */
+    /* SeawaterBuoyancy with LinearEquationOfState (BuoyancyModels/seawater_buoyancy.jl:10-73,
+     * linear_equation_of_state.jl:69-77: b = g (α T - β S), g α T, or -g β S): buoyancy_kind 0 = `buoyancy_tracer`
+     * above (BuoyancyTracer or nothing), 1 = seawater; temperature_tracer / salinity_tracer = tracer index,
+     * -1 for a constant (inactive) one.  Nonlinear equations of state are rejected by the shim. */
+    int32_t buoyancy_kind;
+    int32_t temperature_tracer, salinity_tracer;
+    double  gravitational_acceleration, thermal_expansion, haline_contraction;
 } ob200_model_desc;
 
 /* ---- library / device ----------------------------------------------------------------- */
@@ -190,6 +197,10 @@ int32_t ob200_model_time_step(ob200_model* m, double dt, int32_t euler);
 /* model.clock (TimeSteppers/clock.jl) */
 int32_t ob200_model_clock(const ob200_model* m, double* time, int64_t* iteration);
 int32_t ob200_model_set_clock(ob200_model* m, double time, int64_t iteration, double previous_dt);
+/* maximum(abs, parent(u / v / w)) in one call: the device part of cell_advection_timescale
+ * (Utils/cell_advection_timescale.jl:4-21, used by TimeStepWizard Simulations/time_step_wizard.jl:78-95 and the CFL
+ * diagnostics); NaN if a velocity holds a NaN (NaNChecker, Simulations/nan_checker.jl:33-52) */
+int32_t ob200_model_max_abs_velocities(ob200_model* m, double out[3]);
 /* max |div U| and kinetic energy 0.5*sum(u^2+v^2+w^2) over the interior (diagnostics) */
 int32_t ob200_model_diagnostics(ob200_model* m, double* max_abs_div, double* kinetic_energy);
 

@@ -35,4 +35,5 @@ from .advection import (WENO5, CenteredSecondOrder, CenteredFourthOrder,  # noqa
 from .closures import ScalarDiffusivity  # noqa: F401
 from .solvers import (FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver,  # noqa: F401
                       BatchedTridiagonalSolver, poisson_eigenvalues)
-from .model import NonhydrostaticModel, FPlane, BuoyancyTracer, Buoyancy  # noqa: F401
+from .model import (NonhydrostaticModel, FPlane, BuoyancyTracer, Buoyancy, SeawaterBuoyancy,  # noqa: F401
+                    LinearEquationOfState)

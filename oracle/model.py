@@ -29,6 +29,56 @@ class BuoyancyTracer:
     pass
 
 
+class LinearEquationOfState:
+    """LinearEquationOfState(FT; thermal_expansion=1.67e-4, haline_contraction=7.80e-4) (linear_equation_of_state.jl:6-30)."""
+
+    def __init__(self, thermal_expansion=1.67e-4, haline_contraction=7.80e-4):
+        self.thermal_expansion, self.haline_contraction = thermal_expansion, haline_contraction
+
+
+class SeawaterBuoyancy:
+    """SeawaterBuoyancy(FT; gravitational_acceleration=g_Earth, equation_of_state=LinearEquationOfState(FT),
+    constant_temperature=nothing, constant_salinity=nothing) (seawater_buoyancy.jl:61-73); only the linear equation
+    of state.  `constant_temperature=True` becomes 0 as in :67-68; for a linear EOS the constant value is irrelevant."""
+    g_Earth = 9.80665            # Oceananigans.jl:178 via BuoyancyModels: g_Earth
+
+    def __init__(self, gravitational_acceleration=None, equation_of_state=None, constant_temperature=None,
+                 constant_salinity=None):
+        self.gravitational_acceleration = self.g_Earth if gravitational_acceleration is None else gravitational_acceleration
+        self.equation_of_state = equation_of_state or LinearEquationOfState()
+        self.constant_temperature = 0.0 if constant_temperature is True else constant_temperature
+        self.constant_salinity = 0.0 if constant_salinity is True else constant_salinity
+        assert not (self.constant_temperature is not None and self.constant_salinity is not None)
+
+    def required_tracers(self):
+        """seawater_buoyancy.jl:18-20"""
+        if self.constant_salinity is not None:
+            return ("T",)
+        if self.constant_temperature is not None:
+            return ("S",)
+        return ("T", "S")
+
+
+def buoyancy_perturbation(model, tracers, FT):
+    """buoyancy_perturbation(i, j, k, grid, b, C) as a function (i, j, k, grid) -> array:
+    BuoyancyTracer: C.b (buoyancy_tracer.jl:12); linear SeawaterBuoyancy (linear_equation_of_state.jl:69-77, evaluation order
+    kept): g * (α T - β S), g * α * T (active temperature only), - g * β * S (active salinity only); parameters are FT."""
+    if isinstance(model, BuoyancyTracer):
+        b = tracers["b"]
+        return lambda i, j, k, grid: b[i, j, k]
+    g = FT(model.gravitational_acceleration)
+    al, be = FT(model.equation_of_state.thermal_expansion), FT(model.equation_of_state.haline_contraction)
+    req = model.required_tracers()
+    if req == ("T", "S"):
+        T, S = tracers["T"], tracers["S"]
+        return lambda i, j, k, grid: g * (al * T[i, j, k] - be * S[i, j, k])
+    if req == ("T",):
+        T = tracers["T"]
+        return lambda i, j, k, grid: g * al * T[i, j, k]
+    S = tracers["S"]
+    return lambda i, j, k, grid: -g * be * S[i, j, k]
+
+
 class Buoyancy:
     """Buoyancy(model=BuoyancyTracer(), gravity_unit_vector=ZDirection()) (buoyancy.jl:3-42)."""
 
@@ -62,12 +112,13 @@ class NonhydrostaticModel:
         self.grid = grid
         FT = grid.FT
         self.advection, self.closure, self.coriolis = advection, closure, coriolis
-        if isinstance(buoyancy, BuoyancyTracer):
+        if isinstance(buoyancy, (BuoyancyTracer, SeawaterBuoyancy)):
             buoyancy = Buoyancy(buoyancy)              # regularize_buoyancy
         self.buoyancy = buoyancy
         self.tracer_names = tuple(tracers)
-        if buoyancy is not None:
-            assert "b" in self.tracer_names, "BuoyancyTracer requires tracer :b"
+        if buoyancy is not None:                       # validate_buoyancy (BuoyancyModels.jl:37-46)
+            req = ("b",) if isinstance(buoyancy.model, BuoyancyTracer) else buoyancy.model.required_tracers()
+            assert all(n in self.tracer_names for n in req), f"buoyancy requires tracers {req}"
         bcs = boundary_conditions or {}
 
         def mk(name, loc):
@@ -129,12 +180,12 @@ class NonhydrostaticModel:
         if self.buoyancy is None:
             zb = lambda i, j, k, grid: grid.FT(0) * np.zeros((i.n, j.n, k.n), dtype=grid.FT)
         else:
-            b = self.tracers["b"]
+            bp = buoyancy_perturbation(self.buoyancy.model, self.tracers, g.FT)
             gz = 1 if self.buoyancy.g is None else g.FT(self.buoyancy.g[2])
             if self.buoyancy.g is None:
-                zb = lambda i, j, k, grid: b[i, j, k]
+                zb = bp
             else:
-                zb = lambda i, j, k, grid: gz * b[i, j, k]
+                zb = lambda i, j, k, grid: gz * bp(i, j, k, grid)
         k = R(Nz + 1)
         p[i, j, R(Nz)] = -Izf(i, j, k, g, zb) * g.Δz(F, k)
         for kk in range(Nz - 1, 0, -1):
@@ -156,7 +207,7 @@ class NonhydrostaticModel:
             """x/y_dot_g_b (g_dot_b.jl:1-7): ĝ * b[i,j,k], zero for ZDirection."""
             if buoy is None or buoy.g is None:
                 return 0
-            return FT(buoy.g[d]) * self.tracers["b"][i, j, k]
+            return FT(buoy.g[d]) * buoyancy_perturbation(buoy.model, self.tracers, FT)(i, j, k, g)
         # u: nonhydrostatic_tendency_kernel_functions.jl:61-71
         corx = (-FT(cor.f) * Ixy_fca(i, j, k, g, v)) if cor is not None else zero     # x_f_cross_U
         px = deriv(0, F, C, C)(i, j, k, g, pHY) if pHY is not None else zero

@@ -236,6 +236,21 @@ CONFIGS = {
                                 tracers=("c",), buoyancy=False, ts="RungeKutta3", dt=2e-3),
     "weno_js": dict(size=(10, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="WENO5js",
                     tracers=("b",), buoyancy=True, ts="RungeKutta3", dt=2e-3),
+    # SeawaterBuoyancy with the linear equation of state: T and S active (general kernels, Bounded z),
+    # T and S active on the specialised path (fused kernel for u, v, w, T + per-field kernel for S), temperature only
+    # with tilted gravity, salinity only
+    "seawater_TS_bounded": dict(size=(8, 10, 12), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(1, 1, 1),
+                                adv="WENO5", tracers=("T", "S"), seawater={}, closure=("ThreeDimensional", 1e-3, 1e-3),
+                                f=0.5, ts="RungeKutta3", dt=2e-3),
+    "seawater_TS_periodic_fast": dict(size=(32, 12, 16), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="WENO5",
+                                      tracers=("T", "S"), seawater=dict(gravitational_acceleration=3.0,
+                                                                        eos=(2e-1, 7e-1)), ts="RungeKutta3", dt=2e-3),
+    "seawater_T_tilted": dict(size=(8, 8, 10), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(1, 1, 1),
+                              adv="CenteredFourthOrder", tracers=("T",), seawater=dict(constant_salinity=35.0, eos=(0.3, 0.2)),
+                              tilt=(0.6, 0.0, 0.8), ts="QuasiAdamsBashforth2", dt=2e-3),
+    "seawater_S_only": dict(size=(8, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="UpwindBiasedFifthOrder",
+                            tracers=("S", "c"), seawater=dict(constant_temperature=True, eos=(0.3, 0.2)),
+                            ts="RungeKutta3", dt=2e-3),
 }
 
 
@@ -260,6 +275,12 @@ def build_models(ob, cfg, FT):
     if cfg.get("buoyancy"):
         bu_o = O.Buoyancy(O.BuoyancyTracer(), cfg.get("tilt"))
         bu_b = ob.Buoyancy(ob.BuoyancyTracer(), cfg.get("tilt"))
+    if cfg.get("seawater") is not None:
+        kw = dict(cfg["seawater"])
+        eos = kw.pop("eos", None)
+        mk = lambda M: M.Buoyancy(M.SeawaterBuoyancy(equation_of_state=M.LinearEquationOfState(*eos) if eos else None, **kw),
+                                  cfg.get("tilt"))
+        bu_o, bu_b = mk(O), mk(ob)
     bcs_o = bcs_b = None
     if cfg.get("bcs"):
         bcs_o = {n: {s: O.BoundaryCondition(*kv) for s, kv in d.items()} for n, d in cfg["bcs"].items()}
@@ -408,3 +429,41 @@ def test_slab_decomposition_two_gpus_matches_oracle():
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
                           os.path.join(root, "tests", "dist_check.py")], capture_output=True, text=True, timeout=600)
     assert "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- TimeStepWizard / CFL reductions -------------------------------------------------------
+def test_cell_advection_timescale_and_wizard(ob):
+    """cell_advection_timescale (Utils/cell_advection_timescale.jl:4-21: maxima over the PARENT arrays, halos included) and
+    the TimeStepWizard arithmetic (time_step_wizard.jl:78-95) against the same formulas evaluated on the oracle's arrays"""
+    for name in ("c3_stretched_weno_rk3", "c2_periodic_weno_rk3", "c1_2d_flat_weno_ab2"):
+        cfg = CONFIGS[name]
+        mo, mb = build_models(ob, cfg, np.float64)
+        init_state(mo, mb, ob, 31)
+        mo.time_step(cfg["dt"])
+        ob.time_step(mb, cfg["dt"])
+        g = mo.grid
+        umax = [float(np.max(np.abs(mo.velocities[n].parent))) for n in "uvw"]
+        got = ob.max_abs_velocities(mb)
+        for a, b in zip(got, umax):
+            assert abs(a - b) <= 1e-12 * max(b, 1e-300), (name, got, umax)
+        dmin = []
+        for d in range(3):
+            if g.topology[d] == O.Flat:
+                dmin.append(np.inf)
+            else:
+                dc = g.dC[d]
+                dmin.append(float(dc) if g.regular[d] else float(np.min(dc.parent)))
+        want = min(dm / um if um > 0 else np.inf for dm, um in zip(dmin, umax))
+        tau = ob.cell_advection_timescale(mb)
+        assert abs(tau - want) <= 1e-12 * want, (name, tau, want)
+        wiz = ob.TimeStepWizard(cfl=0.5, max_change=1.2, min_change=0.5, max_Δt=10.0)
+        old = cfg["dt"]
+        new = wiz.new_time_step(old, mb)
+        expect = min(max(min(1.2 * old, 0.5 * want), 0.5 * old), 10.0)
+        assert abs(new - expect) <= 1e-12 * expect
+    # a NaN in a velocity is reported as NaN (NaNChecker)
+    u = mb.velocities["u"]
+    a = u.interior().copy()
+    a[0, 0, 0] = np.nan
+    u.set(a)
+    assert np.isnan(ob.max_abs_velocities(mb)[0])

@@ -377,3 +377,29 @@ def test_c_twin_matches_numpy_oracle(N, zweno):
         r = m.fields[n].interior
         if np.max(np.abs(r)) > 0:
             assert np.max(np.abs(a - r)) <= 1e-13 * np.max(np.abs(r)), n
+
+
+# ---- SeawaterBuoyancy with LinearEquationOfState (linear_equation_of_state.jl:69-77) ---------------------------------
+import oracle as O
+def test_seawater_buoyancy_hydrostatic_pressure_known_answer():
+    """uniform T, S: b = g (alpha T - beta S) is uniform and the downward integral of update_hydrostatic_pressure.jl:10-18, which
+    starts half a cell ABOVE the surface (at the centre of the first halo cell, filled with b0 by the no-flux default), gives
+    pHY' = b0 (z_c - dz / 2); temperature-only and salinity-only variants use g alpha T and -g beta S"""
+    g = O.RectilinearGrid(np.float64, size=(4, 4, 8), x=(0, 1), y=(0, 1), z=(-2, 0), topology=(O.Periodic, O.Periodic, O.Bounded))
+    zc = g.nodes(("c", "c", "c"))[2].ravel()
+    grav, al, be, T0, S0 = 9.5, 2e-4, 8e-4, 12.0, 34.0
+    cases = [(("T", "S"), {}, grav * (al * T0 - be * S0)), (("T",), dict(constant_salinity=35.0), grav * al * T0),
+             (("S",), dict(constant_temperature=True), -grav * be * S0)]
+    for tracers, kw, b0 in cases:
+        bu = O.SeawaterBuoyancy(gravitational_acceleration=grav, equation_of_state=O.LinearEquationOfState(al, be), **kw)
+        m = O.NonhydrostaticModel(g, advection=O.CenteredSecondOrder(), buoyancy=bu, tracers=tracers)
+        vals = {}
+        if "T" in tracers:
+            vals["T"] = np.full((4, 4, 8), T0)
+        if "S" in tracers:
+            vals["S"] = np.full((4, 4, 8), S0)
+        m.set(**vals)
+        p = m.pHY.interior
+        assert np.allclose(p, b0 * (zc.reshape(1, 1, -1) - 0.125), rtol=1e-13, atol=1e-15)
+    with pytest.raises(AssertionError):
+        O.NonhydrostaticModel(g, buoyancy=O.SeawaterBuoyancy(), tracers=("T",))       # validate_buoyancy: S missing
