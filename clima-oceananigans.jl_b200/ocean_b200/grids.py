@@ -112,7 +112,8 @@ class RectilinearGrid:
                     cs = [x, y, z]
                     for d, t in enumerate(topology):
                         if t != Flat:
-                            cs[d] = (0.0, float(next(it)))
+                            Ld = float(next(it))
+                            cs[d] = (0.0, Ld) if d < 2 else (-Ld, 0.0)
                     x, y, z = cs
                     extent = None
                 if not (isinstance(y, tuple) and len(y) == 2):
@@ -147,8 +148,9 @@ class RectilinearGrid:
                 N.append(1), H.append(0)
             else:
                 N.append(int(next(si))), H.append(int(next(hi)))
-                if extent is not None:
-                    coords[d] = (0.0, float(next(it)))
+                if extent is not None:        # the "oceanic" default domain (Grids/input_validation.jl:92-95): z = (-Lz, 0)
+                    Ld = float(next(it))
+                    coords[d] = (0.0, Ld) if d < 2 else (-Ld, 0.0)
                 if coords[d] is None:
                     raise ValueError("missing coordinate specification")
         self.N, self.H = tuple(N), tuple(H)

@@ -144,8 +144,9 @@ class RectilinearGrid:
             else:
                 N.append(int(next(si)))
                 H.append(int(next(hi)))
-                if extent is not None:
-                    coords[d] = (0.0, float(next(ext)))
+                if extent is not None:        # the "oceanic" default domain of input_validation.jl:92-95: z = (-Lz, 0)
+                    Ld = float(next(ext))
+                    coords[d] = (0.0, Ld) if d < 2 else (-Ld, 0.0)
         self.Nx, self.Ny, self.Nz = N
         self.Hx, self.Hy, self.Hz = H
         self.L, self.nodesF, self.nodesC, self.dF, self.dC, self.regular = [], [], [], [], [], []
