@@ -657,7 +657,15 @@ struct ob200_model {
     double time = 0, previous_dt = 1.0 / 0.0;
     long long iteration = 0;
     bool use_fast = true;
-    ~ob200_model() { for (void* p : owned) cudaFree(p); }
+    // side streams / events of this model (independent launches of a stage are forked onto them and joined before the
+    // stage's next dependent kernel); created on first use, released with the model
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr}, hy_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, hy_fork = nullptr, hy_done = nullptr;
+    ~ob200_model() {
+        for (void* p : owned) cudaFree(p);
+        for (cudaStream_t s : {side[0], side[1], side[2], hy_stream}) if (s) cudaStreamDestroy(s);
+        for (cudaEvent_t e : {ev_fork, ev_join[0], ev_join[1], ev_join[2], hy_fork, hy_done}) if (e) cudaEventDestroy(e);
+    }
 };
 template <class FT> static Phys<FT>& physOf(ob200_model* m);
 template <> Phys<float>& physOf<float>(ob200_model* m) { return m->P32; }
@@ -839,26 +847,24 @@ static void model_update_state_after_projection(ob200_model* m, bool fused, bool
 // Fused stage: the hydrostatic integral depends only on the buoyancy tracer, which is final once the tendency kernels
 // have run, so it is enqueued on a side stream and overlaps the pressure solve and the correction (it is a
 // latency-bound column walk that leaves most of the machine idle).  Returns true if it was started.
-static cudaStream_t g_hy_stream = nullptr;
-static cudaEvent_t g_hy_fork = nullptr, g_hy_done = nullptr;
 template <class FT>
 static bool model_hydrostatic_async_begin(ob200_model* m) {
     static const bool off = getenv("OB200_NO_STREAM_SPREAD") != nullptr;
     if (off || !m->pHY) return false;
-    if (!g_hy_stream) {
-        OB_CUDA(cudaStreamCreateWithFlags(&g_hy_stream, cudaStreamNonBlocking));
-        OB_CUDA(cudaEventCreateWithFlags(&g_hy_fork, cudaEventDisableTiming));
-        OB_CUDA(cudaEventCreateWithFlags(&g_hy_done, cudaEventDisableTiming));
+    if (!m->hy_stream) {
+        OB_CUDA(cudaStreamCreateWithFlags(&m->hy_stream, cudaStreamNonBlocking));
+        OB_CUDA(cudaEventCreateWithFlags(&m->hy_fork, cudaEventDisableTiming));
+        OB_CUDA(cudaEventCreateWithFlags(&m->hy_done, cudaEventDisableTiming));
     }
-    OB_CUDA(cudaEventRecord(g_hy_fork, g_stream));
-    OB_CUDA(cudaStreamWaitEvent(g_hy_stream, g_hy_fork, 0));
-    g_override = g_hy_stream;
+    OB_CUDA(cudaEventRecord(m->hy_fork, g_stream));
+    OB_CUDA(cudaStreamWaitEvent(m->hy_stream, m->hy_fork, 0));
+    g_override = m->hy_stream;
     try { model_hydrostatic<FT>(m, true); } catch (...) { g_override = nullptr; throw; }
     g_override = nullptr;
-    OB_CUDA(cudaEventRecord(g_hy_done, g_hy_stream));
+    OB_CUDA(cudaEventRecord(m->hy_done, m->hy_stream));
     return true;
 }
-static void model_hydrostatic_async_end() { OB_CUDA(cudaStreamWaitEvent(g_stream, g_hy_done, 0)); }
+static void model_hydrostatic_async_end(ob200_model* m) { OB_CUDA(cudaStreamWaitEvent(g_stream, m->hy_done, 0)); }
 
 // the fused path: every non-Flat dimension Periodic (not slab-decomposed) and regular, fast FFT solver
 template <class FT>
@@ -883,8 +889,9 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
     // new-state buffer), so they go to side streams forked from the library stream: the tail of one launch (its last,
     // partly filled wave of blocks) overlaps the head of the next instead of leaving SMs idle four times per stage.
     static const bool spread = getenv("OB200_NO_STREAM_SPREAD") == nullptr;
-    static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
-    static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t* side = m->side;
+    cudaEvent_t& ev_fork = m->ev_fork;
+    cudaEvent_t* ev_join = m->ev_join;
     const bool fork = spread && m->use_fast && m->nf > 1;
     if (fork && !ev_fork) {
         OB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -1003,7 +1010,7 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
             model_pressure_step<FT>(m, sdt[s], true, fused);
             m->time += (double)sdt[s];
             if (s < 2) for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);   // store_tendencies!
-            if (hy) model_hydrostatic_async_end();
+            if (hy) model_hydrostatic_async_end(m);
             model_update_state_after_projection<FT>(m, fused, hy);
         }
         m->iteration += 1;
@@ -1024,7 +1031,7 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
         for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);
         m->time += (double)dt;
         m->iteration += 1;
-        if (hy) model_hydrostatic_async_end();
+        if (hy) model_hydrostatic_async_end(m);
         model_update_state_after_projection<FT>(m, fused, hy);
     }
 }
@@ -1095,6 +1102,9 @@ extern "C" int32_t ob200_model_max_abs_velocities(ob200_model* m, double out[3])
     for (int q = 0; q < 3; ++q) out[q] = h[4 * q + 3] > 0 ? (0.0 / 0.0) : h[4 * q + 2];
     API_END
 }
+
+// number of cached tensor-map encodings (tests: the cache is bounded, entries die with the buffers they describe)
+extern "C" int64_t ob200_debug_cached_tensor_maps(void) { return (int64_t)ob::tmau::cached_maps(); }
 
 // knob used by tests to force the general kernels
 extern "C" int32_t ob200_model_use_fast_kernels(ob200_model* m, int32_t on) { m->use_fast = on != 0; return 0; }

@@ -546,6 +546,8 @@ struct FastPoisson {
     // bulk = true: the transform kernels store into LOCAL chunk buffers and the chunks travel to their ranks as large
     // contiguous copies (copy engines over NVLink); false: the kernels store straight into the peers' buffers
     bool bulk_a2a = false;
+    cudaStream_t cpy = nullptr;                 // copy stream + events of the pipelined bulk transposes
+    cudaEvent_t ev_piece[16] = {}, ev_done = nullptr;
     CT* bufC = nullptr;
     int dtk_y = 8;                              // columns per y tile (8, 4, 2 for gathered lines of <= 512, 1024, 2048)
     CUtensorMap tm4_zi, tm4_y, tmr_zf[8], tmr_zi[8], tmr_y[8];
@@ -680,6 +682,9 @@ template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
     if (p->bufA) cudaFree(p->bufA);
     if (p->bufB) cudaFree(p->bufB);
     for (void* q : p->owned) cudaFree(q);
+    if (p->cpy) cudaStreamDestroy(p->cpy);
+    for (cudaEvent_t e : p->ev_piece) if (e) cudaEventDestroy(e);
+    if (p->ev_done) cudaEventDestroy(p->ev_done);
     delete p;
 }
 
@@ -944,11 +949,12 @@ static void distributed_middle_tma(FastPoisson<FT>* p) {
     // bulk transposes are pipelined with the transform: the launch is split (z forward: one launch per destination
     // chunk; y lines: one launch per block of z levels, whose slice of every chunk is contiguous) and each finished
     // piece is copied on a second stream while the next piece is transformed
-    static cudaStream_t cpy = nullptr;
-    static cudaEvent_t ev_piece[16] = {}, ev_done = nullptr;
+    cudaStream_t& cpy = p->cpy;                       // owned by the plan (released in fast_poisson_destroy)
+    cudaEvent_t* ev_piece = p->ev_piece;
+    cudaEvent_t& ev_done = p->ev_done;
     if (p->bulk_a2a && !cpy) {
         OB_CUDA(cudaStreamCreateWithFlags(&cpy, cudaStreamNonBlocking));
-        for (auto& e : ev_piece) OB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (int q = 0; q < 16; ++q) OB_CUDA(cudaEventCreateWithFlags(&ev_piece[q], cudaEventDisableTiming));
         OB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
     }
     A.r_only = -1; A.o_first = 0;

@@ -89,6 +89,7 @@ SYMBOLS = {
     "ob200_model_set_clock": (C.c_int32, [C.c_void_p, C.c_double, C.c_int64, C.c_double]),
     "ob200_model_diagnostics": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ob200_model_max_abs_velocities": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
+    "ob200_debug_cached_tensor_maps": (C.c_int64, []),
     "ob200_comm_unique_id": (C.c_int32, [C.c_char_p]),
     "ob200_comm_init": (C.c_int32, [C.c_int32, C.c_int32, C.c_char_p]),
     "ob200_comm_destroy": (C.c_int32, []),

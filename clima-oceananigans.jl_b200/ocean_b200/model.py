@@ -501,9 +501,15 @@ class NonhydrostaticModel:
         check(lib.ob200_model_diagnostics(self.handle, C.byref(a), C.byref(b)))
         return dict(max_abs_div=a.value, kinetic_energy=b.value)
 
+    def destroy(self):
+        """release the library model now (device memory, streams, events, tensor maps); also done by the finalizer"""
+        if getattr(self, "handle", None) is not None:
+            lib.ob200_model_destroy(self.handle)
+            self.handle = None
+
     def __del__(self):
         try:
-            lib.ob200_model_destroy(self.handle)
+            self.destroy()
         except Exception:
             pass
 

@@ -216,6 +216,8 @@ int32_t ob200_comm_destroy(void);
 int32_t ob200_comm_allreduce(double* values, int32_t n, int32_t op);
 
 /* ---- measurement knobs (no reference counterpart; used by bench.py and the tests) ---------- */
+/* number of cached TMA tensor-map encodings (entries are evicted when the buffers they describe are freed) */
+int64_t ob200_debug_cached_tensor_maps(void);
 /* force the general kernels (on = 0) instead of the specialised headline kernels */
 int32_t ob200_model_use_fast_kernels(ob200_model* m, int32_t on);
 /* per-phase CUDA-event timing on the library stream: phases "tendency" (one event pair per

@@ -467,3 +467,37 @@ def test_cell_advection_timescale_and_wizard(ob):
     a[0, 0, 0] = np.nan
     u.set(a)
     assert np.isnan(ob.max_abs_velocities(mb)[0])
+
+
+# ---- several models in one process: handles own their streams, events and tensor maps ------------------------------------
+def test_two_models_of_different_sizes_interleaved_and_recreated(ob):
+    """create two models of different sizes, step them alternately, destroy one, create a third of yet another size (its
+    buffers may reuse the freed addresses: stale tensor maps would fault or corrupt), and check all against the oracle"""
+    import gc
+    from ocean_b200._lib import lib
+
+    def pair(size, seed):
+        cfg = dict(size=size, topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="WENO5", tracers=("b",), buoyancy=True,
+                   ts="RungeKutta3", dt=2e-3)
+        mo, mb = build_models(ob, cfg, np.float64)
+        init_state(mo, mb, ob, seed)
+        return mo, mb
+    a_o, a_b = pair((32, 16, 16), 41)
+    b_o, b_b = pair((64, 12, 8), 42)
+    for _ in range(2):
+        a_o.time_step(2e-3); ob.time_step(a_b, 2e-3)
+        b_o.time_step(2e-3); ob.time_step(b_b, 2e-3)
+    compare_fields(a_o, a_b, 1e-12, "model A")
+    compare_fields(b_o, b_b, 1e-12, "model B")
+    maps_before = lib.ob200_debug_cached_tensor_maps()
+    assert maps_before > 0                    # both took the TMA-staged fused kernel
+    a_b.destroy()
+    del a_b
+    gc.collect()
+    assert lib.ob200_debug_cached_tensor_maps() < maps_before       # the maps over A's buffers were evicted
+    c_o, c_b = pair((32, 20, 16), 43)
+    for _ in range(2):
+        c_o.time_step(2e-3); ob.time_step(c_b, 2e-3)
+        b_o.time_step(2e-3); ob.time_step(b_b, 2e-3)
+    compare_fields(c_o, c_b, 1e-12, "model C (after A was destroyed)")
+    compare_fields(b_o, b_b, 1e-12, "model B (second round)")
