@@ -650,6 +650,7 @@ struct ob200_model {
     std::vector<std::unique_ptr<ob200_field>> F;    // state (two buffers each)
     std::vector<std::unique_ptr<ob200_field>> Gn, Gm;
     std::unique_ptr<ob200_field> pNHS, pHY;
+    std::unique_ptr<ob200_field> nue;               // SmagorinskyLilly eddy viscosity (diffusivity_fields.νₑ)
     std::unique_ptr<ob200_poisson> solver;
     std::vector<void*> owned;
     Phys<float> P32;
@@ -696,7 +697,9 @@ static void build_phys(ob200_model* m) {
         }
     P.closure = D.closure;
     P.nu = (FT)D.nu;
-    for (int t = 0; t < 8; ++t) P.kappa[t] = (FT)D.kappa[t];
+    for (int t = 0; t < 8; ++t) P.kappa[t] = (FT)(D.closure == OB200_CLOSURE_SMAGORINSKY_LILLY ? D.prandtl[t] : D.kappa[t]);
+    P.smagC = (FT)D.smagorinsky_C; P.smagCb = (FT)D.smagorinsky_Cb;
+    P.nue = m->nue ? m->nue->template p0<FT>() : nullptr;
     P.fplane = D.coriolis_fplane;
     P.f = (FT)D.f;
     P.btr = D.buoyancy_tracer;
@@ -711,7 +714,10 @@ extern "C" int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model*
     if (!desc || !desc->grid || !out) throw Error("null argument");
     if (desc->ntracers < 0 || desc->ntracers > OB200_MAX_TRACERS) throw Error("too many tracers");
     if (desc->advection < 0 || desc->advection > OB200_ADV_WENO5) throw Error("unsupported advection scheme");
-    if (desc->closure < 0 || desc->closure > OB200_CLOSURE_VERTICAL) throw Error("unsupported closure");
+    if (desc->closure < 0 || desc->closure > OB200_CLOSURE_SMAGORINSKY_LILLY) throw Error("unsupported closure");
+    if (desc->closure == OB200_CLOSURE_SMAGORINSKY_LILLY)
+        for (int t = 0; t < desc->ntracers; ++t)
+            if (!(desc->prandtl[t] > 0)) throw Error("SmagorinskyLilly needs a positive Prandtl number for every tracer");
     if (desc->buoyancy_tracer >= desc->ntracers) throw Error("buoyancy tracer index out of range");
     if (desc->buoyancy_kind < 0 || desc->buoyancy_kind > 1) throw Error("unsupported buoyancy model");
     if (desc->buoyancy_kind == 1) {
@@ -741,6 +747,7 @@ extern "C" int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model*
     int32_t ccc[3] = {0, 0, 0};
     m->pNHS.reset(make_field(m->grid, ccc, nullptr, false));
     if (GD.topology[2] != OB200_FLAT) m->pHY.reset(make_field(m->grid, ccc, nullptr, false));
+    if (desc->closure == OB200_CLOSURE_SMAGORINSKY_LILLY) m->nue.reset(make_field(m->grid, ccc, nullptr, false));
     ob200_poisson* s = nullptr;
     if (ob200_poisson_create(m->grid, desc->pressure_solver, &s)) throw Error(ob::g_err);
     m->solver.reset(s);
@@ -768,6 +775,7 @@ extern "C" int32_t ob200_model_field(ob200_model* m, const char* name, ob200_fie
     };
     ob200_field* f = nullptr;
     if (s == "pNHS") f = m->pNHS.get();
+    else if (s == "nu_e") f = m->nue.get();
     else if (s == "pHY") f = m->pHY.get();
     else if (s.rfind("Gn_", 0) == 0) { int q = idx(s.substr(3)); if (q >= 0) f = m->Gn[q].get(); }
     else if (s.rfind("Gm_", 0) == 0) { int q = idx(s.substr(3)); if (q >= 0) f = m->Gm[q].get(); }
@@ -813,10 +821,24 @@ static void model_hydrostatic(ob200_model* m, bool periodic_images) {
     launch_hydrostatic_pressure<FT>(g, b, gz, m->pHY->template p0<FT>(), periodic_images);
 }
 
+// calculate_diffusivities! + fill_halo_regions!(diffusivity_fields) (update_nonhydrostatic_model_state.jl:29-31): needs
+// valid halos of the velocities and of the buoyancy tracers
+template <class FT>
+static void model_diffusivities(ob200_model* m) {
+    if (!m->nue) return;
+    ScopedPhase ph("closure");
+    Phys<FT>& P = physOf<FT>(m);
+    launch_smagorinsky<FT>(P, model_buoyancy<FT>(m), m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(),
+                           m->F[2]->template p0<FT>(), m->nue->template p0<FT>());
+    ob200_field* f = m->nue.get();
+    fill_halos<FT>(&f, 1);
+}
+
 template <class FT>
 static void model_update_state(ob200_model* m, bool tracers_too = true) {
     // update_nonhydrostatic_model_state.jl:14-37
     { ScopedPhase ph("halo"); model_fill_state_halos<FT>(m, 0, tracers_too ? m->nf : 3); }
+    model_diffusivities<FT>(m);
     if (m->pHY) {
         model_hydrostatic<FT>(m, false);
         ScopedPhase ph("halo");
@@ -841,8 +863,8 @@ static void model_update_state_after_projection(ob200_model* m, bool fused, bool
         for (int q = 3; q < m->nf; ++q) v.push_back(m->F[q].get());
         v.push_back(m->pNHS.get());
     }
-    ScopedPhase ph("halo");
-    fill_halos<FT>(v.data(), (int)v.size());
+    { ScopedPhase ph("halo"); fill_halos<FT>(v.data(), (int)v.size()); }
+    model_diffusivities<FT>(m);
 }
 // Fused stage: the hydrostatic integral depends only on the buoyancy tracer, which is final once the tendency kernels
 // have run, so it is enqueued on a side stream and overlaps the pressure solve and the correction (it is a

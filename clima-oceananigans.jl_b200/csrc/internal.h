@@ -63,6 +63,10 @@ struct FusedFields {
 };
 namespace fz { template <class FT> int launch(const Phys<FT>& P, const FusedFields<FT>& a); }
 
+// SmagorinskyLilly eddy viscosity over the interior (the caller fills its halos)
+template <class FT>
+void launch_smagorinsky(const Phys<FT>& P, const Buoy<FT>& B, const FT* u, const FT* v, const FT* w, FT* nue);
+
 template <class FT, class CT>
 void launch_pressure_rhs(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,
                          bool times_dz, CT* rhs);

@@ -776,6 +776,31 @@ __device__ __forceinline__ void block_reduce_store(double s, double s2, double m
     }
 }
 
+// calculate_nonlinear_viscosity! (turbulence_closure_utils.jl:35-38) for SmagorinskyLilly: νₑ over the interior
+template <class FT>
+__global__ void __launch_bounds__(128) smagorinsky_kernel(const __grid_constant__ Phys<FT> P, const Buoy<FT> B, const FT* u,
+                                                          const FT* v, const FT* w, FT* nue) {
+    const GridD<FT>& g = P.g;
+    int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    int k = 1 + blockIdx.z;
+    if (i > g.N[0] || j > g.N[1]) return;
+    Pt q;
+    q.i[0] = i; q.i[1] = j; q.i[2] = k;
+    q.p = i * g.st[0] + j * g.st[1] + k * g.st[2];
+    const FT* U[3] = {u, v, w};
+    nue[q.p] = smagorinsky_nu(P, B, U, q);
+}
+template <class FT>
+void launch_smagorinsky(const Phys<FT>& P, const Buoy<FT>& B, const FT* u, const FT* v, const FT* w, FT* nue) {
+    const GridD<FT>& g = P.g;
+    dim3 blk(32, 4), grd(cdiv(g.N[0], 32), cdiv(g.N[1], 4), g.N[2]);
+    smagorinsky_kernel<FT><<<grd, blk, 0, stream()>>>(P, B, u, v, w, nue);
+    OB_LAUNCH_CHECK();
+}
+template void launch_smagorinsky<float>(const Phys<float>&, const Buoy<float>&, const float*, const float*, const float*, float*);
+template void launch_smagorinsky<double>(const Phys<double>&, const Buoy<double>&, const double*, const double*, const double*, double*);
+
 template <class FT>
 __global__ void reduce_kernel(GridD<FT> g, const FT* p0, int l0, int l1, int l2, int n0, int n1, int n2, double* out4) {
     long long total = (long long)n0 * n1 * n2;

@@ -13,7 +13,7 @@ namespace ob {
 #define OBD __device__ __forceinline__
 
 enum { ADV_NONE = 0, ADV_C2 = 1, ADV_C4 = 2, ADV_U1 = 3, ADV_U3 = 4, ADV_U5 = 5, ADV_WENO5 = 6 };
-enum { CLO_NONE = 0, CLO_3D = 1, CLO_H = 2, CLO_V = 3 };
+enum { CLO_NONE = 0, CLO_3D = 1, CLO_H = 2, CLO_V = 3, CLO_SMAG = 4 };
 enum { SIDE_LEFT = 0, SIDE_RIGHT = 1 };
 
 // buoyancy_perturbation(i, j, k, grid, b, C): BuoyancyTracer (buoyancy_tracer.jl:12) or SeawaterBuoyancy with the linear
@@ -44,7 +44,9 @@ struct Phys {
     int scheme, zweno, buffer;       // buffer = Ná´® of the scheme (Advection.jl:36-40)
     const FT* wc[3][2];              // stretched WENO tables [dim][0 = Face, 1 = Center] or null
     int closure;
-    FT nu, kappa[8];
+    FT nu, kappa[8];                 // ScalarDiffusivity constants; SmagorinskyLilly: kappa[t] = Prandtl number of tracer t
+    const FT* nue;                   // SmagorinskyLilly: eddy viscosity at cell centres (Julia-(0,0,0) pointer), halos filled
+    FT smagC, smagCb;
     int fplane;
     FT f;
     int btr, tilted;                 // buoyancy tracer index (-1 none); tilted gravity flag
@@ -397,6 +399,17 @@ OBD FT zeta3(const GridD<FT>& g, const FT* const* U, Pt q) {             // Î¶â‚
     return (a - b) / (spacing(g, 0, OB_F, q.i[0]) * spacing(g, 1, OB_F, q.i[1]));
 }
 
+// Î½á¶œá¶œá¶œ / Î½á¶ á¶ á¶œ / Î½á¶ á¶œá¶  / Î½á¶œá¶ á¶  of a cell-centred viscosity field (closure_kernel_operators.jl:84-90): at the location of the
+// (comp, dir) stress; the double interpolations are outer(inner) = higher dimension of lower dimension
+// (interpolation_operators.jl:60-71)
+template <class FT>
+OBD FT nu_at_stress(const GridD<FT>& g, const FT* nu, int comp, int dir, Pt q) {
+    if (comp == dir) return nu[q.p];
+    const int a = comp < dir ? comp : dir, b = comp < dir ? dir : comp;
+    if (g.topo[b] == OB_FLAT) return IF(g, nu, q, a);
+    return FT(0.5) * (IF(g, nu, sh(g, q, b, -1), a) + IF(g, nu, q, a));
+}
+
 // A * viscous_flux_{comp}{dir} at q
 template <class FT>
 OBD FT viscous_Aflux(const Phys<FT>& P, int comp, int dir, const FT* const* U, Pt q) {
@@ -407,6 +420,8 @@ OBD FT viscous_Aflux(const Phys<FT>& P, int comp, int dir, const FT* const* U, P
     FT fx = FT(0);
     if (P.closure == CLO_3D) {
         fx = -2 * (P.nu * strain(g, comp, dir, U, q));
+    } else if (P.closure == CLO_SMAG) {      // viscosity(::SmagorinskyLilly, K) = K.Î½â‚‘ (smagorinsky_lilly.jl:23)
+        fx = -2 * (nu_at_stress(g, P.nue, comp, dir, q) * strain(g, comp, dir, U, q));
     } else if (P.closure == CLO_H) {
         if (comp < 2 && comp == dir) fx = -(P.nu * div_xy(g, U, q));
         else if (comp == 1 && dir == 0) fx = -(P.nu * zeta3(g, U, q));
@@ -440,6 +455,11 @@ OBD FT diffusive_Aflux(const Phys<FT>& P, int d, FT kappa, const FT* c, Pt q) {
     int fl[3] = {OB_C, OB_C, OB_C};
     fl[d] = OB_F;
     FT Ar = areaA(g, d, q, fl[0], fl[1], fl[2]);
+    if (P.closure == CLO_SMAG) {             // Îºâ‚‘ = Î½â‚‘ / Pr at cell centres, interpolated to the face (smagorinsky_lilly.jl:205-221)
+        const FT k1 = P.nue[q.p] / kappa;
+        const FT kl = g.topo[d] == OB_FLAT ? k1 : FT(0.5) * (P.nue[q.p - g.st[d]] / kappa + k1);
+        return Ar * (-kl * deriv(g, c, q, d, OB_F));
+    }
     bool active = P.closure == CLO_3D || (P.closure == CLO_H && d < 2) || (P.closure == CLO_V && d == 2);
     return active ? Ar * (-kappa * deriv(g, c, q, d, OB_F)) : Ar * FT(0);
 }
@@ -454,6 +474,45 @@ OBD FT div_q(const Phys<FT>& P, FT kappa, const FT* c, Pt q) {
         t[d] = diffusive_Aflux(P, d, kappa, c, sh(g, q, d, 1)) - diffusive_Aflux(P, d, kappa, c, q);
     }
     return (1 / volume(g, q, OB_C, OB_C, OB_C)) * ((t[0] + t[1]) + t[2]);
+}
+
+// ---- SmagorinskyLilly eddy viscosity: calc_Î½á¶œá¶œá¶œ (smagorinsky_lilly.jl:83-107, 146-153) ---------------------------------
+// âˆ‚z_b at ccf (buoyancy_tracer.jl:16, seawater_buoyancy.jl:166-171, no_buoyancy.jl:9)
+template <class FT>
+OBD FT dz_buoyancy(const GridD<FT>& g, const Buoy<FT>& B, Pt q) {
+    switch (B.mode) {
+        case BUOY_TRACER: return deriv(g, B.T, q, 2, OB_F);
+        case BUOY_TS: return B.g * (B.alpha * deriv(g, B.T, q, 2, OB_F) - B.beta * deriv(g, B.S, q, 2, OB_F));
+        case BUOY_T: return B.g * (B.alpha * deriv(g, B.T, q, 2, OB_F) - B.beta * FT(0));
+        case BUOY_S: return B.g * (B.alpha * FT(0) - B.beta * deriv(g, B.S, q, 2, OB_F));
+        default: return FT(0);
+    }
+}
+template <class FT>
+OBD FT smagorinsky_nu(const Phys<FT>& P, const Buoy<FT>& B, const FT* const* U, Pt q) {
+    const GridD<FT>& g = P.g;
+    auto sq = [&](int a, int b, Pt r) { FT s = strain(g, a, b, U, r); return s * s; };
+    // â„‘_outer á¶œ(â„‘_inner á¶œ(Î£_abÂ²)) with Flat dimensions the identity
+    auto avg2 = [&](int a, int b) {           // a < b: inner = a, outer = b
+        auto inner = [&](Pt r) { return g.topo[a] == OB_FLAT ? sq(a, b, r) : FT(0.5) * (sq(a, b, r) + sq(a, b, sh(g, r, a, 1))); };
+        return g.topo[b] == OB_FLAT ? inner(q) : FT(0.5) * (inner(q) + inner(sh(g, q, b, 1)));
+    };
+    const FT s11 = strain(g, 0, 0, U, q), s22 = strain(g, 1, 1, U, q), s33 = strain(g, 2, 2, U, q);
+    const FT tr = (s11 * s11 + s22 * s22) + s33 * s33;
+    const FT S2 = ((tr + 2 * avg2(0, 1)) + 2 * avg2(0, 2)) + 2 * avg2(1, 2);
+    FT N2 = FT(0);
+    if (B.mode) {
+        const FT a = dz_buoyancy(g, B, q);
+        const FT izc = g.topo[2] == OB_FLAT ? a : FT(0.5) * (a + dz_buoyancy(g, B, sh(g, q, 2, 1)));
+        N2 = izc > FT(0) ? izc : FT(0);
+    }
+    const FT delta = cbrt((spacing(g, 0, OB_C, q.i[0]) * spacing(g, 1, OB_C, q.i[1])) * spacing(g, 2, OB_C, q.i[2]));
+    if (S2 == FT(0)) return FT(0) * ((P.smagC * delta) * (P.smagC * delta)) * sqrt(2 * S2);
+    FT sf = P.smagCb * N2 / S2;
+    sf = sf < FT(1) ? sf : FT(1);
+    const FT stab = sqrt(FT(1) - sf);
+    const FT cd = P.smagC * delta;
+    return (stab * (cd * cd)) * sqrt(2 * S2);
 }
 
 // ---- tendencies: nonhydrostatic_tendency_kernel_functions.jl:44-232 (term order kept) -------

@@ -22,7 +22,7 @@ using Oceananigans.BoundaryConditions: BoundaryCondition, FieldBoundaryCondition
                                        regularize_field_boundary_conditions
 using Oceananigans.Advection: CenteredSecondOrder, CenteredFourthOrder, UpwindBiasedFirstOrder, UpwindBiasedThirdOrder,
                               UpwindBiasedFifthOrder, WENO5
-using Oceananigans.TurbulenceClosures: ScalarDiffusivity, ThreeDimensionalFormulation, HorizontalFormulation,
+using Oceananigans.TurbulenceClosures: ScalarDiffusivity, SmagorinskyLilly, ThreeDimensionalFormulation, HorizontalFormulation,
                                        VerticalFormulation, ExplicitTimeDiscretization
 using Oceananigans.Coriolis: FPlane
 using Oceananigans.BuoyancyModels: Buoyancy, BuoyancyTracer, SeawaterBuoyancy, LinearEquationOfState, ZDirection, required_tracers
@@ -138,6 +138,7 @@ struct ModelDesc
     ntracers::Int32; bcs::NTuple{6 * (3 + MAX_TRACERS), BC}; pressure_solver::Int32
     buoyancy_kind::Int32; temperature_tracer::Int32; salinity_tracer::Int32
     gravitational_acceleration::Float64; thermal_expansion::Float64; haline_contraction::Float64
+    smagorinsky_C::Float64; smagorinsky_Cb::Float64; prandtl::NTuple{MAX_TRACERS,Float64}
 end
 
 topo_code(::Type{Periodic}) = Int32(0); topo_code(::Type{Bounded}) = Int32(1); topo_code(::Type{Flat}) = Int32(2)
@@ -277,8 +278,13 @@ function closure_desc(c::ScalarDiffusivity{<:ExplicitTimeDiscretization, F}, tra
     κ = ntuple(t -> t <= length(tracers) ? Float64(c.κ[tracers[t]]) : 0.0, MAX_TRACERS)
     return (code, Float64(c.ν), κ)
 end
-closure_desc(c, tracers) = throw(ArgumentError("B200(): unsupported closure $(typeof(c)) (LES closures, tuples of closures and " *
-                                               "vertically implicit diffusion are outside the B200 path)"))
+# SmagorinskyLilly (smagorinsky_lilly.jl:6-72): code 4, C / Cb and the Prandtl numbers travel in their own descriptor fields
+closure_desc(c::SmagorinskyLilly{<:ExplicitTimeDiscretization}, tracers) = (4, 0.0, ntuple(_ -> 0.0, MAX_TRACERS))
+smagorinsky_desc(c::SmagorinskyLilly, tracers) =
+    (Float64(c.C), Float64(c.Cb), ntuple(t -> t <= length(tracers) ? Float64(c.Pr isa Number ? c.Pr : c.Pr[tracers[t]]) : 1.0, MAX_TRACERS))
+smagorinsky_desc(c, tracers) = (0.0, 0.0, ntuple(_ -> 1.0, MAX_TRACERS))
+closure_desc(c, tracers) = throw(ArgumentError("B200(): unsupported closure $(typeof(c)) (AnisotropicMinimumDissipation, tuples of closures " *
+                                               "and vertically implicit diffusion are outside the B200 path)"))
 
 "The ENO coefficient tables of WENO5(grid=grid) for stretched dimensions (weno_fifth_order.jl:562-584): [dim][Face, Center]."
 function weno_tables(a::WENO5)
@@ -331,7 +337,7 @@ function model_desc(grid, gh; advection, buoyancy, coriolis, closure, tracers, t
     ptr(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
     desc = ModelDesc(gh, ts, χ, adv_code(advection), advection isa WENO5 ? Int32(advection.zweno) : Int32(1),
                      map(ptr, tabs), clo, ν, κ, fplane, f, btr, tilted, ĝ, length(tracers), bcs, 0,
-                     bkind, iT, iS, grav, α, β)
+                     bkind, iT, iS, grav, α, β, smagorinsky_desc(closure, tracers)...)
     return desc, tabs           # `tabs` must be GC.@preserve'd across ob200_model_create (host pointers are borrowed)
 end
 
@@ -385,10 +391,13 @@ function b200_nonhydrostatic_model(; grid, clock = Clock{eltype(grid)}(0, 0, 1),
     G(prefix) = NamedTuple{names}(wrap(n, prefix, FieldBoundaryConditions(grid, loc_of(n))) for n in names)
     ts = timestepper === :RungeKutta3 ? RungeKutta3TimeStepper(grid, tracers; Gⁿ = G("Gn_"), G⁻ = G("Gm_")) :
                                         QuasiAdamsBashforth2TimeStepper(grid, tracers; Gⁿ = G("Gn_"), G⁻ = G("Gm_"))
+    # diffusivity_fields.νₑ of SmagorinskyLilly is the library's "nu_e" field (κₑ stays the reference's lazy νₑ / Pr operation)
+    diffusivity_fields = closure isa SmagorinskyLilly ?
+        (; νₑ = pfield("nu_e"), κₑ = NamedTuple{tracers}(Tuple(pfield("nu_e") / (closure.Pr isa Number ? closure.Pr : closure.Pr[n]) for n in tracers))) : nothing
     solver = B200PoissonSolver(grid)
     return Oceananigans.Models.NonhydrostaticModels.reference_nonhydrostatic_model(;      # the unchanged constructor body (hook 2)
         grid, clock, advection, buoyancy, coriolis, closure, boundary_conditions = bcs, tracers = tracer_fields,
-        timestepper = ts, velocities, pressures, pressure_solver = solver,
+        timestepper = ts, velocities, pressures, diffusivity_fields, pressure_solver = solver,
         auxiliary_fields = merge(auxiliary_fields, (; b200_handle = handle)))
 end
 

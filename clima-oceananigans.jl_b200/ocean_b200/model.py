@@ -309,6 +309,19 @@ class ScalarDiffusivity:
         self.formulation, self.ν, self.κ = formulation, ν, κ
 
 
+class SmagorinskyLilly:
+    """SmagorinskyLilly(FT; C=0.16, Cb=1.0, Pr=1.0) (src/TurbulenceClosures/turbulence_closure_implementations/
+    smagorinsky_lilly.jl:6-72), explicit time discretisation; Pr is a number or a dict {tracer name: number}."""
+    required_halo = 1
+    formulation = "ThreeDimensional"
+
+    def __init__(self, C=0.16, Cb=1.0, Pr=1.0):
+        self.C, self.Cb, self.Pr = C, Cb, Pr
+
+    def prandtl(self, name):
+        return self.Pr[name] if isinstance(self.Pr, dict) else self.Pr
+
+
 def VerticalScalarDiffusivity(**kw):
     return ScalarDiffusivity("Vertical", **kw)
 
@@ -437,11 +450,17 @@ class NonhydrostaticModel:
             for (dim, li), t in advection.tables.items():
                 self._keep.append(t)
                 d.weno_coeff[dim][li] = t.ctypes.data_as(C.POINTER(C.c_double))
-        d.closure = L.CLOSURE[closure.formulation] if closure is not None else 0
-        if closure is not None:
-            d.nu = float(closure.ν)
+        if isinstance(closure, SmagorinskyLilly):
+            d.closure = L.CLOSURE["SmagorinskyLilly"]
+            d.smagorinsky_C, d.smagorinsky_Cb = float(closure.C), float(closure.Cb)
             for k, name in enumerate(tracers):
-                d.kappa[k] = float(closure.κ[name] if isinstance(closure.κ, dict) else closure.κ)
+                d.prandtl[k] = float(closure.prandtl(name))
+        else:
+            d.closure = L.CLOSURE[closure.formulation] if closure is not None else 0
+            if closure is not None:
+                d.nu = float(closure.ν)
+                for k, name in enumerate(tracers):
+                    d.kappa[k] = float(closure.κ[name] if isinstance(closure.κ, dict) else closure.κ)
         d.coriolis_fplane = int(coriolis is not None)
         if coriolis is not None:
             if not isinstance(coriolis, FPlane):
@@ -482,6 +501,7 @@ class NonhydrostaticModel:
         self.pressures = {"pNHS": self._field("pNHS", "pNHS", (Center,) * 3)}
         if grid.topology[2] != Flat:
             self.pressures["pHY′"] = self._field("pHY", "pHY", (Center,) * 3)
+        self.diffusivity_fields = {"νₑ": self._field("nu_e", "nu_e", (Center,) * 3)} if isinstance(closure, SmagorinskyLilly) else {}
         self.Gn = {n: self._field("Gn_" + (n if n in "uvw" else f"c{tracers.index(n)}"), n, locs[i])
                    for i, n in enumerate(names)}
         self.Gm = {n: self._field("Gm_" + (n if n in "uvw" else f"c{tracers.index(n)}"), n, locs[i])

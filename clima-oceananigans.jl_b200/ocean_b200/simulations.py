@@ -45,6 +45,13 @@ def cell_diffusion_timescale(model):
     clo = model.closure
     if clo is None:
         return math.inf
+    if type(clo).__name__ == "SmagorinskyLilly":      # turbulence_closure_diagnostics.jl:48-53: Δ² / (max νₑ max(1, 1/min Pr))
+        dx, dy, dz = min_spacings(model.grid)
+        Δ = min(dx, dy, dz)
+        prs = list(clo.Pr.values()) if isinstance(clo.Pr, dict) else [clo.Pr]
+        min_pr = min(prs) if model.tracers else 1
+        max_ν = model.diffusivity_fields["νₑ"].reduce()["maxabs"] * max(1, 1 / min_pr)
+        return math.inf if max_ν == 0 else Δ ** 2 / max_ν
     dx, dy, dz = min_spacings(model.grid)
     Δ = {"ThreeDimensional": min(dx, dy, dz), "Horizontal": min(dx, dy), "Vertical": dz}[clo.formulation]
     κs = list(clo.κ.values()) if isinstance(clo.κ, dict) else [clo.κ]

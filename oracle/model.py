@@ -16,7 +16,7 @@ from .grids import Periodic, Bounded, Flat, Center as C, Face as F
 from .fields import Field, FieldBoundaryConditions, fill_halo_regions, apply_flux_bcs, R
 from .operators import deriv, div_ccc, Ixy_fca, Ixy_cfa, Izf
 from .advection import div_Uu, div_Uc
-from .closures import div_τ, div_q
+from .closures import div_τ, div_q, SmagorinskyLilly, smagorinsky_viscosity
 from .solvers import FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver
 
 
@@ -135,6 +135,8 @@ class NonhydrostaticModel:
             self.pressure_solver = FFTBasedPoissonSolver(grid)
         else:
             self.pressure_solver = FourierTridiagonalPoissonSolver(grid)
+        # DiffusivityFields (smagorinsky_lilly.jl:205-221): νₑ at ccc with default boundary conditions
+        self.νe = Field(grid, (C, C, C), FieldBoundaryConditions(grid, (C, C, C))) if isinstance(closure, SmagorinskyLilly) else None
         self.timestepper = timestepper
         self.Gn = {n: Field(grid, self.fields[n].loc) for n in self.names}
         self.Gm = {n: Field(grid, self.fields[n].loc) for n in self.names}
@@ -165,9 +167,36 @@ class NonhydrostaticModel:
     # ---- update_state! ---------------------------------------------------------------
     def update_state(self):
         fill_halo_regions([self.fields[n] for n in self.names])
+        self.calculate_diffusivities()
         self.update_hydrostatic_pressure()
         if self.pHY is not None:
             fill_halo_regions(self.pHY)
+
+    def calculate_diffusivities(self):
+        """calculate_diffusivities! + fill_halo_regions!(diffusivity_fields) (update_nonhydrostatic_model_state.jl:29-31,
+        smagorinsky_lilly.jl:109-127)"""
+        if self.νe is None:
+            return
+        g = self.grid
+        i, j, k = self._box()
+        u, v, w = (self.velocities[n] for n in "uvw")
+        dz_b = None
+        if self.buoyancy is not None:
+            mdl = self.buoyancy.model
+            dz = deriv(2, C, C, F)
+            if isinstance(mdl, BuoyancyTracer):
+                b = self.tracers["b"]
+                dz_b = lambda i, j, k, grid: dz(i, j, k, grid, b)                   # ∂z_b buoyancy_tracer.jl:16
+            else:                                                                    # seawater_buoyancy.jl:166-171
+                FT = g.FT
+                gr, al, be = FT(mdl.gravitational_acceleration), FT(mdl.equation_of_state.thermal_expansion), FT(mdl.equation_of_state.haline_contraction)
+                req = mdl.required_tracers()
+                zero = lambda i, j, k, grid: FT(0)
+                dT = (lambda i, j, k, grid: dz(i, j, k, grid, self.tracers["T"])) if "T" in req else zero
+                dS = (lambda i, j, k, grid: dz(i, j, k, grid, self.tracers["S"])) if "S" in req else zero
+                dz_b = lambda i, j, k, grid: gr * (al * dT(i, j, k, grid) - be * dS(i, j, k, grid))
+        self.νe[i, j, k] = smagorinsky_viscosity(i, j, k, g, self.closure, dz_b, u, v, w)
+        fill_halo_regions(self.νe)
 
     def update_hydrostatic_pressure(self):
         """_update_hydrostatic_pressure! update_hydrostatic_pressure.jl:10-18."""
@@ -214,7 +243,7 @@ class NonhydrostaticModel:
         Gu = (- div_Uu(0, i, j, k, g, adv, U, u) - zero - zero
               - corx
               - px
-              - div_τ(0, i, j, k, g, clo, u, v, w)
+              - div_τ(0, i, j, k, g, clo, u, v, w, self.νe)
               - zero + zero + zero
               + gb(0)
               + zero)
@@ -224,14 +253,14 @@ class NonhydrostaticModel:
         Gv = (- div_Uu(1, i, j, k, g, adv, U, v) - zero - zero
               - cory
               - py
-              - div_τ(1, i, j, k, g, clo, u, v, w)
+              - div_τ(1, i, j, k, g, clo, u, v, w, self.νe)
               - zero + zero + zero
               + gb(1)
               + zero)
         # w: :172-180 (no buoyancy and no pHY′ term)
         Gw = (- div_Uu(2, i, j, k, g, adv, U, w) - zero - zero
               - zero
-              - div_τ(2, i, j, k, g, clo, u, v, w)
+              - div_τ(2, i, j, k, g, clo, u, v, w, self.νe)
               - zero + zero + zero
               + zero)
         self.Gn["u"][i, j, k] = Gu
@@ -239,10 +268,10 @@ class NonhydrostaticModel:
         self.Gn["w"][i, j, k] = Gw
         for name in self.tracer_names:
             c = self.tracers[name]
-            κ = clo.kappa(name) if clo is not None else 0
+            κ = 0 if clo is None else (clo.prandtl(name) if isinstance(clo, SmagorinskyLilly) else clo.kappa(name))
             # :225-231
             Gc = (- div_Uc(i, j, k, g, adv, U, c) - zero - zero
-                  - div_q(i, j, k, g, clo, κ, c)
+                  - div_q(i, j, k, g, clo, κ, c, self.νe)
                   - zero
                   + zero)
             self.Gn[name][i, j, k] = Gc

@@ -248,6 +248,23 @@ CONFIGS = {
     "seawater_T_tilted": dict(size=(8, 8, 10), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(1, 1, 1),
                               adv="CenteredFourthOrder", tracers=("T",), seawater=dict(constant_salinity=35.0, eos=(0.3, 0.2)),
                               tilt=(0.6, 0.0, 0.8), ts="QuasiAdamsBashforth2", dt=2e-3),
+    # SmagorinskyLilly LES closure: eddy viscosity recomputed in update_state!, variable-ν stresses,
+    # κₑ = νₑ / Pr; with a buoyancy tracer (stability correction), on a stretched Bounded z with WENO5(grid), with seawater
+    # buoyancy and per-tracer Prandtl numbers, and in 2-D (Flat z)
+    "smagorinsky_bounded_b": dict(size=(8, 10, 12), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(1, 1, 1),
+                                  adv="CenteredSecondOrder", tracers=("b",), buoyancy=True, smagorinsky={}, f=0.5,
+                                  ts="RungeKutta3", dt=2e-3),
+    "smagorinsky_stretched_weno": dict(size=(12, 8, 14), topology=(O.Periodic, O.Periodic, O.Bounded),
+                                       coords=dict(x=(0, 1), y=(0, 1), z=_zf(14)), adv="WENO5grid", tracers=("b", "c"),
+                                       buoyancy=True, smagorinsky=dict(C=0.2, Cb=0.5, Pr={"b": 0.7, "c": 2.0}),
+                                       ts="RungeKutta3", dt=2e-3,
+                                       bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"top": ("Flux", 1e-4)}}),
+    "smagorinsky_seawater_periodic": dict(size=(32, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="WENO5",
+                                          tracers=("T", "S"), seawater=dict(eos=(0.3, 0.2)), smagorinsky=dict(Cb=1.0, Pr=1.0),
+                                          ts="QuasiAdamsBashforth2", dt=2e-3),
+    "smagorinsky_2d_flat": dict(size=(16, 12), topology=(O.Periodic, O.Bounded, O.Flat), extent=(1, 1),
+                                adv="UpwindBiasedThirdOrder", tracers=("c",), buoyancy=False, smagorinsky=dict(Pr=0.5),
+                                ts="RungeKutta3", dt=2e-3),
     "seawater_S_only": dict(size=(8, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="UpwindBiasedFifthOrder",
                             tracers=("S", "c"), seawater=dict(constant_temperature=True, eos=(0.3, 0.2)),
                             ts="RungeKutta3", dt=2e-3),
@@ -269,6 +286,8 @@ def build_models(ob, cfg, FT):
     if cfg.get("closure"):
         form, nu, ka = cfg["closure"]
         clo_o, clo_b = O.ScalarDiffusivity(form, ν=nu, κ=ka), ob.ScalarDiffusivity(form, ν=nu, κ=ka)
+    if cfg.get("smagorinsky") is not None:
+        clo_o, clo_b = O.SmagorinskyLilly(**cfg["smagorinsky"]), ob.SmagorinskyLilly(**cfg["smagorinsky"])
     cor_o = O.FPlane(cfg["f"]) if cfg.get("f") else None
     cor_b = ob.FPlane(cfg["f"]) if cfg.get("f") else None
     bu_o = bu_b = None
@@ -326,6 +345,8 @@ def test_tendencies_and_steps_match_oracle_f64(ob, name):
     compare_fields(mo, mb, 1e-12, "after set!/projection")
     if mo.pHY is not None:
         assert relerr(mb.pressures["pHY′"].interior(), mo.pHY.interior) < 1e-13
+    if getattr(mo, "νe", None) is not None:          # the eddy viscosity of the LES closure, halos included
+        assert relerr(mb.diffusivity_fields["νₑ"].parent(), mo.νe.parent) < 1e-12
     # tendencies alone
     mo.calculate_tendencies()
     ob.calculate_tendencies(mb)

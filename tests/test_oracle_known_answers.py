@@ -403,3 +403,39 @@ def test_seawater_buoyancy_hydrostatic_pressure_known_answer():
         assert np.allclose(p, b0 * (zc.reshape(1, 1, -1) - 0.125), rtol=1e-13, atol=1e-15)
     with pytest.raises(AssertionError):
         O.NonhydrostaticModel(g, buoyancy=O.SeawaterBuoyancy(), tracers=("T",))       # validate_buoyancy: S missing
+
+
+# ---- SmagorinskyLilly (smagorinsky_lilly.jl:83-107) ----------------------------------------------------------------------
+def test_smagorinsky_viscosity_known_answers():
+    """uniform shear u = S y on a regular grid: Sigma^2 = 2 Sigma_12^2 = S^2 / 2, so nu_e = (C Delta)^2 |S| without buoyancy;
+    with a stable stratification N^2 the stability factor sqrt(1 - Cb N^2 / Sigma^2) multiplies it and N^2 >= Sigma^2 / Cb
+    switches the viscosity off; an unstable stratification (N^2 < 0) leaves it unchanged"""
+    g = O.RectilinearGrid(np.float64, size=(4, 8, 8), x=(0, 1), y=(0, 2), z=(-1, 0), topology=(O.Periodic, O.Bounded, O.Bounded))
+    S, Cs = 0.8, 0.16
+    Δ = np.cbrt(0.25 * 0.25 * 0.125)
+    yc = g.nodes(("f", "c", "c"))[1]
+    zc = g.nodes(("c", "c", "c"))[2]
+    for N2, Cb, want in ((0.0, 1.0, (Cs * Δ) ** 2 * abs(S)), (0.1, 1.0, (Cs * Δ) ** 2 * abs(S) * np.sqrt(1 - 0.1 / (S * S / 2))),
+                         (0.5, 1.0, 0.0), (-0.3, 1.0, (Cs * Δ) ** 2 * abs(S)), (0.1, 0.0, (Cs * Δ) ** 2 * abs(S))):
+        m = O.NonhydrostaticModel(g, advection=O.CenteredSecondOrder(), closure=O.SmagorinskyLilly(C=Cs, Cb=Cb), tracers=("b",),
+                                  buoyancy=O.BuoyancyTracer())
+        m.set(enforce_incompressibility=False, u=S * yc + 0 * zc + np.zeros((4, 8, 8)), b=N2 * zc + np.zeros((4, 8, 8)))
+        ν = m.νe.interior[:, 1:-1, 1:-1]          # away from the walls (the halo fill of u flattens the shear there)
+        assert np.allclose(ν, want, rtol=1e-12, atol=1e-18), (N2, Cb, float(ν.mean()), want)
+    # fluid at rest: nu_e = 0 exactly (the Sigma^2 == 0 branch), and the closure then does nothing
+    m = O.NonhydrostaticModel(g, advection=O.CenteredSecondOrder(), closure=O.SmagorinskyLilly(), tracers=("b",), buoyancy=O.BuoyancyTracer())
+    m.set(b=0.2 * zc + np.zeros((4, 8, 8)))
+    assert np.all(m.νe.parent == 0)
+
+
+def test_smagorinsky_dissipates_kinetic_energy_and_conserves_tracer():
+    """random flow in a closed box, no advection: the LES closure removes kinetic energy; the tracer mean is conserved"""
+    g = O.RectilinearGrid(np.float64, size=(8, 8, 8), extent=(1, 1, 1), topology=(O.Bounded,) * 3)
+    m = O.NonhydrostaticModel(g, advection=None, closure=O.SmagorinskyLilly(Pr=0.5), tracers=("c",), timestepper="RungeKutta3")
+    rng = np.random.default_rng(5)
+    m.set(**{n: rng.uniform(-1, 1, m.fields[n].size()) for n in m.names})
+    ke0, c0 = m.kinetic_energy(), float(np.mean(m.tracers["c"].interior))
+    for _ in range(5):
+        m.time_step(2e-3)
+    assert m.kinetic_energy() < ke0
+    assert abs(float(np.mean(m.tracers["c"].interior)) - c0) < 1e-14
