@@ -317,7 +317,8 @@ def main():
     launches = ob.launch_count() - n0
     lib.ob200_profile_enable(0)
     phases = {}
-    fft_names = ("fft_x_fwd", "fft_y", "fft_z", "fft_z_fwd", "fft_z_inv", "fft_sync", "fft_x_inv")
+    fft_names = ("fft_x_fwd", "fft_y", "fft_z", "fft_z_fwd", "fft_z_inv", "fft_sync", "fft_x_inv", "fft_y_butterfly",
+                 "fft_y_lines", "fft_y_copywait")
     for ph in ("tendency", "poisson", "halo", "pressure_correct", "hydrostatic") + fft_names:
         t, c = C.c_double(), C.c_int64()
         lib.ob200_profile_query(ph.encode(), C.byref(t), C.byref(c))

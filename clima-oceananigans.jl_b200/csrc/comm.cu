@@ -76,7 +76,10 @@ void init(int nranks, int rank, const char id_bytes[128]) {
     g_rank = rank; g_size = nranks;
 }
 static void link_release();
+static void peer_barrier_release();
+void barrier();
 void destroy() {
+    if (g_comm) { cudaStreamSynchronize(stream()); barrier(); cudaStreamSynchronize(stream()); peer_barrier_release(); }
     if (g_comm) link_release();
     if (g_comm) { api.CommDestroy(g_comm); g_comm = nullptr; g_size = 1; g_rank = 0; }
 }
@@ -156,6 +159,93 @@ bool peer_access_ok() {
         fprintf(stderr, "libocean_b200: no peer memory access between the ranks (other host, no P2P or CUDA IPC disabled): "
                         "using the NCCL send/recv and all-to-all paths\n");
     return state != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stream-ordered barrier over all ranks through peer memory: every rank owns R flag words that all ranks map through
+// CUDA IPC; one R-thread kernel stores the epoch number into its own word of every rank (system-scope fence first: the
+// peer-memory stores of the preceding kernels are visible before the flag) and then spins until all R of its own
+// words show the epoch.  A few microseconds (one NVLink round trip) against 20-40 us for the NCCL all-reduce it
+// replaces (two per distributed pressure solve, six per time step).  Falls back to the NCCL barrier without peer access.
+// ---------------------------------------------------------------------------------------------------------------
+struct PeerBarrier {
+    unsigned long long* mine = nullptr;            // R words
+    unsigned long long* peer[64] = {};             // the same block of every rank
+    unsigned long long epoch = 0;
+    int* err = nullptr;
+    bool ready = false;
+};
+static PeerBarrier g_pb;
+static unsigned long long link_timeout_ns();
+__global__ void peer_barrier_kernel(unsigned long long* const* peers, const unsigned long long* mine, int rank, int R,
+                                    unsigned long long epoch, int* err, unsigned long long timeout_ns) {
+    __shared__ unsigned long long* sp[64];
+    const int t = threadIdx.x;
+    if (t < R) sp[t] = peers[t];
+    __syncthreads();
+    if (t >= R) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(sp[t] + rank) = epoch;
+    const volatile unsigned long long* f = mine + t;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*f < epoch) {
+        __nanosleep(32);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) { *err = 2; __threadfence_system(); __trap(); }
+    }
+    __threadfence_system();
+}
+static unsigned long long** g_pb_dev_peers = nullptr;
+static void peer_barrier_setup() {
+    PeerBarrier& B = g_pb;
+    if (B.ready) return;
+    if (g_size > 64) throw Error("peer barrier: more than 64 ranks");
+    OB_CUDA(cudaMalloc(&B.mine, 64 * sizeof(unsigned long long)));
+    OB_CUDA(cudaMemsetAsync(B.mine, 0, 64 * sizeof(unsigned long long), stream()));
+    OB_CUDA(cudaMalloc(&B.err, sizeof(int)));
+    OB_CUDA(cudaMemsetAsync(B.err, 0, sizeof(int), stream()));
+    cudaIpcMemHandle_t h;
+    OB_CUDA(cudaIpcGetMemHandle(&h, B.mine));
+    cudaIpcMemHandle_t *dsend, *drecv;
+    OB_CUDA(cudaMalloc(&dsend, sizeof(h)));
+    OB_CUDA(cudaMalloc(&drecv, sizeof(h) * g_size));
+    OB_CUDA(cudaMemcpyAsync(dsend, &h, sizeof(h), cudaMemcpyHostToDevice, stream()));
+    allgather_bytes(dsend, drecv, sizeof(h));
+    std::vector<cudaIpcMemHandle_t> all(g_size);
+    OB_CUDA(cudaMemcpyAsync(all.data(), drecv, sizeof(h) * g_size, cudaMemcpyDeviceToHost, stream()));
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    cudaFree(dsend); cudaFree(drecv);
+    for (int r = 0; r < g_size; ++r) {
+        if (r == g_rank) { B.peer[r] = B.mine; continue; }
+        void* q = nullptr;
+        OB_CUDA(cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess));
+        B.peer[r] = (unsigned long long*)q;
+    }
+    OB_CUDA(cudaMalloc(&g_pb_dev_peers, 64 * sizeof(unsigned long long*)));
+    OB_CUDA(cudaMemcpyAsync(g_pb_dev_peers, B.peer, 64 * sizeof(unsigned long long*), cudaMemcpyHostToDevice, stream()));
+    barrier();                 // every rank has zeroed its words before anybody publishes an epoch
+    OB_CUDA(cudaStreamSynchronize(stream()));
+    B.ready = true;
+}
+static void peer_barrier_release() {
+    PeerBarrier& B = g_pb;
+    if (!B.ready) return;
+    for (int r = 0; r < g_size; ++r) if (r != g_rank && B.peer[r]) cudaIpcCloseMemHandle(B.peer[r]);
+    cudaFree(B.mine); cudaFree(B.err); cudaFree(g_pb_dev_peers);
+    B = PeerBarrier();
+    g_pb_dev_peers = nullptr;
+}
+// barrier used inside the distributed pressure solve
+void fast_barrier() {
+    static const bool nccl_only = getenv("OB200_NCCL_BARRIER") != nullptr;
+    if (nccl_only || !peer_access_ok()) { barrier(); return; }
+    peer_barrier_setup();
+    PeerBarrier& B = g_pb;
+    B.epoch += 1;
+    peer_barrier_kernel<<<1, 64, 0, stream()>>>(g_pb_dev_peers, B.mine, g_rank, g_size, B.epoch, B.err, link_timeout_ns());
+    count_launch(1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

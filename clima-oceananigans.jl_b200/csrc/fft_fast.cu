@@ -26,7 +26,7 @@ namespace comm {
 bool active(); int rank(); int size(); bool peer_access_ok();
 void group_start(); void group_end();
 void send(const void*, size_t, int); void recv(void*, size_t, int);
-void allgather_bytes(const void*, void*, size_t); void barrier();
+void allgather_bytes(const void*, void*, size_t); void barrier(); void fast_barrier();
 }
 namespace ff {
 
@@ -546,8 +546,15 @@ struct FastPoisson {
     // bulk = true: the transform kernels store into LOCAL chunk buffers and the chunks travel to their ranks as large
     // contiguous copies (copy engines over NVLink); false: the kernels store straight into the peers' buffers
     bool bulk_a2a = false;
-    cudaStream_t cpy = nullptr;                 // copy stream + events of the pipelined bulk transposes
-    cudaEvent_t ev_piece[16] = {}, ev_done = nullptr;
+    bool ysplit = false;                        // gathered y lines as R-point butterflies across chunks + NyL-point lines
+    CUtensorMap tm4_ys, tmr_ys[8];
+    double* lamy2 = nullptr;                    // [R][NyL]: eigenvalue of frequency r + R freq_of_pos(m)
+    typename Cx<FT>::T* twYL = nullptr;         // exp(-2 pi i t / NyL): twiddles of the NyL-point lines
+    double Ly_global = 0;
+    // copy streams (one per peer: copies to different peers run on different copy engines; a single stream serialised
+    // them at ~310 GB/s) + events of the pipelined bulk transposes
+    cudaStream_t cpy = nullptr, cpys[8] = {};
+    cudaEvent_t ev_piece[16] = {}, ev_done = nullptr, ev_dones[8] = {};
     CT* bufC = nullptr;
     int dtk_y = 8;                              // columns per y tile (8, 4, 2 for gathered lines of <= 512, 1024, 2048)
     CUtensorMap tm4_zi, tm4_y, tmr_zf[8], tmr_zi[8], tmr_y[8];
@@ -667,6 +674,7 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
     for (int P = 0; P < p->NyG; ++P) ly[P] = lam(1, freq_of_pos(p->log2[1], P));
     if (p->has_z && !p->tri) for (int P = 0; P < g.N[2]; ++P) lz[P] = lam(2, freq_of_pos(p->log2[2], P));
     p->lamx = up(lx, p->owned); p->lamy = up(ly, p->owned); p->lamz = up(lz, p->owned);
+    p->Ly_global = (double)g.L[1] * p->R;
     setup_tma(p);
     return p;
 }
@@ -683,6 +691,8 @@ template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
     if (p->bufB) cudaFree(p->bufB);
     for (void* q : p->owned) cudaFree(q);
     if (p->cpy) cudaStreamDestroy(p->cpy);
+    for (cudaStream_t s : p->cpys) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : p->ev_dones) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : p->ev_piece) if (e) cudaEventDestroy(e);
     if (p->ev_done) cudaEventDestroy(p->ev_done);
     delete p;
@@ -819,6 +829,36 @@ static void setup_dist_tma(FastPoisson<FT>* p) {
     cuuint32_t b4z[4] = {2 * TMA_TK, 1, (cuuint32_t)Nz, 1}, b4y[4] = {(cuuint32_t)(2 * p->dtk_y), (cuuint32_t)NyL, 1, (cuuint32_t)R};
     if (!encode_map<FT>(&p->tm4_zi, p->bufA, 4, d4, s4, b4z)) return;
     if (!encode_map<FT>(&p->tm4_y, p->bufB, 4, d4, s4, b4y)) return;
+    // split y lines (ADDR_YS), OB200_FFT_YSPLIT=1: measured at 8 ranks (2048-point lines) the split transform needs 0.20 ms of
+    // kernels per solve against ~0.3 ms for the gathered lines, but the phase is bound by the NVLink all-to-all behind it
+    // (125 MB per rank and transpose, 0.23 ms at the ~550 GB/s the 8-rank exchange reaches) and the twelve small launches
+    // of the pipelined form cost what they save: 1.29 (split) vs 1.26 ms per step (gathered), so it stays off by default
+    const char* ys = getenv("OB200_FFT_YSPLIT");
+    p->ysplit = p->bulk_a2a && p->log2[1] - ilog2c(R) >= 4 && (ys ? atoi(ys) != 0 : false);
+    if (p->ysplit) {
+        cuuint32_t b4s[4] = {2 * TMA_TK, (cuuint32_t)NyL, 1, 1}, b3s[3] = {2 * TMA_TK, (cuuint32_t)NyL, 1};
+        if (!encode_map<FT>(&p->tm4_ys, p->bufB, 4, d4, s4, b4s)) return;
+        for (int r = 0; r < R; ++r)
+            if (!encode_map<FT>(&p->tmr_ys[r], p->bufB + (long long)r * chunk, 3, d3, sc, b3s)) return;
+        const int l2 = ilog2c(NyL);
+        std::vector<double> t((size_t)R * NyL);
+        const double PI = 3.14159265358979323846;
+        const double dy = (double)p->Ly_global / p->NyG;
+        for (int r = 0; r < R; ++r)
+            for (int P = 0; P < NyL; ++P) {
+                const int k = r + R * freq_of_pos(l2, P);
+                const double v = 2 * sin(k * PI / p->NyG) / dy;
+                t[(size_t)r * NyL + P] = v * v;
+            }
+        p->lamy2 = up(t, p->owned);
+        std::vector<CT> twl(NyL);
+        const long double PIl = 3.14159265358979323846264338327950288L;
+        for (int k = 0; k < NyL; ++k) {
+            const long double a = -2.0L * PIl * k / NyL;
+            twl[k].x = (FT)cosl(a); twl[k].y = (FT)sinl(a);
+        }
+        p->twYL = up(twl, p->owned);
+    }
     p->dtma_ok = true;
 }
 template <class FT>
@@ -878,6 +918,7 @@ static void run_line_tma(FastPoisson<FT>* p, int dim, int mode) {
     tl::TArgs<FT> A;
     A.tm = dim == 1 ? p->tm_y : p->tm_z;
     A.addr = tl::ADDR_NAT; A.R = 1; A.KXB = p->NXP; A.tpc = p->NXP / TMA_TK; A.NyL = p->N[1]; A.kx_base = 0; A.NXP = p->NXP;
+    A.Nz = p->N[2];
     A.r_only = -1; A.o_first = 0;
     A.line_is_y = dim == 1;
     A.nkx = p->NXP / TMA_TK;
@@ -930,13 +971,64 @@ static void all_to_all(FastPoisson<FT>* p, const typename Cx<FT>::T* src, typena
     cm::group_end();
 }
 
+// Split y transform, the part ACROSS the chunks.  With y = s NyL + yl (s = source rank) and k = k1 + R k2,
+//   X[k1 + R k2] = sum_yl W_NyL^(yl k2) [ W_NyG^(yl k1) sum_s W_R^(s k1) x[s NyL + yl] ],
+// so the NyG-point line is an R-point butterfly over the R chunk slabs (pointwise in (z, yl, kx)), a twiddle, and
+// NyL-point lines inside slab k1 (line_tma_kernel, ADDR_YS).  INV is the exact inverse (conjugate twiddle, conjugate
+// butterfly; the 1 / NyG is applied by the line kernel).  outs[s] lets the backward pass write the own rank's chunk
+// straight into its final place and the others into the staging buffer of the bulk transposes.
+template <class FT> struct YSplitPtrs { typename Cx<FT>::T* p[8]; };
+template <class FT, int RR, bool INV>
+__global__ void __launch_bounds__(256) ysplit_kernel(const typename Cx<FT>::T* __restrict__ in, long long chunk, YSplitPtrs<FT> outs,
+                                                     int NyL, int KXB, int z0, int nz, const typename Cx<FT>::T* __restrict__ tw) {
+    using CT = typename Cx<FT>::T;
+    constexpr int LB = ilog2c(RR);
+    const long long per = (long long)nz * NyL * KXB;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < per; e += (long long)gridDim.x * blockDim.x) {
+        const long long off = (long long)z0 * NyL * KXB + e;
+        const int yl = (int)((off / KXB) % NyL);
+        CT x[RR];
+        if (!INV) {
+#pragma unroll
+            for (int s = 0; s < RR; ++s) x[s] = in[s * chunk + off];
+            dft_reg<RR, false>(x);
+#pragma unroll
+            for (int k1 = 0; k1 < RR; ++k1) {
+                CT v = x[brev(k1, LB)];
+                if (k1 > 0) v = cmul(v, tw[yl * k1]);
+                outs.p[k1][off] = v;
+            }
+        } else {
+#pragma unroll
+            for (int k1 = 0; k1 < RR; ++k1) {
+                CT v = in[k1 * chunk + off];
+                if (k1 > 0) v = cmulc(v, tw[yl * k1]);
+                x[k1] = v;
+            }
+            dft_reg<RR, true>(x);
+#pragma unroll
+            for (int s = 0; s < RR; ++s) outs.p[s][off] = x[brev(s, LB)];
+        }
+    }
+}
+template <class FT, bool INV>
+static void launch_ysplit(FastPoisson<FT>* p, const typename Cx<FT>::T* in, const YSplitPtrs<FT>& outs, int z0, int nz) {
+    const long long chunk = (long long)p->KXB * p->N[1] * p->N[2];
+    const long long per = (long long)nz * p->N[1] * p->KXB;
+    const int blocks = (int)std::min<long long>(148 * 8, (per + 255) / 256);
+#define YS(RV) ysplit_kernel<FT, RV, INV><<<blocks, 256, 0, stream()>>>(in, chunk, outs, p->N[1], p->KXB, z0, nz, p->twY)
+    if (p->R == 2) YS(2); else if (p->R == 4) YS(4); else YS(8);
+#undef YS
+    OB_LAUNCH_CHECK();
+}
+
 // the slab-decomposed middle of the solve through the TMA-pipelined kernel: z forward (stores into the peers' bufB),
 // gathered y lines forward / divide / backward (stores back into the peers' bufA), z backward
 template <class FT>
 static void distributed_middle_tma(FastPoisson<FT>* p) {
     const int R = p->R, KXB = p->KXB, NyL = p->N[1], Nz = p->N[2];
     tl::TArgs<FT> A;
-    A.R = R; A.KXB = KXB; A.NyL = NyL; A.NXP = p->NXP; A.kx_base = 0;
+    A.R = R; A.KXB = KXB; A.NyL = NyL; A.NXP = p->NXP; A.kx_base = 0; A.Nz = Nz;
     A.lamx = p->lamx;
     // z forward
     A.addr = tl::ADDR_ZF; A.tm = p->tm_z;
@@ -954,6 +1046,10 @@ static void distributed_middle_tma(FastPoisson<FT>* p) {
     cudaEvent_t& ev_done = p->ev_done;
     if (p->bulk_a2a && !cpy) {
         OB_CUDA(cudaStreamCreateWithFlags(&cpy, cudaStreamNonBlocking));
+        for (int q = 1; q < R; ++q) {
+            OB_CUDA(cudaStreamCreateWithFlags(&p->cpys[q], cudaStreamNonBlocking));
+            OB_CUDA(cudaEventCreateWithFlags(&p->ev_dones[q], cudaEventDisableTiming));
+        }
         for (int q = 0; q < 16; ++q) OB_CUDA(cudaEventCreateWithFlags(&ev_piece[q], cudaEventDisableTiming));
         OB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
     }
@@ -970,16 +1066,18 @@ static void distributed_middle_tma(FastPoisson<FT>* p) {
                 launch_line_tma<FT, LM_FWD, 3>(A, p->log2[2]);
                 if (r == p->rank) continue;
                 OB_CUDA(cudaEventRecord(ev_piece[q], stream()));
-                OB_CUDA(cudaStreamWaitEvent(cpy, ev_piece[q], 0));
+                OB_CUDA(cudaStreamWaitEvent(p->cpys[q], ev_piece[q], 0));
                 OB_CUDA(cudaMemcpyAsync(p->peerB[r] + (long long)p->rank * chunk_el, p->bufA + (long long)r * chunk_el,
-                                        chunk_bytes, cudaMemcpyDefault, cpy));
+                                        chunk_bytes, cudaMemcpyDefault, p->cpys[q]));
             }
             A.r_only = -1;
-            OB_CUDA(cudaEventRecord(ev_done, cpy));
-            OB_CUDA(cudaStreamWaitEvent(stream(), ev_done, 0));
+            for (int q = 1; q < R; ++q) {
+                OB_CUDA(cudaEventRecord(p->ev_dones[q], p->cpys[q]));
+                OB_CUDA(cudaStreamWaitEvent(stream(), p->ev_dones[q], 0));
+            }
         }
     }
-    { PhaseScope ph("fft_sync"); cm::barrier(); }
+    { PhaseScope ph("fft_sync"); cm::fast_barrier(); }
     // gathered y lines: forward, eigenvalue divide, backward
     A.addr = tl::ADDR_Y; A.tm4 = p->tm4_y;
     for (int r = 0; r < R; ++r) A.tmr[r] = p->tmr_y[r];
@@ -994,7 +1092,48 @@ static void distributed_middle_tma(FastPoisson<FT>* p) {
             else if (l == 10) launch_line_tma<FT, LM_FWD_DIV_INV, 2, 4>(A, l);
             else launch_line_tma<FT, LM_FWD_DIV_INV, 2, 2>(A, l);
         };
-        if (!p->bulk_a2a) {
+        if (p->ysplit) {
+            // butterfly across the chunks, NyL-point lines (forward, divide, backward) inside each chunk, inverse butterfly
+            // per block of z levels with the bulk copies of the finished block behind it
+            YSplitPtrs<FT> inplace, back;
+            for (int r = 0; r < R; ++r) {
+                inplace.p[r] = p->bufB + (long long)r * chunk_el;
+                back.p[r] = r == p->rank ? p->bufA + (long long)p->rank * chunk_el : p->bufC + (long long)r * chunk_el;
+            }
+            tl::TArgs<FT> S = A;
+            S.addr = tl::ADDR_YS; S.tm4 = p->tm4_ys; S.Nz = Nz;
+            for (int r = 0; r < R; ++r) S.tmr[r] = p->tmr_ys[r];
+            S.tpc = cdiv(KXB, TMA_TK); S.nkx = S.tpc; S.r_only = -1;
+            S.lamL = p->lamy2; S.tw = p->twYL;
+            // all three passes per block of z levels: the bulk copies of block b run while block b+1 is transformed
+            static const int nb_env = env_int("OB200_FFT_YBLOCKS", 4);
+            const int NB = Nz >= 64 ? std::max(1, std::min(nb_env, 16)) : 1;
+            const int zb = cdiv(Nz, NB);
+            for (int b = 0; b < NB; ++b) {
+                const int z0 = b * zb, nz = std::min(zb, Nz - z0);
+                if (nz <= 0) break;
+                { PhaseScope pa("fft_y_butterfly"); launch_ysplit<FT, false>(p, p->bufB, inplace, z0, nz); }
+                S.o_first = z0 * R; S.nOther = nz * R;
+                { PhaseScope pb("fft_y_lines"); launch_line_tma<FT, LM_FWD_DIV_INV, 3>(S, p->log2[1] - ilog2c(R)); }
+                { PhaseScope pc("fft_y_butterfly"); launch_ysplit<FT, true>(p, p->bufB, back, z0, nz); }
+                OB_CUDA(cudaEventRecord(ev_piece[b], stream()));
+                for (int q = 1; q < R; ++q) OB_CUDA(cudaStreamWaitEvent(p->cpys[q], ev_piece[b], 0));
+                const long long off = (long long)z0 * NyL * KXB;
+                const size_t bytes = (size_t)nz * NyL * KXB * sizeof(CTt);
+                for (int q = 1; q < R; ++q) {
+                    const int r = (p->rank + q) % R;
+                    OB_CUDA(cudaMemcpyAsync(p->peerA[r] + (long long)p->rank * chunk_el + off, p->bufC + (long long)r * chunk_el + off,
+                                            bytes, cudaMemcpyDefault, p->cpys[q]));
+                }
+            }
+            {
+                PhaseScope pw("fft_y_copywait");
+                for (int q = 1; q < R; ++q) {
+                    OB_CUDA(cudaEventRecord(p->ev_dones[q], p->cpys[q]));
+                    OB_CUDA(cudaStreamWaitEvent(stream(), p->ev_dones[q], 0));
+                }
+            }
+        } else if (!p->bulk_a2a) {
             launch_y();
         } else {
             const int NB = Nz >= 64 ? 4 : 1;                 // blocks of z levels
@@ -1005,21 +1144,23 @@ static void distributed_middle_tma(FastPoisson<FT>* p) {
                 A.o_first = z0; A.nOther = nz;
                 launch_y();
                 OB_CUDA(cudaEventRecord(ev_piece[b], stream()));
-                OB_CUDA(cudaStreamWaitEvent(cpy, ev_piece[b], 0));
+                for (int q = 1; q < R; ++q) OB_CUDA(cudaStreamWaitEvent(p->cpys[q], ev_piece[b], 0));
                 const long long off = (long long)z0 * NyL * KXB;       // chunk layout [z][yl][kx]: a z block is contiguous
                 const size_t bytes = (size_t)nz * NyL * KXB * sizeof(CTt);
                 for (int q = 1; q < R; ++q) {
                     const int r = (p->rank + q) % R;
                     OB_CUDA(cudaMemcpyAsync(p->peerA[r] + (long long)p->rank * chunk_el + off, p->bufC + (long long)r * chunk_el + off,
-                                            bytes, cudaMemcpyDefault, cpy));
+                                            bytes, cudaMemcpyDefault, p->cpys[q]));
                 }
             }
             A.o_first = 0; A.nOther = Nz;
-            OB_CUDA(cudaEventRecord(ev_done, cpy));
-            OB_CUDA(cudaStreamWaitEvent(stream(), ev_done, 0));
+            for (int q = 1; q < R; ++q) {
+                OB_CUDA(cudaEventRecord(p->ev_dones[q], p->cpys[q]));
+                OB_CUDA(cudaStreamWaitEvent(stream(), p->ev_dones[q], 0));
+            }
         }
     }
-    { PhaseScope ph("fft_sync"); cm::barrier(); }
+    { PhaseScope ph("fft_sync"); cm::fast_barrier(); }
     // z backward
     A.addr = tl::ADDR_ZI; A.tm4 = p->tm4_zi; A.kx_base = 0; A.r_only = -1; A.o_first = 0;
     for (int r = 0; r < R; ++r) A.tmr[r] = p->tmr_zi[r];
@@ -1051,7 +1192,7 @@ static void distributed_middle(FastPoisson<FT>* p) {
     A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;
     A.tw = p->twZ; A.lamL = p->lamz; A.lamO = nullptr;
     { PhaseScope ph("fft_z_fwd"); launch_line_any(p, A, p->log2[2], LM_FWD); }
-    { PhaseScope ph("fft_sync"); if (p->p2p) cm::barrier(); else all_to_all(p, p->bufA, p->bufB); }
+    { PhaseScope ph("fft_sync"); if (p->p2p) cm::fast_barrier(); else all_to_all(p, p->bufA, p->bufB); }
     A.in = p->bufB; A.out = p->bufB; A.lin = A.lout = gy;
     if (p->p2p) {      // transposed back on the fly: the part of the line that came from rank s returns to rank s's bufA
         A.out = p->bufA;
@@ -1061,7 +1202,7 @@ static void distributed_middle(FastPoisson<FT>* p) {
     A.NXH = KXB; A.kx0 = p->rank * KXB; A.n = p->NyG; A.line_is_y = 1; A.nOther = Nz;
     A.tw = p->twY; A.lamL = p->lamy; A.lamO = p->lamz;
     { PhaseScope ph("fft_y"); launch_line_any(p, A, p->log2[1], LM_FWD_DIV_INV); }
-    { PhaseScope ph("fft_sync"); if (p->p2p) cm::barrier(); else all_to_all(p, p->bufB, p->bufA); }
+    { PhaseScope ph("fft_sync"); if (p->p2p) cm::fast_barrier(); else all_to_all(p, p->bufB, p->bufA); }
     // backward z: chunk layout -> natural
     A.in = p->bufA; A.out = p->spec; A.lin = blk; A.lout = nat;
     A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;

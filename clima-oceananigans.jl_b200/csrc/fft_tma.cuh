@@ -67,13 +67,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 //             store the part that came from rank s back into rank s's buffer (peer memory).
 // Tiles of the distributed modes are aligned to chunk boundaries; a tile that sticks out of its chunk is clipped
 // by the tensor-map bounds on store and zero-filled on load.
-enum { ADDR_NAT = 0, ADDR_ZF = 1, ADDR_ZI = 2, ADDR_Y = 3 };
+//   ADDR_YS   split y lines: the NyG = R NyL point transform is done as an R-point butterfly across the chunks (separate
+//             elementwise kernel, fft_fast.cu: ysplit_kernel) and NyL-point lines INSIDE each chunk (this kernel, in place on
+//             the chunk buffer, tiles of 8 columns with 128-byte rows instead of the 32-byte rows 2048-point lines allow);
+//             other index o = z R + r (z-major, so that a block of z levels is a contiguous range of o and the three passes
+//             of the split transform can be pipelined per z block with the bulk copies), eigenvalue table lamL[r][m]
+//             (frequency r + R freq(m)).
+enum { ADDR_NAT = 0, ADDR_ZF = 1, ADDR_ZI = 2, ADDR_Y = 3, ADDR_YS = 4 };
 template <class FT>
 struct TArgs {
     CUtensorMap tm;                 // ADDR_NAT / ZF load, ZI store base..., view as reals: dims (2 NXP, Ny, Nz)
     CUtensorMap tm4;                // ADDR_ZI / ADDR_Y: 4-D view of the local chunk buffer (2 KXB, NyL, Nz, R)
     CUtensorMap tmr[8];             // per-rank 3-D chunk views (peer buffers, or chunk r of the local spectrum)
-    int addr, R, KXB, tpc, NyL, kx_base, NXP;
+    int addr, R, KXB, tpc, NyL, kx_base, NXP, Nz;
     int r_only;                     // ADDR_ZF: >= 0 restricts the launch to the tiles of destination chunk r_only (nkx = tpc)
     int o_first;                    // first value of the other index handled by this launch (split launches)
     int line_is_y;                  // 1: lines along y, other = z ; 0: lines along z, other = y
@@ -165,7 +171,10 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
         r = 0;
         if (A.addr == ADDR_ZF && A.r_only >= 0) { r = A.r_only; kx0 = r * A.KXB + TK * kxb; }
         else if (A.addr == ADDR_ZF || A.addr == ADDR_ZI) { r = kxb / A.tpc; kxb -= r * A.tpc; kx0 = r * A.KXB + TK * kxb; }
-        else kx0 = A.kx_base + TK * kxb;
+        else {
+            kx0 = A.kx_base + TK * kxb;
+            if (A.addr == ADDR_YS) r = o % A.R;
+        }
     };
     auto issue_load = [&](int n) {
         int kxb, o, r, kx0;
@@ -183,6 +192,7 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
         }
         else if (A.addr == ADDR_ZF) tma_load_3d(dst, &A.tm, 2 * kx0, o, 0, bar);
         else if (A.addr == ADDR_ZI) tma_load_4d(dst, &A.tm4, 2 * TK * kxb, o, 0, r, bar);
+        else if (A.addr == ADDR_YS) tma_load_4d(dst, &A.tm4, 2 * TK * kxb, 0, o / A.R, r, bar);
         else tma_load_4d(dst, &A.tm4, 2 * TK * kxb, 0, o, 0, bar);
     };
     if (lead && mine > 0) issue_load(0);
@@ -225,12 +235,14 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
                 for (int q = 0; q < RLAST; ++q) x[q] = col[(base + q) * TK];
                 dft_reg<RLAST, false>(x);
                 const int kx = min(kx0 + t, A.NXP - 1);       // columns clipped out of a chunk carry zeros
-                const double lO = A.lamO ? A.lamO[o] : 0.0;
+                const int oz = A.addr == ADDR_YS ? o / A.R : o;
+                const double* lamLr = A.addr == ADDR_YS ? A.lamL + r * N : A.lamL;
+                const double lO = A.lamO ? A.lamO[oz] : 0.0;
                 const double lxo = A.line_is_y ? A.lamx[kx] : (A.lamx[kx] + lO);
 #pragma unroll
                 for (int sidx = 0; sidx < RLAST; ++sidx) {
                     const int m = base + sidx;
-                    const double lL = A.lamL[m];
+                    const double lL = lamLr[m];
                     const double lam = A.line_is_y ? ((lxo + lL) + lO) : (lxo + lL);
                     const CT v = x[brev(sidx, LB)];
                     const double r = (kx == 0 && m == 0 && o == 0) ? 0.0 : -rcp_full(lam);
@@ -257,6 +269,7 @@ __global__ void __launch_bounds__(256) line_tma_kernel(const __grid_constant__ T
                     tma_store_3d(&A.tm, 2 * kx0, A.line_is_y ? b * ROWS : o, A.line_is_y ? o : b * ROWS, s + (size_t)b * ROWS * TK);
             }
             else if (A.addr == ADDR_ZF || A.addr == ADDR_ZI) tma_store_3d(&A.tmr[r], 2 * TK * kxb, o, 0, s);
+            else if (A.addr == ADDR_YS) tma_store_3d(&A.tmr[r], 2 * TK * kxb, 0, o / A.R, s);
             else for (int q = 0; q < A.R; ++q) tma_store_3d(&A.tmr[q], 2 * TK * kxb, 0, o, s + (size_t)q * A.NyL * TK);
             bulk_commit();
         }
