@@ -650,7 +650,8 @@ struct ob200_model {
     std::vector<std::unique_ptr<ob200_field>> F;    // state (two buffers each)
     std::vector<std::unique_ptr<ob200_field>> Gn, Gm;
     std::unique_ptr<ob200_field> pNHS, pHY;
-    std::unique_ptr<ob200_field> nue;               // SmagorinskyLilly eddy viscosity (diffusivity_fields.νₑ)
+    std::unique_ptr<ob200_field> nue;               // SmagorinskyLilly / AMD eddy viscosity (diffusivity_fields.νₑ)
+    std::vector<std::unique_ptr<ob200_field>> kappae;     // AMD eddy diffusivities (diffusivity_fields.κₑ), one per tracer
     std::unique_ptr<ob200_poisson> solver;
     std::vector<void*> owned;
     Phys<float> P32;
@@ -700,6 +701,11 @@ static void build_phys(ob200_model* m) {
     for (int t = 0; t < 8; ++t) P.kappa[t] = (FT)(D.closure == OB200_CLOSURE_SMAGORINSKY_LILLY ? D.prandtl[t] : D.kappa[t]);
     P.smagC = (FT)D.smagorinsky_C; P.smagCb = (FT)D.smagorinsky_Cb;
     P.nue = m->nue ? m->nue->template p0<FT>() : nullptr;
+    P.amdCnu = (FT)D.amd_Cnu; P.amdCb = (FT)D.amd_Cb; P.amdHasCb = D.amd_has_Cb;
+    for (int t = 0; t < 8; ++t) {
+        P.amdCk[t] = (FT)D.amd_Ckappa[t];
+        P.kappae[t] = t < (int)m->kappae.size() ? m->kappae[t]->template p0<FT>() : nullptr;
+    }
     P.fplane = D.coriolis_fplane;
     P.f = (FT)D.f;
     P.btr = D.buoyancy_tracer;
@@ -714,7 +720,7 @@ extern "C" int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model*
     if (!desc || !desc->grid || !out) throw Error("null argument");
     if (desc->ntracers < 0 || desc->ntracers > OB200_MAX_TRACERS) throw Error("too many tracers");
     if (desc->advection < 0 || desc->advection > OB200_ADV_WENO5) throw Error("unsupported advection scheme");
-    if (desc->closure < 0 || desc->closure > OB200_CLOSURE_SMAGORINSKY_LILLY) throw Error("unsupported closure");
+    if (desc->closure < 0 || desc->closure > OB200_CLOSURE_AMD) throw Error("unsupported closure");
     if (desc->closure == OB200_CLOSURE_SMAGORINSKY_LILLY)
         for (int t = 0; t < desc->ntracers; ++t)
             if (!(desc->prandtl[t] > 0)) throw Error("SmagorinskyLilly needs a positive Prandtl number for every tracer");
@@ -747,7 +753,10 @@ extern "C" int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model*
     int32_t ccc[3] = {0, 0, 0};
     m->pNHS.reset(make_field(m->grid, ccc, nullptr, false));
     if (GD.topology[2] != OB200_FLAT) m->pHY.reset(make_field(m->grid, ccc, nullptr, false));
-    if (desc->closure == OB200_CLOSURE_SMAGORINSKY_LILLY) m->nue.reset(make_field(m->grid, ccc, nullptr, false));
+    if (desc->closure == OB200_CLOSURE_SMAGORINSKY_LILLY || desc->closure == OB200_CLOSURE_AMD)
+        m->nue.reset(make_field(m->grid, ccc, nullptr, false));
+    if (desc->closure == OB200_CLOSURE_AMD)
+        for (int t = 0; t < desc->ntracers; ++t) m->kappae.emplace_back(make_field(m->grid, ccc, nullptr, false));
     ob200_poisson* s = nullptr;
     if (ob200_poisson_create(m->grid, desc->pressure_solver, &s)) throw Error(ob::g_err);
     m->solver.reset(s);
@@ -776,6 +785,7 @@ extern "C" int32_t ob200_model_field(ob200_model* m, const char* name, ob200_fie
     ob200_field* f = nullptr;
     if (s == "pNHS") f = m->pNHS.get();
     else if (s == "nu_e") f = m->nue.get();
+    else if (s.rfind("kappa_e", 0) == 0) { int k = std::stoi(s.substr(7)); if (k >= 0 && k < (int)m->kappae.size()) f = m->kappae[k].get(); }
     else if (s == "pHY") f = m->pHY.get();
     else if (s.rfind("Gn_", 0) == 0) { int q = idx(s.substr(3)); if (q >= 0) f = m->Gn[q].get(); }
     else if (s.rfind("Gm_", 0) == 0) { int q = idx(s.substr(3)); if (q >= 0) f = m->Gm[q].get(); }
@@ -828,6 +838,18 @@ static void model_diffusivities(ob200_model* m) {
     if (!m->nue) return;
     ScopedPhase ph("closure");
     Phys<FT>& P = physOf<FT>(m);
+    if (m->desc.closure == OB200_CLOSURE_AMD) {
+        const FT* cs[8]; FT* ks[8];
+        std::vector<ob200_field*> fl = {m->nue.get()};
+        for (size_t t = 0; t < m->kappae.size(); ++t) {
+            cs[t] = m->F[3 + t]->template p0<FT>(); ks[t] = m->kappae[t]->template p0<FT>();
+            fl.push_back(m->kappae[t].get());
+        }
+        launch_amd<FT>(P, model_buoyancy<FT>(m), m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(),
+                       m->F[2]->template p0<FT>(), m->nue->template p0<FT>(), (int)m->kappae.size(), cs, ks);
+        fill_halos<FT>(fl.data(), (int)fl.size());
+        return;
+    }
     launch_smagorinsky<FT>(P, model_buoyancy<FT>(m), m->F[0]->template p0<FT>(), m->F[1]->template p0<FT>(),
                            m->F[2]->template p0<FT>(), m->nue->template p0<FT>());
     ob200_field* f = m->nue.get();

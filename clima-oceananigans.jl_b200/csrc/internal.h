@@ -67,6 +67,11 @@ namespace fz { template <class FT> int launch(const Phys<FT>& P, const FusedFiel
 template <class FT>
 void launch_smagorinsky(const Phys<FT>& P, const Buoy<FT>& B, const FT* u, const FT* v, const FT* w, FT* nue);
 
+// AnisotropicMinimumDissipation: eddy viscosity and the tracers' eddy diffusivities over the interior
+template <class FT>
+void launch_amd(const Phys<FT>& P, const Buoy<FT>& B, const FT* u, const FT* v, const FT* w, FT* nue, int ntr,
+                const FT* const* c, FT* const* ke);
+
 template <class FT, class CT>
 void launch_pressure_rhs(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,
                          bool times_dz, CT* rhs);

@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
             if (visc) f = f + viscous_Aflux(P, B, d, U, q);
         } else {
             if (P.scheme != ADV_NONE) f = tracer_flux(P, d, U[d], A.psi, q);
-            if (visc) f = f + diffusive_Aflux(P, d, kappa, A.psi, q);
+            if (visc) f = f + diffusive_Aflux(P, d, kappa, A.psi, q, P.kappae[comp - 3]);
         }
         return f;
     };
@@ -800,6 +800,40 @@ __global__ void __launch_bounds__(128) smagorinsky_kernel(const __grid_constant_
     const FT* U[3] = {u, v, w};
     nue[q.p] = smagorinsky_nu(P, B, U, q);
 }
+// calculate_nonlinear_viscosity! + calculate_nonlinear_tracer_diffusivity! for AnisotropicMinimumDissipation
+// (anisotropic_minimum_dissipation.jl:222-251): νₑ and every tracer's κₑ over the interior in one launch
+template <class FT>
+struct AmdArgs { const FT* u; const FT* v; const FT* w; FT* nue; int ntr; const FT* c[8]; FT* ke[8]; };
+template <class FT>
+__global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ Phys<FT> P, const Buoy<FT> B, const AmdArgs<FT> A) {
+    const GridD<FT>& g = P.g;
+    int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    int k = 1 + blockIdx.z;
+    if (i > g.N[0] || j > g.N[1]) return;
+    Pt q;
+    q.i[0] = i; q.i[1] = j; q.i[2] = k;
+    q.p = i * g.st[0] + j * g.st[1] + k * g.st[2];
+    const FT* U[3] = {A.u, A.v, A.w};
+    A.nue[q.p] = amd_nu(P, B, U, q);
+    for (int t = 0; t < A.ntr; ++t) A.ke[t][q.p] = amd_kappa(P, P.amdCk[t], U, A.c[t], q);
+}
+template <class FT>
+void launch_amd(const Phys<FT>& P, const Buoy<FT>& B, const FT* u, const FT* v, const FT* w, FT* nue, int ntr,
+                const FT* const* c, FT* const* ke) {
+    const GridD<FT>& g = P.g;
+    AmdArgs<FT> A;
+    A.u = u; A.v = v; A.w = w; A.nue = nue; A.ntr = ntr;
+    for (int t = 0; t < ntr; ++t) { A.c[t] = c[t]; A.ke[t] = ke[t]; }
+    dim3 blk(32, 4), grd(cdiv(g.N[0], 32), cdiv(g.N[1], 4), g.N[2]);
+    amd_kernel<FT><<<grd, blk, 0, stream()>>>(P, B, A);
+    OB_LAUNCH_CHECK();
+}
+template void launch_amd<float>(const Phys<float>&, const Buoy<float>&, const float*, const float*, const float*, float*, int,
+                                const float* const*, float* const*);
+template void launch_amd<double>(const Phys<double>&, const Buoy<double>&, const double*, const double*, const double*, double*, int,
+                                 const double* const*, double* const*);
+
 template <class FT>
 void launch_smagorinsky(const Phys<FT>& P, const Buoy<FT>& B, const FT* u, const FT* v, const FT* w, FT* nue) {
     const GridD<FT>& g = P.g;

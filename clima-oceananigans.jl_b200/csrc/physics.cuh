@@ -13,7 +13,7 @@ namespace ob {
 #define OBD __device__ __forceinline__
 
 enum { ADV_NONE = 0, ADV_C2 = 1, ADV_C4 = 2, ADV_U1 = 3, ADV_U3 = 4, ADV_U5 = 5, ADV_WENO5 = 6 };
-enum { CLO_NONE = 0, CLO_3D = 1, CLO_H = 2, CLO_V = 3, CLO_SMAG = 4 };
+enum { CLO_NONE = 0, CLO_3D = 1, CLO_H = 2, CLO_V = 3, CLO_SMAG = 4, CLO_AMD = 5 };
 enum { SIDE_LEFT = 0, SIDE_RIGHT = 1 };
 
 // buoyancy_perturbation(i, j, k, grid, b, C): BuoyancyTracer (buoyancy_tracer.jl:12) or SeawaterBuoyancy with the linear
@@ -45,8 +45,11 @@ struct Phys {
     const FT* wc[3][2];              // stretched WENO tables [dim][0 = Face, 1 = Center] or null
     int closure;
     FT nu, kappa[8];                 // ScalarDiffusivity constants; SmagorinskyLilly: kappa[t] = Prandtl number of tracer t
-    const FT* nue;                   // SmagorinskyLilly: eddy viscosity at cell centres (Julia-(0,0,0) pointer), halos filled
+    const FT* nue;                   // SmagorinskyLilly / AMD: eddy viscosity at cell centres (Julia-(0,0,0) pointer), halos filled
     FT smagC, smagCb;
+    const FT* kappae[8];             // AnisotropicMinimumDissipation: eddy diffusivity of tracer t at cell centres
+    FT amdCnu, amdCk[8], amdCb;      // Poincaré constants; amdHasCb = 0: buoyancy modification off (Cb = nothing)
+    int amdHasCb;
     int fplane;
     FT f;
     int btr, tilted;                 // buoyancy tracer index (-1 none); tilted gravity flag
@@ -420,7 +423,7 @@ OBD FT viscous_Aflux(const Phys<FT>& P, int comp, int dir, const FT* const* U, P
     FT fx = FT(0);
     if (P.closure == CLO_3D) {
         fx = -2 * (P.nu * strain(g, comp, dir, U, q));
-    } else if (P.closure == CLO_SMAG) {      // viscosity(::SmagorinskyLilly, K) = K.νₑ (smagorinsky_lilly.jl:23)
+    } else if (P.closure == CLO_SMAG || P.closure == CLO_AMD) {      // viscosity(closure, K) = K.νₑ (smagorinsky_lilly.jl:23, anisotropic_minimum_dissipation.jl:24)
         fx = -2 * (nu_at_stress(g, P.nue, comp, dir, q) * strain(g, comp, dir, U, q));
     } else if (P.closure == CLO_H) {
         if (comp < 2 && comp == dir) fx = -(P.nu * div_xy(g, U, q));
@@ -449,12 +452,16 @@ OBD FT div_tau(const Phys<FT>& P, int comp, const FT* const* U, Pt q) {
     return (1 / volume(g, q, l[0], l[1], l[2])) * ((t[0] + t[1]) + t[2]);
 }
 
+// `kappa`: the constant diffusivity (ScalarDiffusivity), the Prandtl number (SmagorinskyLilly); `ke`: the tracer's eddy
+// diffusivity field (AnisotropicMinimumDissipation), else null
 template <class FT>
-OBD FT diffusive_Aflux(const Phys<FT>& P, int d, FT kappa, const FT* c, Pt q) {
+OBD FT diffusive_Aflux(const Phys<FT>& P, int d, FT kappa, const FT* c, Pt q, const FT* ke = nullptr) {
     const GridD<FT>& g = P.g;
     int fl[3] = {OB_C, OB_C, OB_C};
     fl[d] = OB_F;
     FT Ar = areaA(g, d, q, fl[0], fl[1], fl[2]);
+    if (P.closure == CLO_AMD)                // diffusivity(::AMD, K, id) = K.κₑ[id], κᶠᶜᶜ = ℑxᶠᵃᵃ(κₑ) (closure_kernel_operators.jl:88-90)
+        return Ar * (-IF(g, ke, q, d) * deriv(g, c, q, d, OB_F));
     if (P.closure == CLO_SMAG) {             // κₑ = νₑ / Pr at cell centres, interpolated to the face (smagorinsky_lilly.jl:205-221)
         const FT k1 = P.nue[q.p] / kappa;
         const FT kl = g.topo[d] == OB_FLAT ? k1 : FT(0.5) * (P.nue[q.p - g.st[d]] / kappa + k1);
@@ -464,14 +471,14 @@ OBD FT diffusive_Aflux(const Phys<FT>& P, int d, FT kappa, const FT* c, Pt q) {
     return active ? Ar * (-kappa * deriv(g, c, q, d, OB_F)) : Ar * FT(0);
 }
 template <class FT>
-OBD FT div_q(const Phys<FT>& P, FT kappa, const FT* c, Pt q) {
+OBD FT div_q(const Phys<FT>& P, FT kappa, const FT* c, Pt q, const FT* ke = nullptr) {
     if (P.closure == CLO_NONE) return FT(0);
     const GridD<FT>& g = P.g;
     FT t[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         if (g.topo[d] == OB_FLAT) { t[d] = FT(0); continue; }
-        t[d] = diffusive_Aflux(P, d, kappa, c, sh(g, q, d, 1)) - diffusive_Aflux(P, d, kappa, c, q);
+        t[d] = diffusive_Aflux(P, d, kappa, c, sh(g, q, d, 1), ke) - diffusive_Aflux(P, d, kappa, c, q, ke);
     }
     return (1 / volume(g, q, OB_C, OB_C, OB_C)) * ((t[0] + t[1]) + t[2]);
 }
@@ -515,6 +522,104 @@ OBD FT smagorinsky_nu(const Phys<FT>& P, const Buoy<FT>& B, const FT* const* U, 
     return (stab * (cd * cd)) * sqrt(2 * S2);
 }
 
+// ---- AnisotropicMinimumDissipation: calc_νᶜᶜᶜ / calc_κᶜᶜᶜ (anisotropic_minimum_dissipation.jl:180-220, 269-376;
+//      normalised gradients velocity_tracer_gradients.jl:120-242).  Δᶠ at ANY location is 2 Δᶜ at the index passed (:255-267).
+template <class FT, class F>
+OBD FT avg_c(const GridD<FT>& g, int d, Pt q, F f) {          // ℑᶜ along d of a function of the position
+    return g.topo[d] == OB_FLAT ? f(q) : FT(0.5) * (f(q) + f(sh(g, q, d, 1)));
+}
+template <class FT, class F>
+OBD FT avg_cc(const GridD<FT>& g, int inner, int outer, Pt q, F f) {      // ℑ_outer ᶜ (ℑ_inner ᶜ f)
+    return avg_c(g, outer, q, [&](Pt r) { return avg_c(g, inner, r, f); });
+}
+template <class FT>
+struct AmdGrad {            // the normalised velocity gradients as functions of the position
+    const GridD<FT>& g;
+    const FT* const* U;
+    OBD FT df(int d, Pt r) const { return 2 * spacing(g, d, OB_C, r.i[d]); }
+    OBD FT xu(Pt r) const { return deriv(g, U[0], r, 0, OB_C); }
+    OBD FT yv(Pt r) const { return deriv(g, U[1], r, 1, OB_C); }
+    OBD FT zw(Pt r) const { return deriv(g, U[2], r, 2, OB_C); }
+    OBD FT xv(Pt r) const { return df(0, r) / df(1, r) * deriv(g, U[1], r, 0, OB_F); }
+    OBD FT yu(Pt r) const { return df(1, r) / df(0, r) * deriv(g, U[0], r, 1, OB_F); }
+    OBD FT xw(Pt r) const { return df(0, r) / df(2, r) * deriv(g, U[2], r, 0, OB_F); }
+    OBD FT zu(Pt r) const { return df(2, r) / df(0, r) * deriv(g, U[0], r, 2, OB_F); }
+    OBD FT yw(Pt r) const { return df(1, r) / df(2, r) * deriv(g, U[2], r, 1, OB_F); }
+    OBD FT zv(Pt r) const { return df(2, r) / df(1, r) * deriv(g, U[1], r, 2, OB_F); }
+    OBD FT s12(Pt r) const { return FT(0.5) * (yu(r) + xv(r)); }
+    OBD FT s13(Pt r) const { return FT(0.5) * (zu(r) + xw(r)); }
+    OBD FT s23(Pt r) const { return FT(0.5) * (zv(r) + yw(r)); }
+};
+template <class FT>
+OBD FT amd_delta2(const GridD<FT>& g, Pt q) {
+    const FT fx = 2 * spacing(g, 0, OB_C, q.i[0]), fy = 2 * spacing(g, 1, OB_C, q.i[1]), fz = 2 * spacing(g, 2, OB_C, q.i[2]);
+    return 3 / ((1 / (fx * fx) + 1 / (fy * fy)) + 1 / (fz * fz));
+}
+template <class FT>
+OBD FT amd_nu(const Phys<FT>& P, const Buoy<FT>& B, const FT* const* U, Pt q) {
+    const GridD<FT>& g = P.g;
+    const AmdGrad<FT> G{g, U};
+    auto sq = [](FT x) { return x * x; };
+#define AXY(expr) avg_cc(g, 0, 1, q, [&](Pt r) { return expr; })
+#define AXZ(expr) avg_cc(g, 0, 2, q, [&](Pt r) { return expr; })
+#define AYZ(expr) avg_cc(g, 1, 2, q, [&](Pt r) { return expr; })
+    const FT xu = G.xu(q), yv = G.yv(q), zw = G.zw(q);
+    const FT xv2 = AXY(sq(G.xv(r))), yu2 = AXY(sq(G.yu(r))), xw2 = AXZ(sq(G.xw(r))), zu2 = AXZ(sq(G.zu(r))),
+             yw2 = AYZ(sq(G.yw(r))), zv2 = AYZ(sq(G.zv(r)));
+    // norm_tr_∇uᶜᶜᶜ (:315-328)
+    const FT qn = (((((((xu * xu + yv * yv) + zw * zw) + xv2) + yu2) + xw2) + zu2) + yw2) + zv2;
+    if (qn == FT(0)) return FT(0);
+    // norm_uᵢₐ_uⱼₐ_Σᵢⱼᶜᶜᶜ (:269-313), term order kept (Σ₁₁ = ∂x u etc.)
+    const FT t1 = ((((xu * (xu * xu) + yv * xv2) + zw * xw2) + 2 * xu * AXY(G.xv(r) * G.s12(r))) + 2 * xu * AXZ(G.xw(r) * G.s13(r)))
+                  + 2 * AXY(G.xv(r)) * AXZ(G.xw(r)) * AYZ(G.s23(r));
+    const FT t2 = ((((xu * yu2 + yv * (yv * yv)) + zw * yw2) + 2 * yv * AXY(G.yu(r) * G.s12(r)))
+                   + 2 * AXY(G.yu(r)) * AYZ(G.yw(r)) * AXZ(G.s13(r))) + 2 * yv * AYZ(G.yw(r) * G.s23(r));
+    const FT t3 = ((((xu * zu2 + yv * zv2) + zw * (zw * zw)) + 2 * AXZ(G.zu(r)) * AYZ(G.zv(r)) * AXY(G.s12(r)))
+                   + 2 * zw * AXZ(G.zu(r) * G.s13(r))) + 2 * zw * AYZ(G.zv(r) * G.s23(r));
+    const FT rr = (t1 + t2) + t3;
+    FT cbz = FT(0);
+    if (P.amdHasCb && B.mode) {        // Cb_norm_wᵢ_bᵢᶜᶜᶜ (:332-345) / Δᶠz
+        auto db = [&](int d, Pt r) {   // ∂ᶠ of buoyancy_perturbation along d at r
+            const FT del = buoyancy_at(B, r.p) - buoyancy_at(B, r.p - g.st[d]);
+            if (g.topo[d] == OB_FLAT) return FT(0);
+#ifndef OB200_STRICT
+            if (g.regular[d]) return del * g.invd[d];
+#endif
+            return del / spacing(g, d, OB_F, r.i[d]);
+        };
+        const FT wx = (AXZ(G.xw(r)) * G.df(0, q)) * avg_c(g, 0, q, [&](Pt r) { return db(0, r); });
+        const FT wy = (AYZ(G.yw(r)) * G.df(1, q)) * avg_c(g, 1, q, [&](Pt r) { return db(1, r); });
+        const FT wz = (zw * G.df(2, q)) * avg_c(g, 2, q, [&](Pt r) { return db(2, r); });
+        cbz = P.amdCb * ((wx + wy) + wz) / G.df(2, q);
+    }
+    const FT nu = -P.amdCnu * amd_delta2(g, q) * (rr - cbz) / qn;
+    return nu > FT(0) ? nu : FT(0);
+}
+template <class FT>
+OBD FT amd_kappa(const Phys<FT>& P, FT Ck, const FT* const* U, const FT* c, Pt q) {
+    const GridD<FT>& g = P.g;
+    const AmdGrad<FT> G{g, U};
+    auto cx = [&](Pt r) { return G.df(0, r) * deriv(g, c, r, 0, OB_F); };
+    auto cy = [&](Pt r) { return G.df(1, r) * deriv(g, c, r, 1, OB_F); };
+    auto cz = [&](Pt r) { return G.df(2, r) * deriv(g, c, r, 2, OB_F); };
+    const FT cx2 = avg_c(g, 0, q, [&](Pt r) { FT x = cx(r); return x * x; });
+    const FT cy2 = avg_c(g, 1, q, [&](Pt r) { FT x = cy(r); return x * x; });
+    const FT cz2 = avg_c(g, 2, q, [&](Pt r) { FT x = cz(r); return x * x; });
+    const FT sigma = (cx2 + cy2) + cz2;                   // norm_θᵢ²ᶜᶜᶜ (:374-376)
+    if (sigma == FT(0)) return FT(0);
+    const FT icx = avg_c(g, 0, q, cx), icy = avg_c(g, 1, q, cy), icz = avg_c(g, 2, q, cz);
+    // norm_uᵢⱼ_cⱼ_cᵢᶜᶜᶜ (:347-372); the second-last term of cy_uy interpolates norm_∂y_w with ℑxz as the reference does
+    const FT a1 = (G.xu(q) * cx2 + AXY(G.xv(r)) * icx * icy) + AXZ(G.xw(r)) * icx * icz;
+    const FT a2 = (AXY(G.yu(r)) * icy * icx + G.yv(q) * cy2) + AXZ(G.yw(r)) * icy * icz;
+    const FT a3 = (AXZ(G.zu(r)) * icz * icx + AYZ(G.zv(r)) * icz * icy) + G.zw(q) * cz2;
+    const FT theta = (a1 + a2) + a3;
+    const FT ka = -Ck * amd_delta2(g, q) * theta / sigma;
+    return ka > FT(0) ? ka : FT(0);
+#undef AXY
+#undef AXZ
+#undef AYZ
+}
+
 // ---- tendencies: nonhydrostatic_tendency_kernel_functions.jl:44-232 (term order kept) -------
 // comp 0,1,2 = u,v,w ; comp >= 3 = tracer (comp-3)
 template <class FT>
@@ -523,7 +628,7 @@ OBD FT tendency(const Phys<FT>& P, int comp, const FT* const* U, const FT* psi, 
     const GridD<FT>& g = P.g;
     if (comp >= 3) {
         FT G = -div_Uc(P, U, psi, q);
-        G = G - div_q(P, P.kappa[comp - 3], psi, q);
+        G = G - div_q(P, P.kappa[comp - 3], psi, q, P.kappae[comp - 3]);
         return G;
     }
     FT G = -div_Uu(P, comp, U, psi, q);

@@ -22,7 +22,7 @@ using Oceananigans.BoundaryConditions: BoundaryCondition, FieldBoundaryCondition
                                        regularize_field_boundary_conditions
 using Oceananigans.Advection: CenteredSecondOrder, CenteredFourthOrder, UpwindBiasedFirstOrder, UpwindBiasedThirdOrder,
                               UpwindBiasedFifthOrder, WENO5
-using Oceananigans.TurbulenceClosures: ScalarDiffusivity, SmagorinskyLilly, ThreeDimensionalFormulation, HorizontalFormulation,
+using Oceananigans.TurbulenceClosures: ScalarDiffusivity, SmagorinskyLilly, AnisotropicMinimumDissipation, ThreeDimensionalFormulation, HorizontalFormulation,
                                        VerticalFormulation, ExplicitTimeDiscretization
 using Oceananigans.Coriolis: FPlane
 using Oceananigans.BuoyancyModels: Buoyancy, BuoyancyTracer, SeawaterBuoyancy, LinearEquationOfState, ZDirection, required_tracers
@@ -139,6 +139,7 @@ struct ModelDesc
     buoyancy_kind::Int32; temperature_tracer::Int32; salinity_tracer::Int32
     gravitational_acceleration::Float64; thermal_expansion::Float64; haline_contraction::Float64
     smagorinsky_C::Float64; smagorinsky_Cb::Float64; prandtl::NTuple{MAX_TRACERS,Float64}
+    amd_Cnu::Float64; amd_Ckappa::NTuple{MAX_TRACERS,Float64}; amd_Cb::Float64; amd_has_Cb::Int32
 end
 
 topo_code(::Type{Periodic}) = Int32(0); topo_code(::Type{Bounded}) = Int32(1); topo_code(::Type{Flat}) = Int32(2)
@@ -283,7 +284,16 @@ closure_desc(c::SmagorinskyLilly{<:ExplicitTimeDiscretization}, tracers) = (4, 0
 smagorinsky_desc(c::SmagorinskyLilly, tracers) =
     (Float64(c.C), Float64(c.Cb), ntuple(t -> t <= length(tracers) ? Float64(c.Pr isa Number ? c.Pr : c.Pr[tracers[t]]) : 1.0, MAX_TRACERS))
 smagorinsky_desc(c, tracers) = (0.0, 0.0, ntuple(_ -> 1.0, MAX_TRACERS))
-closure_desc(c, tracers) = throw(ArgumentError("B200(): unsupported closure $(typeof(c)) (AnisotropicMinimumDissipation, tuples of closures " *
+# AnisotropicMinimumDissipation (anisotropic_minimum_dissipation.jl:96-105): code 5, constant Poincaré constants only
+closure_desc(c::AnisotropicMinimumDissipation{<:ExplicitTimeDiscretization}, tracers) = (5, 0.0, ntuple(_ -> 0.0, MAX_TRACERS))
+function amd_desc(c::AnisotropicMinimumDissipation, tracers)
+    (c.Cν isa Number && all(x -> x isa Number, values(c.Cκ))) ||
+        throw(ArgumentError("B200(): AnisotropicMinimumDissipation with constant Cν, Cκ only"))
+    Cκ = ntuple(t -> t <= length(tracers) ? Float64(c.Cκ[tracers[t]]) : 0.0, MAX_TRACERS)
+    return (Float64(c.Cν), Cκ, c.Cb === nothing ? 0.0 : Float64(c.Cb), Int32(c.Cb !== nothing))
+end
+amd_desc(c, tracers) = (0.0, ntuple(_ -> 0.0, MAX_TRACERS), 0.0, Int32(0))
+closure_desc(c, tracers) = throw(ArgumentError("B200(): unsupported closure $(typeof(c)) (tuples of closures, function-valued coefficients " *
                                                "and vertically implicit diffusion are outside the B200 path)"))
 
 "The ENO coefficient tables of WENO5(grid=grid) for stretched dimensions (weno_fifth_order.jl:562-584): [dim][Face, Center]."
@@ -337,7 +347,7 @@ function model_desc(grid, gh; advection, buoyancy, coriolis, closure, tracers, t
     ptr(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
     desc = ModelDesc(gh, ts, χ, adv_code(advection), advection isa WENO5 ? Int32(advection.zweno) : Int32(1),
                      map(ptr, tabs), clo, ν, κ, fplane, f, btr, tilted, ĝ, length(tracers), bcs, 0,
-                     bkind, iT, iS, grav, α, β, smagorinsky_desc(closure, tracers)...)
+                     bkind, iT, iS, grav, α, β, smagorinsky_desc(closure, tracers)..., amd_desc(closure, tracers)...)
     return desc, tabs           # `tabs` must be GC.@preserve'd across ob200_model_create (host pointers are borrowed)
 end
 
@@ -392,7 +402,9 @@ function b200_nonhydrostatic_model(; grid, clock = Clock{eltype(grid)}(0, 0, 1),
     ts = timestepper === :RungeKutta3 ? RungeKutta3TimeStepper(grid, tracers; Gⁿ = G("Gn_"), G⁻ = G("Gm_")) :
                                         QuasiAdamsBashforth2TimeStepper(grid, tracers; Gⁿ = G("Gn_"), G⁻ = G("Gm_"))
     # diffusivity_fields.νₑ of SmagorinskyLilly is the library's "nu_e" field (κₑ stays the reference's lazy νₑ / Pr operation)
-    diffusivity_fields = closure isa SmagorinskyLilly ?
+    diffusivity_fields = closure isa AnisotropicMinimumDissipation ?
+        (; νₑ = pfield("nu_e"), κₑ = NamedTuple{tracers}(Tuple(pfield("kappa_e$(t - 1)") for t in 1:length(tracers)))) :
+        closure isa SmagorinskyLilly ?
         (; νₑ = pfield("nu_e"), κₑ = NamedTuple{tracers}(Tuple(pfield("nu_e") / (closure.Pr isa Number ? closure.Pr : closure.Pr[n]) for n in tracers))) : nothing
     solver = B200PoissonSolver(grid)
     return Oceananigans.Models.NonhydrostaticModels.reference_nonhydrostatic_model(;      # the unchanged constructor body (hook 2)

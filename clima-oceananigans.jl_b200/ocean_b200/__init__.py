@@ -9,7 +9,8 @@ from .model import (Field, CenterField, XFaceField, YFaceField, ZFaceField, fill
                     FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver, BatchedTridiagonalSolver,
                     solve, solve_for_pressure, NonhydrostaticModel, WENO5, CenteredSecondOrder,
                     CenteredFourthOrder, UpwindBiasedFirstOrder, UpwindBiasedThirdOrder,
-                    UpwindBiasedFifthOrder, ScalarDiffusivity, SmagorinskyLilly, VerticalScalarDiffusivity,
+                    UpwindBiasedFifthOrder, ScalarDiffusivity, SmagorinskyLilly, AnisotropicMinimumDissipation,
+                    VerticalScalarDiffusivity,
                     HorizontalScalarDiffusivity, FPlane, BuoyancyTracer, Buoyancy, SeawaterBuoyancy,
                     LinearEquationOfState, BoundaryCondition,
                     FluxBoundaryCondition, ValueBoundaryCondition, GradientBoundaryCondition,

@@ -12,7 +12,7 @@ CENTER, FACE = 0, 1
 BC_NONE, BC_PERIODIC, BC_FLUX, BC_VALUE, BC_GRADIENT, BC_OPEN = range(6)
 ADV = {"none": 0, "CenteredSecondOrder": 1, "CenteredFourthOrder": 2, "UpwindBiasedFirstOrder": 3,
        "UpwindBiasedThirdOrder": 4, "UpwindBiasedFifthOrder": 5, "WENO5": 6}
-CLOSURE = {"none": 0, "ThreeDimensional": 1, "Horizontal": 2, "Vertical": 3, "SmagorinskyLilly": 4}
+CLOSURE = {"none": 0, "ThreeDimensional": 1, "Horizontal": 2, "Vertical": 3, "SmagorinskyLilly": 4, "AnisotropicMinimumDissipation": 5}
 TS = {"QuasiAdamsBashforth2": 0, "RungeKutta3": 1}
 SOLVER_AUTO, SOLVER_FFT, SOLVER_FT = 0, 1, 2
 MAX_TRACERS = 8
@@ -42,7 +42,9 @@ class ModelDesc(C.Structure):
                 ("buoyancy_kind", C.c_int32), ("temperature_tracer", C.c_int32), ("salinity_tracer", C.c_int32),
                 ("gravitational_acceleration", C.c_double), ("thermal_expansion", C.c_double),
                 ("haline_contraction", C.c_double),
-                ("smagorinsky_C", C.c_double), ("smagorinsky_Cb", C.c_double), ("prandtl", C.c_double * MAX_TRACERS)]
+                ("smagorinsky_C", C.c_double), ("smagorinsky_Cb", C.c_double), ("prandtl", C.c_double * MAX_TRACERS),
+                ("amd_Cnu", C.c_double), ("amd_Ckappa", C.c_double * MAX_TRACERS), ("amd_Cb", C.c_double),
+                ("amd_has_Cb", C.c_int32)]
 
 
 #: every symbol include/ocean_b200.h declares: name -> (restype, argtypes)

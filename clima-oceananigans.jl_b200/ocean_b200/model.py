@@ -322,6 +322,25 @@ class SmagorinskyLilly:
         return self.Pr[name] if isinstance(self.Pr, dict) else self.Pr
 
 
+class AnisotropicMinimumDissipation:
+    """AnisotropicMinimumDissipation(FT; C=1/12, Cν=nothing, Cκ=nothing, Cb=nothing) (src/TurbulenceClosures/
+    turbulence_closure_implementations/anisotropic_minimum_dissipation.jl:96-105); constant Poincaré constants (Cκ a
+    number or a dict per tracer), explicit time discretisation."""
+    required_halo = 1
+    formulation = "ThreeDimensional"
+
+    def __init__(self, C=1 / 12, Cν=None, Cκ=None, Cb=None):
+        self.Cν = C if Cν is None else Cν
+        self.Cκ = C if Cκ is None else Cκ
+        self.Cb = Cb
+        for v in (self.Cν, self.Cκ):
+            if callable(v):
+                raise ValueError("only constant Poincaré constants are supported on the B200 architecture")
+
+    def Ck(self, name):
+        return self.Cκ[name] if isinstance(self.Cκ, dict) else self.Cκ
+
+
 def VerticalScalarDiffusivity(**kw):
     return ScalarDiffusivity("Vertical", **kw)
 
@@ -450,7 +469,13 @@ class NonhydrostaticModel:
             for (dim, li), t in advection.tables.items():
                 self._keep.append(t)
                 d.weno_coeff[dim][li] = t.ctypes.data_as(C.POINTER(C.c_double))
-        if isinstance(closure, SmagorinskyLilly):
+        if isinstance(closure, AnisotropicMinimumDissipation):
+            d.closure = L.CLOSURE["AnisotropicMinimumDissipation"]
+            d.amd_Cnu = float(closure.Cν)
+            d.amd_has_Cb, d.amd_Cb = int(closure.Cb is not None), float(closure.Cb or 0.0)
+            for k, name in enumerate(tracers):
+                d.amd_Ckappa[k] = float(closure.Ck(name))
+        elif isinstance(closure, SmagorinskyLilly):
             d.closure = L.CLOSURE["SmagorinskyLilly"]
             d.smagorinsky_C, d.smagorinsky_Cb = float(closure.C), float(closure.Cb)
             for k, name in enumerate(tracers):
@@ -501,7 +526,11 @@ class NonhydrostaticModel:
         self.pressures = {"pNHS": self._field("pNHS", "pNHS", (Center,) * 3)}
         if grid.topology[2] != Flat:
             self.pressures["pHY′"] = self._field("pHY", "pHY", (Center,) * 3)
-        self.diffusivity_fields = {"νₑ": self._field("nu_e", "nu_e", (Center,) * 3)} if isinstance(closure, SmagorinskyLilly) else {}
+        self.diffusivity_fields = {}
+        if isinstance(closure, (SmagorinskyLilly, AnisotropicMinimumDissipation)):
+            self.diffusivity_fields["νₑ"] = self._field("nu_e", "nu_e", (Center,) * 3)
+        if isinstance(closure, AnisotropicMinimumDissipation):
+            self.diffusivity_fields["κₑ"] = {n: self._field(f"kappa_e{k}", f"kappa_e_{n}", (Center,) * 3) for k, n in enumerate(tracers)}
         self.Gn = {n: self._field("Gn_" + (n if n in "uvw" else f"c{tracers.index(n)}"), n, locs[i])
                    for i, n in enumerate(names)}
         self.Gm = {n: self._field("Gm_" + (n if n in "uvw" else f"c{tracers.index(n)}"), n, locs[i])

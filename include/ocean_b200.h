@@ -43,7 +43,8 @@ enum { OB200_ADV_NONE = 0, OB200_ADV_CENTERED2 = 1, OB200_ADV_CENTERED4 = 2, OB2
        OB200_ADV_UPWIND3 = 4, OB200_ADV_UPWIND5 = 5, OB200_ADV_WENO5 = 6 };   /* Advection      */
 enum { OB200_CLOSURE_NONE = 0, OB200_CLOSURE_3D = 1, OB200_CLOSURE_HORIZONTAL = 2,
        OB200_CLOSURE_VERTICAL = 3,                           /* ScalarDiffusivity formulations */
-       OB200_CLOSURE_SMAGORINSKY_LILLY = 4 };                /* SmagorinskyLilly LES closure   */
+       OB200_CLOSURE_SMAGORINSKY_LILLY = 4,                  /* SmagorinskyLilly LES closure   */
+       OB200_CLOSURE_AMD = 5 };                              /* AnisotropicMinimumDissipation  */
 enum { OB200_TS_AB2 = 0, OB200_TS_RK3 = 1 };                 /* :QuasiAdamsBashforth2 / :RungeKutta3 */
 enum { OB200_SIDE_WEST = 0, OB200_SIDE_EAST = 1, OB200_SIDE_SOUTH = 2, OB200_SIDE_NORTH = 3,
        OB200_SIDE_BOTTOM = 4, OB200_SIDE_TOP = 5 };
@@ -114,6 +115,11 @@ typedef struct {
      * tracer.  The model field "nu_e" is diffusivity_fields.νₑ. */
     double  smagorinsky_C, smagorinsky_Cb;
     double  prandtl[OB200_MAX_TRACERS];
+    /* AnisotropicMinimumDissipation(Cν, Cκ, Cb) (turbulence_closure_implementations/anisotropic_minimum_dissipation.jl:96-105,
+     * 180-220): constant Poincaré constants; amd_has_Cb = 0 is `Cb = nothing` (no buoyancy modification).  The model fields
+     * "nu_e" and "kappa_e<k>" are diffusivity_fields.νₑ and diffusivity_fields.κₑ[k]. */
+    double  amd_Cnu, amd_Ckappa[OB200_MAX_TRACERS], amd_Cb;
+    int32_t amd_has_Cb;
 } ob200_model_desc;
 
 /* ---- library / device ----------------------------------------------------------------- */
@@ -187,7 +193,7 @@ int32_t ob200_batched_tridiagonal_solve(int32_t ftype, int32_t is_complex, int32
 int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model** out);
 int32_t ob200_model_destroy(ob200_model* m);
 /* model.velocities.u / model.tracers.b / model.pressures.pNHS / timestepper.Gⁿ.u ...
- * names: "u","v","w","c<k>" (k-th tracer, 0-based),"pNHS","pHY","Gn_u",...,"Gm_c0","nu_e" (SmagorinskyLilly).
+ * names: "u","v","w","c<k>" (k-th tracer, 0-based),"pNHS","pHY","Gn_u",...,"Gm_c0","nu_e" (SmagorinskyLilly, AMD),"kappa_e<k>" (AMD).
  * The returned handle is borrowed (owned by the model). */
 int32_t ob200_model_field(ob200_model* m, const char* name, ob200_field** out);
 /* update_state!(model) update_nonhydrostatic_model_state.jl:14-37 */

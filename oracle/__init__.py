@@ -32,7 +32,7 @@ from .fields import (Field, FieldBoundaryConditions, BoundaryCondition,  # noqa:
 from .advection import (WENO5, CenteredSecondOrder, CenteredFourthOrder,  # noqa: F401
                         UpwindBiasedFirstOrder, UpwindBiasedThirdOrder,
                         UpwindBiasedFifthOrder)
-from .closures import ScalarDiffusivity, SmagorinskyLilly  # noqa: F401
+from .closures import ScalarDiffusivity, SmagorinskyLilly, AnisotropicMinimumDissipation  # noqa: F401
 from .solvers import (FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver,  # noqa: F401
                       BatchedTridiagonalSolver, poisson_eigenvalues)
 from .model import (NonhydrostaticModel, FPlane, BuoyancyTracer, Buoyancy, SeawaterBuoyancy,  # noqa: F401

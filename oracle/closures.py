@@ -138,7 +138,7 @@ def viscous_flux(comp, d, clo, νe=None):
     form = clo.formulation
     Σ = {(0, 0): Σ11, (0, 1): Σ12, (0, 2): Σ13, (1, 0): Σ12, (1, 1): Σ22, (1, 2): Σ23,
          (2, 0): Σ13, (2, 1): Σ23, (2, 2): Σ33}[(comp, d)]
-    if isinstance(clo, SmagorinskyLilly):          # viscosity(::SmagorinskyLilly, K) = K.νₑ, interpolated to the flux location
+    if hasattr(clo, "Cν") or isinstance(clo, SmagorinskyLilly):      # viscosity(::SmagorinskyLilly / ::AMD, K) = K.νₑ, interpolated to the flux location
         νloc = _ν_at(_FLUXLOC[(comp, d)], νe)
         return lambda i, j, k, grid, u, v, w: -2 * (νloc(i, j, k, grid) * Σ(i, j, k, grid, u, v, w))
 
@@ -191,7 +191,7 @@ def div_τ(comp, i, j, k, grid, clo, u, v, w, νe=None):
     return 1 / grid.V(i, j, k, *loc) * (terms[0] + terms[1] + terms[2])
 
 
-def div_q(i, j, k, grid, clo, κ, c, νe=None):
+def div_q(i, j, k, grid, clo, κ, c, νe=None, κe_field=None):
     """∇_dot_qᶜ (closure_kernel_operators.jl:43-48) with diffusive_flux_{x,y,z} =
     -κ ∂c (abstract_scalar_diffusivity_closure.jl:205-207).  SmagorinskyLilly: κ is the Prandtl number and the
     diffusivity κₑ = νₑ / Pr (an operation evaluated at cell centres, smagorinsky_lilly.jl:205-221) is interpolated
@@ -205,7 +205,11 @@ def div_q(i, j, k, grid, clo, κ, c, νe=None):
     for d in range(3):
         active = (form == THREE_D) or (form == HORIZONTAL and d < 2) or (form == VERTICAL and d == 2)
         A = area(d, *locs[d])
-        if isinstance(clo, SmagorinskyLilly):
+        if κe_field is not None:        # AnisotropicMinimumDissipation: diffusivity(::AMD, K, id) = K.κₑ[id], a cell-centred field
+            D = deriv(d, *locs[d])
+            κloc = (Ixf, Iyf, Izf)[d]
+            fl = lambda i, j, k, grid, A=A, D=D, κloc=κloc: A(i, j, k, grid) * (-κloc(i, j, k, grid, κe_field) * D(i, j, k, grid, c))
+        elif isinstance(clo, SmagorinskyLilly):
             D = deriv(d, *locs[d])
             κe = lambda i, j, k, grid: νe[i, j, k] / κ
             κloc = (Ixf, Iyf, Izf)[d]
@@ -217,3 +221,152 @@ def div_q(i, j, k, grid, clo, κ, c, νe=None):
             fl = lambda i, j, k, grid, A=A: A(i, j, k, grid) * grid.FT(0)
         terms.append(DELTA[C][d](i, j, k, grid, fl))
     return 1 / grid.V(i, j, k, C, C, C) * (terms[0] + terms[1] + terms[2])
+
+
+# ---- AnisotropicMinimumDissipation (anisotropic_minimum_dissipation.jl:180-359, velocity_tracer_gradients.jl:120-242) ------
+class AnisotropicMinimumDissipation:
+    """AnisotropicMinimumDissipation(FT; C=1/12, Cν=nothing, Cκ=nothing, Cb=nothing) (anisotropic_minimum_dissipation.jl:96-105):
+    νₑ = max(0, -Cν δ² (r - Cb ζ) / q), κₑ = max(0, -Cκ δ² ϑ / σ) per tracer, recomputed in update_state!.  Constant
+    Poincaré constants only (numbers, or a dict per tracer for Cκ)."""
+    formulation = THREE_D
+
+    def __init__(self, C=1 / 12, Cν=None, Cκ=None, Cb=None):
+        self.Cν = C if Cν is None else Cν
+        self.Cκ = C if Cκ is None else Cκ
+        self.Cb = Cb
+        self.required_halo = 1
+
+    def Ck(self, name):
+        return self.Cκ[name] if isinstance(self.Cκ, dict) else self.Cκ
+
+
+def _Δf(d):
+    """Δᶠx / Δᶠy / Δᶠz at ANY location are the ccc ones evaluated at the index passed (:255-267): 2 Δᶜ"""
+    return lambda i, j, k, grid: 2 * grid.spacing(d, C, (i, j, k)[d])
+
+
+_Δfx, _Δfy, _Δfz = _Δf(0), _Δf(1), _Δf(2)
+# plain gradients at their natural locations (velocity_tracer_gradients.jl:6-22)
+_dx_u = lambda i, j, k, g, u, v, w: deriv(0, C, C, C)(i, j, k, g, u)
+_dy_v = lambda i, j, k, g, u, v, w: deriv(1, C, C, C)(i, j, k, g, v)
+_dz_w = lambda i, j, k, g, u, v, w: deriv(2, C, C, C)(i, j, k, g, w)
+_dx_v = lambda i, j, k, g, u, v, w: deriv(0, F, F, C)(i, j, k, g, v)
+_dy_u = lambda i, j, k, g, u, v, w: deriv(1, F, F, C)(i, j, k, g, u)
+_dx_w = lambda i, j, k, g, u, v, w: deriv(0, F, C, C)(i, j, k, g, w)          # ∂x_w = ∂xᶠᶜᶜ (velocity_tracer_gradients.jl:16)
+_dz_u = lambda i, j, k, g, u, v, w: deriv(2, F, C, F)(i, j, k, g, u)
+_dy_w = lambda i, j, k, g, u, v, w: deriv(1, C, F, C)(i, j, k, g, w)
+_dz_v = lambda i, j, k, g, u, v, w: deriv(2, C, F, F)(i, j, k, g, v)
+# normalised gradients (:125-149)
+n_dx_u, n_dy_v, n_dz_w = _dx_u, _dy_v, _dz_w
+n_dx_v = lambda i, j, k, g, u, v, w: _Δfx(i, j, k, g) / _Δfy(i, j, k, g) * _dx_v(i, j, k, g, u, v, w)
+n_dy_u = lambda i, j, k, g, u, v, w: _Δfy(i, j, k, g) / _Δfx(i, j, k, g) * _dy_u(i, j, k, g, u, v, w)
+n_dx_w = lambda i, j, k, g, u, v, w: _Δfx(i, j, k, g) / _Δfz(i, j, k, g) * _dx_w(i, j, k, g, u, v, w)
+n_dz_u = lambda i, j, k, g, u, v, w: _Δfz(i, j, k, g) / _Δfx(i, j, k, g) * _dz_u(i, j, k, g, u, v, w)
+n_dy_w = lambda i, j, k, g, u, v, w: _Δfy(i, j, k, g) / _Δfz(i, j, k, g) * _dy_w(i, j, k, g, u, v, w)
+n_dz_v = lambda i, j, k, g, u, v, w: _Δfz(i, j, k, g) / _Δfy(i, j, k, g) * _dz_v(i, j, k, g, u, v, w)
+n_S11, n_S22, n_S33 = n_dx_u, n_dy_v, n_dz_w
+n_S12 = lambda i, j, k, g, u, v, w: g.FT(0.5) * (n_dy_u(i, j, k, g, u, v, w) + n_dx_v(i, j, k, g, u, v, w))
+n_S13 = lambda i, j, k, g, u, v, w: g.FT(0.5) * (n_dz_u(i, j, k, g, u, v, w) + n_dx_w(i, j, k, g, u, v, w))
+n_S23 = lambda i, j, k, g, u, v, w: g.FT(0.5) * (n_dz_v(i, j, k, g, u, v, w) + n_dy_w(i, j, k, g, u, v, w))
+
+
+def _prod(a, b):
+    return lambda i, j, k, g, u, v, w: a(i, j, k, g, u, v, w) * b(i, j, k, g, u, v, w)
+
+
+def _Ixy(i, j, k, g, f, *a):      # ℑxyᶜᶜᵃ = ℑyᵃᶜᵃ(ℑxᶜᵃᵃ)
+    return Iyc(i, j, k, g, Ixc, f, *a)
+
+
+def _Ixz(i, j, k, g, f, *a):      # ℑxzᶜᵃᶜ = ℑzᵃᵃᶜ(ℑxᶜᵃᵃ)
+    return Izc(i, j, k, g, Ixc, f, *a)
+
+
+def _Iyz(i, j, k, g, f, *a):      # ℑyzᵃᶜᶜ = ℑzᵃᵃᶜ(ℑyᵃᶜᵃ)
+    return Izc(i, j, k, g, Iyc, f, *a)
+
+
+def amd_norm_tr_grad_u(i, j, k, g, u, v, w):
+    """norm_tr_∇uᶜᶜᶜ (:315-328)"""
+    a = (u, v, w)
+    return (n_dx_u(i, j, k, g, *a) ** 2 + n_dy_v(i, j, k, g, *a) ** 2 + n_dz_w(i, j, k, g, *a) ** 2
+            + _Ixy(i, j, k, g, _sq(n_dx_v), *a) + _Ixy(i, j, k, g, _sq(n_dy_u), *a)
+            + _Ixz(i, j, k, g, _sq(n_dx_w), *a) + _Ixz(i, j, k, g, _sq(n_dz_u), *a)
+            + _Iyz(i, j, k, g, _sq(n_dy_w), *a) + _Iyz(i, j, k, g, _sq(n_dz_v), *a))
+
+
+def amd_r(i, j, k, g, u, v, w):
+    """norm_uᵢₐ_uⱼₐ_Σᵢⱼᶜᶜᶜ (:269-313), term order kept"""
+    a = (u, v, w)
+    q = (i, j, k, g)
+    t1 = (n_S11(*q, *a) * n_dx_u(*q, *a) ** 2
+          + n_S22(*q, *a) * _Ixy(*q, _sq(n_dx_v), *a)
+          + n_S33(*q, *a) * _Ixz(*q, _sq(n_dx_w), *a)
+          + 2 * n_dx_u(*q, *a) * _Ixy(*q, _prod(n_dx_v, n_S12), *a)
+          + 2 * n_dx_u(*q, *a) * _Ixz(*q, _prod(n_dx_w, n_S13), *a)
+          + 2 * _Ixy(*q, n_dx_v, *a) * _Ixz(*q, n_dx_w, *a) * _Iyz(*q, n_S23, *a))
+    t2 = (+ n_S11(*q, *a) * _Ixy(*q, _sq(n_dy_u), *a)
+          + n_S22(*q, *a) * n_dy_v(*q, *a) ** 2
+          + n_S33(*q, *a) * _Iyz(*q, _sq(n_dy_w), *a)
+          + 2 * n_dy_v(*q, *a) * _Ixy(*q, _prod(n_dy_u, n_S12), *a)
+          + 2 * _Ixy(*q, n_dy_u, *a) * _Iyz(*q, n_dy_w, *a) * _Ixz(*q, n_S13, *a)
+          + 2 * n_dy_v(*q, *a) * _Iyz(*q, _prod(n_dy_w, n_S23), *a))
+    t3 = (+ n_S11(*q, *a) * _Ixz(*q, _sq(n_dz_u), *a)
+          + n_S22(*q, *a) * _Iyz(*q, _sq(n_dz_v), *a)
+          + n_S33(*q, *a) * n_dz_w(*q, *a) ** 2
+          + 2 * _Ixz(*q, n_dz_u, *a) * _Iyz(*q, n_dz_v, *a) * _Ixy(*q, n_S12, *a)
+          + 2 * n_dz_w(*q, *a) * _Ixz(*q, _prod(n_dz_u, n_S13), *a)
+          + 2 * n_dz_w(*q, *a) * _Iyz(*q, _prod(n_dz_v, n_S23), *a))
+    return t1 + t2 + t3
+
+
+def _amd_δ2(i, j, k, g):
+    return 3 / (1 / _Δfx(i, j, k, g) ** 2 + 1 / _Δfy(i, j, k, g) ** 2 + 1 / _Δfz(i, j, k, g) ** 2)
+
+
+def amd_viscosity(i, j, k, g, clo, bp, u, v, w):
+    """calc_νᶜᶜᶜ (:180-199); bp(i, j, k, grid) is buoyancy_perturbation, or None (then the Cb term is zero, :330)"""
+    FT = g.FT
+    a = (u, v, w)
+    q = amd_norm_tr_grad_u(i, j, k, g, *a)
+    r = amd_r(i, j, k, g, *a)
+    if clo.Cb is None or bp is None:
+        Cbζ = FT(0) * r
+    else:                      # Cb_norm_wᵢ_bᵢᶜᶜᶜ (:332-345) / Δᶠz
+        dxb = lambda i, j, k, g: deriv(0, F, C, C)(i, j, k, g, bp)
+        dyb = lambda i, j, k, g: deriv(1, C, F, C)(i, j, k, g, bp)
+        dzb = lambda i, j, k, g: deriv(2, C, C, F)(i, j, k, g, bp)
+        wx = _Ixz(i, j, k, g, n_dx_w, *a) * _Δfx(i, j, k, g) * Ixc(i, j, k, g, dxb)
+        wy = _Iyz(i, j, k, g, n_dy_w, *a) * _Δfy(i, j, k, g) * Iyc(i, j, k, g, dyb)
+        wz = n_dz_w(i, j, k, g, *a) * _Δfz(i, j, k, g) * Izc(i, j, k, g, dzb)
+        Cbζ = FT(clo.Cb) * (wx + wy + wz) / _Δfz(i, j, k, g)
+    δ2 = _amd_δ2(i, j, k, g)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ν = np.where(q == 0, FT(0), -FT(clo.Cν) * δ2 * (r - Cbζ) / q)
+    return np.maximum(FT(0), ν)
+
+
+def amd_diffusivity(i, j, k, g, Cκ, u, v, w, c):
+    """calc_κᶜᶜᶜ (:201-220) with norm_θᵢ²ᶜᶜᶜ (:374-376) and norm_uᵢⱼ_cⱼ_cᵢᶜᶜᶜ (:347-372)"""
+    FT = g.FT
+    a = (u, v, w)
+    ncx = lambda i, j, k, g: _Δfx(i, j, k, g) * deriv(0, F, C, C)(i, j, k, g, c)
+    ncy = lambda i, j, k, g: _Δfy(i, j, k, g) * deriv(1, C, F, C)(i, j, k, g, c)
+    ncz = lambda i, j, k, g: _Δfz(i, j, k, g) * deriv(2, C, C, F)(i, j, k, g, c)
+    sq1 = lambda f: (lambda i, j, k, g: f(i, j, k, g) ** 2)
+    q = (i, j, k, g)
+    σ = Ixc(*q, sq1(ncx)) + Iyc(*q, sq1(ncy)) + Izc(*q, sq1(ncz))
+    cx = (n_dx_u(*q, *a) * Ixc(*q, sq1(ncx))
+          + _Ixy(*q, n_dx_v, *a) * Ixc(*q, ncx) * Iyc(*q, ncy)
+          + _Ixz(*q, n_dx_w, *a) * Ixc(*q, ncx) * Izc(*q, ncz))
+    cy = (_Ixy(*q, n_dy_u, *a) * Iyc(*q, ncy) * Ixc(*q, ncx)
+          + n_dy_v(*q, *a) * Iyc(*q, sq1(ncy))
+          + _Ixz(*q, n_dy_w, *a) * Iyc(*q, ncy) * Izc(*q, ncz))
+    cz = (_Ixz(*q, n_dz_u, *a) * Izc(*q, ncz) * Ixc(*q, ncx)
+          + _Iyz(*q, n_dz_v, *a) * Izc(*q, ncz) * Iyc(*q, ncy)
+          + n_dz_w(*q, *a) * Izc(*q, sq1(ncz)))
+    ϑ = cx + cy + cz
+    δ2 = _amd_δ2(i, j, k, g)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        κ = np.where(σ == 0, FT(0), -FT(Cκ) * δ2 * ϑ / σ)
+    return np.maximum(FT(0), κ)

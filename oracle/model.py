@@ -16,7 +16,8 @@ from .grids import Periodic, Bounded, Flat, Center as C, Face as F
 from .fields import Field, FieldBoundaryConditions, fill_halo_regions, apply_flux_bcs, R
 from .operators import deriv, div_ccc, Ixy_fca, Ixy_cfa, Izf
 from .advection import div_Uu, div_Uc
-from .closures import div_τ, div_q, SmagorinskyLilly, smagorinsky_viscosity
+from .closures import (div_τ, div_q, SmagorinskyLilly, smagorinsky_viscosity, AnisotropicMinimumDissipation,
+                       amd_viscosity, amd_diffusivity)
 from .solvers import FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver
 
 
@@ -136,7 +137,11 @@ class NonhydrostaticModel:
         else:
             self.pressure_solver = FourierTridiagonalPoissonSolver(grid)
         # DiffusivityFields (smagorinsky_lilly.jl:205-221): νₑ at ccc with default boundary conditions
-        self.νe = Field(grid, (C, C, C), FieldBoundaryConditions(grid, (C, C, C))) if isinstance(closure, SmagorinskyLilly) else None
+        les = isinstance(closure, (SmagorinskyLilly, AnisotropicMinimumDissipation))
+        self.νe = Field(grid, (C, C, C), FieldBoundaryConditions(grid, (C, C, C))) if les else None
+        # AMD: one eddy diffusivity field per tracer (anisotropic_minimum_dissipation.jl:378-389)
+        self.κe = ({n: Field(grid, (C, C, C), FieldBoundaryConditions(grid, (C, C, C))) for n in self.tracer_names}
+                   if isinstance(closure, AnisotropicMinimumDissipation) else None)
         self.timestepper = timestepper
         self.Gn = {n: Field(grid, self.fields[n].loc) for n in self.names}
         self.Gm = {n: Field(grid, self.fields[n].loc) for n in self.names}
@@ -195,6 +200,13 @@ class NonhydrostaticModel:
                 dT = (lambda i, j, k, grid: dz(i, j, k, grid, self.tracers["T"])) if "T" in req else zero
                 dS = (lambda i, j, k, grid: dz(i, j, k, grid, self.tracers["S"])) if "S" in req else zero
                 dz_b = lambda i, j, k, grid: gr * (al * dT(i, j, k, grid) - be * dS(i, j, k, grid))
+        if isinstance(self.closure, AnisotropicMinimumDissipation):
+            bp = buoyancy_perturbation(self.buoyancy.model, self.tracers, g.FT) if self.buoyancy is not None else None
+            self.νe[i, j, k] = amd_viscosity(i, j, k, g, self.closure, bp, u, v, w)
+            for n in self.tracer_names:
+                self.κe[n][i, j, k] = amd_diffusivity(i, j, k, g, self.closure.Ck(n), u, v, w, self.tracers[n])
+            fill_halo_regions([self.νe] + [self.κe[n] for n in self.tracer_names])
+            return
         self.νe[i, j, k] = smagorinsky_viscosity(i, j, k, g, self.closure, dz_b, u, v, w)
         fill_halo_regions(self.νe)
 
@@ -268,10 +280,11 @@ class NonhydrostaticModel:
         self.Gn["w"][i, j, k] = Gw
         for name in self.tracer_names:
             c = self.tracers[name]
-            κ = 0 if clo is None else (clo.prandtl(name) if isinstance(clo, SmagorinskyLilly) else clo.kappa(name))
+            amd = isinstance(clo, AnisotropicMinimumDissipation)
+            κ = 0 if (clo is None or amd) else (clo.prandtl(name) if isinstance(clo, SmagorinskyLilly) else clo.kappa(name))
             # :225-231
             Gc = (- div_Uc(i, j, k, g, adv, U, c) - zero - zero
-                  - div_q(i, j, k, g, clo, κ, c, self.νe)
+                  - div_q(i, j, k, g, clo, κ, c, self.νe, self.κe[name] if amd else None)
                   - zero
                   + zero)
             self.Gn[name][i, j, k] = Gc

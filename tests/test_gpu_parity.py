@@ -265,6 +265,17 @@ CONFIGS = {
     "smagorinsky_2d_flat": dict(size=(16, 12), topology=(O.Periodic, O.Bounded, O.Flat), extent=(1, 1),
                                 adv="UpwindBiasedThirdOrder", tracers=("c",), buoyancy=False, smagorinsky=dict(Pr=0.5),
                                 ts="RungeKutta3", dt=2e-3),
+    # AnisotropicMinimumDissipation (the closure of the C3 source example, ocean_wind_mixing_and_convection.jl:151): C3 physics
+    # with AMD instead of ScalarDiffusivity; with the buoyancy modification Cb and per-tracer Poincaré constants; seawater
+    "amd_c3_stretched_weno": dict(size=(12, 8, 14), topology=(O.Periodic, O.Periodic, O.Bounded),
+                                  coords=dict(x=(0, 1), y=(0, 1), z=_zf(14)), adv="WENO5grid", tracers=("b",), buoyancy=True,
+                                  amd={}, f=1e-2, ts="RungeKutta3", dt=5e-3,
+                                  bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"top": ("Flux", 1e-4), "bottom": ("Gradient", 1e-2)}}),
+    "amd_Cb_bounded": dict(size=(8, 10, 12), topology=(O.Periodic, O.Bounded, O.Bounded), extent=(1, 2, 1),
+                           adv="CenteredSecondOrder", tracers=("b", "c"), buoyancy=True,
+                           amd=dict(Cν=0.1, Cκ={"b": 0.08, "c": 0.2}, Cb=1.0), ts="QuasiAdamsBashforth2", dt=2e-3),
+    "amd_seawater_periodic": dict(size=(32, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="WENO5", tracers=("T", "S"),
+                                  seawater=dict(eos=(0.3, 0.2)), amd=dict(C=1 / 6, Cb=0.5), ts="RungeKutta3", dt=2e-3),
     "seawater_S_only": dict(size=(8, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="UpwindBiasedFifthOrder",
                             tracers=("S", "c"), seawater=dict(constant_temperature=True, eos=(0.3, 0.2)),
                             ts="RungeKutta3", dt=2e-3),
@@ -288,6 +299,8 @@ def build_models(ob, cfg, FT):
         clo_o, clo_b = O.ScalarDiffusivity(form, ν=nu, κ=ka), ob.ScalarDiffusivity(form, ν=nu, κ=ka)
     if cfg.get("smagorinsky") is not None:
         clo_o, clo_b = O.SmagorinskyLilly(**cfg["smagorinsky"]), ob.SmagorinskyLilly(**cfg["smagorinsky"])
+    if cfg.get("amd") is not None:
+        clo_o, clo_b = O.AnisotropicMinimumDissipation(**cfg["amd"]), ob.AnisotropicMinimumDissipation(**cfg["amd"])
     cor_o = O.FPlane(cfg["f"]) if cfg.get("f") else None
     cor_b = ob.FPlane(cfg["f"]) if cfg.get("f") else None
     bu_o = bu_b = None
@@ -347,6 +360,9 @@ def test_tendencies_and_steps_match_oracle_f64(ob, name):
         assert relerr(mb.pressures["pHY′"].interior(), mo.pHY.interior) < 1e-13
     if getattr(mo, "νe", None) is not None:          # the eddy viscosity of the LES closure, halos included
         assert relerr(mb.diffusivity_fields["νₑ"].parent(), mo.νe.parent) < 1e-12
+        if getattr(mo, "κe", None) is not None:
+            for n in mo.tracer_names:
+                assert relerr(mb.diffusivity_fields["κₑ"][n].parent(), mo.κe[n].parent) < 1e-12, n
     # tendencies alone
     mo.calculate_tendencies()
     ob.calculate_tendencies(mb)

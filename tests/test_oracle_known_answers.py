@@ -439,3 +439,26 @@ def test_smagorinsky_dissipates_kinetic_energy_and_conserves_tracer():
         m.time_step(2e-3)
     assert m.kinetic_energy() < ke0
     assert abs(float(np.mean(m.tracers["c"].interior)) - c0) < 1e-14
+
+
+# ---- AnisotropicMinimumDissipation (anisotropic_minimum_dissipation.jl:180-220) -----------------------------------------------
+def test_amd_known_answers():
+    """(1) AMD switches itself off in laminar shear (u = S y): r = 0, so nu_e = 0 although q > 0.
+    (2) axisymmetric strain u = x, v = y, w = -2 z on cubic cells of size D: q = 6, r = 1 + 1 - 8 = -6, delta^2 = 4 D^2, so
+    nu_e = C_nu 4 D^2; a tracer c = gamma z in that flow: sigma = (2 D gamma)^2, theta = -2 sigma, so kappa_e = 8 C_kappa D^2."""
+    g = O.RectilinearGrid(np.float64, size=(8, 8, 8), x=(0, 1), y=(0, 1), z=(-1, 0), topology=(O.Bounded,) * 3)
+    D = 1 / 8
+    mk = lambda: O.NonhydrostaticModel(g, advection=O.CenteredSecondOrder(), closure=O.AnisotropicMinimumDissipation(Cν=1 / 12, Cκ=1 / 6),
+                                       tracers=("c",))
+    m = mk()
+    yc = g.nodes(("f", "c", "c"))[1]
+    m.set(enforce_incompressibility=False, u=0.7 * yc + np.zeros((9, 8, 8)))
+    assert np.all(m.νe.interior[2:-2, 2:-2, 2:-2] == 0)
+    m = mk()
+    xf, yf, zf = g.nodes(("f", "c", "c"))[0], g.nodes(("c", "f", "c"))[1], g.nodes(("c", "c", "f"))[2]
+    zc = g.nodes(("c", "c", "c"))[2]
+    m.set(enforce_incompressibility=False, u=xf + np.zeros((9, 8, 8)), v=yf + np.zeros((8, 9, 8)), w=-2 * zf + np.zeros((8, 8, 9)),
+          c=0.3 * zc + np.zeros((8, 8, 8)))
+    inner = (slice(2, -2),) * 3
+    assert np.allclose(m.νe.interior[inner], (1 / 12) * 4 * D * D, rtol=1e-12)
+    assert np.allclose(m.κe["c"].interior[inner], 8 * (1 / 6) * D * D, rtol=1e-12)
