@@ -652,6 +652,7 @@ struct ob200_model {
     std::unique_ptr<ob200_field> pNHS, pHY;
     std::unique_ptr<ob200_field> nue;               // SmagorinskyLilly / AMD eddy viscosity (diffusivity_fields.νₑ)
     std::vector<std::unique_ptr<ob200_field>> kappae;     // AMD eddy diffusivities (diffusivity_fields.κₑ), one per tracer
+    std::unique_ptr<ob200_field> ivd_scratch;             // Thomas scratch of the vertically implicit diffusion step
     std::unique_ptr<ob200_poisson> solver;
     std::vector<void*> owned;
     Phys<float> P32;
@@ -697,6 +698,7 @@ static void build_phys(ob200_model* m) {
             }
         }
     P.closure = D.closure;
+    P.vitd = D.closure_vertically_implicit;
     P.nu = (FT)D.nu;
     for (int t = 0; t < 8; ++t) P.kappa[t] = (FT)(D.closure == OB200_CLOSURE_SMAGORINSKY_LILLY ? D.prandtl[t] : D.kappa[t]);
     P.smagC = (FT)D.smagorinsky_C; P.smagCb = (FT)D.smagorinsky_Cb;
@@ -721,6 +723,13 @@ extern "C" int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model*
     if (desc->ntracers < 0 || desc->ntracers > OB200_MAX_TRACERS) throw Error("too many tracers");
     if (desc->advection < 0 || desc->advection > OB200_ADV_WENO5) throw Error("unsupported advection scheme");
     if (desc->closure < 0 || desc->closure > OB200_CLOSURE_AMD) throw Error("unsupported closure");
+    if (desc->closure_vertically_implicit) {
+        // implicit_diffusion_solver (vertically_implicit_diffusion_solver.jl:95-108) + the supported set of this library
+        if (desc->closure != OB200_CLOSURE_3D && desc->closure != OB200_CLOSURE_VERTICAL)
+            throw Error("VerticallyImplicitTimeDiscretization is supported for ScalarDiffusivity (ThreeDimensional / Vertical) only");
+        if (desc->grid->desc.topology[2] != OB200_BOUNDED)
+            throw Error("VerticallyImplicitTimeDiscretization can only be specified on grids that are Bounded in the z-direction.");
+    }
     if (desc->closure == OB200_CLOSURE_SMAGORINSKY_LILLY)
         for (int t = 0; t < desc->ntracers; ++t)
             if (!(desc->prandtl[t] > 0)) throw Error("SmagorinskyLilly needs a positive Prandtl number for every tracer");
@@ -757,6 +766,7 @@ extern "C" int32_t ob200_model_create(const ob200_model_desc* desc, ob200_model*
         m->nue.reset(make_field(m->grid, ccc, nullptr, false));
     if (desc->closure == OB200_CLOSURE_AMD)
         for (int t = 0; t < desc->ntracers; ++t) m->kappae.emplace_back(make_field(m->grid, ccc, nullptr, false));
+    if (desc->closure_vertically_implicit) m->ivd_scratch.reset(make_field(m->grid, ccc, nullptr, false));
     ob200_poisson* s = nullptr;
     if (ob200_poisson_create(m->grid, desc->pressure_solver, &s)) throw Error(ob::g_err);
     m->solver.reset(s);
@@ -993,6 +1003,18 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
         for (int q = 0; q < m->nf; ++q) std::swap(m->F[q]->base, m->F[q]->alt);
     }
 }
+// implicit_step! of every prognostic field right after its substep (runge_kutta_3.jl:178-185, quasi_adams_bashforth_2.jl:137-144)
+template <class FT>
+static void model_implicit_step(ob200_model* m, FT dt) {
+    if (!m->desc.closure_vertically_implicit) return;
+    ScopedPhase ph("closure");
+    const GridD<FT>& g = gridD<FT>(m->grid);
+    Phys<FT>& P = physOf<FT>(m);
+    for (int q = 0; q < m->nf; ++q)
+        launch_implicit_vertical_diffusion<FT>(g, m->F[q]->template p0<FT>(), m->ivd_scratch->template p0<FT>(),
+                                               q < 3 ? P.nu : P.kappa[q - 3], dt, q == 2);
+}
+
 extern "C" int32_t ob200_model_calculate_tendencies(ob200_model* m) {
     API_BEGIN
     if (m->grid->ftype == OB200_F32) { Substep<float> s{SUB_NONE, 0, 0, 0}; model_tendencies<float>(m, s); }
@@ -1050,6 +1072,7 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
         const bool fused = model_fused_periodic<FT>(m);
         for (int s = 0; s < 3; ++s) {
             model_tendencies<FT>(m, ss[s]);
+            model_implicit_step<FT>(m, sdt[s]);
             const bool hy = fused && model_hydrostatic_async_begin<FT>(m);
             model_pressure_step<FT>(m, sdt[s], true, fused);
             m->time += (double)sdt[s];
@@ -1070,6 +1093,7 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
         Substep<FT> ss{SUB_AB2, dt, FT(1.5) + chi, FT(0.5) + chi};
         const bool fused = model_fused_periodic<FT>(m);
         model_tendencies<FT>(m, ss);
+        model_implicit_step<FT>(m, dt);
         const bool hy = fused && model_hydrostatic_async_begin<FT>(m);
         model_pressure_step<FT>(m, dt, true, fused);
         for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);

@@ -67,6 +67,9 @@ namespace fz { template <class FT> int launch(const Phys<FT>& P, const FusedFiel
 template <class FT>
 void launch_smagorinsky(const Phys<FT>& P, const Buoy<FT>& B, const FT* u, const FT* v, const FT* w, FT* nue);
 
+// vertically implicit diffusion step of one field, in place (scratch: a field-sized buffer for the Thomas coefficients)
+template <class FT>
+void launch_implicit_vertical_diffusion(const GridD<FT>& g, FT* field_p0, FT* scratch_p0, FT kappa, FT dt, bool z_face);
 // AnisotropicMinimumDissipation: eddy viscosity and the tracers' eddy diffusivities over the interior
 template <class FT>
 void launch_amd(const Phys<FT>& P, const Buoy<FT>& B, const FT* u, const FT* v, const FT* w, FT* nue, int ntr,

@@ -800,6 +800,59 @@ __global__ void __launch_bounds__(128) smagorinsky_kernel(const __grid_constant_
     const FT* U[3] = {u, v, w};
     nue[q.p] = smagorinsky_nu(P, B, U, q);
 }
+// implicit_step! (vertically_implicit_diffusion_solver.jl:153-195) = solve!(field, ::BatchedTridiagonalSolver, field, ...)
+// (batched_tridiagonal_solver.jl:91-122) with the coefficient functions ivd_lower_diagonal / ivd_diagonal / ivd_upper_diagonal
+// (:27-72) evaluated on the fly for a constant diffusivity: one (i, j) column per thread, in place, k = 1 .. Nz.
+// ZFACE: the field lives at z Faces (w): the reference's Face variants of the coefficients.
+template <class FT, bool ZFACE>
+__global__ void __launch_bounds__(128) ivd_kernel(GridD<FT> g, FT* f, FT* t, FT kappa, FT dt) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+    if (i > g.N[0]) return;
+    const long long p = i * g.st[0] + j * g.st[1], sz = g.st[2];
+    const int Nz = g.N[2];
+    auto dzc = [&](int k) { return spacing(g, 2, OB_C, k); };
+    auto dzf = [&](int k) { return spacing(g, 2, OB_F, k); };
+    auto kdz2 = [&](int kc, int kf) { return kappa / dzc(kc) / dzf(kf); };          // κ_Δz²
+    auto upper = [&](int k) -> FT {
+        if (ZFACE) return k < 1 ? FT(0) : -dt * kdz2(k, k);
+        return k > Nz - 1 ? FT(0) : -dt * kdz2(k, k + 1);
+    };
+    auto lower = [&](int k) -> FT {
+        if (k < 1) return FT(0);
+        return ZFACE ? -dt * kdz2(k + 1, k) : -dt * kdz2(k + 1, k + 1);
+    };
+    auto diag = [&](int k) -> FT { return FT(1) - dt * FT(0) - upper(k) - lower(k - 1); };
+    const FT eps10 = 10 * (sizeof(FT) == 4 ? FT(1.1920928955078125e-07) : FT(2.220446049250313e-16));
+    FT beta = diag(1);
+    FT prev = f[p + sz] / beta;
+    f[p + sz] = prev;
+    for (int k = 2; k <= Nz; ++k) {
+        const FT ck = upper(k - 1), bk = diag(k), ak = lower(k - 1);
+        const FT tk = ck / beta;
+        t[p + k * sz] = tk;
+        beta = bk - ak * tk;
+        if (!(fabs(beta) > eps10)) break;
+        const FT r = (f[p + k * sz] - ak * prev) / beta;
+        f[p + k * sz] = r;
+        prev = r;
+    }
+    FT nxt = f[p + (long long)Nz * sz];
+    for (int k = Nz - 1; k >= 1; --k) {
+        const FT v = f[p + k * sz] - t[p + (k + 1) * sz] * nxt;
+        f[p + k * sz] = v;
+        nxt = v;
+    }
+}
+template <class FT>
+void launch_implicit_vertical_diffusion(const GridD<FT>& g, FT* field_p0, FT* scratch_p0, FT kappa, FT dt, bool z_face) {
+    dim3 blk(64), grd(cdiv(g.N[0], 64), g.N[1]);
+    if (z_face) ivd_kernel<FT, true><<<grd, blk, 0, stream()>>>(g, field_p0, scratch_p0, kappa, dt);
+    else ivd_kernel<FT, false><<<grd, blk, 0, stream()>>>(g, field_p0, scratch_p0, kappa, dt);
+    OB_LAUNCH_CHECK();
+}
+template void launch_implicit_vertical_diffusion<float>(const GridD<float>&, float*, float*, float, float, bool);
+template void launch_implicit_vertical_diffusion<double>(const GridD<double>&, double*, double*, double, double, bool);
+
 // calculate_nonlinear_viscosity! + calculate_nonlinear_tracer_diffusivity! for AnisotropicMinimumDissipation
 // (anisotropic_minimum_dissipation.jl:222-251): νₑ and every tracer's κₑ over the interior in one launch
 template <class FT>

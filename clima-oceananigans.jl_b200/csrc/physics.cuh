@@ -44,6 +44,7 @@ struct Phys {
     int scheme, zweno, buffer;       // buffer = Nᴮ of the scheme (Advection.jl:36-40)
     const FT* wc[3][2];              // stretched WENO tables [dim][0 = Face, 1 = Center] or null
     int closure;
+    int vitd;                        // VerticallyImplicitTimeDiscretization (ScalarDiffusivity, Bounded z): see viscous_Aflux
     FT nu, kappa[8];                 // ScalarDiffusivity constants; SmagorinskyLilly: kappa[t] = Prandtl number of tracer t
     const FT* nue;                   // SmagorinskyLilly / AMD: eddy viscosity at cell centres (Julia-(0,0,0) pointer), halos filled
     FT smagC, smagCb;
@@ -421,6 +422,12 @@ OBD FT viscous_Aflux(const Phys<FT>& P, int comp, int dir, const FT* const* U, P
     if (comp != dir) { fl[comp] = OB_F; fl[dir] = OB_F; }
     FT Ar = areaA(g, dir, q, fl[0], fl[1], fl[2]);
     FT fx = FT(0);
+    if (P.vitd && dir == 2 && !(q.i[2] == 1 || q.i[2] == g.N[2] + 1)) {
+        // vertically implicit diffusion on a Bounded z (abstract_scalar_diffusivity_closure.jl:232-249): away from the two
+        // boundary indices only the part of the z flux that has no z derivative stays explicit: -ν ∂x w (u), -ν ∂y w (v), 0 (w)
+        if (comp < 2) fx = -(P.nu * deriv(g, U[2], q, comp, OB_F));
+        return Ar * fx;
+    }
     if (P.closure == CLO_3D) {
         fx = -2 * (P.nu * strain(g, comp, dir, U, q));
     } else if (P.closure == CLO_SMAG || P.closure == CLO_AMD) {      // viscosity(closure, K) = K.νₑ (smagorinsky_lilly.jl:23, anisotropic_minimum_dissipation.jl:24)
@@ -468,6 +475,8 @@ OBD FT diffusive_Aflux(const Phys<FT>& P, int d, FT kappa, const FT* c, Pt q, co
         return Ar * (-kl * deriv(g, c, q, d, OB_F));
     }
     bool active = P.closure == CLO_3D || (P.closure == CLO_H && d < 2) || (P.closure == CLO_V && d == 2);
+    // vertically implicit diffusion: the explicit z flux only at k == 1 and k == Nz + 1 (:251-255)
+    if (P.vitd && d == 2 && !(q.i[2] == 1 || q.i[2] == g.N[2] + 1)) active = false;
     return active ? Ar * (-kappa * deriv(g, c, q, d, OB_F)) : Ar * FT(0);
 }
 template <class FT>

@@ -23,7 +23,7 @@ using Oceananigans.BoundaryConditions: BoundaryCondition, FieldBoundaryCondition
 using Oceananigans.Advection: CenteredSecondOrder, CenteredFourthOrder, UpwindBiasedFirstOrder, UpwindBiasedThirdOrder,
                               UpwindBiasedFifthOrder, WENO5
 using Oceananigans.TurbulenceClosures: ScalarDiffusivity, SmagorinskyLilly, AnisotropicMinimumDissipation, ThreeDimensionalFormulation, HorizontalFormulation,
-                                       VerticalFormulation, ExplicitTimeDiscretization
+                                       VerticalFormulation, ExplicitTimeDiscretization, VerticallyImplicitTimeDiscretization
 using Oceananigans.Coriolis: FPlane
 using Oceananigans.BuoyancyModels: Buoyancy, BuoyancyTracer, SeawaterBuoyancy, LinearEquationOfState, ZDirection, required_tracers
 using Oceananigans.TimeSteppers: RungeKutta3TimeStepper, QuasiAdamsBashforth2TimeStepper, Clock
@@ -140,6 +140,7 @@ struct ModelDesc
     gravitational_acceleration::Float64; thermal_expansion::Float64; haline_contraction::Float64
     smagorinsky_C::Float64; smagorinsky_Cb::Float64; prandtl::NTuple{MAX_TRACERS,Float64}
     amd_Cnu::Float64; amd_Ckappa::NTuple{MAX_TRACERS,Float64}; amd_Cb::Float64; amd_has_Cb::Int32
+    closure_vertically_implicit::Int32
 end
 
 topo_code(::Type{Periodic}) = Int32(0); topo_code(::Type{Bounded}) = Int32(1); topo_code(::Type{Flat}) = Int32(2)
@@ -272,7 +273,11 @@ adv_code(::WENO5) = 6
 adv_code(a) = throw(ArgumentError("B200(): unsupported advection scheme $(typeof(a))"))
 
 closure_desc(::Nothing, tracers) = (0, 0.0, ntuple(_ -> 0.0, MAX_TRACERS))
-function closure_desc(c::ScalarDiffusivity{<:ExplicitTimeDiscretization, F}, tracers) where F
+# ScalarDiffusivity with either time discretisation (VerticallyImplicit: ThreeDimensional / Vertical formulation on a Bounded z;
+# the library runs the tridiagonal solves itself, so the time stepper's `implicit_solver` stays `nothing`)
+vertically_implicit(::ScalarDiffusivity{<:VerticallyImplicitTimeDiscretization}) = Int32(1)
+vertically_implicit(::Any) = Int32(0)
+function closure_desc(c::ScalarDiffusivity{<:Any, F}, tracers) where F
     (c.ν isa Number && all(κ -> κ isa Number, values(c.κ))) ||
         throw(ArgumentError("B200(): ScalarDiffusivity with constant ν and κ only"))
     code = F <: ThreeDimensionalFormulation ? 1 : F <: HorizontalFormulation ? 2 : 3
@@ -347,7 +352,8 @@ function model_desc(grid, gh; advection, buoyancy, coriolis, closure, tracers, t
     ptr(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
     desc = ModelDesc(gh, ts, χ, adv_code(advection), advection isa WENO5 ? Int32(advection.zweno) : Int32(1),
                      map(ptr, tabs), clo, ν, κ, fplane, f, btr, tilted, ĝ, length(tracers), bcs, 0,
-                     bkind, iT, iS, grav, α, β, smagorinsky_desc(closure, tracers)..., amd_desc(closure, tracers)...)
+                     bkind, iT, iS, grav, α, β, smagorinsky_desc(closure, tracers)..., amd_desc(closure, tracers)...,
+                     vertically_implicit(closure))
     return desc, tabs           # `tabs` must be GC.@preserve'd across ob200_model_create (host pointers are borrowed)
 end
 

@@ -44,7 +44,7 @@ class ModelDesc(C.Structure):
                 ("haline_contraction", C.c_double),
                 ("smagorinsky_C", C.c_double), ("smagorinsky_Cb", C.c_double), ("prandtl", C.c_double * MAX_TRACERS),
                 ("amd_Cnu", C.c_double), ("amd_Ckappa", C.c_double * MAX_TRACERS), ("amd_Cb", C.c_double),
-                ("amd_has_Cb", C.c_int32)]
+                ("amd_has_Cb", C.c_int32), ("closure_vertically_implicit", C.c_int32)]
 
 
 #: every symbol include/ocean_b200.h declares: name -> (restype, argtypes)

@@ -299,9 +299,14 @@ class ScalarDiffusivity:
     """ScalarDiffusivity(formulation; ν, κ) (scalar_diffusivity.jl:60-76), constants only."""
     required_halo = 1
 
-    def __init__(self, formulation="ThreeDimensional", ν=0.0, κ=0.0, nu=None, kappa=None):
+    def __init__(self, formulation="ThreeDimensional", ν=0.0, κ=0.0, nu=None, kappa=None, time_discretization="Explicit"):
         ν = nu if nu is not None else ν
         κ = kappa if kappa is not None else κ
+        if time_discretization not in ("Explicit", "VerticallyImplicit"):
+            raise ValueError("time_discretization must be 'Explicit' or 'VerticallyImplicit'")
+        if time_discretization == "VerticallyImplicit" and formulation == "Horizontal":
+            raise ValueError("VerticallyImplicitTimeDiscretization is not supported for HorizontalScalarDiffusivity")
+        self.time_discretization = time_discretization
         if callable(ν) or callable(κ) or isinstance(ν, np.ndarray):
             raise ValueError("only constant ν, κ are supported on the B200 architecture")
         if formulation not in L.CLOSURE:
@@ -483,6 +488,7 @@ class NonhydrostaticModel:
         else:
             d.closure = L.CLOSURE[closure.formulation] if closure is not None else 0
             if closure is not None:
+                d.closure_vertically_implicit = int(closure.time_discretization == "VerticallyImplicit")
                 d.nu = float(closure.ν)
                 for k, name in enumerate(tracers):
                     d.kappa[k] = float(closure.κ[name] if isinstance(closure.κ, dict) else closure.κ)

@@ -120,6 +120,10 @@ typedef struct {
      * "nu_e" and "kappa_e<k>" are diffusivity_fields.νₑ and diffusivity_fields.κₑ[k]. */
     double  amd_Cnu, amd_Ckappa[OB200_MAX_TRACERS], amd_Cb;
     int32_t amd_has_Cb;
+    /* ScalarDiffusivity(VerticallyImplicitTimeDiscretization(), ...) (TurbulenceClosures/vertically_implicit_diffusion_solver.jl,
+     * abstract_scalar_diffusivity_closure.jl:214-255): 1 = the z-derivative parts of the vertical fluxes are integrated
+     * implicitly by a tridiagonal solve after every substep (ThreeDimensional / Vertical formulation, Bounded z only) */
+    int32_t closure_vertically_implicit;
 } ob200_model_desc;
 
 /* ---- library / device ----------------------------------------------------------------- */

@@ -20,11 +20,19 @@ class ScalarDiffusivity:
     """ScalarDiffusivity(formulation; ν=0, κ=0) (scalar_diffusivity.jl:60-76); κ is a number
     or a dict {tracer name: number}."""
 
-    def __init__(self, formulation=THREE_D, ν=0.0, κ=0.0):
+    def __init__(self, formulation=THREE_D, ν=0.0, κ=0.0, time_discretization="Explicit"):
         self.formulation = formulation
         self.ν = ν
         self.κ = κ
         self.required_halo = 1
+        # ExplicitTimeDiscretization / VerticallyImplicitTimeDiscretization (implicit_explicit_time_discretization.jl)
+        assert time_discretization in ("Explicit", "VerticallyImplicit")
+        assert not (time_discretization == "VerticallyImplicit" and formulation == HORIZONTAL)
+        self.time_discretization = time_discretization
+
+    @property
+    def vitd(self):
+        return self.time_discretization == "VerticallyImplicit"
 
     def kappa(self, name):
         return self.κ[name] if isinstance(self.κ, dict) else self.κ
@@ -144,6 +152,25 @@ def viscous_flux(comp, d, clo, νe=None):
 
     def ν(grid):
         return grid.FT(clo.ν)
+    if getattr(clo, "vitd", False) and d == 2:
+        # VerticallyImplicitTimeDiscretization on a vertically Bounded grid (abstract_scalar_diffusivity_closure.jl:232-255):
+        # the explicit flux only at k == 1 and k == Nz + 1, elsewhere what stays explicit: -ν ∂x w / -ν ∂y w (u, v), 0 (w)
+        import copy
+        ex = copy.copy(clo)
+        ex.time_discretization = "Explicit"
+        explicit = viscous_flux(comp, d, ex, νe)
+        if comp == 0:
+            ivd = lambda i, j, k, grid, u, v, w: -(ν(grid) * deriv(0, F, C, F)(i, j, k, grid, w))
+        elif comp == 1:
+            ivd = lambda i, j, k, grid, u, v, w: -(ν(grid) * deriv(1, C, F, F)(i, j, k, grid, w))
+        else:
+            ivd = lambda i, j, k, grid, u, v, w: grid.FT(0)
+
+        def fl(i, j, k, grid, u, v, w):
+            kk = k.arr(2)
+            edge = (kk == 1) | (kk == grid.Nz + 1)
+            return np.where(edge, explicit(i, j, k, grid, u, v, w), ivd(i, j, k, grid, u, v, w))
+        return fl
     if form == THREE_D:
         return lambda i, j, k, grid, u, v, w: -2 * (ν(grid) * Σ(i, j, k, grid, u, v, w))
     if form == HORIZONTAL:
@@ -214,6 +241,13 @@ def div_q(i, j, k, grid, clo, κ, c, νe=None, κe_field=None):
             κe = lambda i, j, k, grid: νe[i, j, k] / κ
             κloc = (Ixf, Iyf, Izf)[d]
             fl = lambda i, j, k, grid, A=A, D=D, κloc=κloc: A(i, j, k, grid) * (-κloc(i, j, k, grid, κe) * D(i, j, k, grid, c))
+        elif active and d == 2 and getattr(clo, "vitd", False):      # diffusive_flux_z with VITD (:251-255)
+            D = deriv(d, *locs[d])
+
+            def fl(i, j, k, grid, A=A, D=D):
+                kk = k.arr(2)
+                edge = (kk == 1) | (kk == grid.Nz + 1)
+                return A(i, j, k, grid) * np.where(edge, -κ * D(i, j, k, grid, c), grid.FT(0))
         elif active:
             D = deriv(d, *locs[d])
             fl = lambda i, j, k, grid, A=A, D=D: A(i, j, k, grid) * (-κ * D(i, j, k, grid, c))
@@ -370,3 +404,28 @@ def amd_diffusivity(i, j, k, g, Cκ, u, v, w, c):
     with np.errstate(divide="ignore", invalid="ignore"):
         κ = np.where(σ == 0, FT(0), -FT(Cκ) * δ2 * ϑ / σ)
     return np.maximum(FT(0), κ)
+
+
+# ---- vertically implicit diffusion (vertically_implicit_diffusion_solver.jl:19-195) --------------------------------------------
+def ivd_coefficients(grid, Δt, κ, z_face_field):
+    """lower / main / upper diagonals (functions of k only for constant κ and regular x, y) of
+    (1 - Δt ∂z κ ∂z) cⁿ⁺¹ = c★ as the reference builds them: ivd_lower_diagonal / ivd_diagonal / ivd_upper_diagonal for a
+    field whose z location is Center (u, v, tracers: :27-46) or Face (w: :48-66).  Returned as the a (k = 1..Nz-1), b (1..Nz),
+    c (1..Nz-1) vectors of BatchedTridiagonalSolver."""
+    from .fields import R
+    FT, Nz = grid.FT, grid.Nz
+    κ, Δt = FT(κ), FT(Δt)
+    dzc = lambda k: np.asarray(grid.Δz(C, R(k))).ravel()[0]
+    dzf = lambda k: np.asarray(grid.Δz(F, R(k))).ravel()[0]
+    κΔz2 = lambda kc, kf: κ / dzc(kc) / dzf(kf)                   # κ_Δz² :25
+    if not z_face_field:
+        upper = lambda k: FT(0) if k > Nz - 1 else -Δt * κΔz2(k, k + 1)
+        lower = lambda k: FT(0) if k < 1 else -Δt * κΔz2(k + 1, k + 1)
+    else:
+        upper = lambda k: FT(0) if k < 1 else -Δt * κΔz2(k, k)
+        lower = lambda k: FT(0) if k < 1 else -Δt * κΔz2(k + 1, k)
+    diag = lambda k: FT(1) - Δt * FT(0) - upper(k) - lower(k - 1)
+    a = np.array([lower(k) for k in range(1, Nz)], dtype=FT)
+    b = np.array([diag(k) for k in range(1, Nz + 1)], dtype=FT)
+    c = np.array([upper(k) for k in range(1, Nz)], dtype=FT)
+    return a, b, c

@@ -17,8 +17,8 @@ from .fields import Field, FieldBoundaryConditions, fill_halo_regions, apply_flu
 from .operators import deriv, div_ccc, Ixy_fca, Ixy_cfa, Izf
 from .advection import div_Uu, div_Uc
 from .closures import (div_τ, div_q, SmagorinskyLilly, smagorinsky_viscosity, AnisotropicMinimumDissipation,
-                       amd_viscosity, amd_diffusivity)
-from .solvers import FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver
+                       amd_viscosity, amd_diffusivity, ivd_coefficients)
+from .solvers import FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver, BatchedTridiagonalSolver
 
 
 class FPlane:
@@ -347,6 +347,7 @@ class NonhydrostaticModel:
                     f[i, j, k] = f[i, j, k] + Δt * γ * Gn[i, j, k]
                 else:
                     f[i, j, k] = f[i, j, k] + Δt * (γ * Gn[i, j, k] + ζ * Gm[i, j, k])
+            self.implicit_step(sΔt)              # stage_Δt(Δt, γ, ζ) = Δt (γ + ζ)
             self.calculate_pressure_correction(sΔt)
             self.pressure_correct_velocities(sΔt)
             self.clock.time += float(sΔt)
@@ -374,12 +375,31 @@ class NonhydrostaticModel:
         for n in self.names:                     # ab2_step_field! :158-166
             f, Gn, Gm = self.fields[n], self.Gn[n], self.Gm[n]
             f[i, j, k] = f[i, j, k] + Δt * ((FT(1.5) + χ) * Gn[i, j, k] - (FT(0.5) + χ) * Gm[i, j, k])
+        self.implicit_step(Δt)
         self.calculate_pressure_correction(Δt)
         self.pressure_correct_velocities(Δt)
         self.store_tendencies()
         self.clock.time += float(Δt)
         self.clock.iteration += 1
         self.update_state()
+
+    def implicit_step(self, Δt):
+        """implicit_step!(field, implicit_solver, closure, ...) for every prognostic field right after its substep
+        (runge_kutta_3.jl:178-185, quasi_adams_bashforth_2.jl:137-144, vertically_implicit_diffusion_solver.jl:153-195):
+        in-place tridiagonal solve over k = 1..Nz of every column"""
+        clo = self.closure
+        if clo is None or not getattr(clo, "vitd", False):
+            return
+        g = self.grid
+        assert g.topology[2] == Bounded, "VerticallyImplicitTimeDiscretization needs a Bounded z"
+        for n in self.names:
+            f = self.fields[n]
+            κ = clo.ν if n in "uvw" else clo.kappa(n)
+            a, b, c = ivd_coefficients(g, Δt, κ, z_face_field=(n == "w"))
+            solver = BatchedTridiagonalSolver(g, a, b, c)
+            ϕ = f.interior[:, :, :g.Nz]            # a view: the solve is in place, rhs = the field itself
+            solver.t = np.zeros(ϕ.shape, dtype=g.FT)
+            solver.solve(ϕ, ϕ)
 
     # ---- diagnostics ------------------------------------------------------------------------
     def max_divergence(self):

@@ -276,6 +276,16 @@ CONFIGS = {
                            amd=dict(Cν=0.1, Cκ={"b": 0.08, "c": 0.2}, Cb=1.0), ts="QuasiAdamsBashforth2", dt=2e-3),
     "amd_seawater_periodic": dict(size=(32, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="WENO5", tracers=("T", "S"),
                                   seawater=dict(eos=(0.3, 0.2)), amd=dict(C=1 / 6, Cb=0.5), ts="RungeKutta3", dt=2e-3),
+    # VerticallyImplicitTimeDiscretization: the z-derivative parts of the vertical fluxes go through the
+    # batched tridiagonal solve after every substep; C3 physics (stretched Bounded z) with the ThreeDimensional formulation, and
+    # the Vertical formulation in a closed box with AB2
+    "vitd_c3_stretched_weno": dict(size=(12, 8, 14), topology=(O.Periodic, O.Periodic, O.Bounded),
+                                   coords=dict(x=(0, 1), y=(0, 1), z=_zf(14)), adv="WENO5grid", tracers=("b",), buoyancy=True,
+                                   closure=("ThreeDimensional", 1e-2, 2e-2), vitd=True, f=1e-2, ts="RungeKutta3", dt=5e-3,
+                                   bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"top": ("Flux", 1e-4), "bottom": ("Gradient", 1e-2)}}),
+    "vitd_vertical_box_ab2": dict(size=(8, 9, 10), topology=(O.Bounded,) * 3, extent=(1, 1, 1), adv="UpwindBiasedFifthOrder",
+                                  tracers=("b", "c"), buoyancy=True, closure=("Vertical", 5e-2, 3e-2), vitd=True,
+                                  ts="QuasiAdamsBashforth2", dt=2e-2),
     "seawater_S_only": dict(size=(8, 8, 8), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="UpwindBiasedFifthOrder",
                             tracers=("S", "c"), seawater=dict(constant_temperature=True, eos=(0.3, 0.2)),
                             ts="RungeKutta3", dt=2e-3),
@@ -296,7 +306,9 @@ def build_models(ob, cfg, FT):
     clo_o = clo_b = None
     if cfg.get("closure"):
         form, nu, ka = cfg["closure"]
-        clo_o, clo_b = O.ScalarDiffusivity(form, ν=nu, κ=ka), ob.ScalarDiffusivity(form, ν=nu, κ=ka)
+        td = "VerticallyImplicit" if cfg.get("vitd") else "Explicit"
+        clo_o = O.ScalarDiffusivity(form, ν=nu, κ=ka, time_discretization=td)
+        clo_b = ob.ScalarDiffusivity(form, ν=nu, κ=ka, time_discretization=td)
     if cfg.get("smagorinsky") is not None:
         clo_o, clo_b = O.SmagorinskyLilly(**cfg["smagorinsky"]), ob.SmagorinskyLilly(**cfg["smagorinsky"])
     if cfg.get("amd") is not None:

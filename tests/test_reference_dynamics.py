@@ -185,15 +185,20 @@ def test_stratified_fluid_remains_at_rest_with_tilted_gravity(be, tracer):
 @pytest.mark.parametrize("ts", ["QuasiAdamsBashforth2", "RungeKutta3"])
 @pytest.mark.parametrize("topo", [("Periodic",) * 3, ("Periodic", "Periodic", "Bounded"), ("Periodic", "Bounded", "Bounded"),
                                   ("Bounded",) * 3])
-@pytest.mark.parametrize("form", ["ThreeDimensional", "Vertical", "Horizontal"])
-def test_scalar_diffusivity_budget(be, ts, topo, form):
-    """the mean of a diffusing field is conserved (no-flux walls, periodic wrap)"""
+@pytest.mark.parametrize("form,td", [("ThreeDimensional", "Explicit"), ("Vertical", "Explicit"), ("Horizontal", "Explicit"),
+                                     ("ThreeDimensional", "VerticallyImplicit"), ("Vertical", "VerticallyImplicit")])
+def test_scalar_diffusivity_budget(be, ts, topo, form, td):
+    """the mean of a diffusing field is conserved (no-flux walls, periodic wrap); explicit and vertically implicit time
+    discretisations (the latter on vertically Bounded domains only, test_dynamics.jl:419-424)"""
     M = be.M
+    if td == "VerticallyImplicit" and topo[2] == "Periodic":
+        pytest.skip("VerticallyImplicitTimeDiscretization needs a Bounded z")
     g = be.grid(size=(4, 4, 4), extent=(1, 1, 1), topology=topo)
     names = ["c"] + [n for n, t in zip("uvw", topo) if t == "Periodic"]
     rng = np.random.default_rng(7)
     for name in names:
-        m = M.NonhydrostaticModel(g, advection=M.CenteredSecondOrder(), closure=M.ScalarDiffusivity(form, ν=1.0, κ=1.0),
+        m = M.NonhydrostaticModel(g, advection=M.CenteredSecondOrder(),
+                                  closure=M.ScalarDiffusivity(form, ν=1.0, κ=1.0, time_discretization=td),
                                   tracers=("c",), timestepper=ts)
         shape = be.interior(m, name).shape
         f0 = rng.uniform(0, 1, shape)
@@ -326,3 +331,28 @@ def test_grid_docstring_examples(which):
     s = _grid_summary(mk(size=(32, Ny, Nz), x=(0, 200), y=cheb, z=hyper, topology=("Periodic", "Bounded", "Bounded")), None, None)
     assert s[0][:3] == (0.0, 200.0, 6.25) and close(s[1][0], -50.0) and close(s[1][1], 50.0)
     assert close(s[1][2], 0.273905) and close(s[1][3], 5.22642)
+
+
+# ---- vertically implicit diffusion: cosine decay with a time step far above the explicit limit ---------------------------------
+@pytest.mark.parametrize("name", ["c", "u"])
+def test_vertically_implicit_cosine_diffusion(be, name):
+    """test_dynamics.jl:62-80 (test_diffusion_cosine) with VerticallyImplicitTimeDiscretization: cos(m z) decays as
+    exp(-kappa m^2 t); backward Euler in time, so the check uses the discrete amplification factor 1 / (1 + dt kappa lam) with the
+    second-order eigenvalue lam of the grid, which the scheme reproduces to round-off; dt = 20 x the explicit stability limit"""
+    M = be.M
+    N, kap = 32, 1.0
+    g = be.grid(size=(4, 4, N), x=(0, 1), y=(0, 1), z=(-1, 0), topology=("Periodic", "Periodic", "Bounded"))
+    m = M.NonhydrostaticModel(g, advection=None, closure=M.ScalarDiffusivity("Vertical", ν=kap, κ=kap, time_discretization="VerticallyImplicit"),
+                              tracers=("c",), timestepper="QuasiAdamsBashforth2")
+    mz = 2 * math.pi
+    prof = lambda x, y, z: np.cos(mz * z) + 0 * x + 0 * y
+    be.set(m, **{name: evaluate(be, m, name, prof)})
+    dz = 1.0 / N
+    dt = 20 * dz * dz / (2 * kap)
+    lam = (2 * math.sin(mz * dz / 2) / dz) ** 2
+    nsteps = 5
+    for _ in range(nsteps):
+        be.step(m, dt)
+    want = evaluate(be, m, name, prof) / (1 + dt * kap * lam) ** nsteps
+    got = be.interior(m, name)
+    assert np.max(np.abs(got - want)) < 1e-12
