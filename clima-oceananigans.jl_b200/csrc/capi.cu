@@ -252,6 +252,7 @@ static void build_gridD(ob200_grid* G, GridD<FT>& g) {
         g.L[d] = (FT)D.L[d];
         g.d[d] = (FT)D.delta[d];
         g.dC[d] = g.dF[d] = nullptr;
+        g.izC = g.izF = nullptr;
         if (D.topology[d] == OB200_FLAT) {
             if (D.N[d] != 1 || D.H[d] != 0) throw Error("Flat dimensions must have N = 1 and H = 0");
             g.O[d] = 0; g.S[d] = 1; g.regular[d] = 1; g.d[d] = 1; g.L[d] = 1;
@@ -289,6 +290,14 @@ static void upload_metrics(ob200_grid* G, GridD<FT>& g, const ob200_grid_desc* s
             OB_CUDA(cudaMemcpy(dptr, v.data(), v.size() * sizeof(FT), cudaMemcpyHostToDevice));
             G->owned.push_back(dptr);
             (w == 0 ? g.dC[d] : g.dF[d]) = dptr - lo;
+            if (d == 2) {
+                for (auto& x : v) x = FT(1) / x;
+                FT* iptr = nullptr;
+                OB_CUDA(cudaMalloc(&iptr, v.size() * sizeof(FT)));
+                OB_CUDA(cudaMemcpy(iptr, v.data(), v.size() * sizeof(FT), cudaMemcpyHostToDevice));
+                G->owned.push_back(iptr);
+                (w == 0 ? g.izC : g.izF) = iptr - lo;
+            }
         }
     }
 }
@@ -966,6 +975,7 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
             ff.Gm[q] = m->Gm[q]->template p0<FT>();
             ff.Gn[q] = m->Gn[q]->template p0<FT>();
             ff.nw[q] = ss.mode == SUB_NONE ? nullptr : f->template alt0<FT>();
+            for (int s = 0; s < 6; ++s) { ff.fbc[q].kind[s] = f->bcs[s].kind; ff.fbc[q].val[s] = (FT)f->bcs[s].value; }
         }
         first = fz::launch<FT>(P, ff);
     }

@@ -32,6 +32,8 @@ struct GridD {
     FT invd[3];             // 1 / d[] (regular dimensions: derivatives multiply instead of dividing)
     const FT* dC[3];        // stretched: Δ at centers, pre-offset: dC[d][i] with Julia index i
     const FT* dF[3];        // stretched: Δ at faces
+    const FT* izC;          // stretched z: 1 / dC[2][k], 1 / dF[2][k] (same indexing; tendency_fused.cu)
+    const FT* izF;
     FT L[3];
 };
 

@@ -60,6 +60,7 @@ struct FusedFields {
     FT* nw[FUSED_MAXF];              // out-of-place new state (null: tendencies only)
     const FT* pHY;
     Substep<FT> ss;
+    FluxBC<FT> fbc[FUSED_MAXF];      // constant Flux boundary conditions (Bounded z variant)
 };
 namespace fz { template <class FT> int launch(const Phys<FT>& P, const FusedFields<FT>& a); }
 

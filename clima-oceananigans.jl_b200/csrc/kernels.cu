@@ -369,8 +369,21 @@ __global__ void __launch_bounds__(128) tendency_general_kernel(const __grid_cons
 // functions (physics.cuh) as the kernel above; the divergence of the summed fluxes differs from the sum of the two
 // divergences by rounding only.
 // =============================================================================================
-template <class FT, int COMP>
-__global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_constant__ Phys<FT> P, const __grid_constant__ TendArgs<FT> A, int Kc) {
+// SPEC = 1: the configuration class of BASELINE config 3 (x, y Periodic and regular, z Bounded, WENO5, vertical gravity,
+// explicit closure): the kernel works on a LOCAL copy of the physics descriptor whose flags are overwritten with these
+// constants, so that after inlining every run-time scheme / topology / regularity branch of the operator tree folds away.
+template <class FT, int COMP, int SPEC>
+__global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_constant__ Phys<FT> Pin, const __grid_constant__ TendArgs<FT> A, int Kc) {
+    Phys<FT> Pl;
+    if constexpr (SPEC == 1) {
+        Pl = Pin;
+        Pl.g.topo[0] = OB_PERIODIC; Pl.g.topo[1] = OB_PERIODIC; Pl.g.topo[2] = OB_BOUNDED;
+        Pl.g.regular[0] = 1; Pl.g.regular[1] = 1;
+        Pl.scheme = ADV_WENO5; Pl.buffer = 2;
+        Pl.wc[0][0] = nullptr; Pl.wc[0][1] = nullptr; Pl.wc[1][0] = nullptr; Pl.wc[1][1] = nullptr;
+        Pl.tilted = 0; Pl.vitd = 0;
+    }
+    const Phys<FT>& P = SPEC ? Pl : Pin;
     const GridD<FT>& g = P.g;
     constexpr int TXS = 32, TYS = 8;
     constexpr int B = COMP < 3 ? COMP : 3;
@@ -389,7 +402,8 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
     const FT* U[3] = {A.U[0], A.U[1], A.U[2]};
     const int comp = COMP == 3 ? A.comp : COMP;
     const bool visc = P.closure != CLO_NONE;
-    const FT kappa = COMP == 3 ? P.kappa[comp - 3] : FT(0);
+    const FT kappa = COMP == 3 ? Pin.kappa[comp - 3] : FT(0);
+    const FT* kappae = COMP == 3 ? Pin.kappae[comp - 3] : nullptr;
     auto face = [&](int d, Pt q) -> FT {       // area-weighted advective + viscous / diffusive flux at q along d
         FT f = FT(0);
         if (COMP < 3) {
@@ -397,7 +411,7 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
             if (visc) f = f + viscous_Aflux(P, B, d, U, q);
         } else {
             if (P.scheme != ADV_NONE) f = tracer_flux(P, d, U[d], A.psi, q);
-            if (visc) f = f + diffusive_Aflux(P, d, kappa, A.psi, q, P.kappae[comp - 3]);
+            if (visc) f = f + diffusive_Aflux(P, d, kappa, A.psi, q, kappae);
         }
         return f;
     };
@@ -477,14 +491,20 @@ void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], 
     static const bool no_shared = getenv("OB200_NO_SHARED_GENERAL") != nullptr;
     bool shared = !no_shared && (P.scheme != ADV_NONE || P.closure != CLO_NONE);
     for (int d = 0; d < 3; ++d) shared = shared && P.g.topo[d] != OB_FLAT && P.g.N[d] >= 2;
+    static const bool no_spec = getenv("OB200_NO_SPEC_GENERAL") != nullptr;
+    const bool spec = !no_spec && P.g.topo[0] == OB_PERIODIC && P.g.topo[1] == OB_PERIODIC && P.g.topo[2] == OB_BOUNDED &&
+                      P.g.regular[0] && P.g.regular[1] && P.scheme == ADV_WENO5 && P.buffer == 2 && !P.tilted && !P.vitd &&
+                      !P.wc[0][0] && !P.wc[0][1] && !P.wc[1][0] && !P.wc[1][1];
     if (shared) {
         const int Kc = 32;
         dim3 bs(32, 8, 1), gs(cdiv(P.g.N[0], 31), cdiv(P.g.N[1], 7), cdiv(P.g.N[2], Kc));
         switch (comp) {
-            case 0: tendency_shared_kernel<FT, 0><<<gs, bs, 0, stream()>>>(P, A, Kc); break;
-            case 1: tendency_shared_kernel<FT, 1><<<gs, bs, 0, stream()>>>(P, A, Kc); break;
-            case 2: tendency_shared_kernel<FT, 2><<<gs, bs, 0, stream()>>>(P, A, Kc); break;
-            default: tendency_shared_kernel<FT, 3><<<gs, bs, 0, stream()>>>(P, A, Kc); break;
+#define SHK(C, S) tendency_shared_kernel<FT, C, S><<<gs, bs, 0, stream()>>>(P, A, Kc)
+            case 0: if (spec) SHK(0, 1); else SHK(0, 0); break;
+            case 1: if (spec) SHK(1, 1); else SHK(1, 0); break;
+            case 2: if (spec) SHK(2, 1); else SHK(2, 0); break;
+            default: if (spec) SHK(3, 1); else SHK(3, 0); break;
+#undef SHK
         }
         OB_LAUNCH_CHECK();
         return;

@@ -7,6 +7,7 @@
 // same quantities for the headline configuration with shared sub-expressions.
 #pragma once
 #include "common.cuh"
+#include "weno_fast.cuh"
 
 namespace ob {
 
@@ -223,6 +224,27 @@ OBD FT biased_raw(const Phys<FT>& P, int side, const FT* psi, Pt q, int d, int l
         case ADV_WENO5: {
             FT cf[9];
             const FT* tab = P.wc[d][loc == OB_F ? 0 : 1];
+#ifndef OB200_STRICT
+            // `side` is per-thread data (the sign of the advecting velocity): both variants below evaluate ONE
+            // reconstruction with the window / coefficients selected by `side`, so a warp with mixed signs does not
+            // execute the reconstruction twice
+            if (tab == nullptr) {
+                const bool pos = side == SIDE_LEFT;
+                const FT w0 = f[-3 * s], w1 = f[-2 * s], w2 = f[-s], w3 = f[0], w4 = f[s], w5 = f[2 * s];
+                return P.zweno ? wf::weno_upwind<FT, true>(pos, w0, w1, w2, w3, w4, w5)
+                               : wf::weno_upwind<FT, false>(pos, w0, w1, w2, w3, w4, w5);
+            }
+            {
+                const int n2 = g.N[d] + 2;
+                const FT* t0 = tab + ((long long)(side == SIDE_LEFT ? 1 : 0) * n2 + idx) * 3;
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) cf[3 * m + c] = t0[(long long)m * n2 * 3 + c];
+                const FT* w = f + (side == SIDE_LEFT ? -3 : -2) * s;
+                return weno5_core(side, P.zweno, w[0], w[s], w[2 * s], w[3 * s], w[4 * s], cf);
+            }
+#else
             if (tab == nullptr) {
                 weno_uniform_coeffs(side, cf);
             } else {                       // retrieve_coeff :526-539: table[r+2][idx]
@@ -236,6 +258,7 @@ OBD FT biased_raw(const Phys<FT>& P, int side, const FT* psi, Pt q, int d, int l
             if (side == SIDE_LEFT)
                 return weno5_core(side, P.zweno, f[-3 * s], f[-2 * s], f[-s], f[0], f[s], cf);
             return weno5_core(side, P.zweno, f[-2 * s], f[-s], f[0], f[s], f[2 * s], cf);
+#endif
         }
         case ADV_U5:                       // upwind_biased_fifth_order.jl:24-46
             if (side == SIDE_LEFT)

@@ -75,6 +75,14 @@ struct Args {
     FT invdx, invdy, f;
     int fplane, do_sub;
     FT ca, cb;             // psi_new = psi + ca * G + cb * G^-
+    // Bounded (stretched) z variant
+    const FT* izC;         // 1 / Δz of cell k, 1 / Δz at face k (Julia index k)
+    const FT* izF;
+    const FT* tabF;        // WENO coefficient tables of z: reconstruction at Faces (u, v, c) / at Centers (w)
+    const FT* tabC;
+    FT vh[2], v24;         // -24 ν / Δx, -24 ν / Δy, -24 ν    (viscous fluxes in the 24 x units of the momentum fluxes)
+    FT th[2], t2;          // -2 κ / Δx, -2 κ / Δy, -2 κ       (diffusive fluxes of the tracer, 2 x units)
+    FT fbb[NF], fbt[NF];   // constant Flux boundary conditions at the bottom / top (0: none)
 };
 
 // ---- work decomposition: whole tiles in lockstep rounds, then the leftover tiles split along z ----------------
@@ -175,24 +183,123 @@ __device__ __forceinline__ FT flux(const FT* __restrict__ S, const int (&so)[SLO
     }
 }
 
-// one field of one level for a cell thread: first the faces that are exchanged (x, y), then the z-top face
-template <class FT, bool ZW, int B, int PE>
-__device__ __forceinline__ void cell_fluxes_xy(const FT* S, const int (&so)[SLOTS], int FB, int e, bool first, FT& Fx, FT& Fy,
-                                               FT& Fz) {
-    constexpr int NQL = B == 2 ? -1 : 0;
-    if (first) Fz = flux<FT, ZW, 2, B, NQL, PE>(S, so, FB, e);
-    Fx = flux<FT, ZW, 0, B, 0, PE>(S, so, FB, e);
-    Fy = flux<FT, ZW, 1, B, 0, PE>(S, so, FB, e);
+// ---- Bounded, vertically stretched z (BASELINE config 3) ---------------------------------------------------------
+// Same units and conventions as flux(); k is the level the block is at.  What changes against the periodic variant:
+//   * interpolants along z fall back to the second-order average next to the walls
+//     (topologically_conditional_interpolation.jl:19-80 with the buffer of WENO5 = 2: fourth-order symmetric for
+//     2 < k < N-1, left-biased 2 < k < N, right-biased 1 < k < N-1);
+//   * reconstructions along z use the stretched-grid coefficient tables (weno_fifth_order.jl:526-553) with the uniform
+//     smoothness indicators, i.e. physics.cuh weno5_core with the window / table row selected by the upwind side;
+//   * every face carries the viscous / diffusive flux of ScalarDiffusivity, -ν (∂_A u_B + ∂_B u_A) resp. -κ ∂_A c
+//     (closure_kernel_operators.jl:22-48): the two differences are the central pairs of the windows that the advective
+//     flux loads anyway (the advected field along A, the advecting velocity along B), so no extra shared-memory reads.
+template <class FT, bool ZW>
+__device__ __forceinline__ FT zrecon2(const FT* __restrict__ tab, int N, int kq, bool pos, FT a, FT b, FT cc, FT d, FT g, FT i2) {
+    const bool outL = kq > 2 && kq < N, outR = kq > 1 && kq < N - 1;
+    if (!(outL || outR)) return i2;
+    const int n3 = 3 * (N + 2);
+    const FT* t = tab + ((pos ? n3 : 0) + 3 * kq);
+    FT cf[9];
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) cf[3 * m + q] = __ldg(t + m * n3 + q);
+    const FT r = 2 * weno5_core<FT>(pos ? SIDE_LEFT : SIDE_RIGHT, ZW ? 1 : 0, a, b, cc, d, g, cf);
+    if (outL && outR) return r;
+    return (pos ? outL : outR) ? r : i2;
 }
-template <class FT, bool ZW, int B, int PE>
-__device__ __forceinline__ void cell_flux_z(const FT* S, const int (&so)[SLOTS], int FB, int e, FT& Fz, FT& dFz) {
+
+template <class FT, bool ZW, int A, int B, int NQ, int PE, int NF>
+__device__ __forceinline__ FT fluxb(const Args<FT, NF>& c, int k, const FT* __restrict__ S, const int (&so)[SLOTS], int FB, int e) {
+    constexpr int sA = A == 0 ? 1 : BX;
+    const int kq = k + NQ;
+    if constexpr (B != 3 && A == B) {
+        FT w[6];
+        if constexpr (A < 2) {
+            const FT* q = S + FB * SLOTS * PE + so[NQ + 3] + e + sA;
+#pragma unroll
+            for (int n = 0; n < 6; ++n) w[n] = q[(n - 3) * sA];
+            const FT ut = interp12<FT>(w[1], w[2], w[3], w[4]);
+            const FT visc = (2 * c.vh[A]) * (w[3] - w[2]);
+            return fma(ut, weno_sel6<FT, ZW>(ut > FT(0), w[0], w[1], w[2], w[3], w[4], w[5]), visc);
+        } else {
+            const FT* q = S + FB * SLOTS * PE + e;
+#pragma unroll
+            for (int n = 0; n < 6; ++n) w[n] = q[so[NQ + 1 + n]];          // levels kq-2 .. kq+3 (w faces around centre kq)
+            const bool oc = kq > 2 && kq < c.Nz - 1;
+            const FT i2 = w[2] + w[3];
+            const FT ut = oc ? interp12<FT>(w[1], w[2], w[3], w[4]) : FT(6) * i2;
+            const bool pos = ut > FT(0);
+            const FT rec = zrecon2<FT, ZW>(c.tabC, c.Nz, kq, pos, pos ? w[0] : w[1], pos ? w[1] : w[2], pos ? w[2] : w[3],
+                                           pos ? w[3] : w[4], pos ? w[4] : w[5], i2);
+            const FT visc = ((2 * c.v24) * __ldg(c.izC + kq)) * (w[3] - w[2]);
+            return fma(ut, rec, visc);
+        }
+    } else {
+        FT ut, visc = FT(0);
+        if constexpr (B == 3) {
+            ut = S[A * SLOTS * PE + so[NQ + 3] + e];
+        } else if constexpr (B < 2) {
+            constexpr int sB = B == 0 ? 1 : BX;
+            const FT* q = S + A * SLOTS * PE + so[NQ + 3] + e;
+            const FT cm = q[-sB], c0 = q[0];
+            ut = interp12<FT>(q[-2 * sB], cm, c0, q[sB]);
+            visc = c.vh[B] * (c0 - cm);
+        } else {            // w advected by u / v: the advecting velocity is interpolated along z at face level k
+            const FT* q = S + A * SLOTS * PE + e;
+            const FT cm = q[so[NQ + 2]], c0 = q[so[NQ + 3]];
+            const bool oc = kq > 2 && kq < c.Nz - 1;
+            ut = oc ? interp12<FT>(q[so[NQ + 1]], cm, c0, q[so[NQ + 4]]) : FT(6) * (cm + c0);
+            visc = (c.v24 * __ldg(c.izF + kq)) * (c0 - cm);
+        }
+        const bool pos = ut > FT(0);
+        if constexpr (A == 1) {
+            const FT* q = S + FB * SLOTS * PE + so[NQ + 3] + e;
+            const FT w2 = q[-BX], w3 = q[0];
+            visc = fma(B == 3 ? c.th[1] : c.vh[1], w3 - w2, visc);
+            return fma(ut, weno_sel6<FT, ZW>(pos, q[-3 * BX], q[-2 * BX], w2, w3, q[BX], q[2 * BX]), visc);
+        } else if constexpr (A == 0) {
+            const int base = FB * SLOTS * PE + so[NQ + 3] + e;
+            const int A0 = pos ? base : base - 1, t = pos ? 1 : -1;
+            const FT a = S[A0 - 3 * t], b = S[A0 - 2 * t], cc = S[A0 - t], d = S[A0], g = S[A0 + t];
+            visc = fma(B == 3 ? c.th[0] : c.vh[0], pos ? d - cc : cc - d, visc);
+            return fma(ut, wf::weno_face2<FT, ZW>(a, b, cc, d, g, pos ? cc : a, pos ? cc : g), visc);
+        } else {            // z face at level kq of u, v or the tracer: natural windows kq-3 .. kq+1 (left) / kq-2 .. kq+2 (right)
+            const FT* q = S + FB * SLOTS * PE + e;
+            const FT a = q[pos ? so[NQ] : so[NQ + 1]], b = q[pos ? so[NQ + 1] : so[NQ + 2]], cc = q[pos ? so[NQ + 2] : so[NQ + 3]],
+                     d = q[pos ? so[NQ + 3] : so[NQ + 4]], g = q[pos ? so[NQ + 4] : so[NQ + 5]];
+            const FT lo = pos ? cc : b, hi = pos ? d : cc;                 // levels kq-1, kq
+            visc = fma((B == 3 ? c.t2 : c.v24) * __ldg(c.izF + kq), hi - lo, visc);
+            return fma(ut, zrecon2<FT, ZW>(c.tabF, c.Nz, kq, pos, a, b, cc, d, g, lo + hi), visc);
+        }
+    }
+}
+
+template <class FT, bool ZW, int ZT, int A, int B, int NQ, int PE, int NF>
+__device__ __forceinline__ FT fluxs(const Args<FT, NF>& c, int k, const FT* __restrict__ S, const int (&so)[SLOTS], int FB, int e) {
+    if constexpr (ZT) return fluxb<FT, ZW, A, B, NQ, PE, NF>(c, k, S, so, FB, e);
+    else return flux<FT, ZW, A, B, NQ, PE>(S, so, FB, e);
+}
+
+// one field of one level for a cell thread: first the faces that are exchanged (x, y), then the z-top face
+template <class FT, bool ZW, int ZT, int B, int PE, int NF>
+__device__ __forceinline__ void cell_fluxes_xy(const Args<FT, NF>& c, int k, const FT* S, const int (&so)[SLOTS], int FB, int e,
+                                               bool first, FT& Fx, FT& Fy, FT& Fz) {
+    constexpr int NQL = B == 2 ? -1 : 0;
+    if (first) Fz = fluxs<FT, ZW, ZT, 2, B, NQL, PE, NF>(c, k, S, so, FB, e);
+    Fx = fluxs<FT, ZW, ZT, 0, B, 0, PE, NF>(c, k, S, so, FB, e);
+    Fy = fluxs<FT, ZW, ZT, 1, B, 0, PE, NF>(c, k, S, so, FB, e);
+}
+template <class FT, bool ZW, int ZT, int B, int PE, int NF>
+__device__ __forceinline__ void cell_flux_z(const Args<FT, NF>& c, int k, const FT* S, const int (&so)[SLOTS], int FB, int e,
+                                            FT& Fz, FT& dFz) {
     constexpr int NQH = B == 2 ? 0 : 1;
-    const FT Fn = flux<FT, ZW, 2, B, NQH, PE>(S, so, FB, e);
+    const FT Fn = fluxs<FT, ZW, ZT, 2, B, NQH, PE, NF>(c, k, S, so, FB, e);
     dFz = Fn - Fz;
     Fz = Fn;
 }
 
-template <class FT, bool ZW, int NT, bool HAS_GM, int R, int GRP>
+template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, int R, int GRP>
 __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT* sX, unsigned long long* full,
                                            unsigned long long* done) {
     using GR = Groups<NT>;
@@ -250,17 +357,17 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
 #pragma unroll
                 for (int s = 0; s < FPG; ++s) {
                     const int f = F0 + s;
-                    if (f == 0) cell_fluxes_xy<FT, ZW, 0, PE>(S, so, 0, e, it == 0, Fx[s], Fy[s], Fz[s]);
-                    else if (f == 1) cell_fluxes_xy<FT, ZW, 1, PE>(S, so, 1, e, it == 0, Fx[s], Fy[s], Fz[s]);
-                    else if (f == 2) cell_fluxes_xy<FT, ZW, 2, PE>(S, so, 2, e, it == 0, Fx[s], Fy[s], Fz[s]);
-                    else cell_fluxes_xy<FT, ZW, 3, PE>(S, so, f, e, it == 0, Fx[s], Fy[s], Fz[s]);
+                    if (f == 0) cell_fluxes_xy<FT, ZW, ZT, 0, PE, NF>(c, k, S, so, 0, e, it == 0, Fx[s], Fy[s], Fz[s]);
+                    else if (f == 1) cell_fluxes_xy<FT, ZW, ZT, 1, PE, NF>(c, k, S, so, 1, e, it == 0, Fx[s], Fy[s], Fz[s]);
+                    else if (f == 2) cell_fluxes_xy<FT, ZW, ZT, 2, PE, NF>(c, k, S, so, 2, e, it == 0, Fx[s], Fy[s], Fz[s]);
+                    else cell_fluxes_xy<FT, ZW, ZT, 3, PE, NF>(c, k, S, so, f, e, it == 0, Fx[s], Fy[s], Fz[s]);
                     sFx[f * G_::FXE + ty * (TX + 1) + (f == 0 ? tx + 1 : tx)] = Fx[s];
                     sFy[f * G_::FYE + (f == 1 ? ty + 1 : ty) * TX + tx] = Fy[s];
                     {
-                        if (f == 0) cell_flux_z<FT, ZW, 0, PE>(S, so, 0, e, Fz[s], dFz[s]);
-                        else if (f == 1) cell_flux_z<FT, ZW, 1, PE>(S, so, 1, e, Fz[s], dFz[s]);
-                        else if (f == 2) cell_flux_z<FT, ZW, 2, PE>(S, so, 2, e, Fz[s], dFz[s]);
-                        else cell_flux_z<FT, ZW, 3, PE>(S, so, f, e, Fz[s], dFz[s]);
+                        if (f == 0) cell_flux_z<FT, ZW, ZT, 0, PE, NF>(c, k, S, so, 0, e, Fz[s], dFz[s]);
+                        else if (f == 1) cell_flux_z<FT, ZW, ZT, 1, PE, NF>(c, k, S, so, 1, e, Fz[s], dFz[s]);
+                        else if (f == 2) cell_flux_z<FT, ZW, ZT, 2, PE, NF>(c, k, S, so, 2, e, Fz[s], dFz[s]);
+                        else cell_flux_z<FT, ZW, ZT, 3, PE, NF>(c, k, S, so, f, e, Fz[s], dFz[s]);
                     }
                 }
             } else if (edge) {
@@ -272,17 +379,17 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
                     const int f = F0 + s;
                     FT ex, ey_;
                     if (f == 0) {
-                        ex = flux<FT, ZW, 0, 0, 0, PE>(S, so, 0, rx - 1);
-                        ey_ = flux<FT, ZW, 1, 0, 0, PE>(S, so, 0, ey + nrows * BX);
+                        ex = fluxs<FT, ZW, ZT, 0, 0, 0, PE, NF>(c, k, S, so, 0, rx - 1);
+                        ey_ = fluxs<FT, ZW, ZT, 1, 0, 0, PE, NF>(c, k, S, so, 0, ey + nrows * BX);
                     } else if (f == 1) {
-                        ex = flux<FT, ZW, 0, 1, 0, PE>(S, so, 1, rx + TX);
-                        ey_ = flux<FT, ZW, 1, 1, 0, PE>(S, so, 1, ey - BX);
+                        ex = fluxs<FT, ZW, ZT, 0, 1, 0, PE, NF>(c, k, S, so, 1, rx + TX);
+                        ey_ = fluxs<FT, ZW, ZT, 1, 1, 0, PE, NF>(c, k, S, so, 1, ey - BX);
                     } else if (f == 2) {
-                        ex = flux<FT, ZW, 0, 2, 0, PE>(S, so, 2, rx + TX);
-                        ey_ = flux<FT, ZW, 1, 2, 0, PE>(S, so, 2, ey + nrows * BX);
+                        ex = fluxs<FT, ZW, ZT, 0, 2, 0, PE, NF>(c, k, S, so, 2, rx + TX);
+                        ey_ = fluxs<FT, ZW, ZT, 1, 2, 0, PE, NF>(c, k, S, so, 2, ey + nrows * BX);
                     } else {
-                        ex = flux<FT, ZW, 0, 3, 0, PE>(S, so, f, rx + TX);
-                        ey_ = flux<FT, ZW, 1, 3, 0, PE>(S, so, f, ey + nrows * BX);
+                        ex = fluxs<FT, ZW, ZT, 0, 3, 0, PE, NF>(c, k, S, so, f, rx + TX);
+                        ey_ = fluxs<FT, ZW, ZT, 1, 3, 0, PE, NF>(c, k, S, so, f, ey + nrows * BX);
                     }
                     if (tx < nrows) sFx[f * G_::FXE + tx * (TX + 1) + (f == 0 ? 0 : TX)] = ex;
                     sFy[f * G_::FYE + (f == 1 ? 0 : nrows) * TX + tx] = ey_;
@@ -298,8 +405,19 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
                     const FT oy = sFy[f * G_::FYE + (f == 1 ? ty : ty + 1) * TX + tx];
                     const FT dFx = f == 0 ? Fx[s] - ox : ox - Fx[s];
                     const FT dFy = f == 1 ? Fy[s] - oy : oy - Fy[s];
-                    FT Gv = f < 3 ? -fma(cmx, dFx, fma(cmy, dFy, cmz * dFz[s]))
-                                  : -fma(ctx_, dFx, fma(cty, dFy, ctz * dFz[s]));
+                    FT Gv;
+                    if constexpr (ZT) {           // Az / V = 1 / Δz of the level (cell for u, v, c; face for w)
+                        const FT iz = __ldg((f == 2 ? c.izF : c.izC) + k);
+                        Gv = f < 3 ? -fma(cmx, dFx, fma(cmy, dFy, (iz * FT(1.0 / 24.0)) * dFz[s]))
+                                   : -fma(ctx_, dFx, fma(cty, dFy, (iz * FT(0.5)) * dFz[s]));
+                        if (f != 2) {             // apply_z_bcs! (apply_flux_bcs.jl:111-160): constant Flux BCs
+                            if (k == 1) Gv = fma(c.fbb[f], iz, Gv);
+                            if (k == c.Nz) Gv = fma(-c.fbt[f], iz, Gv);
+                        }
+                    } else {
+                        Gv = f < 3 ? -fma(cmx, dFx, fma(cmy, dFy, cmz * dFz[s]))
+                                   : -fma(ctx_, dFx, fma(cty, dFy, ctz * dFz[s]));
+                    }
                     if (f == 0) {
                         if (c.fplane) {           // - x_f_cross_U = + f * ℑxyᶠᶜᵃ(v)   (f_plane.jl:42)
                             const FT* v = S + 1 * SLOTS * PE + so[3] + e;
@@ -329,7 +447,7 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
     }
 }
 
-template <class FT, bool ZW, int NT, bool HAS_GM, int R>
+template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, int R>
 __global__ void __launch_bounds__(TX*(Groups<NT>::NG*(R + 1) + 1), 1)
 tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
     using GR = Groups<NT>;
@@ -381,13 +499,13 @@ tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
         return;
     }
     const int grp = warp / (R + 1);
-    if (grp == 0) group_main<FT, ZW, NT, HAS_GM, R, 0>(c, S, sX, full, done);
-    else if (grp == 1) group_main<FT, ZW, NT, HAS_GM, R, 1>(c, S, sX, full, done);
-    else if (NG > 2) group_main<FT, ZW, NT, HAS_GM, R, (NG > 2 ? 2 : 0)>(c, S, sX, full, done);
+    if (grp == 0) group_main<FT, ZW, ZT, NT, HAS_GM, R, 0>(c, S, sX, full, done);
+    else if (grp == 1) group_main<FT, ZW, ZT, NT, HAS_GM, R, 1>(c, S, sX, full, done);
+    else if (NG > 2) group_main<FT, ZW, ZT, NT, HAS_GM, R, (NG > 2 ? 2 : 0)>(c, S, sX, full, done);
 }
 
 // ---- host side --------------------------------------------------------------------------------
-template <class FT, bool ZW, int NT, bool HAS_GM, int R>
+template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, int R>
 static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     using GR = Groups<NT>;
     constexpr int NF = GR::NF;
@@ -405,15 +523,28 @@ static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     c.Ny = g.N[1]; c.Nz = g.N[2];
     c.ntx = g.N[0] / TX;
     c.ntiles = c.ntx * cdiv(g.N[1], R);
-    const FT invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
-    c.cf[0] = (g.d[1] * g.d[2]) * invV; c.cf[1] = (g.d[0] * g.d[2]) * invV; c.cf[2] = (g.d[0] * g.d[1]) * invV;
     c.invdx = 1 / g.d[0]; c.invdy = 1 / g.d[1];
+    if (ZT) {
+        c.cf[0] = c.invdx; c.cf[1] = c.invdy; c.cf[2] = FT(0);
+        c.izC = g.izC; c.izF = g.izF; c.tabF = P.wc[2][0]; c.tabC = P.wc[2][1];
+        const FT nu = P.closure == CLO_3D ? P.nu : FT(0), kap = P.closure == CLO_3D ? P.kappa[0] : FT(0);
+        c.v24 = -24 * nu; c.vh[0] = c.v24 * c.invdx; c.vh[1] = c.v24 * c.invdy;
+        c.t2 = -2 * kap; c.th[0] = c.t2 * c.invdx; c.th[1] = c.t2 * c.invdy;
+        for (int f = 0; f < NF; ++f) {
+            c.fbb[f] = a.fbc[f].kind[4] == 2 ? a.fbc[f].val[4] : FT(0);
+            c.fbt[f] = a.fbc[f].kind[5] == 2 ? a.fbc[f].val[5] : FT(0);
+        }
+    } else {
+        const FT invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
+        c.cf[0] = (g.d[1] * g.d[2]) * invV; c.cf[1] = (g.d[0] * g.d[2]) * invV; c.cf[2] = (g.d[0] * g.d[1]) * invV;
+        c.izC = c.izF = c.tabF = c.tabC = nullptr;
+    }
     c.f = P.f; c.fplane = P.fplane;
     const Substep<FT>& ss = a.ss;
     c.do_sub = ss.mode != SUB_NONE;
     c.ca = ss.mode == SUB_RK3_FIRST ? ss.c1 : ss.dt * ss.c1;
     c.cb = ss.mode == SUB_RK3 ? ss.dt * ss.c2 : (ss.mode == SUB_AB2 ? -(ss.dt * ss.c2) : FT(0));
-    auto kern = tendency_fused_kernel<FT, ZW, NT, HAS_GM, R>;
+    auto kern = tendency_fused_kernel<FT, ZW, ZT, NT, HAS_GM, R>;
     static bool attr_set = false;      // per instantiation
     if (!attr_set) {
         OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
@@ -435,32 +566,47 @@ static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     OB_LAUNCH_CHECK();
 }
 
-template <class FT, bool ZW, int NT, int R>
+template <class FT, bool ZW, int ZT, int NT, int R>
 static void launch_gm(const Phys<FT>& P, const FusedFields<FT>& a) {
     const bool has_gm = a.ss.mode == SUB_RK3 || a.ss.mode == SUB_AB2;
-    if (has_gm) launch_variant<FT, ZW, NT, true, R>(P, a);
-    else launch_variant<FT, ZW, NT, false, R>(P, a);
+    if (has_gm) launch_variant<FT, ZW, ZT, NT, true, R>(P, a);
+    else launch_variant<FT, ZW, ZT, NT, false, R>(P, a);
 }
 
 template <class FT>
 int launch(const Phys<FT>& P, const FusedFields<FT>& a) {
     const GridD<FT>& g = P.g;
     static const bool off = getenv("OB200_NO_FUSED_TENDENCY") != nullptr;
+    static const bool offb = getenv("OB200_NO_FUSED_BOUNDED") != nullptr;
     if (off) return 0;
-    if (P.scheme != ADV_WENO5 || P.closure != CLO_NONE || P.tilted) return 0;
-    if (g.topo[0] != OB_PERIODIC || (g.topo[1] != OB_PERIODIC && g.topo[1] != OB_COMM) || g.topo[2] != OB_PERIODIC) return 0;
-    for (int d = 0; d < 3; ++d) {
-        if (!g.regular[d] || P.wc[d][0] || P.wc[d][1] || g.H[d] < 3) return 0;
-    }
+    if (P.scheme != ADV_WENO5 || P.tilted) return 0;
+    if (g.topo[0] != OB_PERIODIC || (g.topo[1] != OB_PERIODIC && g.topo[1] != OB_COMM)) return 0;
+    for (int d = 0; d < 3; ++d)
+        if (g.H[d] < 3 || (d < 2 && (!g.regular[d] || P.wc[d][0] || P.wc[d][1]))) return 0;
     if (g.N[0] % TX || (g.S[0] * sizeof(FT)) % 16 || g.total >= (1LL << 31)) return 0;
     if (a.nf < 3) return 0;
     const int nt = std::min(a.nf - 3, 1);
-#define GO(NTV, RV)                                                                        \
-    { if (P.zweno) launch_gm<FT, true, NTV, RV>(P, a); else launch_gm<FT, false, NTV, RV>(P, a); }
+    // ZT = 1: Bounded, vertically stretched z with ScalarDiffusivity (or no closure) and constant Flux BCs in z
+    int zt;
+    if (g.topo[2] == OB_PERIODIC) {
+        if (!g.regular[2] || P.wc[2][0] || P.wc[2][1] || P.closure != CLO_NONE) return 0;
+        zt = 0;
+    } else if (g.topo[2] == OB_BOUNDED) {
+        if (offb || nt == 0 || g.regular[2] || !g.izC || !g.izF || !P.wc[2][0] || !P.wc[2][1] || g.N[2] < 6) return 0;
+        if ((P.closure != CLO_NONE && P.closure != CLO_3D) || P.vitd) return 0;
+        for (int s = 4; s < 6; ++s)
+            if (a.fbc[2].kind[s] == 2 && a.fbc[2].val[s] != FT(0)) return 0;      // w has no Flux BCs on a Bounded z
+        zt = 1;
+    } else {
+        return 0;
+    }
+#define GO(ZTV, NTV, RV)                                                                        \
+    { if (P.zweno) launch_gm<FT, true, ZTV, NTV, RV>(P, a); else launch_gm<FT, false, ZTV, NTV, RV>(P, a); }
     // rows per tile: the largest for which the block (NG (R + 1) + 1 warps) keeps 72 registers per thread and the rings
     // + exchange buffers fit 227 KB; measured at 256^3: R = 12 3.13 ms per step, 11: 3.16, 10: 3.26, 9: 3.19
-    if (nt == 0) GO(0, 8)
-    else GO(1, 12)
+    if (zt) GO(1, 1, 12)
+    else if (nt == 0) GO(0, 0, 8)
+    else GO(0, 1, 12)
 #undef GO
     return 3 + nt;
 }

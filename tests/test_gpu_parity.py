@@ -222,6 +222,18 @@ CONFIGS = {
                                   coords=dict(x=(0, 1), y=(0, 1), z=_zf(14)), adv="WENO5grid", tracers=("b",),
                                   buoyancy=True, closure=("ThreeDimensional", 1e-4, 1e-4), f=1e-2, ts="RungeKutta3", dt=5e-3,
                                   bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"top": ("Flux", 1e-4), "bottom": ("Gradient", 1e-2)}}),
+    # the same physics on the fused persistent kernel (Nx a multiple of 32; tendency_fused.cu, Bounded-z variant): rows per
+    # tile 12 against Ny = 16 (a partial tile); JS weights + AB2 + no closure + no Coriolis; value / gradient BCs on u, v
+    "c3_fused_stretched_weno_rk3": dict(size=(32, 16, 14), topology=(O.Periodic, O.Periodic, O.Bounded),
+                                        coords=dict(x=(0, 1), y=(0, 1), z=_zf(14)), adv="WENO5grid", tracers=("b",),
+                                        buoyancy=True, closure=("ThreeDimensional", 1e-4, 2e-4), f=1e-2, ts="RungeKutta3", dt=5e-3,
+                                        bcs={"u": {"top": ("Flux", -1e-3)},
+                                             "b": {"top": ("Flux", 1e-4), "bottom": ("Gradient", 1e-2)}}),
+    "c3_fused_js_ab2_no_closure": dict(size=(32, 12, 8), topology=(O.Periodic, O.Periodic, O.Bounded),
+                                       coords=dict(x=(0, 2), y=(0, 1), z=_zf(8)), adv="WENO5grid_js", tracers=("b", "c"),
+                                       buoyancy=True, ts="QuasiAdamsBashforth2", dt=5e-3,
+                                       bcs={"v": {"top": ("Value", 0.1), "bottom": ("Gradient", -0.2)},
+                                            "b": {"bottom": ("Flux", -2e-4)}, "c": {"top": ("Flux", 3e-4)}}),
     "channel_bounded_yz_weno": dict(size=(8, 12, 10), topology=(O.Periodic, O.Bounded, O.Bounded), extent=(1, 1, 1),
                                     adv="WENO5", tracers=("b",), buoyancy=True, closure=("Horizontal", 1e-3, 1e-3),
                                     ts="RungeKutta3", dt=2e-3),
@@ -301,6 +313,8 @@ def build_models(ob, cfg, FT):
         ao, ab = O.WENO5(FT, zweno=False), ob.WENO5(FT, zweno=False)
     elif adv == "WENO5grid":
         ao, ab = O.WENO5(grid=go), ob.WENO5(grid=gb)
+    elif adv == "WENO5grid_js":
+        ao, ab = O.WENO5(grid=go, zweno=False), ob.WENO5(grid=gb, zweno=False)
     else:
         ao, ab = getattr(O, adv)(), getattr(ob, adv)()
     clo_o = clo_b = None
@@ -395,7 +409,7 @@ def test_tendencies_and_steps_match_oracle_f64(ob, name):
     assert abs(mb.clock.time - mo.clock.time) < 1e-15 and mb.clock.iteration == 4
 
 
-@pytest.mark.parametrize("name", ["c2_periodic_weno_rk3", "c3_stretched_weno_rk3", "c1_2d_flat_weno_ab2"])
+@pytest.mark.parametrize("name", ["c2_periodic_weno_rk3", "c3_stretched_weno_rk3", "c3_fused_stretched_weno_rk3", "c1_2d_flat_weno_ab2"])
 def test_steps_match_oracle_f32(ob, name):
     cfg = CONFIGS[name]
     mo, mb = build_models(ob, cfg, np.float32)
@@ -419,6 +433,26 @@ def test_fast_and_general_kernels_agree(ob):
         ob.time_step(m2, cfg["dt"])
     for n in m1.names:
         assert relerr(m1.fields[n].interior(), m2.fields[n].interior()) < 1e-13
+
+
+def test_fused_bounded_z_kernel_agrees_with_general_kernels(ob):
+    """C3 physics at 64 x 40 x 48 (five tile rows of 12, the last partial; chunks of the leftover tiles split along z): the
+    fused Bounded-z kernel against the general per-field kernels on the same state, three RK3 steps"""
+    cfg = dict(CONFIGS["c3_fused_stretched_weno_rk3"], size=(64, 40, 48), coords=dict(x=(0, 2), y=(0, 1.5), z=_zf(48)))
+    mo, m1 = build_models(ob, cfg, np.float64)
+    _, m2 = build_models(ob, cfg, np.float64)
+    m2.use_fast_kernels(False)
+    init_state(mo, m1, ob, 29)
+    init_state(mo, m2, ob, 29)
+    ob.calculate_tendencies(m1)
+    ob.calculate_tendencies(m2)
+    for n in m1.names:
+        assert relerr(m1.Gn[n].interior(), m2.Gn[n].interior()) < 1e-12, f"tendency {n}"
+    for _ in range(3):
+        ob.time_step(m1, cfg["dt"])
+        ob.time_step(m2, cfg["dt"])
+    for n in m1.names:
+        assert relerr(m1.fields[n].interior(), m2.fields[n].interior()) < 1e-12, n
 
 
 def test_ab2_first_step_is_euler_and_simulation_runs(ob):
