@@ -38,6 +38,10 @@ NCU_TRAFFIC_BYTES_PER_FUSED_LAUNCH = 2.45e9
 # ... and of one per-field launch of the round-1 kernel (profiles/r1_summary.md), used when the fused kernel is switched off
 NCU_TRAFFIC_BYTES_PER_FIELD_LAUNCH = 8.93e8
 
+# ... and of one fused Bounded-z launch of BASELINE config 3 at 512 x 512 x 256 F64 (profiles/r2_summary.md, capture r2i:
+# 6.12 + 4.28 GB against 8.41 GB algorithmic)
+NCU_TRAFFIC_BYTES_PER_FUSED_LAUNCH_C3 = 1.04e10
+
 METRIC = "grid-point updates/sec (RK3 step, 256^3 WENO5+FFT)"
 UNIT = "grid-point updates/s"
 
@@ -344,7 +348,8 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     tend = phases["tendency"]
     W = 8 if a.ftype == "f64" else 4
-    fused = a.config != "c3" and os.environ.get("OB200_NO_FUSED_TENDENCY") is None
+    fused = os.environ.get("OB200_NO_FUSED_TENDENCY") is None and (
+        a.config != "c3" or (os.environ.get("OB200_NO_FUSED_BOUNDED") is None and shape_g[0] % 32 == 0))
     # algorithmic words per point: 4F+1 for stages 2,3 and 3F+1 for stage 1, per stage;
     # the fused kernel does a whole stage per launch, the per-field kernels a F-th of it
     words_stage = ((3 * F + 1) + 2 * (4 * F + 1)) / 3.0
@@ -353,13 +358,15 @@ def main():
     tend_launches = a.steps * 3 * per_launch
     avg_ms = tend["ms_total"] / max(1, tend_launches)
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    headline_shape = a.config == "c2" and not a.size and a.ftype == "f64"
+    headline_shape = a.config in ("c2", "c3") and not a.size and a.ftype == "f64" and (fused or a.config == "c2")
+    ncu_traffic = (NCU_TRAFFIC_BYTES_PER_FUSED_LAUNCH_C3 if a.config == "c3" else
+                   (NCU_TRAFFIC_BYTES_PER_FUSED_LAUNCH if fused else NCU_TRAFFIC_BYTES_PER_FIELD_LAUNCH))
     kname = ("fz::tendency_fused_kernel: tendencies + substep of all prognostic fields, one launch per stage" if fused else
              ("tendency_shared_kernel (general, per prognostic field)" if a.config == "c3"
               else "tma::tendency_tma_kernel (per prognostic field)"))
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (NCU_TRAFFIC_BYTES_PER_FUSED_LAUNCH if fused else NCU_TRAFFIC_BYTES_PER_FIELD_LAUNCH) if headline_shape else None,
+                "traffic": ncu_traffic if headline_shape else None,
                 "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
                                   "(profiles/r2_summary.md)" if headline_shape else None,
                 "algorithmic_bytes_per_launch": alg_bytes,

@@ -695,6 +695,7 @@ static void build_phys(ob200_model* m) {
     for (int d = 0; d < 3; ++d)
         for (int l = 0; l < 2; ++l) {
             P.wc[d][l] = nullptr;
+            if (d == 2) P.wzp[l] = nullptr;
             if (D.advection == OB200_ADV_WENO5 && D.weno_coeff[d][l]) {
                 size_t n = 4 * (size_t)(P.g.N[d] + 2) * 3;
                 std::vector<FT> h(n);
@@ -704,6 +705,24 @@ static void build_phys(ob200_model* m) {
                 OB_CUDA(cudaMemcpy(dp, h.data(), n * sizeof(FT), cudaMemcpyHostToDevice));
                 m->owned.push_back(dp);
                 P.wc[d][l] = dp;
+                if (d == 2) {
+                    // the same coefficients packed for tendency_fused.cu: entry (k, side) = 10 values at (2 k + side) * 10,
+                    // side 1 = left-biased: 2 x the nine coefficients of the window ordered towards the face (the right-biased
+                    // row is the natural one reversed), so both sides are one arithmetic on one 80-byte row
+                    const int n2 = P.g.N[d] + 2;
+                    std::vector<FT> pk((size_t)n2 * 2 * 10, FT(0));
+                    for (int kk = 0; kk < n2; ++kk)
+                        for (int j = 0; j < 9; ++j) {
+                            const int mL = j / 3, cL = j % 3, jr = 8 - j, mR = jr / 3, cR = jr % 3;
+                            pk[((size_t)2 * kk + 1) * 10 + j] = 2 * h[((size_t)(1 + mL) * n2 + kk) * 3 + cL];
+                            pk[((size_t)2 * kk + 0) * 10 + j] = 2 * h[((size_t)(0 + mR) * n2 + kk) * 3 + cR];
+                        }
+                    FT* pp = nullptr;
+                    OB_CUDA(cudaMalloc(&pp, pk.size() * sizeof(FT)));
+                    OB_CUDA(cudaMemcpy(pp, pk.data(), pk.size() * sizeof(FT), cudaMemcpyHostToDevice));
+                    m->owned.push_back(pp);
+                    P.wzp[l] = pp;
+                }
             }
         }
     P.closure = D.closure;

@@ -44,6 +44,7 @@ struct Phys {
     GridD<FT> g;
     int scheme, zweno, buffer;       // buffer = Nᴮ of the scheme (Advection.jl:36-40)
     const FT* wc[3][2];              // stretched WENO tables [dim][0 = Face, 1 = Center] or null
+    const FT* wzp[2];                // the z tables packed per (index, side) for tendency_fused.cu (capi.cu build_phys)
     int closure;
     int vitd;                        // VerticallyImplicitTimeDiscretization (ScalarDiffusivity, Bounded z): see viscous_Aflux
     FT nu, kappa[8];                 // ScalarDiffusivity constants; SmagorinskyLilly: kappa[t] = Prandtl number of tracer t

@@ -78,7 +78,7 @@ struct Args {
     // Bounded (stretched) z variant
     const FT* izC;         // 1 / Δz of cell k, 1 / Δz at face k (Julia index k)
     const FT* izF;
-    const FT* tabF;        // WENO coefficient tables of z: reconstruction at Faces (u, v, c) / at Centers (w)
+    const FT* tabF;        // packed WENO coefficient tables of z (Phys::wzp): reconstruction at Faces (u, v, c) / Centers (w)
     const FT* tabC;
     FT vh[2], v24;         // -24 ν / Δx, -24 ν / Δy, -24 ν    (viscous fluxes in the 24 x units of the momentum fluxes)
     FT th[2], t2;          // -2 κ / Δx, -2 κ / Δy, -2 κ       (diffusive fluxes of the tracer, 2 x units)
@@ -189,22 +189,29 @@ __device__ __forceinline__ FT flux(const FT* __restrict__ S, const int (&so)[SLO
 //     (topologically_conditional_interpolation.jl:19-80 with the buffer of WENO5 = 2: fourth-order symmetric for
 //     2 < k < N-1, left-biased 2 < k < N, right-biased 1 < k < N-1);
 //   * reconstructions along z use the stretched-grid coefficient tables (weno_fifth_order.jl:526-553) with the uniform
-//     smoothness indicators, i.e. physics.cuh weno5_core with the window / table row selected by the upwind side;
+//     smoothness indicators (weno_fast.cuh weno_face_tab2: one arithmetic for both sides on the window ordered towards the
+//     face, with the packed 80-byte table row of (index, side) fetched by five 16-byte loads);
 //   * every face carries the viscous / diffusive flux of ScalarDiffusivity, -ν (∂_A u_B + ∂_B u_A) resp. -κ ∂_A c
 //     (closure_kernel_operators.jl:22-48): the two differences are the central pairs of the windows that the advective
 //     flux loads anyway (the advected field along A, the advecting velocity along B), so no extra shared-memory reads.
+// twice the upwind reconstruction along z at index kq; (a .. g) = the window ordered towards the face, (x2, x0) as in
+// weno_fast.cuh, i2 = the sum of the two values next to the face
 template <class FT, bool ZW>
-__device__ __forceinline__ FT zrecon2(const FT* __restrict__ tab, int N, int kq, bool pos, FT a, FT b, FT cc, FT d, FT g, FT i2) {
+__device__ __forceinline__ FT zrecon2(const FT* __restrict__ tab, int N, int kq, bool pos, FT a, FT b, FT cc, FT d, FT g, FT x2,
+                                      FT x0, FT i2) {
     const bool outL = kq > 2 && kq < N, outR = kq > 1 && kq < N - 1;
     if (!(outL || outR)) return i2;
-    const int n3 = 3 * (N + 2);
-    const FT* t = tab + ((pos ? n3 : 0) + 3 * kq);
-    FT cf[9];
+    FT cf[10];
+    if constexpr (sizeof(FT) == 8) {
+        const double2* t = reinterpret_cast<const double2*>(tab) + (2 * kq + (pos ? 1 : 0)) * 5;
 #pragma unroll
-    for (int m = 0; m < 3; ++m)
+        for (int q = 0; q < 5; ++q) { const double2 v = __ldg(t + q); cf[2 * q] = v.x; cf[2 * q + 1] = v.y; }
+    } else {
+        const float2* t = reinterpret_cast<const float2*>(tab) + (2 * kq + (pos ? 1 : 0)) * 5;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) cf[3 * m + q] = __ldg(t + m * n3 + q);
-    const FT r = 2 * weno5_core<FT>(pos ? SIDE_LEFT : SIDE_RIGHT, ZW ? 1 : 0, a, b, cc, d, g, cf);
+        for (int q = 0; q < 5; ++q) { const float2 v = __ldg(t + q); cf[2 * q] = v.x; cf[2 * q + 1] = v.y; }
+    }
+    const FT r = wf::weno_face_tab2<FT, ZW>(a, b, cc, d, g, x2, x0, cf);
     if (outL && outR) return r;
     return (pos ? outL : outR) ? r : i2;
 }
@@ -230,8 +237,9 @@ __device__ __forceinline__ FT fluxb(const Args<FT, NF>& c, int k, const FT* __re
             const FT i2 = w[2] + w[3];
             const FT ut = oc ? interp12<FT>(w[1], w[2], w[3], w[4]) : FT(6) * i2;
             const bool pos = ut > FT(0);
-            const FT rec = zrecon2<FT, ZW>(c.tabC, c.Nz, kq, pos, pos ? w[0] : w[1], pos ? w[1] : w[2], pos ? w[2] : w[3],
-                                           pos ? w[3] : w[4], pos ? w[4] : w[5], i2);
+            const FT wc_ = pos ? w[2] : w[3];
+            const FT rec = zrecon2<FT, ZW>(c.tabC, c.Nz, kq, pos, pos ? w[0] : w[5], pos ? w[1] : w[4], wc_, pos ? w[3] : w[2],
+                                           pos ? w[4] : w[1], pos ? wc_ : w[5], pos ? wc_ : w[1], i2);
             const FT visc = ((2 * c.v24) * __ldg(c.izC + kq)) * (w[3] - w[2]);
             return fma(ut, rec, visc);
         }
@@ -266,11 +274,11 @@ __device__ __forceinline__ FT fluxb(const Args<FT, NF>& c, int k, const FT* __re
             return fma(ut, wf::weno_face2<FT, ZW>(a, b, cc, d, g, pos ? cc : a, pos ? cc : g), visc);
         } else {            // z face at level kq of u, v or the tracer: natural windows kq-3 .. kq+1 (left) / kq-2 .. kq+2 (right)
             const FT* q = S + FB * SLOTS * PE + e;
-            const FT a = q[pos ? so[NQ] : so[NQ + 1]], b = q[pos ? so[NQ + 1] : so[NQ + 2]], cc = q[pos ? so[NQ + 2] : so[NQ + 3]],
-                     d = q[pos ? so[NQ + 3] : so[NQ + 4]], g = q[pos ? so[NQ + 4] : so[NQ + 5]];
-            const FT lo = pos ? cc : b, hi = pos ? d : cc;                 // levels kq-1, kq
-            visc = fma((B == 3 ? c.t2 : c.v24) * __ldg(c.izF + kq), hi - lo, visc);
-            return fma(ut, zrecon2<FT, ZW>(c.tabF, c.Nz, kq, pos, a, b, cc, d, g, lo + hi), visc);
+            const int oa = pos ? so[NQ] : so[NQ + 5], ob_ = pos ? so[NQ + 1] : so[NQ + 4], oc = pos ? so[NQ + 2] : so[NQ + 3],
+                      od = pos ? so[NQ + 3] : so[NQ + 2], og = pos ? so[NQ + 4] : so[NQ + 1];
+            const FT a = q[oa], b = q[ob_], cc = q[oc], d = q[od], g = q[og];
+            visc = fma((B == 3 ? c.t2 : c.v24) * __ldg(c.izF + kq), pos ? d - cc : cc - d, visc);     // levels kq-1, kq
+            return fma(ut, zrecon2<FT, ZW>(c.tabF, c.Nz, kq, pos, a, b, cc, d, g, pos ? cc : a, pos ? cc : g, cc + d), visc);
         }
     }
 }
@@ -526,7 +534,7 @@ static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     c.invdx = 1 / g.d[0]; c.invdy = 1 / g.d[1];
     if (ZT) {
         c.cf[0] = c.invdx; c.cf[1] = c.invdy; c.cf[2] = FT(0);
-        c.izC = g.izC; c.izF = g.izF; c.tabF = P.wc[2][0]; c.tabC = P.wc[2][1];
+        c.izC = g.izC; c.izF = g.izF; c.tabF = P.wzp[0]; c.tabC = P.wzp[1];
         const FT nu = P.closure == CLO_3D ? P.nu : FT(0), kap = P.closure == CLO_3D ? P.kappa[0] : FT(0);
         c.v24 = -24 * nu; c.vh[0] = c.v24 * c.invdx; c.vh[1] = c.v24 * c.invdy;
         c.t2 = -2 * kap; c.th[0] = c.t2 * c.invdx; c.th[1] = c.t2 * c.invdy;
@@ -592,7 +600,7 @@ int launch(const Phys<FT>& P, const FusedFields<FT>& a) {
         if (!g.regular[2] || P.wc[2][0] || P.wc[2][1] || P.closure != CLO_NONE) return 0;
         zt = 0;
     } else if (g.topo[2] == OB_BOUNDED) {
-        if (offb || nt == 0 || g.regular[2] || !g.izC || !g.izF || !P.wc[2][0] || !P.wc[2][1] || g.N[2] < 6) return 0;
+        if (offb || nt == 0 || g.regular[2] || !g.izC || !g.izF || !P.wzp[0] || !P.wzp[1] || g.N[2] < 6) return 0;
         if ((P.closure != CLO_NONE && P.closure != CLO_3D) || P.vitd) return 0;
         for (int s = 4; s < 6; ++s)
             if (a.fbc[2].kind[s] == 2 && a.fbc[2].val[s] != FT(0)) return 0;      // w has no Flux BCs on a Bounded z
@@ -604,7 +612,7 @@ int launch(const Phys<FT>& P, const FusedFields<FT>& a) {
     { if (P.zweno) launch_gm<FT, true, ZTV, NTV, RV>(P, a); else launch_gm<FT, false, ZTV, NTV, RV>(P, a); }
     // rows per tile: the largest for which the block (NG (R + 1) + 1 warps) keeps 72 registers per thread and the rings
     // + exchange buffers fit 227 KB; measured at 256^3: R = 12 3.13 ms per step, 11: 3.16, 10: 3.26, 9: 3.19
-    if (zt) GO(1, 1, 12)
+    if (zt) GO(1, 1, 12)         // Bounded z at 512 x 512 x 256: R = 12 15.4 ms per step of tendencies, 10: 17.2, 8: 15.4
     else if (nt == 0) GO(0, 0, 8)
     else GO(0, 1, 12)
 #undef GO

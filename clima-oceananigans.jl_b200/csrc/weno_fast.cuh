@@ -132,6 +132,52 @@ __device__ __forceinline__ FT weno_face2(FT a, FT b, FT c, FT d, FT e, FT x2, FT
     }
 }
 
+// weno_face2 on a STRETCHED axis (weno_fifth_order.jl:526-553: the candidate polynomials take their coefficients from
+// per-index tables, the smoothness indicators stay the uniform ones): cf = the nine coefficients of the three candidates
+// for the window ordered TOWARDS the face, pre-multiplied by 2 -- p0 (c, d, e), p1 (b, c, d), p2 (a, b, c) -- so that the
+// right-biased side is the same arithmetic on the mirrored window with the mirrored table row.
+template <class FT, bool ZW>
+__device__ __forceinline__ FT weno_face_tab2(FT a, FT b, FT c, FT d, FT e, FT x2, FT x0, const FT (&cf)[10]) {
+    const FT t2 = fma(FT(-2), b, a) + c, t1 = fma(FT(-2), c, b) + d, t0 = fma(FT(-2), d, c) + e;
+    const FT s2 = fma(FT(2), x2 - b, t2), s1 = b - d, s0 = fma(FT(2), x0 - d, t0);
+    const FT k133 = K<FT>(0), eps4 = K<FT>(1);
+    const FT D2 = fma(s2, s2, fma(k133 * t2, t2, eps4));      // 4 (beta_k + eps)
+    const FT D1 = fma(s1, s1, fma(k133 * t1, t1, eps4));
+    const FT D0 = fma(s0, s0, fma(k133 * t0, t0, eps4));
+    const FT p0 = fma(cf[0], c, fma(cf[1], d, cf[2] * e));
+    const FT p1 = fma(cf[3], b, fma(cf[4], c, cf[5] * d));
+    const FT p2 = fma(cf[6], a, fma(cf[7], b, cf[8] * c));
+    if constexpr (sizeof(FT) == 8) {
+        const FT E0 = D0 * D0, E1 = D1 * D1, E2 = D2 * D2;
+        const FT P12 = E1 * E2, P02 = E0 * E2, P01 = E0 * E1;
+        FT g0, g1, g2;       // 10 x the unnormalised weights
+        if (ZW) {
+            const FT tau = D2 - D0, tt = tau * tau, PI = E0 * P12;
+            g0 = FT(3) * fma(tt, P12, PI);
+            g1 = FT(6) * fma(tt, P02, PI);
+            g2 = fma(tt, P01, PI);
+        } else {
+            g0 = FT(3) * P12; g1 = FT(6) * P02; g2 = P01;
+        }
+        const FT den = (g0 + g1) + g2;
+        const FT S = fma(g0, p0, fma(g1, p1, g2 * p2));
+        const FT r0 = rcp_seed(den);
+        const FT er = fma(-den, r0, FT(1));
+        const FT q0 = S * r0;
+        return fma(q0, fma(er, er, er), q0);     // S / den
+    } else {
+        FT a0, a1, a2;
+        if (ZW) {
+            const FT tau = D2 - D0;
+            const FT q0 = __fdividef(tau, D0), q1 = __fdividef(tau, D1), q2 = __fdividef(tau, D2);
+            a0 = FT(3) * fma(q0, q0, FT(1)); a1 = FT(6) * fma(q1, q1, FT(1)); a2 = fma(q2, q2, FT(1));
+        } else {
+            a0 = __fdividef(FT(3), D0 * D0); a1 = __fdividef(FT(6), D1 * D1); a2 = __fdividef(FT(1), D2 * D2);
+        }
+        return __fdividef(fma(a0, p0, fma(a1, p1, a2 * p2)), (a0 + a1) + a2);
+    }
+}
+
 // upwind selection of the window out of the six values psi[f-3 .. f+2] around face f
 template <class FT, bool ZW>
 __device__ __forceinline__ FT weno_upwind(bool pos, FT w0, FT w1, FT w2, FT w3, FT w4, FT w5) {
