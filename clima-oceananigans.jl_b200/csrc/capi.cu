@@ -271,6 +271,16 @@ static void build_gridD(ob200_grid* G, GridD<FT>& g) {
 
 template <class FT>
 static void upload_metrics(ob200_grid* G, GridD<FT>& g, const ob200_grid_desc* src) {
+    if (g.regular[2] && g.topo[2] == OB_BOUNDED) {
+        // constant reciprocal spacings in the table form the Bounded-z fused tendency kernel reads (tendency_fused.cu)
+        const int lo = -g.H[2] - 1, hi = g.N[2] + g.H[2] + 2;
+        std::vector<FT> v(hi - lo + 1, FT(1) / g.d[2]);
+        FT* iptr = nullptr;
+        OB_CUDA(cudaMalloc(&iptr, v.size() * sizeof(FT)));
+        OB_CUDA(cudaMemcpy(iptr, v.data(), v.size() * sizeof(FT), cudaMemcpyHostToDevice));
+        G->owned.push_back(iptr);
+        g.izC = g.izF = iptr - lo;
+    }
     for (int d = 0; d < 3; ++d) {
         if (g.regular[d]) continue;
         for (int w = 0; w < 2; ++w) {
@@ -725,6 +735,20 @@ static void build_phys(ob200_model* m) {
                 }
             }
         }
+    if (D.advection == OB200_ADV_WENO5 && P.g.topo[2] == OB_BOUNDED && P.g.regular[2] && !P.wzp[0]) {
+        // regular Bounded z: the uniform coefficients (weno_fifth_order.jl:518-524) in the same packed form; the window
+        // ordered towards the face makes the two sides' rows identical
+        const double cu[9] = {1.0 / 3, 5.0 / 6, -1.0 / 6, -1.0 / 6, 5.0 / 6, 1.0 / 3, 1.0 / 3, -7.0 / 6, 11.0 / 6};
+        const int n2 = P.g.N[2] + 2;
+        std::vector<FT> pk((size_t)n2 * 2 * 10, FT(0));
+        for (int r = 0; r < 2 * n2; ++r)
+            for (int j = 0; j < 9; ++j) pk[(size_t)r * 10 + j] = (FT)(2 * cu[j]);
+        FT* pp = nullptr;
+        OB_CUDA(cudaMalloc(&pp, pk.size() * sizeof(FT)));
+        OB_CUDA(cudaMemcpy(pp, pk.data(), pk.size() * sizeof(FT), cudaMemcpyHostToDevice));
+        m->owned.push_back(pp);
+        P.wzp[0] = P.wzp[1] = pp;
+    }
     P.closure = D.closure;
     P.vitd = D.closure_vertically_implicit;
     P.nu = (FT)D.nu;

@@ -10,9 +10,15 @@
 //     (bit-reversed in, natural out), so NO reordering pass exists anywhere: spectral data
 //     simply lives in bit-reversed order along such a dimension, and the eigenvalue tables are
 //     uploaded in that same order.
-//   * any other length (Periodic non-power-of-two, and Bounded = DCT-II / DCT-III with the
-//     FFTW REDFT10 / REDFT01/(2N) conventions): direct O(n^2) evaluation from an exact
-//     twiddle table; spectral order natural.
+//   * Bounded dims (DCT-II / DCT-III with the FFTW REDFT10 / REDFT01/(2N) conventions): Makhoul's algorithm -- the
+//     even / odd permutation of the line (index_permutations.jl:18-94 does the same for the reference's GPU transforms,
+//     discrete_transforms.jl:140-183) folded into the global load / store, one complex FFT of the same length, and a
+//     pairwise (k, n-k) twiddle that also separates the transforms of the real and the imaginary part of the line.
+//     Power-of-two lengths keep the spectrum in bit-reversed positions like the Periodic ones.
+//   * non-power-of-two lengths (Periodic, or the FFT inside a Bounded transform): Bluestein's chirp-z algorithm on the
+//     same shared-memory butterflies with M = the power of two >= 2n - 1; spectral order natural.
+//   * lengths whose M does not fit shared memory (n > 2048), n = 1 and OB200_DIRECT_TRANSFORMS=1: direct O(n^2)
+//     evaluation from an exact twiddle table (the round-1 path, kept as the cross-check of the fast ones).
 // A block transforms T lines that are adjacent along the contiguous (x) direction so that
 // every global access is a run of T consecutive complex numbers.
 #include "internal.h"
@@ -27,7 +33,7 @@ template <class FT> struct Cx;
 template <> struct Cx<float> { using T = float2; };
 template <> struct Cx<double> { using T = double2; };
 
-enum { TK_POW2 = 0, TK_DFT = 1, TK_DCT = 2 };
+enum { TK_POW2 = 0, TK_DFT = 1, TK_DCT = 2, TK_DCT_POW2 = 3, TK_BLUE = 4, TK_DCT_BLUE = 5 };
 enum { MODE_FWD = 0, MODE_INV = 1, MODE_FWD_DIV_INV = 2 };
 
 template <class FT>
@@ -39,7 +45,11 @@ struct FftArgs {
     long long strideA, strideB;    // between adjacent lines
     int T;                         // lines per block (adjacent along A)
     int kind;
-    const typename Cx<FT>::T* tw;  // POW2: n/2 entries exp(-2 pi i k/n); DFT: n entries; DCT: 4n cos (x only)
+    const typename Cx<FT>::T* tw;  // POW2: n/2 entries exp(-2 pi i k/n); DFT: n entries; DCT: 4n cos (x only);
+                                   // DCT_POW2: n/2 FFT twiddles + n exp(-i pi k/(2n)); BLUE: M/2 FFT twiddles + n chirp
+                                   // exp(-i pi k^2/n); DCT_BLUE: the same + n exp(-i pi k/(2n))
+    int M, log2M;                  // Bluestein: convolution length
+    const typename Cx<FT>::T* bhat;// Bluestein: FFT_M of the conjugate chirp / M, in bit-reversed positions (global memory)
     FT scale;                      // applied after the inverse transform (1/n, or 1/(2n) for DCT)
     // eigenvalue divide (MODE_FWD_DIV_INV): lam[dim] in storage order, dims of (line, A, B)
     const double* lam[3];
@@ -74,16 +84,17 @@ __device__ __forceinline__ void pow2_fft_smem(typename Cx<FT>::T* s, const typen
         for (int st = 0; st < log2n; ++st) {
             int h = half >> st;
             int tstep = 1 << st;          // twiddle index step: n/(2h)
+            const int lh = log2n - 1 - st;        // h = 2^lh: shifts instead of integer divisions
             for (int w = threadIdx.x; w < total; w += blockDim.x) {
-                int t = w / half, bf = w - t * half;
-                int j = ((bf / h) * (h << 1)) + (bf % h);
+                int t = w >> (log2n - 1), bf = w & (half - 1);
+                int r = bf & (h - 1), j = ((bf >> lh) << (lh + 1)) + r;
                 CT* x = s + t * LS;
                 CT a = x[j], b = x[j + h];
                 CT su, di;
                 su.x = a.x + b.x; su.y = a.y + b.y;
                 di.x = a.x - b.x; di.y = a.y - b.y;
                 x[j] = su;
-                x[j + h] = cmul(di, tw[(bf % h) * tstep]);
+                x[j + h] = cmul(di, tw[r * tstep]);
             }
             __syncthreads();
         }
@@ -91,11 +102,12 @@ __device__ __forceinline__ void pow2_fft_smem(typename Cx<FT>::T* s, const typen
         for (int st = log2n - 1; st >= 0; --st) {
             int h = half >> st;
             int tstep = 1 << st;
+            const int lh = log2n - 1 - st;
             for (int w = threadIdx.x; w < total; w += blockDim.x) {
-                int t = w / half, bf = w - t * half;
-                int j = ((bf / h) * (h << 1)) + (bf % h);
+                int t = w >> (log2n - 1), bf = w & (half - 1);
+                int r = bf & (h - 1), j = ((bf >> lh) << (lh + 1)) + r;
                 CT* x = s + t * LS;
-                CT a = x[j], b = cmulc(x[j + h], tw[(bf % h) * tstep]);
+                CT a = x[j], b = cmulc(x[j + h], tw[r * tstep]);
                 CT su, di;
                 su.x = a.x + b.x; su.y = a.y + b.y;
                 di.x = a.x - b.x; di.y = a.y - b.y;
@@ -105,6 +117,96 @@ __device__ __forceinline__ void pow2_fft_smem(typename Cx<FT>::T* s, const typen
             __syncthreads();
         }
     }
+}
+
+// ---- Makhoul DCT-II / DCT-III around a complex FFT of the same length ------------------------------------------------------
+// position of element m of the line in the transform's input: evens ascending, then odds descending
+__device__ __forceinline__ int dct_perm(int m, int n) { return (m & 1) ? n - 1 - (m >> 1) : (m >> 1); }
+template <bool BR> __device__ __forceinline__ int spos(int k, int log2n) {
+    return BR ? (int)(__brev((unsigned)k) >> (32 - log2n)) : k;
+}
+// after the FFT V of the permuted line: Y_k = 2 Re(w_k V_k) separately for the real and the imaginary part of the line,
+// i.e. with A = w_k V_k, B = w_k conj(V_{n-k}): Y_k = (Re A + Re B) + i (Im A - Im B); in place on the pair (k, n-k)
+template <class FT, bool BR>
+__device__ __forceinline__ void dct_post(typename Cx<FT>::T* s, const typename Cx<FT>::T* wk, int n, int log2n, int T, int LS) {
+    using CT = typename Cx<FT>::T;
+    const int np = n / 2 + 1, total = T * np;
+    for (int w = threadIdx.x; w < total; w += blockDim.x) {
+        const int t = w / np, k = w - t * np, m = (n - k) % n;
+        if (m < k) continue;
+        CT* x = s + t * LS;
+        const int pk = spos<BR>(k, log2n), pm = spos<BR>(m, log2n);
+        const CT Vk = x[pk], Vm = x[pm];
+        CT A = cmul(wk[k], Vk), B = cmulc(wk[k], Vm), Y;      // w conj(V) = conj(conj(w) V); cmulc(a, b) = a conj(b)
+        Y.x = A.x + B.x; Y.y = A.y - B.y;
+        x[pk] = Y;
+        if (m != k) {
+            A = cmul(wk[m], Vm); B = cmulc(wk[m], Vk);
+            Y.x = A.x + B.x; Y.y = A.y - B.y;
+            x[pm] = Y;
+        }
+    }
+    __syncthreads();
+}
+// before the inverse FFT: R_k = conj(w_k) [(Re Y_k + Im Y_{n-k}) + i (Im Y_k - Re Y_{n-k})], Y_n := 0; the unnormalised
+// inverse FFT of R is 2n x the permuted line, which is REDFT01's scaling
+template <class FT, bool BR>
+__device__ __forceinline__ void dct_pre(typename Cx<FT>::T* s, const typename Cx<FT>::T* wk, int n, int log2n, int T, int LS) {
+    using CT = typename Cx<FT>::T;
+    const int np = n / 2 + 1, total = T * np;
+    for (int w = threadIdx.x; w < total; w += blockDim.x) {
+        const int t = w / np, k = w - t * np, m = (n - k) % n;
+        if (m < k) continue;
+        CT* x = s + t * LS;
+        const int pk = spos<BR>(k, log2n), pm = spos<BR>(m, log2n);
+        const CT Yk = x[pk];
+        CT Ym = x[pm], Z;
+        if (k == 0) { Ym.x = 0; Ym.y = 0; }
+        Z.x = Yk.x + Ym.y; Z.y = Yk.y - Ym.x;
+        x[pk] = cmulc(Z, wk[k]);
+        if (m != k) {
+            Z.x = Ym.x + Yk.y; Z.y = Ym.y - Yk.x;
+            x[pm] = cmulc(Z, wk[m]);
+        }
+    }
+    __syncthreads();
+}
+
+// ---- Bluestein: DFT of any length n as a circular convolution of length M = 2^log2M >= 2n - 1 ---------------------------------
+// X_k = c_k sum_j (x_j c_j) conj(c_{k-j}), c_m = exp(-i pi m^2 / n).  INVERSE: the unnormalised inverse DFT as
+// conj(DFT(conj(x))).  Natural order in and out, in place in the first n entries of each line (LS >= M).
+template <class FT, bool INVERSE>
+__device__ __forceinline__ void blue_dft(typename Cx<FT>::T* s, const typename Cx<FT>::T* twM, const typename Cx<FT>::T* chirp,
+                                         const typename Cx<FT>::T* __restrict__ bhat, int n, int M, int log2M, int T, int LS) {
+    using CT = typename Cx<FT>::T;
+    const int total = T * M;
+    for (int w = threadIdx.x; w < total; w += blockDim.x) {
+        const int t = w / M, j = w - t * M;
+        CT v;
+        v.x = 0; v.y = 0;
+        if (j < n) {
+            v = s[t * LS + j];
+            if (INVERSE) v.y = -v.y;
+            v = cmul(v, chirp[j]);
+        }
+        s[t * LS + j] = v;
+    }
+    __syncthreads();
+    pow2_fft_smem<FT, false>(s, twM, M, log2M, T, LS);
+    for (int w = threadIdx.x; w < total; w += blockDim.x) {
+        const int t = w / M, j = w - t * M;
+        s[t * LS + j] = cmul(s[t * LS + j], bhat[j]);
+    }
+    __syncthreads();
+    pow2_fft_smem<FT, true>(s, twM, M, log2M, T, LS);
+    const int tn = T * n;
+    for (int w = threadIdx.x; w < tn; w += blockDim.x) {
+        const int t = w / n, j = w - t * n;
+        CT v = cmul(s[t * LS + j], chirp[j]);
+        if (INVERSE) v.y = -v.y;
+        s[t * LS + j] = v;
+    }
+    __syncthreads();
 }
 
 // direct O(n^2) transforms: s (input) -> o (output), both in shared memory
@@ -156,34 +258,51 @@ __global__ void fft_lines_kernel(FftArgs<FT> A) {
     using CT = typename Cx<FT>::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CT* s = reinterpret_cast<CT*>(smem_raw);
-    const int n = A.n, T = A.T, LS = n + A.pad;
+    const int n = A.n, T = A.T, kind = A.kind;
+    const bool blue = kind == TK_BLUE || kind == TK_DCT_BLUE, fdct = kind == TK_DCT_POW2 || kind == TK_DCT_BLUE;
+    const bool direct = kind == TK_DFT || kind == TK_DCT;
+    const int LS = (blue ? A.M : n) + A.pad;
     CT* s2 = s + T * LS;                                  // second buffer (direct kinds only)
-    CT* stw = A.kind == TK_POW2 ? s2 : s2 + T * LS;       // twiddle copy
-    int ntw = A.kind == TK_POW2 ? n / 2 : (A.kind == TK_DFT ? n : 4 * n);
+    CT* stw = direct ? s2 + T * LS : s2;                  // twiddle copy
+    const int nfft = blue ? A.M / 2 : n / 2;              // butterflies' twiddles come first in the fast kinds' tables
+    const int ntw = kind == TK_POW2 ? n / 2 : kind == TK_DFT ? n : kind == TK_DCT ? 4 * n
+                  : kind == TK_DCT_POW2 ? n / 2 + n : kind == TK_BLUE ? A.M / 2 + n : A.M / 2 + 2 * n;
     for (int w = threadIdx.x; w < ntw; w += blockDim.x) stw[w] = A.tw[w];
+    const CT* chirp = stw + nfft;                         // Bluestein kinds
+    const CT* wk = stw + nfft + (blue ? n : 0);           // Makhoul kinds
 
     int a0 = blockIdx.x * T, b = blockIdx.y;
     int nl = min(T, A.nA - a0);                           // lines in this block
     long long base = a0 * A.strideA + b * A.strideB;
     int total = nl * n;
+    // Makhoul: the even / odd permutation is applied where the line is in physical space -- on the load before a forward
+    // transform, on the store after an inverse one
+    const bool perm_in = fdct && MODE != MODE_INV, perm_out = fdct && MODE != MODE_FWD;
     // load: consecutive threads take consecutive memory
     if (A.stride == 1) {
         for (int w = threadIdx.x; w < total; w += blockDim.x) {
             int t = w / n, m = w - t * n;
-            s[t * LS + m] = A.data[base + t * A.strideA + m];
+            s[t * LS + (perm_in ? dct_perm(m, n) : m)] = A.data[base + t * A.strideA + m];
         }
     } else {
         for (int w = threadIdx.x; w < total; w += blockDim.x) {
             int m = w / nl, t = w - m * nl;
-            s[t * LS + m] = A.data[base + t * A.strideA + m * A.stride];
+            s[t * LS + (perm_in ? dct_perm(m, n) : m)] = A.data[base + t * A.strideA + m * A.stride];
         }
     }
     __syncthreads();
 
     CT* cur = s;
     if (MODE == MODE_FWD || MODE == MODE_FWD_DIV_INV) {
-        if (A.kind == TK_POW2) pow2_fft_smem<FT, false>(s, stw, n, A.log2n, nl, LS);
-        else { direct_smem<FT, false>(s, s2, stw, n, nl, LS, A.kind); cur = s2; }
+        if (kind == TK_POW2) pow2_fft_smem<FT, false>(s, stw, n, A.log2n, nl, LS);
+        else if (kind == TK_DCT_POW2) {
+            pow2_fft_smem<FT, false>(s, stw, n, A.log2n, nl, LS);
+            dct_post<FT, true>(s, wk, n, A.log2n, nl, LS);
+        } else if (kind == TK_BLUE) blue_dft<FT, false>(s, stw, chirp, A.bhat, n, A.M, A.log2M, nl, LS);
+        else if (kind == TK_DCT_BLUE) {
+            blue_dft<FT, false>(s, stw, chirp, A.bhat, n, A.M, A.log2M, nl, LS);
+            dct_post<FT, false>(s, wk, n, 0, nl, LS);
+        } else { direct_smem<FT, false>(s, s2, stw, n, nl, LS, kind); cur = s2; }
     }
     if (MODE == MODE_FWD_DIV_INV) {
         // phi_hat = -b_hat / (lx + ly + lz) ; phi_hat[1,1,1] = 0   (fft_based_poisson_solver.jl:106-111)
@@ -203,10 +322,17 @@ __global__ void fft_lines_kernel(FftArgs<FT> A) {
         __syncthreads();
     }
     if (MODE == MODE_INV || MODE == MODE_FWD_DIV_INV) {
-        if (A.kind == TK_POW2) pow2_fft_smem<FT, true>(cur, stw, n, A.log2n, nl, LS);
-        else {
+        if (kind == TK_POW2) pow2_fft_smem<FT, true>(cur, stw, n, A.log2n, nl, LS);
+        else if (kind == TK_DCT_POW2) {
+            dct_pre<FT, true>(cur, wk, n, A.log2n, nl, LS);
+            pow2_fft_smem<FT, true>(cur, stw, n, A.log2n, nl, LS);
+        } else if (kind == TK_BLUE) blue_dft<FT, true>(cur, stw, chirp, A.bhat, n, A.M, A.log2M, nl, LS);
+        else if (kind == TK_DCT_BLUE) {
+            dct_pre<FT, false>(cur, wk, n, 0, nl, LS);
+            blue_dft<FT, true>(cur, stw, chirp, A.bhat, n, A.M, A.log2M, nl, LS);
+        } else {
             CT* dst = cur == s ? s2 : s;
-            direct_smem<FT, true>(cur, dst, stw, n, nl, LS, A.kind);
+            direct_smem<FT, true>(cur, dst, stw, n, nl, LS, kind);
             cur = dst;
         }
     }
@@ -219,7 +345,7 @@ __global__ void fft_lines_kernel(FftArgs<FT> A) {
                 int id[3];
                 id[A.dimL] = m; id[A.dimA] = a0 + t; id[A.dimB] = b;
                 A.phi_p0[(id[0] + 1) * A.phi_st[0] + (id[1] + 1) * A.phi_st[1] + (id[2] + 1) * A.phi_st[2]] =
-                    cur[t * LS + m].x * A.scale;
+                    cur[t * LS + (perm_out ? dct_perm(m, n) : m)].x * A.scale;
             }
         } else {
             for (int w = threadIdx.x; w < total; w += blockDim.x) {
@@ -227,7 +353,7 @@ __global__ void fft_lines_kernel(FftArgs<FT> A) {
                 int id[3];
                 id[A.dimL] = m; id[A.dimA] = a0 + t; id[A.dimB] = b;
                 A.phi_p0[(id[0] + 1) * A.phi_st[0] + (id[1] + 1) * A.phi_st[1] + (id[2] + 1) * A.phi_st[2]] =
-                    cur[t * LS + m].x * A.scale;
+                    cur[t * LS + (perm_out ? dct_perm(m, n) : m)].x * A.scale;
             }
         }
         return;
@@ -235,14 +361,14 @@ __global__ void fft_lines_kernel(FftArgs<FT> A) {
     if (A.stride == 1) {
         for (int w = threadIdx.x; w < total; w += blockDim.x) {
             int t = w / n, m = w - t * n;
-            CT v = cur[t * LS + m];
+            CT v = cur[t * LS + (perm_out ? dct_perm(m, n) : m)];
             if (scale) { v.x *= A.scale; v.y *= A.scale; }
             A.data[base + t * A.strideA + m] = v;
         }
     } else {
         for (int w = threadIdx.x; w < total; w += blockDim.x) {
             int m = w / nl, t = w - m * nl;
-            CT v = cur[t * LS + m];
+            CT v = cur[t * LS + (perm_out ? dct_perm(m, n) : m)];
             if (scale) { v.x *= A.scale; v.y *= A.scale; }
             A.data[base + t * A.strideA + m * A.stride] = v;
         }
@@ -358,7 +484,8 @@ struct PoissonPlan {
     CT* source = nullptr;      // tridiagonal: transformed source term
     FT* scratch = nullptr;     // tridiagonal: t
     CT* tw[3] = {nullptr, nullptr, nullptr};
-    int tkind[3], log2n[3];
+    CT* bhat[3] = {nullptr, nullptr, nullptr};      // Bluestein kinds: transformed conjugate chirp
+    int tkind[3], log2n[3], M[3] = {0, 0, 0}, log2M[3] = {0, 0, 0};
     double* lam[3] = {nullptr, nullptr, nullptr};   // storage order
     double* dzF = nullptr;     // device, indexable by Julia index 0..Nz+1 (offset applied)
     double* dzC = nullptr;
@@ -378,6 +505,8 @@ template <class T> static T* dev_upload(const std::vector<T>& h, std::vector<voi
     owned.push_back(d);
     return d;
 }
+
+template <class FT> static void launch_lines(FftArgs<FT>& A, int mode, bool contiguous_lines);
 
 template <class FT>
 PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double* dzF_host, const double* dzC_host) {
@@ -414,8 +543,16 @@ PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double*
         int n = g.N[d];
         p->N[d] = n; p->topo[d] = g.topo[d];
         bool pow2 = n >= 2 && (n & (n - 1)) == 0;
-        int tk = g.topo[d] == OB_BOUNDED ? TK_DCT : (pow2 ? TK_POW2 : TK_DFT);
+        static const bool force_direct = getenv("OB200_DIRECT_TRANSFORMS") != nullptr;
+        int M = 1;
+        while (M < 2 * n - 1) M <<= 1;
+        const bool blue_ok = n >= 2 && M <= 4096;
+        int tk;
+        if (g.topo[d] == OB_BOUNDED) tk = force_direct ? TK_DCT : (pow2 ? TK_DCT_POW2 : (blue_ok ? TK_DCT_BLUE : TK_DCT));
+        else tk = pow2 ? TK_POW2 : (!force_direct && blue_ok ? TK_BLUE : TK_DFT);
         p->tkind[d] = tk; p->log2n[d] = ilog2(n);
+        const bool blue = tk == TK_BLUE || tk == TK_DCT_BLUE;
+        if (blue) { p->M[d] = M; p->log2M[d] = ilog2(M); }
         if (g.topo[d] == OB_FLAT || (kind == 2 && d == 2)) {    // not transformed
             if (g.topo[d] == OB_FLAT) {
                 std::vector<double> z(n, 0.0);
@@ -425,12 +562,50 @@ PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double*
         }
         // twiddles, computed in long double and rounded once
         std::vector<CT> tw;
-        int ntw = tk == TK_POW2 ? n / 2 : (tk == TK_DFT ? n : 4 * n);
-        tw.resize(std::max(1, ntw));
-        for (int k = 0; k < ntw; ++k) {
-            long double ang = tk == TK_DCT ? (long double)PI * k / (2.0L * n) : -2.0L * (long double)PI * k / n;
-            tw[k].x = (FT)cosl(ang);
-            tw[k].y = tk == TK_DCT ? (FT)0 : (FT)sinl(ang);
+        const long double PIL = 3.14159265358979323846264338327950288L;
+        if (tk == TK_POW2 || tk == TK_DFT || tk == TK_DCT) {
+            int ntw = tk == TK_POW2 ? n / 2 : (tk == TK_DFT ? n : 4 * n);
+            tw.resize(std::max(1, ntw));
+            for (int k = 0; k < ntw; ++k) {
+                long double ang = tk == TK_DCT ? (long double)PI * k / (2.0L * n) : -2.0L * (long double)PI * k / n;
+                tw[k].x = (FT)cosl(ang);
+                tw[k].y = tk == TK_DCT ? (FT)0 : (FT)sinl(ang);
+            }
+        } else {
+            // butterflies' twiddles (length n or M), [chirp exp(-i pi k^2 / n)], [Makhoul exp(-i pi k / (2n))]
+            const int nf = blue ? M : n;
+            auto push = [&](long double ang) { CT c; c.x = (FT)cosl(ang); c.y = (FT)sinl(ang); tw.push_back(c); };
+            for (int k = 0; k < nf / 2; ++k) push(-2.0L * PIL * k / nf);
+            if (blue)
+                for (int k = 0; k < n; ++k) push(-PIL * (long double)(((long long)k * k) % (2LL * n)) / n);
+            if (tk != TK_BLUE)
+                for (int k = 0; k < n; ++k) push(-PIL * k / (2.0L * n));
+            if (blue) {
+                // FFT_M of b (b_m = conj(chirp_|m|), |m| < n, wrapped) in long double, divided by M, in the bit-reversed
+                // positions the decimation-in-frequency butterflies leave the spectrum in
+                std::vector<long double> br(M, 0.0L), bi(M, 0.0L);
+                for (int m2 = 0; m2 < n; ++m2) {
+                    long double ang = PIL * (long double)(((long long)m2 * m2) % (2LL * n)) / n;
+                    br[m2] = cosl(ang); bi[m2] = sinl(ang);
+                    if (m2) { br[M - m2] = br[m2]; bi[M - m2] = bi[m2]; }
+                }
+                const int lg = ilog2(M);
+                for (int i = 0; i < M; ++i) { int j = bitrev(i, lg); if (j > i) { std::swap(br[i], br[j]); std::swap(bi[i], bi[j]); } }
+                for (int len = 2; len <= M; len <<= 1)
+                    for (int i = 0; i < M; i += len)
+                        for (int j = 0; j < len / 2; ++j) {
+                            long double a = -2.0L * PIL * j / len, wr = cosl(a), wi = sinl(a);
+                            int u = i + j, v = u + len / 2;
+                            long double tr = br[v] * wr - bi[v] * wi, ti = br[v] * wi + bi[v] * wr;
+                            br[v] = br[u] - tr; bi[v] = bi[u] - ti; br[u] += tr; bi[u] += ti;
+                        }
+                std::vector<CT> bh(M);
+                for (int pos = 0; pos < M; ++pos) {
+                    int f = bitrev(pos, lg);
+                    bh[pos].x = (FT)(br[f] / M); bh[pos].y = (FT)(bi[f] / M);
+                }
+                p->bhat[d] = dev_upload(bh, p->owned);
+            }
         }
         p->tw[d] = dev_upload(tw, p->owned);
         // eigenvalues (poisson_eigenvalues.jl:8-31), Float64, then permuted to storage order
@@ -441,8 +616,26 @@ PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double*
             lam[i] = v * v;
         }
         std::vector<double> lp(n);
-        for (int i = 0; i < n; ++i) lp[i] = lam[tk == TK_POW2 ? bitrev(i, p->log2n[d]) : i];
+        for (int i = 0; i < n; ++i) lp[i] = lam[(tk == TK_POW2 || tk == TK_DCT_POW2) ? bitrev(i, p->log2n[d]) : i];
         p->lam[d] = dev_upload(lp, p->owned);
+    }
+    // (Periodic, Periodic, Bounded) on a regular grid: the half-spectrum x / y passes of fft_fast.cu around a z pass of this
+    // file's line kernel (Makhoul DCT, eigenvalue divide, inverse DCT) applied to the half spectrum in place
+    if (kind == 1 && !p->fast && g.regular[2] && ff::fast_ft_supported<FT>(g) && getenv("OB200_NO_FAST_FFT") == nullptr &&
+        (p->tkind[2] == TK_DCT_POW2 || p->tkind[2] == TK_DCT_BLUE)) {
+        p->fast = ff::fast_poisson_create<FT>(g);
+        ff::fast_poisson_set_zhook<FT>(p->fast, [p]() {
+            const ff::FastSpecInfo I = ff::fast_poisson_spec_info<FT>(p->fast);
+            FftArgs<FT> A;
+            A.data = (CT*)I.spec; A.n = I.Nz; A.log2n = p->log2n[2]; A.stride = (long long)I.NXP * I.Ny;
+            A.dimL = 2; A.dimA = 0; A.dimB = 1;
+            A.nA = I.NXH; A.nB = I.Ny; A.strideA = 1; A.strideB = I.NXP;
+            A.kind = p->tkind[2]; A.tw = p->tw[2]; A.M = p->M[2]; A.log2M = p->log2M[2]; A.bhat = p->bhat[2];
+            A.scale = (FT)(1.0 / (2.0 * A.n));
+            A.lam[0] = I.lamx; A.lam[1] = I.lamy; A.lam[2] = p->lam[2];
+            A.phi_p0 = nullptr;
+            launch_lines<FT>(A, MODE_FWD_DIV_INV, false);
+        });
     }
     if (kind == 2) {
         int Nz = g.N[2];
@@ -473,6 +666,8 @@ template <class FT> void poisson_plan_destroy(PoissonPlan<FT>* p) {
 template <class FT> void* poisson_storage(PoissonPlan<FT>* p) { return p->kind == 2 ? (void*)p->source : (void*)p->storage; }
 template <class FT> int poisson_kind(PoissonPlan<FT>* p) { return p->kind; }
 
+template <class FT> static void launch_lines(FftArgs<FT>& A, int mode, bool contiguous_lines);
+
 template <class FT>
 static void run_pass(PoissonPlan<FT>* p, typename Cx<FT>::T* data, int d, int mode, const GridD<FT>* gphi, FT* phi_p0) {
     using CT = typename Cx<FT>::T;
@@ -485,23 +680,37 @@ static void run_pass(PoissonPlan<FT>* p, typename Cx<FT>::T* data, int d, int mo
     A.nA = p->N[A.dimA]; A.nB = p->N[A.dimB];
     A.strideA = st[A.dimA]; A.strideB = st[A.dimB];
     A.kind = p->tkind[d]; A.tw = p->tw[d];
-    A.scale = p->tkind[d] == TK_DCT ? (FT)(1.0 / (2.0 * A.n)) : (FT)(1.0 / A.n);
+    A.M = p->M[d]; A.log2M = p->log2M[d]; A.bhat = p->bhat[d];
+    const bool is_dct = A.kind == TK_DCT || A.kind == TK_DCT_POW2 || A.kind == TK_DCT_BLUE;
+    A.scale = is_dct ? (FT)(1.0 / (2.0 * A.n)) : (FT)(1.0 / A.n);
     for (int q = 0; q < 3; ++q) A.lam[q] = p->lam[q];
     A.phi_p0 = phi_p0;
     if (gphi) for (int q = 0; q < 3; ++q) A.phi_st[q] = gphi->st[q];
+    launch_lines<FT>(A, mode, d == 0);
+}
+
+// lines per block and launch of fft_lines_kernel for a filled argument block
+template <class FT>
+static void launch_lines(FftArgs<FT>& A, int mode, bool contiguous_lines) {
+    using CT = typename Cx<FT>::T;
+    const bool blue = A.kind == TK_BLUE || A.kind == TK_DCT_BLUE, direct = A.kind == TK_DFT || A.kind == TK_DCT;
     A.pad = 1;
-    int LS = A.n + A.pad;
-    int nbuf = A.kind == TK_POW2 ? 1 : 2;
-    int ntw = A.kind == TK_POW2 ? A.n / 2 : (A.kind == TK_DFT ? A.n : 4 * A.n);
-    // lines per block: fill ~64-96 KB of shared memory, at least 16 B * T contiguous
-    int T = 16;
+    int LS = (blue ? A.M : A.n) + A.pad;
+    int nbuf = direct ? 2 : 1;
+    int ntw = A.kind == TK_POW2 ? A.n / 2 : A.kind == TK_DFT ? A.n : A.kind == TK_DCT ? 4 * A.n
+            : A.kind == TK_DCT_POW2 ? A.n / 2 + A.n : A.kind == TK_BLUE ? A.M / 2 + A.n : A.M / 2 + 2 * A.n;
+    // lines per block: 8 adjacent lines = 128-byte runs of the strided passes; more lines per block mean fewer resident
+    // blocks to cover the per-stage barriers (256^3, ms per solve: T = 16 2.83, 8 2.32, 4 2.37; 512 threads 2.39)
+    static const int t_env = getenv("OB200_LINES_T") ? atoi(getenv("OB200_LINES_T")) : 0;
+    static const int thr_env = getenv("OB200_LINES_THREADS") ? atoi(getenv("OB200_LINES_THREADS")) : 0;
+    int T = t_env > 0 ? t_env : 8;
     while (T > 1 && ((size_t)nbuf * T * LS + ntw) * sizeof(CT) > 96 * 1024) T >>= 1;
-    if (d == 0) { int Tm = std::max(1, 4096 / A.n); T = std::min(T, Tm); }
+    if (contiguous_lines) { int Tm = std::max(1, 4096 / A.n); T = std::min(T, Tm); }
     T = std::min(T, A.nA);
     A.T = T;
     size_t smem = ((size_t)nbuf * T * LS + ntw) * sizeof(CT);
     dim3 grd(cdiv(A.nA, T), A.nB);
-    int threads = 256;
+    int threads = thr_env > 0 ? thr_env : 256;
     auto launch = [&](auto kern) {
         OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         kern<<<grd, threads, smem, stream()>>>(A);

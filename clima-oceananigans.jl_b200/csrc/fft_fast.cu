@@ -537,6 +537,7 @@ struct FastPoisson {
     double *lamx = nullptr, *lamy = nullptr, *lamz = nullptr;
     std::vector<void*> owned;
     int tri = 0;                                // Fourier-tridiagonal solve: z is Bounded and solved by Thomas
+    std::function<void()> zhook;                // ... or transformed by the caller's DCT pass (regular z, FFT-based solver)
     const double *dzF = nullptr, *dzC = nullptr; // device, Julia-indexed 0..Nz+1 (owned by the PoissonPlan)
     FT* tsc = nullptr;                          // Thomas scratch t, [Nz][Ny][NXP]
     bool tma_ok = false;                        // persistent TMA-pipelined y / z passes (fft_tma.cuh)
@@ -682,6 +683,10 @@ FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
 template <class FT> void fast_poisson_set_tridiagonal(FastPoisson<FT>* p, const double* dzF_dev, const double* dzC_dev) {
     p->dzF = dzF_dev; p->dzC = dzC_dev;
 }
+template <class FT> FastSpecInfo fast_poisson_spec_info(FastPoisson<FT>* p) {
+    return FastSpecInfo{(void*)p->spec, p->NXH, p->NXP, p->N[1], p->N[2], p->lamx, p->lamy};
+}
+template <class FT> void fast_poisson_set_zhook(FastPoisson<FT>* p, std::function<void()> hook) { p->zhook = std::move(hook); }
 template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
     if (!p) return;
     cudaFree(p->spec);
@@ -1362,7 +1367,7 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
         A.wrap[d] = g.topo[d] == OB_PERIODIC ? (long long)g.N[d] * g.st[d] : 0;
     }
     A.x0 = 1 - g.O[0];
-    A.tri = p->tri; A.dzC = g.regular[2] ? nullptr : g.dC[2]; A.dx = g.d[0]; A.dy = g.d[1]; A.dz = g.d[2];
+    A.tri = p->zhook ? 0 : p->tri; A.dzC = g.regular[2] ? nullptr : g.dC[2]; A.dx = g.d[0]; A.dy = g.d[1]; A.dz = g.d[2];
     // divᶜᶜᶜ (divergence_operators.jl:16-19): 1/V * (δx(Ax u) + δy(Ay v) + δz(Az w)), then / Δt
     A.ax = g.d[1] * g.d[2]; A.ay = g.d[0] * g.d[2]; A.az = g.d[0] * g.d[1];
     A.invV = 1 / ((g.d[0] * g.d[1]) * g.d[2]);
@@ -1372,6 +1377,10 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
     { PhaseScope ph("fft_x_fwd"); run_x<FT, true>(p, A); }
     if (p->R > 1) {
         if (p->dtma_ok) distributed_middle_tma(p); else distributed_middle(p);
+    } else if (p->zhook) {
+        { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
+        { PhaseScope ph("fft_z"); p->zhook(); }
+        { PhaseScope ph("fft_y"); run_line(p, 1, LM_INV); }
     } else if (p->tri) {
         { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
         { PhaseScope ph("fft_z"); run_thomas(p); }
@@ -1390,6 +1399,8 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
 #define INST(FT)                                                                                   \
     template bool fast_ft_supported<FT>(const GridD<FT>&);                                          \
     template void fast_poisson_set_tridiagonal<FT>(FastPoisson<FT>*, const double*, const double*); \
+    template FastSpecInfo fast_poisson_spec_info<FT>(FastPoisson<FT>*);                             \
+    template void fast_poisson_set_zhook<FT>(FastPoisson<FT>*, std::function<void()>);              \
     template bool fast_poisson_supported<FT>(const GridD<FT>&);                                     \
     template FastPoisson<FT>* fast_poisson_create<FT>(const GridD<FT>&);                            \
     template void fast_poisson_destroy<FT>(FastPoisson<FT>*);                                       \

@@ -1,6 +1,7 @@
 // internal.h -- host-side launcher declarations shared by the translation units.
 #pragma once
 #include "common.cuh"
+#include <functional>
 #include "physics.cuh"
 
 namespace ob {
@@ -119,6 +120,11 @@ template <class FT> bool fast_ft_supported(const GridD<FT>& g);
 template <class FT> void fast_poisson_set_tridiagonal(FastPoisson<FT>* p, const double* dzF_dev, const double* dzC_dev);
 template <class FT> FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g);
 template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p);
+// z Bounded on a regular grid inside the FFT-based solver: the z pass (DCT, eigenvalue divide, inverse DCT on the half
+// spectrum) is the caller's hook (fft.cu); info = the half spectrum [Nz][Ny][NXP] and the eigenvalue tables in its order
+struct FastSpecInfo { void* spec; int NXH, NXP, Ny, Nz; const double* lamx; const double* lamy; };
+template <class FT> FastSpecInfo fast_poisson_spec_info(FastPoisson<FT>* p);
+template <class FT> void fast_poisson_set_zhook(FastPoisson<FT>* p, std::function<void()> hook);
 // source term = div(u,v,w)/dt computed on the fly, or a real Nx*Ny*Nz device array `real_in`
 template <class FT>
 void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,

@@ -594,13 +594,15 @@ int launch(const Phys<FT>& P, const FusedFields<FT>& a) {
     if (g.N[0] % TX || (g.S[0] * sizeof(FT)) % 16 || g.total >= (1LL << 31)) return 0;
     if (a.nf < 3) return 0;
     const int nt = std::min(a.nf - 3, 1);
-    // ZT = 1: Bounded, vertically stretched z with ScalarDiffusivity (or no closure) and constant Flux BCs in z
+    // ZT = 1: Bounded z (stretched with WENO5(grid) tables, or regular) with ScalarDiffusivity (or no closure) and constant
+    // Flux BCs in z
     int zt;
     if (g.topo[2] == OB_PERIODIC) {
         if (!g.regular[2] || P.wc[2][0] || P.wc[2][1] || P.closure != CLO_NONE) return 0;
         zt = 0;
     } else if (g.topo[2] == OB_BOUNDED) {
-        if (offb || nt == 0 || g.regular[2] || !g.izC || !g.izF || !P.wzp[0] || !P.wzp[1] || g.N[2] < 6) return 0;
+        if (offb || nt == 0 || !g.izC || !g.izF || !P.wzp[0] || !P.wzp[1] || g.N[2] < 6) return 0;
+        if (!g.regular[2] && (!P.wc[2][0] || !P.wc[2][1])) return 0;      // stretched z without coefficient tables
         if ((P.closure != CLO_NONE && P.closure != CLO_3D) || P.vitd) return 0;
         for (int s = 4; s < 6; ++s)
             if (a.fbc[2].kind[s] == 2 && a.fbc[2].val[s] != FT(0)) return 0;      // w has no Flux BCs on a Bounded z

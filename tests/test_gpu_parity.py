@@ -97,8 +97,9 @@ TOPOS8 = [(a, b, c) for a in (O.Periodic, O.Bounded) for b in (O.Periodic, O.Bou
 
 
 @pytest.mark.parametrize("topo", TOPOS8)
-@pytest.mark.parametrize("N", [(16, 8, 32), (7, 11, 6)])
+@pytest.mark.parametrize("N", [(16, 8, 32), (7, 11, 6), (48, 20, 96)])
 def test_fft_poisson_matches_oracle_and_laplacian(ob, topo, N):
+    """power-of-two lengths: radix-2 butterflies (Periodic) / Makhoul's DCT around them (Bounded); other lengths: Bluestein"""
     rng = np.random.default_rng(13)
     go, gb = make_pair(ob, np.float64, N, topo, extent=(1.0, 2.0, 3.0))
     rhs, _ = _rhs(go, rng)
@@ -234,6 +235,14 @@ CONFIGS = {
                                        buoyancy=True, ts="QuasiAdamsBashforth2", dt=5e-3,
                                        bcs={"v": {"top": ("Value", 0.1), "bottom": ("Gradient", -0.2)},
                                             "b": {"bottom": ("Flux", -2e-4)}, "c": {"top": ("Flux", 3e-4)}}),
+    # regular Bounded z, the usual horizontally periodic LES box: fused Bounded-z kernel with the uniform coefficients in table
+    # form, FFT-based solver with the half-spectrum x / y passes around a Makhoul DCT in z (Nz = 16) / Bluestein inside it (12)
+    "ppb_regular_fused_weno_rk3": dict(size=(32, 16, 16), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(2, 1, 1),
+                                       adv="WENO5", tracers=("b",), buoyancy=True, closure=("ThreeDimensional", 2e-4, 1e-4),
+                                       f=1e-2, ts="RungeKutta3", dt=4e-3,
+                                       bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"bottom": ("Flux", -1e-4)}}),
+    "ppb_regular_fused_nz12_ab2": dict(size=(32, 16, 12), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(1, 1, 0.5),
+                                       adv="WENO5", tracers=("b",), buoyancy=True, ts="QuasiAdamsBashforth2", dt=4e-3),
     "channel_bounded_yz_weno": dict(size=(8, 12, 10), topology=(O.Periodic, O.Bounded, O.Bounded), extent=(1, 1, 1),
                                     adv="WENO5", tracers=("b",), buoyancy=True, closure=("Horizontal", 1e-3, 1e-3),
                                     ts="RungeKutta3", dt=2e-3),

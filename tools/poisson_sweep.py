@@ -6,6 +6,8 @@
   fft  FFTBasedPoissonSolver, triply periodic (solve_for_pressure!: divergence of a seeded velocity field fused in)
   ft   FourierTridiagonalPoissonSolver, (Periodic, Periodic, Bounded) with the vertical stretching of the ocean
        wind-mixing / convection example (examples/ocean_wind_mixing_and_convection.jl:41-54)
+  topo FFTBasedPoissonSolver on a regular grid for all eight (Periodic | Bounded)^3 topologies (Bounded = DCT by Makhoul's
+       algorithm; a non-power-of-two N runs Bluestein's); OB200_DIRECT_TRANSFORMS=1 times the O(n^2) transforms instead
   cpu  the CPU stand-in of SURVEY.md 8(d)(iii): the same triply periodic solve with scipy.fft (pocketfft, all host
        threads) -- rfftn, eigenvalue divide, irfftn -- timed on the box's host cores (bounded: N <= 256)
 
@@ -58,7 +60,7 @@ def cpu_solve_time(N, reps=3):
 def main():
     args = sys.argv[1:]
     mode = "fft"
-    if args and args[0] in ("fft", "ft", "cpu"):
+    if args and args[0] in ("fft", "ft", "cpu", "topo"):
         mode = args.pop(0)
     sizes = [int(x) for x in (args or ["128", "256", "512"])]
     out = []
@@ -75,6 +77,56 @@ def main():
     arch = ob.B200(0)
     stream = torch.cuda.current_stream()
     lib.ob200_set_stream(C.c_void_p(stream.cuda_stream))
+    if mode == "topo":
+        for N in sizes:
+            for topo in [(a, b, c) for a in "PB" for b in "PB" for c in "PB"]:
+                names = tuple({"P": "Periodic", "B": "Bounded"}[t] for t in topo)
+                g = ob.RectilinearGrid(arch, np.float64, size=(N, N, N), extent=(1, 1, 1), topology=names)
+                s = ob.FFTBasedPoissonSolver(g)
+                rng = np.random.default_rng(4)
+                U = {}
+                for d, (n, f) in enumerate((("u", ob.XFaceField), ("v", ob.YFaceField), ("w", ob.ZFaceField))):
+                    U[n] = f(g)
+                    a = rng.uniform(-1, 1, U[n].size())
+                    if topo[d] == "B":                    # impenetrable walls
+                        sl = [slice(None)] * 3
+                        sl[d] = 0
+                        a[tuple(sl)] = 0
+                        sl[d] = -1
+                        a[tuple(sl)] = 0
+                    U[n].set(a)
+                ob.fill_halo_regions(list(U.values()))
+                phi = ob.CenterField(g)
+                for _ in range(2):
+                    ob.solve_for_pressure(phi, s, 1.0, U)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 10
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(reps):
+                    ob.solve_for_pressure(phi, s, 1.0, U)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                # the reference's own check: lap(phi) == div(U) (test/dependencies_for_poisson_solvers.jl:86-104)
+                ob.fill_halo_regions(phi)
+                p = phi.parent()
+                d_, H = 1.0 / N, 3
+                I = slice(H, N + H)
+                c = p[I, I, I]
+                lap = ((p[H + 1:N + H + 1, I, I] - 2 * c + p[H - 1:N + H - 1, I, I]) +
+                       (p[I, H + 1:N + H + 1, I] - 2 * c + p[I, H - 1:N + H - 1, I]) +
+                       (p[I, I, H + 1:N + H + 1] - 2 * c + p[I, I, H - 1:N + H - 1])) / d_ ** 2
+                u, v, w = (U[n].parent() for n in "uvw")
+                div = ((u[H + 1:N + H + 1, I, I] - u[I, I, I]) + (v[I, H + 1:N + H + 1, I] - v[I, I, I]) +
+                       (w[I, I, H + 1:N + H + 1] - w[I, I, I])) / d_
+                res = float(np.max(np.abs(lap - div)) / np.max(np.abs(div)))
+                out.append({"solver": "FFTBasedPoissonSolver", "topology": "".join(topo), "N": N, "ms_per_solve": ms,
+                            "points_per_s": N ** 3 / (ms * 1e-3), "residual": res,
+                            "transforms": "direct O(n^2)" if os.environ.get("OB200_DIRECT_TRANSFORMS") else "fast"})
+                del s, phi, U, g
+        print(json.dumps(out))
+        return
     for N in sizes:
         if mode == "fft":
             g = ob.RectilinearGrid(arch, np.float64, size=(N, N, N), extent=(1, 1, 1), topology=("Periodic",) * 3)
