@@ -470,6 +470,66 @@ extern "C" int32_t ob200_field_get_parent_async(const ob200_field* f, void* host
     else field_get_parent<double>(const_cast<ob200_field*>(f), host, false);
     API_END
 }
+// ---- output path: the gather / reduction runs on the device into a stream-ordered temporary, the (small) result travels on
+// the download stream like ob200_field_get_parent_async
+static void interior_size(const ob200_field* f, int n[3]) {
+    const ob200_grid_desc& D = f->grid->desc;
+    for (int d = 0; d < 3; ++d)
+        n[d] = D.N[d] + ((f->loc[d] == OB200_FACE && D.topology[d] == OB200_BOUNDED) ? 1 : 0);
+}
+template <class FT, class Launch>
+static void device_result_to_host(size_t count, void* host, Launch&& launch) {
+    if (count == 0) return;
+    ensure_copy_streams();
+    FT* tmp = nullptr;
+    OB_CUDA(cudaMallocAsync(&tmp, count * sizeof(FT), stream()));
+    launch(tmp);
+    cudaEvent_t ready;
+    OB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    OB_CUDA(cudaEventRecord(ready, stream()));
+    OB_CUDA(cudaStreamWaitEvent(g_d2h, ready, 0));
+    OB_CUDA(cudaEventDestroy(ready));           // released once the recorded work has completed
+    OB_CUDA(cudaMemcpyAsync(host, tmp, count * sizeof(FT), cudaMemcpyDeviceToHost, g_d2h));
+    OB_CUDA(cudaFreeAsync(tmp, g_d2h));
+}
+template <class FT>
+static void field_slice(const ob200_field* f, const int32_t lo[3], const int32_t hi[3], void* host) {
+    const GridD<FT>& g = gridD<FT>(f->grid);
+    const ob200_grid_desc& D = f->grid->desc;
+    int ni[3], l[3], n[3];
+    interior_size(f, ni);
+    for (int d = 0; d < 3; ++d) {
+        const int H = D.topology[d] == OB200_FLAT ? 0 : D.H[d];
+        if (lo[d] < 1 - H || hi[d] > ni[d] + H || hi[d] < lo[d]) throw Error("field slice: index range outside the field (halos included)");
+        l[d] = lo[d]; n[d] = hi[d] - lo[d] + 1;
+    }
+    const FT* p0 = f->template p0<FT>();
+    device_result_to_host<FT>((size_t)n[0] * n[1] * n[2], host, [&](FT* tmp) { launch_slice<FT>(g, p0, l, n, tmp); });
+}
+template <class FT>
+static void field_average(const ob200_field* f, const int32_t dims[3], void* host) {
+    const GridD<FT>& g = gridD<FT>(f->grid);
+    int n[3], a[3];
+    interior_size(f, n);
+    size_t outs = 1;
+    for (int d = 0; d < 3; ++d) { a[d] = dims[d] != 0; outs *= a[d] ? 1 : (size_t)n[d]; }
+    const FT* p0 = f->template p0<FT>();
+    device_result_to_host<FT>(outs, host, [&](FT* tmp) { launch_average<FT>(g, p0, n, a, tmp); });
+}
+extern "C" int32_t ob200_field_slice_async(const ob200_field* f, const int32_t lo[3], const int32_t hi[3], void* host) {
+    API_BEGIN
+    if (!f || !lo || !hi || !host) throw Error("null argument");
+    if (f->grid->ftype == OB200_F32) field_slice<float>(f, lo, hi, host);
+    else field_slice<double>(f, lo, hi, host);
+    API_END
+}
+extern "C" int32_t ob200_field_average_async(const ob200_field* f, const int32_t dims[3], void* host) {
+    API_BEGIN
+    if (!f || !dims || !host) throw Error("null argument");
+    if (f->grid->ftype == OB200_F32) field_average<float>(f, dims, host);
+    else field_average<double>(f, dims, host);
+    API_END
+}
 extern "C" int32_t ob200_field_device_view(const ob200_field* f, void** base, int64_t off[1], int64_t st[3]) {
     const ob200_grid* G = f->grid;
     bool s = G->ftype == OB200_F32;
@@ -1166,6 +1226,11 @@ extern "C" int32_t ob200_model_time_step(ob200_model* m, double dt, int32_t eule
 extern "C" int32_t ob200_model_clock(const ob200_model* m, double* t, int64_t* it) {
     if (t) *t = m->time;
     if (it) *it = m->iteration;
+    return 0;
+}
+extern "C" int32_t ob200_model_previous_time_step(const ob200_model* m, double* dt) {
+    if (!m || !dt) return 1;
+    *dt = m->previous_dt;
     return 0;
 }
 extern "C" int32_t ob200_model_set_clock(ob200_model* m, double t, int64_t it, double pdt) {

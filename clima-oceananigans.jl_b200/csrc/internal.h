@@ -98,6 +98,10 @@ void launch_reduce(const GridD<FT>& g, const FT* p0, const int n[3], double* out
 // same over the Julia box [lo, lo + n) (e.g. the whole parent array, halos included)
 template <class FT>
 void launch_reduce_box(const GridD<FT>& g, const FT* p0, const int lo[3], const int n[3], double* out4);
+// output path: dense copy of an index box (Julia indices lo .. lo + n - 1, halos allowed) / mean over the flagged dimensions
+// of the interior box n; p0 = the field's Julia-(0,0,0) pointer
+template <class FT> void launch_slice(const GridD<FT>& g, const FT* p0, const int lo[3], const int n[3], FT* out);
+template <class FT> void launch_average(const GridD<FT>& g, const FT* p0, const int n[3], const int dims[3], FT* out);
 template <class FT>
 void launch_max_divergence(const GridD<FT>& g, const FT* u, const FT* v, const FT* w, double* out4);
 

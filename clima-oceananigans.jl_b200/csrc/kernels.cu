@@ -980,4 +980,60 @@ void launch_max_divergence(const GridD<FT>& g, const FT* u, const FT* v, const F
 template void launch_max_divergence<float>(const GridD<float>&, const float*, const float*, const float*, double*);
 template void launch_max_divergence<double>(const GridD<double>&, const double*, const double*, const double*, double*);
 
+// ---- output path: on-device slicing and averaging (OutputWriters/fetch_output.jl:24-36 with a FieldSlicer; AveragedField /
+// mean(field, dims = ...)) so that only what is written leaves the device --------------------------------------------------
+template <class FT>
+__global__ void slice_kernel(const FT* __restrict__ p0, long long sy, long long sz, int lo0, int lo1, int lo2, int n0, int n1,
+                             long long total, FT* __restrict__ out) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % n0), j = (int)((t / n0) % n1), k = (int)(t / ((long long)n0 * n1));
+        out[t] = p0[(lo0 + i) + (lo1 + j) * sy + (lo2 + k) * sz];
+    }
+}
+template <class FT>
+void launch_slice(const GridD<FT>& g, const FT* p0, const int lo[3], const int n[3], FT* out) {
+    const long long total = (long long)n[0] * n[1] * n[2];
+    if (total <= 0) return;
+    const int blocks = (int)std::min<long long>(148 * 16, (total + 255) / 256);
+    slice_kernel<FT><<<blocks, 256, 0, stream()>>>(p0, g.st[1], g.st[2], lo[0], lo[1], lo[2], n[0], n[1], total, out);
+    OB_LAUNCH_CHECK();
+}
+template void launch_slice<float>(const GridD<float>&, const float*, const int[3], const int[3], float*);
+template void launch_slice<double>(const GridD<double>&, const double*, const int[3], const int[3], double*);
+
+// one block per output element: sums the box of the averaged dimensions in Float64 in a fixed order (thread-strided partial
+// sums, then a shared-memory tree), so the result does not depend on scheduling
+template <class FT>
+__global__ void __launch_bounds__(256) average_kernel(const FT* __restrict__ p0, long long sy, long long sz, int n0, int n1, int n2,
+                                                       int a0, int a1, int a2, FT* __restrict__ out) {
+    const int m0 = a0 ? 1 : n0, m1 = a1 ? 1 : n1;
+    const int o = blockIdx.x;
+    const int oi = o % m0, oj = (o / m0) % m1, ok = o / (m0 * m1);
+    const int r0 = a0 ? n0 : 1, r1 = a1 ? n1 : 1, r2 = a2 ? n2 : 1;
+    const long long cnt = (long long)r0 * r1 * r2;
+    double acc = 0;
+    for (long long t = threadIdx.x; t < cnt; t += blockDim.x) {
+        const int i = (int)(t % r0), j = (int)((t / r0) % r1), k = (int)(t / ((long long)r0 * r1));
+        acc += (double)p0[(1 + oi + i) + (1 + oj + j) * sy + (1 + ok + k) * sz];
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[o] = (FT)(sh[0] / (double)cnt);
+}
+template <class FT>
+void launch_average(const GridD<FT>& g, const FT* p0, const int n[3], const int dims[3], FT* out) {
+    const long long outs = (long long)(dims[0] ? 1 : n[0]) * (dims[1] ? 1 : n[1]) * (dims[2] ? 1 : n[2]);
+    if (outs <= 0) return;
+    if (outs >= (1LL << 31)) throw Error("average: too many output elements");
+    average_kernel<FT><<<(int)outs, 256, 0, stream()>>>(p0, g.st[1], g.st[2], n[0], n[1], n[2], dims[0], dims[1], dims[2], out);
+    OB_LAUNCH_CHECK();
+}
+template void launch_average<float>(const GridD<float>&, const float*, const int[3], const int[3], float*);
+template void launch_average<double>(const GridD<double>&, const double*, const int[3], const int[3], double*);
+
 }  // namespace ob

@@ -42,6 +42,7 @@ import Oceananigans.Solvers: solve!
 import Oceananigans.Models.NonhydrostaticModels: PressureSolver, solve_for_pressure!
 import Oceananigans.Utils: launch!
 
+import Statistics
 const lib = "libocean_b200.so"
 
 "The new architecture singleton (src/Architectures.jl:68-75).  `device` selects the CUDA device of this process."
@@ -454,6 +455,40 @@ function reduce_field(f::B200Field)
     check(ccall((:ob200_field_reduce, lib), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}, Ref{Float64}, Ref{Int32}),
                 field_handle(f), s, s2, m, nan))
     return (sum = s[], sumsq = s2[], maxabs = m[], has_nan = nan[] != 0)
+end
+
+# ---- output path: OutputWriters/fetch_output.jl:24-36 with a FieldSlicer, horizontal averages, checkpoints -----------------------
+# the slice / mean is formed on the device; only it travels (download stream; ob200_sync before the host array is read)
+function fetch_slice(f::B200Field, lo::NTuple{3, Int}, hi::NTuple{3, Int})
+    out = Array{eltype(f.grid)}(undef, (hi .- lo .+ 1)...)
+    check(ccall((:ob200_field_slice_async, lib), Int32, (Ptr{Cvoid}, Ref{NTuple{3, Int32}}, Ref{NTuple{3, Int32}}, Ptr{Cvoid}),
+                field_handle(f), Int32.(lo), Int32.(hi), out))
+    check(ccall((:ob200_sync, lib), Int32, ()))
+    return out
+end
+function Oceananigans.OutputWriters.fetch_output(f::B200Field, model, slicer)
+    n, H = size(f), Oceananigans.Grids.halo_size(f.grid)
+    rng(r, d) = r isa Colon ? (slicer.with_halos ? (1 - H[d], n[d] + H[d]) : (1, n[d])) : r isa Int ? (r, r) : (first(r), last(r))
+    b = (rng(slicer.i, 1), rng(slicer.j, 2), rng(slicer.k, 3))
+    return fetch_slice(f, first.(b), last.(b))
+end
+function Statistics.mean(f::B200Field; dims)
+    flags = ntuple(d -> Int32(d in dims), 3)
+    out = Array{eltype(f.grid)}(undef, ntuple(d -> flags[d] == 1 ? 1 : size(f, d), 3)...)
+    check(ccall((:ob200_field_average_async, lib), Int32, (Ptr{Cvoid}, Ref{NTuple{3, Int32}}, Ptr{Cvoid}), field_handle(f), flags, out))
+    check(ccall((:ob200_sync, lib), Int32, ()))
+    return out
+end
+# Checkpointer pickup (checkpointer.jl:201-262): after set!-ing the parents of the prognostic fields, G^n and G^- from the file
+function restore_clock!(model::B200Model, time, iteration, previous_Δt)
+    check(ccall((:ob200_model_set_clock, lib), Int32, (Ptr{Cvoid}, Float64, Int64, Float64), handle(model), time, iteration, previous_Δt))
+    model.clock.time = time; model.clock.iteration = iteration
+    return nothing
+end
+function previous_time_step(model::B200Model)
+    dt = Ref{Float64}()
+    check(ccall((:ob200_model_previous_time_step, lib), Int32, (Ptr{Cvoid}, Ref{Float64}), handle(model), dt))
+    return dt[]
 end
 
 # cell_advection_timescale(model) (Utils/cell_advection_timescale.jl:4-21) without downloading the velocities: the three

@@ -15,6 +15,7 @@ from .model import (Field, CenterField, XFaceField, YFaceField, ZFaceField, fill
                     LinearEquationOfState, BoundaryCondition,
                     FluxBoundaryCondition, ValueBoundaryCondition, GradientBoundaryCondition,
                     update_state, calculate_tendencies, set_model, time_step, sync)
+from .output_writers import FieldSlicer, fetch_output, horizontal_average, Checkpointer  # noqa: F401
 from .simulations import (Simulation, run, TimeStepWizard, cell_advection_timescale,  # noqa: F401
                           cell_diffusion_timescale, max_abs_velocities)
 

@@ -90,6 +90,9 @@ SYMBOLS = {
     "ob200_model_time_step": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32]),
     "ob200_model_clock": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ob200_model_set_clock": (C.c_int32, [C.c_void_p, C.c_double, C.c_int64, C.c_double]),
+    "ob200_model_previous_time_step": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
+    "ob200_field_slice_async": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
+    "ob200_field_average_async": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "ob200_model_diagnostics": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ob200_model_max_abs_velocities": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     "ob200_debug_cached_tensor_maps": (C.c_int64, []),

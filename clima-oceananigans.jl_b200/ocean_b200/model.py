@@ -110,6 +110,32 @@ class Field:
         p[self._islice()] = np.asarray(value, dtype=self.grid.FT).reshape(n)
         self.set_parent(p)
 
+    def slice(self, lo, hi, out=None, sync=True):
+        """dense copy of the index box lo..hi (Julia indices, 1-based, inclusive; halo indices allowed), gathered on the device:
+        only the box travels to the host (fetch_output with a FieldSlicer, OutputWriters/fetch_output.jl:24-36).  With
+        sync=False the array is valid after sync() / ob200_sync_downloads."""
+        shape = tuple(int(h) - int(l) + 1 for l, h in zip(lo, hi))
+        if out is None:
+            out = np.empty(shape, dtype=self.grid.FT, order="F")
+        check(lib.ob200_field_slice_async(self.handle, (C.c_int32 * 3)(*[int(x) for x in lo]),
+                                          (C.c_int32 * 3)(*[int(x) for x in hi]), out.ctypes.data_as(C.c_void_p)))
+        if sync:
+            check(lib.ob200_sync())
+        return out
+
+    def average(self, dims, out=None, sync=True):
+        """mean(field, dims=...) over the interior, reduced on the device (AveragedField); dims: 1-based dimension numbers as in
+        the reference, e.g. (1, 2) for a horizontal average.  Averaged dimensions keep extent 1."""
+        flags = [1 if (d + 1) in tuple(dims) else 0 for d in range(3)]
+        n = self.size()
+        shape = tuple(1 if flags[d] else n[d] for d in range(3))
+        if out is None:
+            out = np.empty(shape, dtype=self.grid.FT, order="F")
+        check(lib.ob200_field_average_async(self.handle, (C.c_int32 * 3)(*flags), out.ctypes.data_as(C.c_void_p)))
+        if sync:
+            check(lib.ob200_sync())
+        return out
+
     def reduce(self):
         s, s2, mx, nan = C.c_double(), C.c_double(), C.c_double(), C.c_int32()
         check(lib.ob200_field_reduce(self.handle, C.byref(s), C.byref(s2), C.byref(mx), C.byref(nan)))

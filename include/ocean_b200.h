@@ -167,6 +167,14 @@ int32_t ob200_field_get_parent_async(const ob200_field* f, void* host_parent);
  * recent ones have been delivered to host memory (OutputWriters/fetch_output.jl:24-36 is the synchronous analogue) */
 int32_t ob200_mark_download_batch(void);
 int32_t ob200_sync_downloads(int32_t keep_in_flight);
+/* output path (OutputWriters/fetch_output.jl:24-36 with a FieldSlicer, OutputWriters/field_slicer.jl; AveragedField /
+ * mean(field, dims = ...)): the index box lo[d]..hi[d] (Julia indices, 1-based, halo indices allowed) is gathered ON THE DEVICE
+ * into a dense column-major array of hi - lo + 1, resp. the interior is averaged over the dimensions with dims[d] != 0
+ * (result: column-major, averaged dimensions of extent 1; Float64 accumulation in a fixed order); only the result travels to
+ * the host, on the download stream: host memory (pinned for a truly asynchronous copy) is valid after ob200_sync() or
+ * ob200_sync_downloads() like ob200_field_get_parent_async */
+int32_t ob200_field_slice_async(const ob200_field* f, const int32_t lo[3], const int32_t hi[3], void* host_dst);
+int32_t ob200_field_average_async(const ob200_field* f, const int32_t dims[3], void* host_dst);
 /* internal device storage: base pointer, index of Julia (1,1,1), strides in elements */
 int32_t ob200_field_device_view(const ob200_field* f, void** base, int64_t offset111[1],
                                 int64_t strides[3]);
@@ -213,6 +221,9 @@ int32_t ob200_model_time_step(ob200_model* m, double dt, int32_t euler);
 /* model.clock (TimeSteppers/clock.jl) */
 int32_t ob200_model_clock(const ob200_model* m, double* time, int64_t* iteration);
 int32_t ob200_model_set_clock(ob200_model* m, double time, int64_t iteration, double previous_dt);
+/* the Δt of the last step (QuasiAdamsBashforth2 compares it with the next one, quasi_adams_bashforth_2.jl:76-81): saved by
+ * the Checkpointer so that a restored run continues bit for bit (OutputWriters/checkpointer.jl:64-95,201-262) */
+int32_t ob200_model_previous_time_step(const ob200_model* m, double* dt);
 /* maximum(abs, parent(u / v / w)) in one call: the device part of cell_advection_timescale
  * (Utils/cell_advection_timescale.jl:4-21, used by TimeStepWizard Simulations/time_step_wizard.jl:78-95 and the CFL
  * diagnostics); NaN if a velocity holds a NaN (NaNChecker, Simulations/nan_checker.jl:33-52) */

@@ -639,3 +639,52 @@ def test_two_models_of_different_sizes_interleaved_and_recreated(ob):
         b_o.time_step(2e-3); ob.time_step(b_b, 2e-3)
     compare_fields(c_o, c_b, 1e-12, "model C (after A was destroyed)")
     compare_fields(b_o, b_b, 1e-12, "model B (second round)")
+
+
+# ---- output path: on-device slices / averages, checkpoints ------------------------------------------
+def test_on_device_slices_and_averages(ob):
+    rng = np.random.default_rng(41)
+    for topo, FT in (((O.Periodic, O.Bounded, O.Bounded), np.float64), ((O.Periodic, O.Periodic, O.Periodic), np.float32)):
+        _, gb = make_pair(ob, FT, (12, 9, 7), topo, extent=(1, 1, 1))
+        for loc in (("Center", "Center", "Center"), ("Center", "Face", "Face")):
+            f = ob.Field(loc, gb)
+            p = rng.uniform(-1, 1, f.parent_size).astype(FT)
+            f.set_parent(p)
+            H, n = gb.H, f.size()
+            # an xy plane with halos, a yz plane without, a single column, the whole parent
+            for sl in (ob.FieldSlicer(k=3, with_halos=True), ob.FieldSlicer(i=5), ob.FieldSlicer(i=2, j=(2, 4)),
+                       ob.FieldSlicer(with_halos=True), ob.FieldSlicer(i=(3, 9), j=(1, n[1]), k=(2, 2))):
+                lo, hi = sl.box(f)
+                want = p[tuple(slice(H[d] + lo[d] - 1, H[d] + hi[d]) for d in range(3))]
+                assert np.array_equal(ob.fetch_output(f, sl), want)
+            inter = p[tuple(slice(H[d], H[d] + n[d]) for d in range(3))].astype(np.float64)
+            tol = 1e-13 if FT == np.float64 else 1e-6
+            for dims in ((1, 2), (3,), (1,), (1, 2, 3), (2, 3)):
+                want = inter.mean(axis=tuple(d - 1 for d in dims), keepdims=True)
+                got = f.average(dims)
+                assert got.shape == want.shape and np.max(np.abs(got - want)) < tol * max(1.0, np.max(np.abs(want)))
+            assert np.allclose(ob.horizontal_average(f), inter.mean(axis=(0, 1)), rtol=0, atol=tol)
+    with pytest.raises(ob.B200Error):
+        f.slice((0, 1, 1), (99, 1, 1))
+
+
+@pytest.mark.parametrize("name", ["c2_periodic_weno_rk3", "c3_fused_js_ab2_no_closure", "smagorinsky_bounded_b"])
+def test_checkpoint_resume_is_bitwise(ob, name, tmp_path):
+    """Checkpointer (checkpointer.jl:64-95) + set!(model, filepath) (:201-262): 3 steps, checkpoint, restore into a NEW model,
+    3 more steps == 6 steps straight, bit for bit (fields, G^n / G^-, clock; AB2 keeps its history and its previous time step)"""
+    cfg = CONFIGS[name]
+    mo, m1 = build_models(ob, cfg, np.float64)
+    init_state(mo, m1, ob, 43)
+    for _ in range(3):
+        ob.time_step(m1, cfg["dt"])
+    path = ob.Checkpointer(m1, dir=str(tmp_path), prefix="ck").write()
+    for _ in range(3):
+        ob.time_step(m1, cfg["dt"])
+    _, m2 = build_models(ob, cfg, np.float64)
+    ob.Checkpointer.restore(m2, path)
+    assert m2.clock.iteration == 3
+    for _ in range(3):
+        ob.time_step(m2, cfg["dt"])
+    assert m2.clock.iteration == m1.clock.iteration and m2.clock.time == m1.clock.time
+    for n in m1.names:
+        assert np.array_equal(m1.fields[n].parent(), m2.fields[n].parent()), n
