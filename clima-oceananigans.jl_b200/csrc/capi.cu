@@ -742,10 +742,15 @@ struct ob200_model {
     // side streams / events of this model (independent launches of a stage are forked onto them and joined before the
     // stage's next dependent kernel); created on first use, released with the model
     cudaStream_t side[3] = {nullptr, nullptr, nullptr}, hy_stream = nullptr;
+    // neighbour exchange of a stage in flight on its own stream while the next stage's interior tiles run (model_halo_*)
+    cudaStream_t halo_stream = nullptr;
+    cudaEvent_t ev_halo_a = nullptr, ev_halo_b = nullptr;
+    bool halo_pending = false;
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, hy_fork = nullptr, hy_done = nullptr;
     ~ob200_model() {
         for (void* p : owned) cudaFree(p);
-        for (cudaStream_t s : {side[0], side[1], side[2], hy_stream}) if (s) cudaStreamDestroy(s);
+        for (cudaStream_t s : {side[0], side[1], side[2], hy_stream, halo_stream}) if (s) cudaStreamDestroy(s);
+        for (cudaEvent_t e : {ev_halo_a, ev_halo_b}) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : {ev_fork, ev_join[0], ev_join[1], ev_join[2], hy_fork, hy_done}) if (e) cudaEventDestroy(e);
     }
 };
@@ -990,6 +995,47 @@ static void model_update_state(ob200_model* m, bool tracers_too = true) {
         fill_halos<FT>(&ph_, 1);
     }
 }
+// fill_halos in two phases on two streams (slab-decomposed y, peer-memory exchange): the Periodic halos of the owned rows on the
+// library stream, then the neighbour exchange + the Periodic halos of the received rows on the model's halo stream.  The next
+// tendency launch runs its interior tiles meanwhile and calls model_halo_join before its boundary tiles
+// (Distributed/halo_communication.jl:62-183 overlaps the same way with asynchronous MPI requests).
+template <class FT>
+static void fill_halos_overlapped(ob200_model* m, ob200_field* const* fields, int n) {
+    const ob200_grid* G = fields[0]->grid;
+    const GridD<FT>& g = gridD<FT>(G);
+    if (!m->halo_stream) {
+        OB_CUDA(cudaStreamCreateWithFlags(&m->halo_stream, cudaStreamNonBlocking));
+        OB_CUDA(cudaEventCreateWithFlags(&m->ev_halo_a, cudaEventDisableTiming));
+        OB_CUDA(cudaEventCreateWithFlags(&m->ev_halo_b, cudaEventDisableTiming));
+    }
+    auto batch = [&](int start) {
+        HaloBatch<FT> hb;
+        hb.n = std::min(MAXF, n - start);
+        for (int q = 0; q < hb.n; ++q) {
+            ob200_field* f = fields[start + q];
+            hb.p0[q] = f->p0<FT>();
+            for (int d = 0; d < 3; ++d) hb.loc[q][d] = f->loc[d];
+            for (int s = 0; s < 6; ++s) { hb.bc_kind[q][s] = f->bcs[s].kind; hb.bc_val[q][s] = (FT)f->bcs[s].value; }
+        }
+        return hb;
+    };
+    for (int start = 0; start < n; start += MAXF) launch_fill_halos_phase<FT>(g, batch(start), 0);
+    OB_CUDA(cudaEventRecord(m->ev_halo_a, g_stream));
+    OB_CUDA(cudaStreamWaitEvent(m->halo_stream, m->ev_halo_a, 0));
+    g_override = m->halo_stream;
+    try {
+        for (int start = 0; start < n; start += MAXF) launch_fill_halos_phase<FT>(g, batch(start), 1);
+    } catch (...) { g_override = nullptr; throw; }
+    g_override = nullptr;
+    OB_CUDA(cudaEventRecord(m->ev_halo_b, m->halo_stream));
+    m->halo_pending = true;
+}
+static void model_halo_join(ob200_model* m) {
+    if (!m->halo_pending) return;
+    OB_CUDA(cudaStreamWaitEvent(g_stream, m->ev_halo_b, 0));
+    m->halo_pending = false;
+}
+
 // update_state! as it runs inside time_step!, after model_pressure_step(..., tracers_too = true): tracer halos are
 // already valid, so pHY' is integrated first and velocities + pHY' share ONE halo fill (one neighbour exchange
 // on the slab-decomposed path instead of two).  Same values as the reference sequence.
@@ -997,7 +1043,8 @@ static void model_update_state(ob200_model* m, bool tracers_too = true) {
 // hydrostatic integral read their operands with periodic wrap-around, so ALL halo fills of the stage (state
 // before the solve, pNHS after it, state + pHY' here) collapse into this one single-launch shell fill.
 template <class FT>
-static void model_update_state_after_projection(ob200_model* m, bool fused, bool hydrostatic_done = false) {
+static void model_update_state_after_projection(ob200_model* m, bool fused, bool hydrostatic_done = false,
+                                                bool overlap_next = false) {
     std::vector<ob200_field*> v = {m->F[0].get(), m->F[1].get(), m->F[2].get()};
     if (m->pHY) {
         if (!hydrostatic_done) model_hydrostatic<FT>(m, fused);
@@ -1006,6 +1053,12 @@ static void model_update_state_after_projection(ob200_model* m, bool fused, bool
     if (fused) {
         for (int q = 3; q < m->nf; ++q) v.push_back(m->F[q].get());
         v.push_back(m->pNHS.get());
+    }
+    static const bool no_overlap = getenv("OB200_NO_HALO_OVERLAP") != nullptr;
+    if (overlap_next && fused && !no_overlap && !m->nue && m->use_fast && halo_overlap_supported<FT>(gridD<FT>(m->grid))) {
+        ScopedPhase ph("halo");
+        fill_halos_overlapped<FT>(m, v.data(), (int)v.size());
+        return;
     }
     { ScopedPhase ph("halo"); fill_halos<FT>(v.data(), (int)v.size()); }
     model_diffusivities<FT>(m);
@@ -1080,8 +1133,18 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
             ff.nw[q] = ss.mode == SUB_NONE ? nullptr : f->template alt0<FT>();
             for (int s = 0; s < 6; ++s) { ff.fbc[q].kind[s] = f->bcs[s].kind; ff.fbc[q].val[s] = (FT)f->bcs[s].value; }
         }
-        first = fz::launch<FT>(P, ff);
+        if (m->halo_pending) {
+            // the neighbour exchange of the previous stage is still in flight on the halo stream: tile rows that read only rows
+            // this rank owns go first, the boundary tile rows once the exchange has landed
+            first = fz::launch<FT>(P, ff, 1);
+            model_halo_join(m);
+            if (first) fz::launch<FT>(P, ff, 2);
+            else first = fz::launch<FT>(P, ff, 0);
+        } else {
+            first = fz::launch<FT>(P, ff, 0);
+        }
     }
+    model_halo_join(m);
     if (fork) OB_CUDA(cudaEventRecord(ev_fork, g_stream));
     for (int q = first; q < m->nf; ++q) {
         ob200_field* f = m->F[q].get();
@@ -1191,7 +1254,7 @@ static void model_time_step(ob200_model* m, double dt_in, bool euler) {
             m->time += (double)sdt[s];
             if (s < 2) for (int q = 0; q < m->nf; ++q) std::swap(m->Gn[q]->base, m->Gm[q]->base);   // store_tendencies!
             if (hy) model_hydrostatic_async_end(m);
-            model_update_state_after_projection<FT>(m, fused, hy);
+            model_update_state_after_projection<FT>(m, fused, hy, s < 2);
         }
         m->iteration += 1;
     } else {

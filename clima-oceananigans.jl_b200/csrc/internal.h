@@ -18,6 +18,10 @@ struct HaloBatch {
     FT bc_val[MAXF][6];
 };
 template <class FT> void launch_fill_halos(const GridD<FT>& g, const HaloBatch<FT>& hb);
+// the slab-decomposed fill in two phases (kernels.cu): 0 = Periodic halos of the owned rows, 1 = neighbour exchange + Periodic
+// halos of the received rows; for the overlap of phase 1 with the interior tiles of the next tendency launch
+template <class FT> bool halo_overlap_supported(const GridD<FT>& g);
+template <class FT> void launch_fill_halos_phase(const GridD<FT>& g, const HaloBatch<FT>& hb, int phase);
 // slab-decomposed dimension d: exchange `np` boundary planes (interior extent of the other dimensions) with the ring
 // neighbours through peer memory; need_lo / need_hi select which of this rank's halos are filled
 template <class FT>
@@ -63,7 +67,9 @@ struct FusedFields {
     Substep<FT> ss;
     FluxBC<FT> fbc[FUSED_MAXF];      // constant Flux boundary conditions (Bounded z variant)
 };
-namespace fz { template <class FT> int launch(const Phys<FT>& P, const FusedFields<FT>& a); }
+// part: 0 = every tile; 1 = the tile rows whose stencils stay inside the rows this rank owns along a slab-decomposed y (they
+// need no neighbour data); 2 = the remaining (boundary) tile rows.  Returns the number of fields handled, 0 = not applicable.
+namespace fz { template <class FT> int launch(const Phys<FT>& P, const FusedFields<FT>& a, int part = 0); }
 
 // SmagorinskyLilly eddy viscosity over the interior (the caller fills its halos)
 template <class FT>

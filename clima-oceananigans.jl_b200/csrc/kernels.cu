@@ -62,7 +62,7 @@ __global__ void fill_halo_kernel(GridD<FT> g, HaloBatch<FT> hb, int d, int a, in
 // dimension has no group of its own -- its halos come from the neighbour exchange, done BEFORE this launch on the
 // interior extent of the other dimensions -- but it is always walked over its full extent and never wrapped, so
 // the corner cells pick up the exchanged values.
-struct ShellGroup { int D, lo[3], n[3]; long long count; };
+struct ShellGroup { int D, HD, lo[3], n[3]; long long count; };    // HD: a FullyConnected dimension walked over its 2H halo rows only (-1: none)
 struct ShellPlan { ShellGroup g[3]; int ng; long long total; };
 
 template <class FT>
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) fill_halo_shell_kernel(GridD<FT> g, HaloB
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         int v;
-        if (d == G.D) v = id[d] < g.H[d] ? id[d] + 1 - g.H[d] : g.N[d] + 1 + (id[d] - g.H[d]);
+        if (d == G.D || d == G.HD) v = id[d] < g.H[d] ? id[d] + 1 - g.H[d] : g.N[d] + 1 + (id[d] - g.H[d]);
         else v = G.lo[d] + id[d];
         int sv = v;
         if (g.topo[d] == OB_PERIODIC) sv = v < 1 ? v + g.N[d] : (v > g.N[d] ? v - g.N[d] : v);
@@ -111,17 +111,22 @@ static bool shell_fill_supported(const GridD<FT>& g, bool with_comm) {
     }
     return any;
 }
+// comm_rows: how a FullyConnected dimension is walked -- 0 its full extent (the exchange has been done), 1 its interior only
+// (the exchange is still in flight: everything interior tiles read), 2 its halo rows only (after the exchange)
 template <class FT>
-static void launch_shell(const GridD<FT>& g, const HaloBatch<FT>& hb) {
+static void launch_shell(const GridD<FT>& g, const HaloBatch<FT>& hb, int comm_rows = 0) {
     ShellPlan P{};
     bool done[3] = {false, false, false};
     for (int D = 2; D >= 0; --D) {
         if (g.topo[D] != OB_PERIODIC) continue;
         ShellGroup& G = P.g[P.ng++];
         G.D = D;
+        G.HD = -1;
         G.count = 1;
         for (int d = 0; d < 3; ++d) {
             if (d == D) { G.lo[d] = 0; G.n[d] = 2 * g.H[d]; }
+            else if (g.topo[d] == OB_COMM && comm_rows == 1) { G.lo[d] = 1; G.n[d] = g.N[d]; }
+            else if (g.topo[d] == OB_COMM && comm_rows == 2) { G.HD = d; G.lo[d] = 0; G.n[d] = 2 * g.H[d]; }
             else if (g.topo[d] == OB_FLAT || (g.topo[d] == OB_PERIODIC && done[d])) { G.lo[d] = 1; G.n[d] = g.N[d]; }
             else { G.lo[d] = 1 - g.H[d]; G.n[d] = g.N[d] + 2 * g.H[d]; }
             G.count *= G.n[d];
@@ -270,6 +275,28 @@ int single_comm_dim(const GridD<FT>& g) {       // the slab-decomposed dimension
 }
 template int single_comm_dim<float>(const GridD<float>&);
 template int single_comm_dim<double>(const GridD<double>&);
+
+// The same fill in two phases, for the overlap of the neighbour exchange with the interior tiles of the next tendency
+// launch (halo_communication.jl:62-183 fills asynchronously; here the caller puts phase 1 on a side stream):
+//   phase 0: the Periodic halos of the rows this rank owns -- all that tiles away from the slab boundary read;
+//   phase 1: the exchange of the boundary planes through peer memory, then the Periodic halos of the received rows.
+template <class FT>
+bool halo_overlap_supported(const GridD<FT>& g) {
+    const int dc = single_comm_dim(g);
+    return dc >= 0 && peer_halo_enabled() && shell_fill_supported(g, true) && g.N[dc] >= g.H[dc];
+}
+template bool halo_overlap_supported<float>(const GridD<float>&);
+template bool halo_overlap_supported<double>(const GridD<double>&);
+template <class FT>
+void launch_fill_halos_phase(const GridD<FT>& g, const HaloBatch<FT>& hb, int phase) {
+    if (hb.n == 0) return;
+    const int dc = single_comm_dim(g);
+    if (phase == 0) { launch_shell<FT>(g, hb, 1); return; }
+    launch_exchange_planes<FT>(g, hb, dc, g.H[dc], true, true);
+    launch_shell<FT>(g, hb, 2);
+}
+template void launch_fill_halos_phase<float>(const GridD<float>&, const HaloBatch<float>&, int);
+template void launch_fill_halos_phase<double>(const GridD<double>&, const HaloBatch<double>&, int);
 
 template <class FT>
 void launch_fill_halos(const GridD<FT>& g, const HaloBatch<FT>& hb) {

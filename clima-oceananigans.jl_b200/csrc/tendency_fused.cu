@@ -71,6 +71,7 @@ struct Args {
     long long sy, sz;
     int O[3];
     int Ny, Nz, ntx, ntiles, chunk;
+    int tile0, tsplit, tskip;      // tile t of this launch is tile t + tile0 (+ tskip for t >= tsplit) of the grid (part launches)
     FT cf[3];              // area[A] / V (further scaled per field class in the kernel)
     FT invdx, invdy, f;
     int fplane, do_sub;
@@ -326,6 +327,7 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
     Work wk(c.ntiles, c.Nz, c.chunk);
     int tile, kfirst, len;
     while (wk.next(tile, kfirst, len)) {
+        tile += c.tile0 + (tile >= c.tsplit ? c.tskip : 0);
         const int bx = tile % c.ntx, by = tile / c.ntx;
         const int i0 = 1 + bx * TX, j0 = 1 + by * R, k0 = 1 + kfirst;
         const int nrows = min(R, c.Ny - j0 + 1);
@@ -479,6 +481,7 @@ tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
         int tile, kfirst, len;
         const bool lead = (threadIdx.x & 31) == 0;
         while (wk.next(tile, kfirst, len)) {
+            tile += c.tile0 + (tile >= c.tsplit ? c.tskip : 0);
             const int bx = tile % c.ntx, by = tile / c.ntx;
             const int i0 = 1 + bx * TX, j0 = 1 + by * R, k0 = 1 + kfirst;
             const int cx = i0 - HALO - 2 + c.O[0], cy = j0 - HALO - 1 + c.O[1], cz0 = c.O[2] - 1;
@@ -514,7 +517,7 @@ tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
 
 // ---- host side --------------------------------------------------------------------------------
 template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, int R>
-static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
+static bool launch_variant(const Phys<FT>& P, const FusedFields<FT>& a, int part) {
     using GR = Groups<NT>;
     constexpr int NF = GR::NF;
     using G_ = Geo<FT, R, NF>;
@@ -530,7 +533,20 @@ static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     for (int d = 0; d < 3; ++d) c.O[d] = g.O[d];
     c.Ny = g.N[1]; c.Nz = g.N[2];
     c.ntx = g.N[0] / TX;
-    c.ntiles = c.ntx * cdiv(g.N[1], R);
+    {
+        const int nty = cdiv(g.N[1], R);
+        c.ntiles = c.ntx * nty;
+        c.tile0 = 0; c.tsplit = 1 << 30; c.tskip = 0;
+        if (part) {
+            // tile rows at the high end whose stencil (HALO rows beyond the tile) reaches past row Ny
+            int nb_hi = 0;
+            while (nb_hi < nty && (nty - nb_hi) * R + HALO > g.N[1]) ++nb_hi;
+            const int nint = nty - nb_hi - 1;          // tile rows 1 .. nty - nb_hi - 1 (R >= HALO: row 0 is the only low one)
+            if (nint < 1 || R < HALO) return false;
+            if (part == 1) { c.tile0 = c.ntx; c.ntiles = nint * c.ntx; }
+            else { c.ntiles = (1 + nb_hi) * c.ntx; c.tsplit = c.ntx; c.tskip = nint * c.ntx; }
+        }
+    }
     c.invdx = 1 / g.d[0]; c.invdy = 1 / g.d[1];
     if (ZT) {
         c.cf[0] = c.invdx; c.cf[1] = c.invdy; c.cf[2] = FT(0);
@@ -572,17 +588,18 @@ static void launch_variant(const Phys<FT>& P, const FusedFields<FT>& a) {
     c.chunk = cdiv((long long)(c.ntiles - (c.ntiles / grid) * grid) * c.Nz, grid);
     kern<<<grid, TX * (GR::NG * (R + 1) + 1), G_::SMEM, stream()>>>(c);
     OB_LAUNCH_CHECK();
+    return true;
 }
 
 template <class FT, bool ZW, int ZT, int NT, int R>
-static void launch_gm(const Phys<FT>& P, const FusedFields<FT>& a) {
+static bool launch_gm(const Phys<FT>& P, const FusedFields<FT>& a, int part) {
     const bool has_gm = a.ss.mode == SUB_RK3 || a.ss.mode == SUB_AB2;
-    if (has_gm) launch_variant<FT, ZW, ZT, NT, true, R>(P, a);
-    else launch_variant<FT, ZW, ZT, NT, false, R>(P, a);
+    if (has_gm) return launch_variant<FT, ZW, ZT, NT, true, R>(P, a, part);
+    return launch_variant<FT, ZW, ZT, NT, false, R>(P, a, part);
 }
 
 template <class FT>
-int launch(const Phys<FT>& P, const FusedFields<FT>& a) {
+int launch(const Phys<FT>& P, const FusedFields<FT>& a, int part) {
     const GridD<FT>& g = P.g;
     static const bool off = getenv("OB200_NO_FUSED_TENDENCY") != nullptr;
     static const bool offb = getenv("OB200_NO_FUSED_BOUNDED") != nullptr;
@@ -610,18 +627,19 @@ int launch(const Phys<FT>& P, const FusedFields<FT>& a) {
     } else {
         return 0;
     }
+    bool ok = false;
 #define GO(ZTV, NTV, RV)                                                                        \
-    { if (P.zweno) launch_gm<FT, true, ZTV, NTV, RV>(P, a); else launch_gm<FT, false, ZTV, NTV, RV>(P, a); }
+    { ok = P.zweno ? launch_gm<FT, true, ZTV, NTV, RV>(P, a, part) : launch_gm<FT, false, ZTV, NTV, RV>(P, a, part); }
     // rows per tile: the largest for which the block (NG (R + 1) + 1 warps) keeps 72 registers per thread and the rings
     // + exchange buffers fit 227 KB; measured at 256^3: R = 12 3.13 ms per step, 11: 3.16, 10: 3.26, 9: 3.19
     if (zt) GO(1, 1, 12)         // Bounded z at 512 x 512 x 256: R = 12 15.4 ms per step of tendencies, 10: 17.2, 8: 15.4
     else if (nt == 0) GO(0, 0, 8)
     else GO(0, 1, 12)
 #undef GO
-    return 3 + nt;
+    return ok ? 3 + nt : 0;
 }
-template int launch<float>(const Phys<float>&, const FusedFields<float>&);
-template int launch<double>(const Phys<double>&, const FusedFields<double>&);
+template int launch<float>(const Phys<float>&, const FusedFields<float>&, int);
+template int launch<double>(const Phys<double>&, const FusedFields<double>&, int);
 
 }  // namespace fz
 }  // namespace ob
