@@ -158,11 +158,10 @@ def build_config(ob, np, a, arch, world, rank, FTYPE):
     """returns (model, dt, points per GPU, global shape, workload string, fields, algorithmic words per point per step)"""
     cfg = a.config
     if cfg == "c3":
-        if world != 1:
-            raise SystemExit("config c3 runs on one GPU (the Fourier-tridiagonal solver is not slab-decomposed)")
+        # weak scaling on several GPUs: the slab of every rank is the single-GPU grid, y is decomposed
         s = a.size or 512
         Nx, Ny, Nz = s, s, max(16, s // 2)
-        g = ob.RectilinearGrid(arch, FTYPE, size=(Nx, Ny, Nz), x=(0, 64), y=(0, 64), z=c3_z_faces(Nz),
+        g = ob.RectilinearGrid(arch, FTYPE, size=(Nx, Ny * world, Nz), x=(0, 64), y=(0, 64 * world), z=c3_z_faces(Nz),
                                topology=("Periodic", "Periodic", "Bounded"))
         bcs = {"u": {"top": ob.BoundaryCondition("Flux", -1e-4)},
                "b": {"top": ob.BoundaryCondition("Flux", 1e-8), "bottom": ob.BoundaryCondition("Gradient", 1e-5)}}
@@ -176,9 +175,10 @@ def build_config(ob, np, a, arch, world, rank, FTYPE):
         zc = 0.5 * (zf[1:] + zf[:-1])
         vals["b"] = 1e-5 * zc.reshape(1, 1, Nz) + 1e-7 * rng.uniform(-1, 1, (Nx, Ny, Nz))
         ob.set_model(m, **vals)
-        wl = (f"C3: {Nx}x{Ny}x{Nz} (Periodic, Periodic, Bounded) vertically stretched z, WENO5(grid) + tracer b + FPlane + "
-              f"ScalarDiffusivity + flux/gradient BCs, Fourier-tridiagonal pressure solve, RK3")
-        return m, 0.05, Nx * Ny * Nz, (Nx, Ny, Nz), wl, 4, 110.0
+        wl = (f"C3: {Nx}x{Ny * world}x{Nz} (Periodic, Periodic, Bounded) vertically stretched z, WENO5(grid) + tracer b + FPlane + "
+              f"ScalarDiffusivity + flux/gradient BCs, Fourier-tridiagonal pressure solve, RK3"
+              + (f", y slab-decomposed over {world} GPUs" if world > 1 else ""))
+        return m, 0.05, Nx * Ny * Nz, (Nx, Ny * world, Nz), wl, 4, 110.0
     if cfg == "c5-strong":
         s = a.size or 1024
         if s % world:

@@ -414,7 +414,7 @@ struct LArgs {
     int line_is_y;                 // 1: line along y (other = z) ; 0: line along z (other = y)
 };
 
-enum { LM_FWD = 0, LM_INV = 1, LM_FWD_DIV_INV = 2 };
+enum { LM_FWD = 0, LM_INV = 1, LM_FWD_DIV_INV = 2, LM_COPY = 3 };       // LM_COPY: change of layout only
 
 // pointer to element (kx, m = 0, o) and a functor for the m-th element of that line: the natural layout is an
 // affine function of m; the blocked / split / peer-memory layouts of the slab-decomposed solve go through Lay::addr
@@ -445,7 +445,8 @@ __global__ void __launch_bounds__(256) line_kernel(const __grid_constant__ LArgs
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CT* s = reinterpret_cast<CT*>(smem_raw);
     CT* stw = s + A.T * G::LS;
-    for (int w = threadIdx.x; w < N; w += blockDim.x) stw[w] = A.tw[w];
+    if constexpr (MODE != LM_COPY)
+        for (int w = threadIdx.x; w < N; w += blockDim.x) stw[w] = A.tw[w];
     const int x0 = blockIdx.x * A.T, o = blockIdx.y;
     const int nl = min(A.T, A.NXH - x0);
     // thread -> (line t, first element m0); blockDim is a multiple of T, so t is fixed and m advances by mstep:
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(256) line_kernel(const __grid_constant__ LArgs
 #pragma unroll
             for (int e = 0; e < LU; ++e) if (m + e * mstep < N) {
                 v[e] = sl[G::pos(m + e * mstep)];
-                if (MODE != LM_FWD) { v[e].x *= A.scale; v[e].y *= A.scale; }
+                if (MODE != LM_FWD && MODE != LM_COPY) { v[e].x *= A.scale; v[e].y *= A.scale; }
             }
 #pragma unroll
             for (int e = 0; e < LU; ++e) if (m + e * mstep < N) *out.at(m + e * mstep) = v[e];
@@ -586,13 +587,16 @@ bool fast_poisson_supported(const GridD<FT>& g) {
 
 template <class FT> static void setup_tma(FastPoisson<FT>* p);
 
-// Fourier-tridiagonal fast path: x, y Periodic power-of-two regular; z Bounded with any spacing; single GPU
+// Fourier-tridiagonal fast path: x, y Periodic power-of-two regular; z Bounded with any spacing; y may be slab-decomposed
 template <class FT>
 bool fast_ft_supported(const GridD<FT>& g) {
-    if (g.topo[0] != OB_PERIODIC || g.topo[1] != OB_PERIODIC || g.topo[2] != OB_BOUNDED) return false;
+    if (g.topo[0] != OB_PERIODIC || (g.topo[1] != OB_PERIODIC && g.topo[1] != OB_COMM) || g.topo[2] != OB_BOUNDED) return false;
+    const int R = g.topo[1] == OB_COMM ? comm::size() : 1;
     if (!pow2(g.N[0]) || g.N[0] < 32 || g.N[0] > 2048) return false;
-    if (!pow2(g.N[1]) || g.N[1] < 16 || g.N[1] > 2048) return false;
+    if (!pow2(g.N[1]) || g.N[1] * R < 16 || g.N[1] * R > 2048) return false;
     if (!g.regular[0] || !g.regular[1] || g.N[2] < 2) return false;
+    // slab-decomposed in y: the z lines change layout through the power-of-two line kernel (distributed_middle_tri)
+    if (R > 1 && (!pow2(R) || R > 8 || !pow2(g.N[2]) || g.N[2] < 16 || g.N[2] > 1024)) return false;
     return true;
 }
 
@@ -753,6 +757,7 @@ static void launch_line_any(FastPoisson<FT>* p, LArgs<FT>& A, int log2n, int mod
     size_t smem = line_smem(log2n, T, sizeof(CT));
     if (mode == LM_FWD) launch_line<FT, LM_FWD>(A, log2n, grd, smem);
     else if (mode == LM_INV) launch_line<FT, LM_INV>(A, log2n, grd, smem);
+    else if (mode == LM_COPY) launch_line<FT, LM_COPY>(A, log2n, grd, smem);
     else launch_line<FT, LM_FWD_DIV_INV>(A, log2n, grd, smem);
 }
 
@@ -1215,6 +1220,105 @@ static void distributed_middle(FastPoisson<FT>* p) {
     { PhaseScope ph("fft_z_inv"); launch_line_any(p, A, p->log2[2], LM_INV); }
 }
 
+// ---- slab-decomposed Fourier-tridiagonal solve -------------------------------------------------------------------------------
+// Thomas sweep on the gathered layout: this rank holds its KXB wavenumbers kx of ALL NyG y modes and all Nz levels, element
+// (kx, m = s NyL + yl, z) at s * chunk + (z NyL + yl) KXB + kx.  Same arithmetic as thomas_half_kernel.
+template <class FT>
+__global__ void __launch_bounds__(128) thomas_gathered_kernel(typename Cx<FT>::T* spec, FT* tsc, int KXB, int kx0, int NyL, int NyG,
+                                                               int Nz, long long chunk, const double* lamx, const double* lamy,
+                                                               const double* dzF, const double* dzC) {
+    using CT = typename Cx<FT>::T;
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+    if (kx >= KXB) return;
+    const long long col = (long long)(m / NyL) * chunk + (long long)(m % NyL) * KXB + kx, pl = (long long)NyL * KXB;
+    const double lam = lamx[kx0 + kx] + lamy[m];
+    auto diag = [&](int k) -> double {     // k is 1-based
+        if (k == 1) return -1 / dzF[2] - dzC[1] * lam;
+        if (k == Nz) return -1 / dzF[Nz] - dzC[Nz] * lam;
+        return -(1 / dzF[k + 1] + 1 / dzF[k]) - dzC[k] * lam;
+    };
+    const double eps10 = 10 * (sizeof(FT) == 4 ? 1.1920928955078125e-07 : 2.220446049250313e-16);
+    double beta = diag(1);
+    CT f1 = spec[col], prev;
+    prev.x = (FT)((double)f1.x / beta); prev.y = (FT)((double)f1.y / beta);
+    spec[col] = prev;
+    for (int k = 2; k <= Nz; ++k) {
+        const double ak = 1 / dzF[k];
+        const FT t = (FT)(ak / beta);
+        tsc[col + (k - 1) * pl] = t;
+        beta = diag(k) - ak * (double)t;
+        if (!(fabs(beta) > eps10)) break;
+        const CT fk = spec[col + (k - 1) * pl];
+        CT r;
+        r.x = (FT)(((double)fk.x - ak * (double)prev.x) / beta);
+        r.y = (FT)(((double)fk.y - ak * (double)prev.y) / beta);
+        spec[col + (k - 1) * pl] = r;
+        prev = r;
+    }
+    CT nxt = spec[col + (long long)(Nz - 1) * pl];
+    for (int k = Nz - 1; k >= 1; --k) {
+        const FT t = tsc[col + k * pl];
+        CT v = spec[col + (k - 1) * pl];
+        v.x -= t * nxt.x; v.y -= t * nxt.y;
+        spec[col + (k - 1) * pl] = v;
+        nxt = v;
+    }
+    if (kx0 + kx == 0 && m == 0) {         // the horizontal-mean column: phi .-= mean(phi)
+        double sum = 0;
+        for (int k = 0; k < Nz; ++k) sum += (double)spec[col + k * pl].x;
+        const FT mean = (FT)(sum / Nz);
+        for (int k = 0; k < Nz; ++k) { CT v = spec[col + k * pl]; v.x -= mean; v.y = 0; spec[col + k * pl] = v; }
+    }
+}
+
+// x is transformed locally (run_x); then: the z lines move to the chunk layout of their destination ranks (no transform: z is
+// solved, not transformed), all-to-all, forward y lines over the gathered y, Thomas in z, backward y lines stored transposed
+// back, all-to-all, chunk layout -> natural.  fourier_tridiagonal_poisson_solver.jl:74-101 on a y-slab decomposition.
+template <class FT>
+static void distributed_middle_tri(FastPoisson<FT>* p) {
+    int NyL = p->N[1], Nz = p->N[2], KXB = p->KXB;
+    long long chunk = (long long)KXB * NyL * Nz;
+    Lay nat = natural_lay(p->NXP, (long long)p->NXP * NyL, p->NXP);
+    Lay blk{};
+    blk.inv_kxb = 1.0f / KXB; blk.inv_split = 0.f;
+    blk.kxb = KXB; blk.split = 1 << 30; blk.s_blk = chunk; blk.s_ml = (long long)NyL * KXB; blk.s_mh = 0; blk.s_o = KXB;
+    Lay gy{};
+    gy.inv_kxb = 0.f; gy.inv_split = 1.0f / NyL;
+    gy.kxb = 1 << 30; gy.split = NyL; gy.s_blk = 0; gy.s_ml = KXB; gy.s_mh = chunk; gy.s_o = (long long)NyL * KXB;
+    LArgs<FT> A;
+    A.in = p->spec; A.out = p->bufA; A.lin = nat; A.lout = blk;
+    if (p->p2p) {
+        A.lout.pmode = 1;
+        for (int r = 0; r < p->R; ++r) A.lout.ptr[r] = p->peerB[r] + (long long)p->rank * chunk;
+    }
+    A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;
+    A.tw = p->twN; A.lamL = nullptr; A.lamO = nullptr;
+    { PhaseScope ph("fft_z_fwd"); launch_line_any(p, A, p->log2[2], LM_COPY); }
+    { PhaseScope ph("fft_sync"); if (p->p2p) cm::fast_barrier(); else all_to_all(p, p->bufA, p->bufB); }
+    A.in = p->bufB; A.out = p->bufB; A.lin = A.lout = gy;
+    A.NXH = KXB; A.kx0 = p->rank * KXB; A.n = p->NyG; A.line_is_y = 1; A.nOther = Nz;
+    A.tw = p->twY; A.lamL = p->lamy; A.lamO = nullptr;
+    { PhaseScope ph("fft_y"); launch_line_any(p, A, p->log2[1], LM_FWD); }
+    {
+        PhaseScope ph("fft_z");
+        dim3 blk3(64), grd3(cdiv(KXB, 64), p->NyG);
+        thomas_gathered_kernel<FT><<<grd3, blk3, 0, stream()>>>(p->bufB, p->tsc, KXB, p->rank * KXB, NyL, p->NyG, Nz, chunk, p->lamx,
+                                                                p->lamy, p->dzF, p->dzC);
+        OB_LAUNCH_CHECK();
+    }
+    if (p->p2p) {
+        A.out = p->bufA;
+        A.lout.pmode = 2;
+        for (int r = 0; r < p->R; ++r) A.lout.ptr[r] = p->peerA[r] + (long long)p->rank * chunk;
+    }
+    { PhaseScope ph("fft_y"); launch_line_any(p, A, p->log2[1], LM_INV); }
+    { PhaseScope ph("fft_sync"); if (p->p2p) cm::fast_barrier(); else all_to_all(p, p->bufB, p->bufA); }
+    A.in = p->bufA; A.out = p->spec; A.lin = blk; A.lout = nat;
+    A.NXH = p->NXP; A.kx0 = 0; A.n = Nz; A.line_is_y = 0; A.nOther = NyL;
+    A.tw = p->twN; A.lamL = nullptr; A.lamO = nullptr;
+    { PhaseScope ph("fft_z_inv"); launch_line_any(p, A, p->log2[2], LM_COPY); }
+}
+
 // persistent bulk-copy-pipelined x passes (fft_xtma.cuh); false if the configuration is not covered
 template <class FT, bool FWD>
 static bool run_x_tma(FastPoisson<FT>* p, XArgs<FT>& A) {
@@ -1375,7 +1479,9 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
     A.has_z = p->has_z;
     A.phi_p0 = phi_p0; A.Hx = g.H[0];
     { PhaseScope ph("fft_x_fwd"); run_x<FT, true>(p, A); }
-    if (p->R > 1) {
+    if (p->R > 1 && p->tri) {
+        distributed_middle_tri(p);
+    } else if (p->R > 1) {
         if (p->dtma_ok) distributed_middle_tma(p); else distributed_middle(p);
     } else if (p->zhook) {
         { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
