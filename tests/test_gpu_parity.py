@@ -464,6 +464,34 @@ def test_fused_bounded_z_kernel_agrees_with_general_kernels(ob):
         assert relerr(m1.fields[n].interior(), m2.fields[n].interior()) < 1e-12, n
 
 
+@pytest.mark.parametrize("size", [(32, 5, 6), (64, 13, 7), (96, 25, 9), (32, 12, 33), (32, 3, 16)])
+@pytest.mark.parametrize("stretched", [True, False])
+def test_fused_bounded_z_kernel_odd_shapes(ob, size, stretched):
+    """tile rows of 12 against Ny smaller than, equal to and not a multiple of it; Nz at the minimum the kernel takes (6), odd and
+    longer than the ring; regular and stretched z: fused Bounded-z kernel against the general kernels, tendencies and two steps"""
+    cfg = dict(CONFIGS["c3_fused_stretched_weno_rk3"], size=size)
+    if stretched:
+        cfg["coords"] = dict(x=(0, 1), y=(0, 1), z=_zf(size[2]))
+    else:
+        cfg.pop("coords")
+        cfg["extent"] = (1, 1, 1)
+        cfg["adv"] = "WENO5"
+    mo, m1 = build_models(ob, cfg, np.float64)
+    _, m2 = build_models(ob, cfg, np.float64)
+    m2.use_fast_kernels(False)
+    init_state(mo, m1, ob, 37)
+    init_state(mo, m2, ob, 37)
+    ob.calculate_tendencies(m1)
+    ob.calculate_tendencies(m2)
+    for n in m1.names:
+        assert relerr(m1.Gn[n].interior(), m2.Gn[n].interior()) < 1e-12, f"tendency {n}"
+    for _ in range(2):
+        ob.time_step(m1, cfg["dt"])
+        ob.time_step(m2, cfg["dt"])
+    for n in m1.names:
+        assert relerr(m1.fields[n].interior(), m2.fields[n].interior()) < 1e-12, n
+
+
 def test_c3_128x128x64_one_step_matches_oracle(ob):
     """BASELINE config 3 physics on a 128 x 128 x 64 slice of its grid, one RK3 step on the fused Bounded-z kernel against
     the NumPy oracle (about 20 s of oracle time)"""
