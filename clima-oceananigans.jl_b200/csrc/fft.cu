@@ -637,6 +637,36 @@ PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double*
             launch_lines<FT>(A, MODE_FWD_DIV_INV, false);
         });
     }
+    // Bounded y (channels): the same half-spectrum x passes, this file's DCT over the y lines of the half spectrum (forward and
+    // backward pass), and for z the Periodic lines of fft_fast.cu, the DCT hook above's twin, or the Thomas sweep
+    if (!p->fast && ff::fast_bounded_y_supported<FT>(g) && getenv("OB200_NO_FAST_FFT") == nullptr && p->tkind[1] == TK_DCT_POW2 &&
+        ((kind == 1 && g.regular[2] && (g.topo[2] == OB_PERIODIC || p->tkind[2] == TK_DCT_POW2 || p->tkind[2] == TK_DCT_BLUE)) ||
+         (kind == 2 && g.topo[2] == OB_BOUNDED))) {
+        p->fast = ff::fast_poisson_create<FT>(g);
+        auto lines = [p](int d, int mode) {
+            const ff::FastSpecInfo I = ff::fast_poisson_spec_info<FT>(p->fast);
+            FftArgs<FT> A;
+            A.data = (CT*)I.spec; A.n = p->N[d]; A.log2n = p->log2n[d];
+            A.dimL = d; A.dimA = 0; A.dimB = d == 1 ? 2 : 1;
+            A.stride = d == 1 ? (long long)I.NXP : (long long)I.NXP * I.Ny;
+            A.nA = I.NXH; A.strideA = 1;
+            A.nB = d == 1 ? I.Nz : I.Ny; A.strideB = d == 1 ? (long long)I.NXP * I.Ny : (long long)I.NXP;
+            A.kind = p->tkind[d]; A.tw = p->tw[d]; A.M = p->M[d]; A.log2M = p->log2M[d]; A.bhat = p->bhat[d];
+            A.scale = (FT)(1.0 / (2.0 * A.n));
+            A.lam[0] = I.lamx; A.lam[1] = p->lam[1]; A.lam[2] = p->lam[2];
+            A.phi_p0 = nullptr;
+            launch_lines<FT>(A, mode, false);
+        };
+        ff::fast_poisson_set_yhook<FT>(p->fast, [lines](int inverse) { lines(1, inverse ? MODE_INV : MODE_FWD); }, p->lam[1]);
+        if (kind == 1 && g.topo[2] == OB_BOUNDED) ff::fast_poisson_set_zhook<FT>(p->fast, [lines]() { lines(2, MODE_FWD_DIV_INV); });
+        if (kind == 2) {
+            int Nz = g.N[2];
+            std::vector<double> f(dzF_host, dzF_host + Nz + 2), c(dzC_host, dzC_host + Nz + 2);
+            p->dzF = dev_upload(f, p->owned);
+            p->dzC = dev_upload(c, p->owned);
+            ff::fast_poisson_set_tridiagonal<FT>(p->fast, p->dzF, p->dzC);
+        }
+    }
     if (kind == 2) {
         int Nz = g.N[2];
         OB_CUDA(cudaMalloc(&p->source, tot * sizeof(CT)));

@@ -539,6 +539,7 @@ struct FastPoisson {
     std::vector<void*> owned;
     int tri = 0;                                // Fourier-tridiagonal solve: z is Bounded and solved by Thomas
     std::function<void()> zhook;                // ... or transformed by the caller's DCT pass (regular z, FFT-based solver)
+    std::function<void(int)> yhook;             // Bounded y: the caller's forward (0) / backward (1) DCT pass over the y lines
     const double *dzF = nullptr, *dzC = nullptr; // device, Julia-indexed 0..Nz+1 (owned by the PoissonPlan)
     FT* tsc = nullptr;                          // Thomas scratch t, [Nz][Ny][NXP]
     bool tma_ok = false;                        // persistent TMA-pipelined y / z passes (fft_tma.cuh)
@@ -599,6 +600,19 @@ bool fast_ft_supported(const GridD<FT>& g) {
     if (R > 1 && (!pow2(R) || R > 8 || !pow2(g.N[2]) || g.N[2] < 16 || g.N[2] > 1024)) return false;
     return true;
 }
+
+// x Periodic power-of-two, y Bounded power-of-two (transformed by the caller's hook), z Periodic power-of-two or Bounded;
+// regular x, y; one GPU
+template <class FT>
+bool fast_bounded_y_supported(const GridD<FT>& g) {
+    if (g.topo[0] != OB_PERIODIC || g.topo[1] != OB_BOUNDED || g.topo[2] == OB_FLAT || g.topo[2] == OB_COMM) return false;
+    if (!pow2(g.N[0]) || g.N[0] < 32 || g.N[0] > 2048 || !pow2(g.N[1]) || g.N[1] < 16 || g.N[1] > 2048) return false;
+    if (!g.regular[0] || !g.regular[1]) return false;
+    if (g.topo[2] == OB_PERIODIC && (!pow2(g.N[2]) || g.N[2] < 16 || g.N[2] > 1024 || !g.regular[2])) return false;
+    return g.N[2] >= 2;
+}
+template bool fast_bounded_y_supported<float>(const GridD<float>&);
+template bool fast_bounded_y_supported<double>(const GridD<double>&);
 
 template <class FT>
 FastPoisson<FT>* fast_poisson_create(const GridD<FT>& g) {
@@ -691,6 +705,11 @@ template <class FT> FastSpecInfo fast_poisson_spec_info(FastPoisson<FT>* p) {
     return FastSpecInfo{(void*)p->spec, p->NXH, p->NXP, p->N[1], p->N[2], p->lamx, p->lamy};
 }
 template <class FT> void fast_poisson_set_zhook(FastPoisson<FT>* p, std::function<void()> hook) { p->zhook = std::move(hook); }
+// lamy_dev: the eigenvalues of the caller's y transform in ITS storage order (they replace the Periodic table of the plan)
+template <class FT> void fast_poisson_set_yhook(FastPoisson<FT>* p, std::function<void(int)> hook, const double* lamy_dev) {
+    p->yhook = std::move(hook);
+    p->lamy = const_cast<double*>(lamy_dev);
+}
 template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p) {
     if (!p) return;
     cudaFree(p->spec);
@@ -1483,18 +1502,12 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
         distributed_middle_tri(p);
     } else if (p->R > 1) {
         if (p->dtma_ok) distributed_middle_tma(p); else distributed_middle(p);
-    } else if (p->zhook) {
-        { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
-        { PhaseScope ph("fft_z"); p->zhook(); }
-        { PhaseScope ph("fft_y"); run_line(p, 1, LM_INV); }
-    } else if (p->tri) {
-        { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
-        { PhaseScope ph("fft_z"); run_thomas(p); }
-        { PhaseScope ph("fft_y"); run_line(p, 1, LM_INV); }
     } else if (p->has_z) {
-        { PhaseScope ph("fft_y"); run_line(p, 1, LM_FWD); }
-        { PhaseScope ph("fft_z"); run_line(p, 2, LM_FWD_DIV_INV); }
-        { PhaseScope ph("fft_y"); run_line(p, 1, LM_INV); }
+        // y: Periodic lines of this file, or the caller's DCT pass (Bounded y); z: the caller's DCT pass (regular Bounded z),
+        // the Thomas sweep (Fourier-tridiagonal solve) or Periodic lines with the eigenvalue divide
+        { PhaseScope ph("fft_y"); if (p->yhook) p->yhook(0); else run_line(p, 1, LM_FWD); }
+        { PhaseScope ph("fft_z"); if (p->zhook) p->zhook(); else if (p->tri) run_thomas(p); else run_line(p, 2, LM_FWD_DIV_INV); }
+        { PhaseScope ph("fft_y"); if (p->yhook) p->yhook(1); else run_line(p, 1, LM_INV); }
     } else {
         PhaseScope ph("fft_y");
         run_line(p, 1, LM_FWD_DIV_INV);
@@ -1507,6 +1520,7 @@ void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, con
     template void fast_poisson_set_tridiagonal<FT>(FastPoisson<FT>*, const double*, const double*); \
     template FastSpecInfo fast_poisson_spec_info<FT>(FastPoisson<FT>*);                             \
     template void fast_poisson_set_zhook<FT>(FastPoisson<FT>*, std::function<void()>);              \
+    template void fast_poisson_set_yhook<FT>(FastPoisson<FT>*, std::function<void(int)>, const double*); \
     template bool fast_poisson_supported<FT>(const GridD<FT>&);                                     \
     template FastPoisson<FT>* fast_poisson_create<FT>(const GridD<FT>&);                            \
     template void fast_poisson_destroy<FT>(FastPoisson<FT>*);                                       \

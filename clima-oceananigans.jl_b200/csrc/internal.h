@@ -135,6 +135,8 @@ template <class FT> void fast_poisson_destroy(FastPoisson<FT>* p);
 struct FastSpecInfo { void* spec; int NXH, NXP, Ny, Nz; const double* lamx; const double* lamy; };
 template <class FT> FastSpecInfo fast_poisson_spec_info(FastPoisson<FT>* p);
 template <class FT> void fast_poisson_set_zhook(FastPoisson<FT>* p, std::function<void()> hook);
+template <class FT> bool fast_bounded_y_supported(const GridD<FT>& g);
+template <class FT> void fast_poisson_set_yhook(FastPoisson<FT>* p, std::function<void(int)> hook, const double* lamy_dev);
 // source term = div(u,v,w)/dt computed on the fly, or a real Nx*Ny*Nz device array `real_in`
 template <class FT>
 void fast_poisson_solve(FastPoisson<FT>* p, const GridD<FT>& g, const FT* u, const FT* v, const FT* w, FT dt,

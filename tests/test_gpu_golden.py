@@ -128,9 +128,11 @@ def _zf(n, p=1.5):
     return -np.linspace(1, 0, n + 1) ** p
 
 
+@pytest.mark.parametrize("ytopo", ["Periodic", "Bounded"])
 @pytest.mark.parametrize("size", [(32, 16, 12), (64, 32, 20)])
-def test_fast_fourier_tridiagonal_matches_oracle(ob, size):
-    kw = dict(size=size, x=(0, 1), y=(0, 2), z=_zf(size[2]), topology=("Periodic", "Periodic", "Bounded"))
+def test_fast_fourier_tridiagonal_matches_oracle(ob, size, ytopo):
+    """half-spectrum x passes, Periodic y lines or the DCT over a Bounded y (channel), Thomas sweep on the half spectrum"""
+    kw = dict(size=size, x=(0, 1), y=(0, 2), z=_zf(size[2]), topology=("Periodic", ytopo, "Bounded"))
     go, gb = O.RectilinearGrid(np.float64, **kw), ob.RectilinearGrid(ob.arch, np.float64, **kw)
     rhs = poisson_rhs(go, 301)
     po = O.Field(go, auxiliary=True)

@@ -97,9 +97,10 @@ TOPOS8 = [(a, b, c) for a in (O.Periodic, O.Bounded) for b in (O.Periodic, O.Bou
 
 
 @pytest.mark.parametrize("topo", TOPOS8)
-@pytest.mark.parametrize("N", [(16, 8, 32), (7, 11, 6), (48, 20, 96)])
+@pytest.mark.parametrize("N", [(16, 8, 32), (7, 11, 6), (48, 20, 96), (32, 16, 16), (64, 32, 24)])
 def test_fft_poisson_matches_oracle_and_laplacian(ob, topo, N):
-    """power-of-two lengths: radix-2 butterflies (Periodic) / Makhoul's DCT around them (Bounded); other lengths: Bluestein"""
+    """power-of-two lengths: radix-2 butterflies (Periodic) / Makhoul's DCT around them (Bounded); other lengths: Bluestein; the
+    last two sizes take the half-spectrum x passes when x is Periodic and y a power of two (y Periodic or Bounded, any z)"""
     rng = np.random.default_rng(13)
     go, gb = make_pair(ob, np.float64, N, topo, extent=(1.0, 2.0, 3.0))
     rhs, _ = _rhs(go, rng)
