@@ -408,7 +408,16 @@ __global__ void thomas_kernel(int Nx, int Ny, int Nz, const double* a, const dou
         FT t = (FT)(ck / beta);
         tsc[col + (k - 1) * pl] = t;
         beta = bk - ak * (double)t;
-        if (!(fabs(beta) > eps10)) break;
+        // The reference leaves phi[k..] at whatever the array held (batched_tridiagonal_solver.jl:104).  For the solver's own
+        // columns (ONTHEFLY) that content is defined here -- the right-hand side, as in thomas_half_kernel -- and the singular
+        // horizontal-mean column of the Neumann problem is ALWAYS pinned at its last row (its pivot is zero in exact
+        // arithmetic, rounding noise otherwise): the constant it leaves open is removed with the mean, and the solution no
+        // longer depends on noise / noise or on the solver's history.
+        if (!(fabs(beta) > eps10) || (ONTHEFLY && k == Nz && lam == 0.0)) {
+            if (ONTHEFLY)
+                for (int q = k; q <= Nz; ++q) phi[col + (q - 1) * pl] = f[col + (q - 1) * pl];
+            break;
+        }
         VT fk = f[col + (k - 1) * pl];
         VT r;
         if constexpr (sizeof(VT) == sizeof(FT)) { r = (VT)(((double)fk - ak * (double)prev) / beta); }
@@ -451,19 +460,39 @@ template void batched_tridiagonal<double>(int, int, int, bool, const double*, co
 // ---------------------------------------------------------------------------------------------
 // mean removal + real copy for the Fourier-tridiagonal solver (…_poisson_solver.jl:93-99)
 // ---------------------------------------------------------------------------------------------
+// one partial sum per block, each in a fixed order (no atomics: the mean, and with it every bit of the solution, must not
+// depend on the order in which blocks happen to finish)
+constexpr int MEAN_BLOCKS = 1024;
 template <class FT>
-__global__ void sum_real_kernel(const typename Cx<FT>::T* x, long long n, double* out) {
+__global__ void __launch_bounds__(256) sum_real_kernel(const typename Cx<FT>::T* x, long long n, double* partial) {
     double s = 0;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
         s += (double)x[t].x;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffff, s, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+    __shared__ double sh[256];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 template <class FT>
-__global__ void sub_mean_copy_kernel(typename Cx<FT>::T* x, int Nx, int Ny, int Nz, const double* sum,
-                                     FT* phi_p0, long long s0, long long s1, long long s2) {
+__global__ void __launch_bounds__(256) sub_mean_copy_kernel(typename Cx<FT>::T* x, int Nx, int Ny, int Nz, const double* partial,
+                                                            int nparts, FT* phi_p0, long long s0, long long s1, long long s2) {
     long long n = (long long)Nx * Ny * Nz;
-    FT mean = (FT)(*sum / (double)n);
+    __shared__ double sh[256];
+    {   // every block sums the partials in the same order
+        double s = 0;
+        for (int q = threadIdx.x; q < nparts; q += blockDim.x) s += partial[q];
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+    }
+    FT mean = (FT)(sh[0] / (double)n);
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long long)Nx * Ny));
         FT v = x[t].x - mean;
@@ -679,7 +708,7 @@ PoissonPlan<FT>* poisson_plan_create(const GridD<FT>& g, int kind, const double*
         p->dzF = dev_upload(f, p->owned);
         p->dzC = dev_upload(c, p->owned);
         p->lower = dev_upload(low, p->owned);
-        std::vector<double> z(1, 0.0);
+        std::vector<double> z(MEAN_BLOCKS, 0.0);
         p->msum = dev_upload(z, p->owned);
     }
     return p;
@@ -787,11 +816,10 @@ void poisson_solve(PoissonPlan<FT>* p, const GridD<FT>& g, FT* phi_p0) {
     }
     for (int q = nd - 1; q >= 0; --q) run_pass(p, p->storage, dims[q], MODE_INV, (const GridD<FT>*)nullptr, (FT*)nullptr);
     long long tot = (long long)Nx * Ny * Nz;
-    OB_CUDA(cudaMemsetAsync(p->msum, 0, sizeof(double), stream()));
-    int blocks = (int)std::min<long long>(148 * 8, (tot + 255) / 256);
+    int blocks = (int)std::min<long long>(MEAN_BLOCKS, (tot + 255) / 256);
     sum_real_kernel<FT><<<blocks, 256, 0, stream()>>>(p->storage, tot, p->msum);
     OB_LAUNCH_CHECK();
-    sub_mean_copy_kernel<FT><<<blocks, 256, 0, stream()>>>(p->storage, Nx, Ny, Nz, p->msum, phi_p0, g.st[0], g.st[1], g.st[2]);
+    sub_mean_copy_kernel<FT><<<blocks, 256, 0, stream()>>>(p->storage, Nx, Ny, Nz, p->msum, blocks, phi_p0, g.st[0], g.st[1], g.st[2]);
     OB_LAUNCH_CHECK();
 }
 

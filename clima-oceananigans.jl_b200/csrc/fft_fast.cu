@@ -1267,6 +1267,11 @@ __global__ void __launch_bounds__(128) thomas_gathered_kernel(typename Cx<FT>::T
         tsc[col + (k - 1) * pl] = t;
         beta = diag(k) - ak * (double)t;
         if (!(fabs(beta) > eps10)) break;
+        // the horizontal-mean column of a Neumann problem is singular: its last pivot is zero in exact arithmetic and rounding
+        // noise otherwise, and noise / noise would add an arbitrary, input-bit-sensitive constant (it is removed with the mean
+        // below, but costs eps * |constant| of accuracy and bit reproducibility).  The reference's `break` is the same pin
+        // whenever the noise happens to be below its threshold; here the column is always pinned.
+        if (k == Nz && lam == 0.0) break;
         const CT fk = spec[col + (k - 1) * pl];
         CT r;
         r.x = (FT)(((double)fk.x - ak * (double)prev.x) / beta);
@@ -1448,6 +1453,11 @@ __global__ void __launch_bounds__(128) thomas_half_kernel(typename Cx<FT>::T* sp
         tsc[col + (k - 1) * pl] = t;
         beta = diag(k) - ak * (double)t;
         if (!(fabs(beta) > eps10)) break;
+        // the horizontal-mean column of a Neumann problem is singular: its last pivot is zero in exact arithmetic and rounding
+        // noise otherwise, and noise / noise would add an arbitrary, input-bit-sensitive constant (it is removed with the mean
+        // below, but costs eps * |constant| of accuracy and bit reproducibility).  The reference's `break` is the same pin
+        // whenever the noise happens to be below its threshold; here the column is always pinned.
+        if (k == Nz && lam == 0.0) break;
         const CT fk = spec[col + (k - 1) * pl];
         CT r;
         r.x = (FT)(((double)fk.x - ak * (double)prev.x) / beta);

@@ -582,6 +582,11 @@ class NonhydrostaticModel:
         check(lib.ob200_model_diagnostics(self.handle, C.byref(a), C.byref(b)))
         return dict(max_abs_div=a.value, kinetic_energy=b.value)
 
+    def set_clock(self, time=0.0, iteration=0, previous_Δt=float("inf")):
+        """model.clock.time / .iteration = ...; previous_Δt = inf makes the next QuasiAdamsBashforth2 step a forward-Euler step
+        with G^- cleared, as for a new model (quasi_adams_bashforth_2.jl:76-81)"""
+        check(lib.ob200_model_set_clock(self.handle, float(time), int(iteration), float(previous_Δt)))
+
     def destroy(self):
         """release the library model now (device memory, streams, events, tensor maps); also done by the finalizer"""
         if getattr(self, "handle", None) is not None:
