@@ -672,7 +672,8 @@ __global__ void __launch_bounds__(128) pressure_correct_periodic_v2_kernel(GridD
         const V2 pz = e == 0 ? pzm : pc[0];
         uu[e].x -= ((pc[e].x - pxm[e]) / g.d[0]) * dt;  uu[e].y -= ((pc[e].y - pc[e].x) / g.d[0]) * dt;
         vv[e].x -= ((pc[e].x - py[e].x) / g.d[1]) * dt; vv[e].y -= ((pc[e].y - py[e].y) / g.d[1]) * dt;
-        ww[e].x -= ((pc[e].x - pz.x) / g.d[2]) * dt;    ww[e].y -= ((pc[e].y - pz.y) / g.d[2]) * dt;
+        const FT dz = spacing(g, 2, OB_F, k0 + e);          // regular: g.d[2]; stretched: the level's own Δz at the face
+        ww[e].x -= ((pc[e].x - pz.x) / dz) * dt;        ww[e].y -= ((pc[e].y - pz.y) / dz) * dt;
         *reinterpret_cast<V2*>(u + q) = uu[e];
         *reinterpret_cast<V2*>(v + q) = vv[e];
         *reinterpret_cast<V2*>(w + q) = ww[e];
@@ -699,7 +700,9 @@ template <class FT>
 void launch_pressure_correct(const GridD<FT>& g, FT* u, FT* v, FT* w, const FT* p, FT dt, bool periodic_wrap) {
     dim3 blk(64, 4, 1), grd(cdiv(g.N[0], 64), cdiv(g.N[1], 4), g.N[2]);
     static const bool no_v2 = getenv("OB200_NO_PC_V2") != nullptr;
-    bool v2 = periodic_wrap && !no_v2 && g.N[0] % 2 == 0 && g.N[2] % 2 == 0;
+    // v2: two cells x two levels per thread.  With valid halos of p (not periodic_wrap) it serves every 3-D grid with regular
+    // x, y and even Nx, Nz: Periodic dimensions are read with wrap-around (the same values), the others from their halos
+    bool v2 = !no_v2 && g.N[0] % 2 == 0 && g.N[2] % 2 == 0 && g.regular[0] && g.regular[1] && (periodic_wrap || g.regular[2] || g.dF[2]);
     for (int d = 0; d < 3; ++d) v2 = v2 && g.topo[d] != OB_FLAT;      // 3-D only: all three corrections active
     if (v2) {
         dim3 b2(32, 4, 1), g2(cdiv(g.N[0] / 2, 32), cdiv(g.N[1], 4), g.N[2] / 2);
