@@ -167,7 +167,9 @@ def build_config(ob, np, a, arch, world, rank, FTYPE):
                "b": {"top": ob.BoundaryCondition("Flux", 1e-8), "bottom": ob.BoundaryCondition("Gradient", 1e-5)}}
         m = ob.NonhydrostaticModel(g, advection=ob.WENO5(grid=g),
                                    tracers=("b",), buoyancy=ob.Buoyancy(ob.BuoyancyTracer(), None), coriolis=ob.FPlane(1e-4),
-                                   closure=ob.ScalarDiffusivity("ThreeDimensional", ν=1e-4, κ=1e-4),
+                                   closure=(ob.AnisotropicMinimumDissipation() if a.closure == "amd" else
+                                            ob.SmagorinskyLilly() if a.closure == "smagorinsky" else
+                                            ob.ScalarDiffusivity("ThreeDimensional", ν=1e-4, κ=1e-4)),
                                    timestepper="RungeKutta3", boundary_conditions=bcs)
         rng = np.random.default_rng(3)
         vals = {n: 1e-2 * rng.uniform(-1, 1, m.fields[n].size()) for n in "uvw"}
@@ -177,7 +179,8 @@ def build_config(ob, np, a, arch, world, rank, FTYPE):
         ob.set_model(m, **vals)
         wl = (f"C3: {Nx}x{Ny * world}x{Nz} (Periodic, Periodic, Bounded) vertically stretched z, WENO5(grid) + tracer b + FPlane + "
               f"ScalarDiffusivity + flux/gradient BCs, Fourier-tridiagonal pressure solve, RK3"
-              + (f", y slab-decomposed over {world} GPUs" if world > 1 else ""))
+              + (f", y slab-decomposed over {world} GPUs" if world > 1 else "")
+              + ("" if a.closure == "scalar" else f" [closure: {a.closure} instead of ScalarDiffusivity]"))
         return m, 0.05, Nx * Ny * Nz, (Nx, Ny * world, Nz), wl, 4, 110.0
     if cfg == "c5-strong":
         s = a.size or 1024
@@ -244,6 +247,8 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="scale the configuration: replaces 256 (c2) / 512 (c3, c5-weak) / 1024")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5-weak", "c5-strong"])
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--closure", default="scalar", choices=["scalar", "amd", "smagorinsky"],
+                    help="config c3 only: ScalarDiffusivity (BASELINE configs[2]) or the LES closure of its source example")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-dist-parity", action="store_true")
@@ -349,7 +354,7 @@ def main():
     tend = phases["tendency"]
     W = 8 if a.ftype == "f64" else 4
     fused = os.environ.get("OB200_NO_FUSED_TENDENCY") is None and (
-        a.config != "c3" or (os.environ.get("OB200_NO_FUSED_BOUNDED") is None and shape_g[0] % 32 == 0))
+        a.config != "c3" or (os.environ.get("OB200_NO_FUSED_BOUNDED") is None and shape_g[0] % 32 == 0 and a.closure == "scalar"))
     # algorithmic words per point: 4F+1 for stages 2,3 and 3F+1 for stage 1, per stage;
     # the fused kernel does a whole stage per launch, the per-field kernels a F-th of it
     words_stage = ((3 * F + 1) + 2 * (4 * F + 1)) / 3.0

@@ -918,6 +918,13 @@ __global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ Phys<F
     q.i[0] = i; q.i[1] = j; q.i[2] = k;
     q.p = i * g.st[0] + j * g.st[1] + k * g.st[2];
     const FT* U[3] = {A.u, A.v, A.w};
+    if (g.topo[0] != OB_FLAT && g.topo[1] != OB_FLAT && g.topo[2] != OB_FLAT) {
+        FT nu, ka[8];
+        amd_cell<FT>(P, B, U, A.ntr, A.c, q, nu, ka);
+        A.nue[q.p] = nu;
+        for (int t = 0; t < A.ntr; ++t) A.ke[t][q.p] = ka[t];
+        return;
+    }
     A.nue[q.p] = amd_nu(P, B, U, q);
     for (int t = 0; t < A.ntr; ++t) A.ke[t][q.p] = amd_kappa(P, P.amdCk[t], U, A.c[t], q);
 }

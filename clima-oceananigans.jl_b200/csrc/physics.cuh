@@ -653,6 +653,122 @@ OBD FT amd_kappa(const Phys<FT>& P, FT Ck, const FT* const* U, const FT* c, Pt q
 #undef AYZ
 }
 
+// calc_νᶜᶜᶜ and calc_κᶜᶜᶜ of ALL tracers for one cell of a 3-D grid (no Flat dimension) from ONE evaluation of every normalised
+// gradient: the 6 off-diagonal gradients at the 4 points of their averaging stencil (24 values), the 3 diagonal ones, the
+// spacing ratios Δᶠ_a / Δᶠ_b once per distinct index pair.  Same expressions, the same order of operations inside each
+// expression as amd_nu / amd_kappa above (which evaluate every gradient again at every use: 10 000 instructions and 550
+// loads per cell); stretched spacings enter as reciprocals (one rounding of difference).
+template <class FT>
+OBD void amd_cell(const Phys<FT>& P, const Buoy<FT>& B, const FT* const* U, int ntr, const FT* const* c, Pt q, FT& nu_out,
+                  FT* ka_out) {
+    const GridD<FT>& g = P.g;
+    const long long st[3] = {g.st[0], g.st[1], g.st[2]};
+    FT f[3][2], iF[3][2], iC[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        f[d][0] = 2 * spacing(g, d, OB_C, q.i[d]);
+        f[d][1] = g.regular[d] ? f[d][0] : 2 * spacing(g, d, OB_C, q.i[d] + 1);
+        iF[d][0] = g.regular[d] ? g.invd[d] : 1 / spacing(g, d, OB_F, q.i[d]);
+        iF[d][1] = g.regular[d] ? g.invd[d] : 1 / spacing(g, d, OB_F, q.i[d] + 1);
+        iC[d] = g.regular[d] ? g.invd[d] : 1 / spacing(g, d, OB_C, q.i[d]);
+    }
+    // R[a][b] = Δᶠ_n(index + a) / Δᶠ_m(index + b)
+    auto ratios = [&](int n, int m, FT (&R)[2][2]) {
+        R[0][0] = f[n][0] / f[m][0];
+        R[1][0] = g.regular[n] ? R[0][0] : f[n][1] / f[m][0];
+        R[0][1] = g.regular[m] ? R[0][0] : f[n][0] / f[m][1];
+        R[1][1] = g.regular[n] ? R[0][1] : (g.regular[m] ? R[1][0] : f[n][1] / f[m][1]);
+    };
+    FT Rxy[2][2], Ryx[2][2], Rxz[2][2], Rzx[2][2], Ryz[2][2], Rzy[2][2];
+    ratios(0, 1, Rxy); ratios(1, 0, Ryx); ratios(0, 2, Rxz); ratios(2, 0, Rzx); ratios(1, 2, Ryz); ratios(2, 1, Rzy);
+    // normalised gradient of component `comp` along `dd` at the point q + a * st[da] + b * st[db]; (da, db) = the two averaged
+    // dimensions; the ratio and the reciprocal face spacing are the caller's
+    auto grad = [&](int comp, int dd, long long p, FT ratio, FT inv) { return ratio * ((U[comp][p] - U[comp][p - st[dd]]) * inv); };
+    auto avg4 = [](const FT (&F)[2][2]) { return FT(0.5) * (FT(0.5) * (F[0][0] + F[1][0]) + FT(0.5) * (F[0][1] + F[1][1])); };
+    auto avg4p = [](const FT (&F)[2][2], const FT (&G2)[2][2]) {
+        return FT(0.5) * (FT(0.5) * (F[0][0] * G2[0][0] + F[1][0] * G2[1][0]) + FT(0.5) * (F[0][1] * G2[0][1] + F[1][1] * G2[1][1]));
+    };
+    FT xv[2][2], yu[2][2], xw[2][2], zu[2][2], yw[2][2], zv[2][2], s12[2][2], s13[2][2], s23[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const long long pxy = q.p + a * st[0] + b * st[1], pxz = q.p + a * st[0] + b * st[2], pyz = q.p + a * st[1] + b * st[2];
+            xv[a][b] = grad(1, 0, pxy, Rxy[a][b], iF[0][a]);
+            yu[a][b] = grad(0, 1, pxy, Ryx[b][a], iF[1][b]);
+            xw[a][b] = grad(2, 0, pxz, Rxz[a][b], iF[0][a]);
+            zu[a][b] = grad(0, 2, pxz, Rzx[b][a], iF[2][b]);
+            yw[a][b] = grad(2, 1, pyz, Ryz[a][b], iF[1][a]);
+            zv[a][b] = grad(1, 2, pyz, Rzy[b][a], iF[2][b]);
+            s12[a][b] = FT(0.5) * (yu[a][b] + xv[a][b]);
+            s13[a][b] = FT(0.5) * (zu[a][b] + xw[a][b]);
+            s23[a][b] = FT(0.5) * (zv[a][b] + yw[a][b]);
+        }
+    const FT xu = (U[0][q.p + st[0]] - U[0][q.p]) * iC[0], yv = (U[1][q.p + st[1]] - U[1][q.p]) * iC[1],
+             zw = (U[2][q.p + st[2]] - U[2][q.p]) * iC[2];
+    const FT xv2 = avg4p(xv, xv), yu2 = avg4p(yu, yu), xw2 = avg4p(xw, xw), zu2 = avg4p(zu, zu), yw2 = avg4p(yw, yw), zv2 = avg4p(zv, zv);
+    const FT Axv = avg4(xv), Ayu = avg4(yu), Axw = avg4(xw), Azu = avg4(zu), Ayw = avg4(yw), Azv = avg4(zv);
+    const FT delta2 = amd_delta2(g, q);
+    // ---- viscosity (amd_nu) ----
+    const FT qn = (((((((xu * xu + yv * yv) + zw * zw) + xv2) + yu2) + xw2) + zu2) + yw2) + zv2;
+    FT nu = FT(0);
+    if (qn != FT(0)) {
+        const FT t1 = ((((xu * (xu * xu) + yv * xv2) + zw * xw2) + 2 * xu * avg4p(xv, s12)) + 2 * xu * avg4p(xw, s13))
+                      + 2 * Axv * Axw * avg4(s23);
+        const FT t2 = ((((xu * yu2 + yv * (yv * yv)) + zw * yw2) + 2 * yv * avg4p(yu, s12))
+                       + 2 * Ayu * Ayw * avg4(s13)) + 2 * yv * avg4p(yw, s23);
+        const FT t3 = ((((xu * zu2 + yv * zv2) + zw * (zw * zw)) + 2 * Azu * Azv * avg4(s12))
+                       + 2 * zw * avg4p(zu, s13)) + 2 * zw * avg4p(zv, s23);
+        const FT rr = (t1 + t2) + t3;
+        FT cbz = FT(0);
+        if (P.amdHasCb && B.mode) {
+            const FT b0 = buoyancy_at(B, q.p);
+            FT adb[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                adb[d] = FT(0.5) * ((b0 - buoyancy_at(B, q.p - st[d])) * iF[d][0] + (buoyancy_at(B, q.p + st[d]) - b0) * iF[d][1]);
+            const FT wx = (Axw * f[0][0]) * adb[0], wy = (Ayw * f[1][0]) * adb[1], wz = (zw * f[2][0]) * adb[2];
+            cbz = P.amdCb * ((wx + wy) + wz) / f[2][0];
+        }
+        nu = -P.amdCnu * delta2 * (rr - cbz) / qn;
+        nu = nu > FT(0) ? nu : FT(0);
+    }
+    nu_out = nu;
+    // ---- diffusivities (amd_kappa) ----
+    if (ntr > 0) {
+        FT ywxz[2][2];          // ∂y w interpolated with ℑxz, as the reference's cy_uy does
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) ywxz[a][b] = grad(2, 1, q.p + a * st[0] + b * st[2], Ryz[0][b], iF[1][0]);
+        const FT Aywxz = avg4(ywxz);
+        for (int t = 0; t < ntr; ++t) {
+            const FT* cc = c[t];
+            const FT c0 = cc[q.p];
+            FT cg[3][2];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                cg[d][0] = f[d][0] * ((c0 - cc[q.p - st[d]]) * iF[d][0]);
+                cg[d][1] = f[d][1] * ((cc[q.p + st[d]] - c0) * iF[d][1]);
+            }
+            const FT cx2 = FT(0.5) * (cg[0][0] * cg[0][0] + cg[0][1] * cg[0][1]), cy2 = FT(0.5) * (cg[1][0] * cg[1][0] + cg[1][1] * cg[1][1]),
+                     cz2 = FT(0.5) * (cg[2][0] * cg[2][0] + cg[2][1] * cg[2][1]);
+            const FT sigma = (cx2 + cy2) + cz2;
+            FT ka = FT(0);
+            if (sigma != FT(0)) {
+                const FT icx = FT(0.5) * (cg[0][0] + cg[0][1]), icy = FT(0.5) * (cg[1][0] + cg[1][1]), icz = FT(0.5) * (cg[2][0] + cg[2][1]);
+                const FT a1 = (xu * cx2 + Axv * icx * icy) + Axw * icx * icz;
+                const FT a2 = (Ayu * icy * icx + yv * cy2) + Aywxz * icy * icz;
+                const FT a3 = (Azu * icz * icx + Azv * icz * icy) + zw * cz2;
+                const FT theta = (a1 + a2) + a3;
+                ka = -P.amdCk[t] * delta2 * theta / sigma;
+                ka = ka > FT(0) ? ka : FT(0);
+            }
+            ka_out[t] = ka;
+        }
+    }
+}
+
 // ---- tendencies: nonhydrostatic_tendency_kernel_functions.jl:44-232 (term order kept) -------
 // comp 0,1,2 = u,v,w ; comp >= 3 = tracer (comp-3)
 template <class FT>
