@@ -1133,6 +1133,17 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
             ff.nw[q] = ss.mode == SUB_NONE ? nullptr : f->template alt0<FT>();
             for (int s = 0; s < 6; ++s) { ff.fbc[q].kind[s] = f->bcs[s].kind; ff.fbc[q].val[s] = (FT)f->bcs[s].value; }
         }
+        // a closure the fused kernel does not evaluate itself (LES closures; any closure on the triply periodic variant): its flux
+        // divergence alone goes into G^n through the general shared-face kernel, and the fused kernel adds everything else
+        static const bool no_split = getenv("OB200_NO_CLOSURE_SPLIT") != nullptr;
+        if (fz::supported<FT>(P, m->nf) == 2 && !no_split && closure_only_supported<FT>(P)) {
+            model_halo_join(m);
+            const int nfused = 3 + std::min(m->nf - 3, 1);
+            const Substep<FT> none{SUB_NONE, FT(0), FT(0), FT(0)};
+            for (int q = 0; q < nfused; ++q)
+                launch_tendency_general<FT>(P, q, U, ff.state[q], pHY, b, ff.fbc[q], ff.Gn[q], ff.Gm[q], nullptr, none, true);
+            ff.accumulate = true;
+        }
         if (m->halo_pending) {
             // the neighbour exchange of the previous stage is still in flight on the halo stream: tile rows that read only rows
             // this rank owns go first, the boundary tile rows once the exchange has landed

@@ -45,7 +45,9 @@ struct FluxBC {            // constant Flux boundary conditions of the field bei
 template <class FT>
 void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi,
                              const FT* pHY, const Buoy<FT>& b, const FluxBC<FT>& fbc, FT* Gn,
-                             const FT* Gm, FT* psi_new, const Substep<FT>& ss);
+                             const FT* Gm, FT* psi_new, const Substep<FT>& ss, bool closure_only = false);
+// true if launch_tendency_general(..., closure_only = true) is available for this model (3-D grid)
+template <class FT> bool closure_only_supported(const Phys<FT>& P);
 // fast path (triply periodic, regular, WENO5 uniform, no closure/coriolis); returns false if
 // the configuration is not covered
 template <class FT>
@@ -66,10 +68,16 @@ struct FusedFields {
     const FT* pHY;
     Substep<FT> ss;
     FluxBC<FT> fbc[FUSED_MAXF];      // constant Flux boundary conditions (Bounded z variant)
+    bool accumulate = false;         // G^n already holds the closure's part (launch_tendency_general closure_only): add to it
 };
 // part: 0 = every tile; 1 = the tile rows whose stencils stay inside the rows this rank owns along a slab-decomposed y (they
 // need no neighbour data); 2 = the remaining (boundary) tile rows.  Returns the number of fields handled, 0 = not applicable.
-namespace fz { template <class FT> int launch(const Phys<FT>& P, const FusedFields<FT>& a, int part = 0); }
+namespace fz {
+template <class FT> int launch(const Phys<FT>& P, const FusedFields<FT>& a, int part = 0);
+// 0: not applicable; 1: handles the model's closure itself (or there is none); 2: applicable if the closure's flux divergence
+// is precomputed into G^n (FusedFields::accumulate)
+template <class FT> int supported(const Phys<FT>& P, int nf);
+}
 
 // SmagorinskyLilly eddy viscosity over the interior (the caller fills its halos)
 template <class FT>

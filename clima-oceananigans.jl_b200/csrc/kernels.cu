@@ -348,6 +348,7 @@ struct TendArgs {
     Substep<FT> ss;
     FluxBC<FT> fbc;
     int comp;
+    int closure_only;      // G^n = -div(tau) / -div(q) of the closure alone (the fused kernel adds the rest, tendency_fused.cu)
 };
 
 // COMP (0, 1, 2 = u, v, w; 3 = any tracer) is a template parameter so that the staggering flags of every operator in
@@ -428,16 +429,16 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
     const bool need_x = outy && i <= g.N[0] + 1, need_y = outx && j <= g.N[1] + 1;
     const FT* U[3] = {A.U[0], A.U[1], A.U[2]};
     const int comp = COMP == 3 ? A.comp : COMP;
-    const bool visc = P.closure != CLO_NONE;
+    const bool visc = P.closure != CLO_NONE, adv = P.scheme != ADV_NONE && !A.closure_only;
     const FT kappa = COMP == 3 ? Pin.kappa[comp - 3] : FT(0);
     const FT* kappae = COMP == 3 ? Pin.kappae[comp - 3] : nullptr;
     auto face = [&](int d, Pt q) -> FT {       // area-weighted advective + viscous / diffusive flux at q along d
         FT f = FT(0);
         if (COMP < 3) {
-            if (P.scheme != ADV_NONE) f = momentum_flux(P, d, B, U[d], A.psi, q);
+            if (adv) f = momentum_flux(P, d, B, U[d], A.psi, q);
             if (visc) f = f + viscous_Aflux(P, B, d, U, q);
         } else {
-            if (P.scheme != ADV_NONE) f = tracer_flux(P, d, U[d], A.psi, q);
+            if (adv) f = tracer_flux(P, d, U[d], A.psi, q);
             if (visc) f = f + diffusive_Aflux(P, d, kappa, A.psi, q, kappae);
         }
         return f;
@@ -467,6 +468,9 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
             int l[3] = {OB_C, OB_C, OB_C};
             if (COMP < 3) l[COMP] = OB_F;
             FT G = -((1 / volume(g, q, l[0], l[1], l[2])) * ((dFx + dFy) + dFz));
+            if (A.closure_only) {
+                A.Gn[q.p] = G;
+            } else {
             if (COMP == 0) {
                 if (P.fplane) {          // x_f_cross_U = -f ℑxyᶠᶜᵃ(v)   (f_plane.jl:42)
                     FT a0 = IF(g, U[1], q, 0);
@@ -500,24 +504,35 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
             if (ss.mode == SUB_RK3_FIRST) A.psi_new[q.p] = A.psi[q.p] + ss.c1 * G;
             else if (ss.mode == SUB_RK3) A.psi_new[q.p] = A.psi[q.p] + ss.dt * (ss.c1 * G + ss.c2 * A.Gm[q.p]);
             else if (ss.mode == SUB_AB2) A.psi_new[q.p] = A.psi[q.p] + ss.dt * (ss.c1 * G - ss.c2 * A.Gm[q.p]);
+            }
         }
         q = sh(g, q, 2, 1);
     }
 }
 
 template <class FT>
+bool closure_only_supported(const Phys<FT>& P) {
+    if (getenv("OB200_NO_SHARED_GENERAL") != nullptr || P.closure == CLO_NONE) return false;
+    for (int d = 0; d < 3; ++d) if (P.g.topo[d] == OB_FLAT || P.g.N[d] < 2) return false;
+    return true;
+}
+template bool closure_only_supported<float>(const Phys<float>&);
+template bool closure_only_supported<double>(const Phys<double>&);
+
+template <class FT>
 void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], const FT* psi,
                              const FT* pHY, const Buoy<FT>& b, const FluxBC<FT>& fbc, FT* Gn,
-                             const FT* Gm, FT* psi_new, const Substep<FT>& ss) {
+                             const FT* Gm, FT* psi_new, const Substep<FT>& ss, bool closure_only) {
     TendArgs<FT> A;
     for (int d = 0; d < 3; ++d) A.U[d] = U[d];
     A.psi = psi; A.pHY = pHY; A.b = b; A.Gn = Gn; A.Gm = Gm; A.psi_new = psi_new;
-    A.ss = ss; A.fbc = fbc; A.comp = comp;
+    A.ss = ss; A.fbc = fbc; A.comp = comp; A.closure_only = closure_only ? 1 : 0;
     // shared-face variant: 3-D grids (every direction has two faces to pair) with a halo wide enough for the one
     // extra face position per direction
     static const bool no_shared = getenv("OB200_NO_SHARED_GENERAL") != nullptr;
     bool shared = !no_shared && (P.scheme != ADV_NONE || P.closure != CLO_NONE);
     for (int d = 0; d < 3; ++d) shared = shared && P.g.topo[d] != OB_FLAT && P.g.N[d] >= 2;
+    if (closure_only && !shared) throw Error("closure-only tendencies need the shared-face kernel (3-D grid)");
     static const bool no_spec = getenv("OB200_NO_SPEC_GENERAL") != nullptr;
     const bool spec = !no_spec && P.g.topo[0] == OB_PERIODIC && P.g.topo[1] == OB_PERIODIC && P.g.topo[2] == OB_BOUNDED &&
                       P.g.regular[0] && P.g.regular[1] && P.scheme == ADV_WENO5 && P.buffer == 2 && !P.tilted && !P.vitd &&
@@ -548,10 +563,10 @@ void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], 
 }
 template void launch_tendency_general<float>(const Phys<float>&, int, const float* const[3], const float*,
                                              const float*, const Buoy<float>&, const FluxBC<float>&, float*,
-                                             const float*, float*, const Substep<float>&);
+                                             const float*, float*, const Substep<float>&, bool);
 template void launch_tendency_general<double>(const Phys<double>&, int, const double* const[3], const double*,
                                               const double*, const Buoy<double>&, const FluxBC<double>&, double*,
-                                              const double*, double*, const Substep<double>&);
+                                              const double*, double*, const Substep<double>&, bool);
 
 // =============================================================================================
 // pressure source term: rhs = div(U*) / dt (x Δzᶜ for the tridiagonal solver)

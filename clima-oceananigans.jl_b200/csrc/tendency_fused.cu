@@ -308,7 +308,7 @@ __device__ __forceinline__ void cell_flux_z(const Args<FT, NF>& c, int k, const 
     Fz = Fn;
 }
 
-template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, int R, int GRP>
+template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, bool ACC, int R, int GRP>
 __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT* sX, unsigned long long* full,
                                            unsigned long long* done) {
     using GR = Groups<NT>;
@@ -443,6 +443,7 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
                         }
                         if (c.pHY) Gv = Gv - (ph - phy) * c.invdy;
                     }
+                    if constexpr (ACC) Gv = Gv + c.Gn[f][p];
                     c.Gn[f][p] = Gv;
                     if (c.do_sub) {
                         const FT ps = S[f * SLOTS * PE + so[3] + e];
@@ -457,7 +458,7 @@ __device__ __forceinline__ void group_main(const Args<FT, 3 + NT>& c, FT* S, FT*
     }
 }
 
-template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, int R>
+template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, bool ACC, int R>
 __global__ void __launch_bounds__(TX*(Groups<NT>::NG*(R + 1) + 1), 1)
 tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
     using GR = Groups<NT>;
@@ -510,13 +511,13 @@ tendency_fused_kernel(const __grid_constant__ Args<FT, 3 + NT> c) {
         return;
     }
     const int grp = warp / (R + 1);
-    if (grp == 0) group_main<FT, ZW, ZT, NT, HAS_GM, R, 0>(c, S, sX, full, done);
-    else if (grp == 1) group_main<FT, ZW, ZT, NT, HAS_GM, R, 1>(c, S, sX, full, done);
-    else if (NG > 2) group_main<FT, ZW, ZT, NT, HAS_GM, R, (NG > 2 ? 2 : 0)>(c, S, sX, full, done);
+    if (grp == 0) group_main<FT, ZW, ZT, NT, HAS_GM, ACC, R, 0>(c, S, sX, full, done);
+    else if (grp == 1) group_main<FT, ZW, ZT, NT, HAS_GM, ACC, R, 1>(c, S, sX, full, done);
+    else if (NG > 2) group_main<FT, ZW, ZT, NT, HAS_GM, ACC, R, (NG > 2 ? 2 : 0)>(c, S, sX, full, done);
 }
 
 // ---- host side --------------------------------------------------------------------------------
-template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, int R>
+template <class FT, bool ZW, int ZT, int NT, bool HAS_GM, bool ACC, int R>
 static bool launch_variant(const Phys<FT>& P, const FusedFields<FT>& a, int part) {
     using GR = Groups<NT>;
     constexpr int NF = GR::NF;
@@ -551,7 +552,8 @@ static bool launch_variant(const Phys<FT>& P, const FusedFields<FT>& a, int part
     if (ZT) {
         c.cf[0] = c.invdx; c.cf[1] = c.invdy; c.cf[2] = FT(0);
         c.izC = g.izC; c.izF = g.izF; c.tabF = P.wzp[0]; c.tabC = P.wzp[1];
-        const FT nu = P.closure == CLO_3D ? P.nu : FT(0), kap = P.closure == CLO_3D ? P.kappa[0] : FT(0);
+        // with a.accumulate the closure's part is already in G^n: no viscous terms here
+        const FT nu = (P.closure == CLO_3D && !a.accumulate) ? P.nu : FT(0), kap = (P.closure == CLO_3D && !a.accumulate) ? P.kappa[0] : FT(0);
         c.v24 = -24 * nu; c.vh[0] = c.v24 * c.invdx; c.vh[1] = c.v24 * c.invdy;
         c.t2 = -2 * kap; c.th[0] = c.t2 * c.invdx; c.th[1] = c.t2 * c.invdy;
         for (int f = 0; f < NF; ++f) {
@@ -568,7 +570,7 @@ static bool launch_variant(const Phys<FT>& P, const FusedFields<FT>& a, int part
     c.do_sub = ss.mode != SUB_NONE;
     c.ca = ss.mode == SUB_RK3_FIRST ? ss.c1 : ss.dt * ss.c1;
     c.cb = ss.mode == SUB_RK3 ? ss.dt * ss.c2 : (ss.mode == SUB_AB2 ? -(ss.dt * ss.c2) : FT(0));
-    auto kern = tendency_fused_kernel<FT, ZW, ZT, NT, HAS_GM, R>;
+    auto kern = tendency_fused_kernel<FT, ZW, ZT, NT, HAS_GM, ACC, R>;
     static bool attr_set = false;      // per instantiation
     if (!attr_set) {
         OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
@@ -594,39 +596,70 @@ static bool launch_variant(const Phys<FT>& P, const FusedFields<FT>& a, int part
 template <class FT, bool ZW, int ZT, int NT, int R>
 static bool launch_gm(const Phys<FT>& P, const FusedFields<FT>& a, int part) {
     const bool has_gm = a.ss.mode == SUB_RK3 || a.ss.mode == SUB_AB2;
-    if (has_gm) return launch_variant<FT, ZW, ZT, NT, true, R>(P, a, part);
-    return launch_variant<FT, ZW, ZT, NT, false, R>(P, a, part);
+    // the accumulate form (closure's part precomputed into G^n) exists for the variants with a tracer
+    if constexpr (NT == 1) {
+        if (a.accumulate) {
+            if (has_gm) return launch_variant<FT, ZW, ZT, NT, true, true, R>(P, a, part);
+            return launch_variant<FT, ZW, ZT, NT, false, true, R>(P, a, part);
+        }
+    } else {
+        if (a.accumulate) return false;
+    }
+    if (has_gm) return launch_variant<FT, ZW, ZT, NT, true, false, R>(P, a, part);
+    return launch_variant<FT, ZW, ZT, NT, false, false, R>(P, a, part);
 }
+
+// the configuration checks: returns -1 (not applicable) or the z variant (0 Periodic regular, 1 Bounded); `native` = the kernel
+// computes the model's closure itself (none, or ScalarDiffusivity ThreeDimensional on the Bounded variant)
+template <class FT>
+static int classify(const Phys<FT>& P, int nf, bool& native) {
+    const GridD<FT>& g = P.g;
+    static const bool off = getenv("OB200_NO_FUSED_TENDENCY") != nullptr;
+    static const bool offb = getenv("OB200_NO_FUSED_BOUNDED") != nullptr;
+    native = false;
+    if (off) return -1;
+    if (P.scheme != ADV_WENO5 || P.tilted || P.vitd) return -1;
+    if (g.topo[0] != OB_PERIODIC || (g.topo[1] != OB_PERIODIC && g.topo[1] != OB_COMM)) return -1;
+    for (int d = 0; d < 3; ++d)
+        if (g.H[d] < 3 || (d < 2 && (!g.regular[d] || P.wc[d][0] || P.wc[d][1]))) return -1;
+    if (g.N[0] % TX || (g.S[0] * sizeof(FT)) % 16 || g.total >= (1LL << 31)) return -1;
+    if (nf < 3) return -1;
+    const int nt = std::min(nf - 3, 1);
+    // ZT = 1: Bounded z (stretched with WENO5(grid) tables, or regular) with ScalarDiffusivity (or no closure) and constant
+    // Flux BCs in z
+    if (g.topo[2] == OB_PERIODIC) {
+        if (!g.regular[2] || P.wc[2][0] || P.wc[2][1]) return -1;
+        native = P.closure == CLO_NONE;
+        return 0;
+    }
+    if (g.topo[2] == OB_BOUNDED) {
+        if (offb || nt == 0 || !g.izC || !g.izF || !P.wzp[0] || !P.wzp[1] || g.N[2] < 6) return -1;
+        if (!g.regular[2] && (!P.wc[2][0] || !P.wc[2][1])) return -1;      // stretched z without coefficient tables
+        native = P.closure == CLO_NONE || P.closure == CLO_3D;
+        return 1;
+    }
+    return -1;
+}
+template <class FT>
+int supported(const Phys<FT>& P, int nf) {
+    bool native;
+    const int zt = classify(P, nf, native);
+    return zt < 0 ? 0 : (native ? 1 : (nf > 3 ? 2 : 0));
+}
+template int supported<float>(const Phys<float>&, int);
+template int supported<double>(const Phys<double>&, int);
 
 template <class FT>
 int launch(const Phys<FT>& P, const FusedFields<FT>& a, int part) {
     const GridD<FT>& g = P.g;
-    static const bool off = getenv("OB200_NO_FUSED_TENDENCY") != nullptr;
-    static const bool offb = getenv("OB200_NO_FUSED_BOUNDED") != nullptr;
-    if (off) return 0;
-    if (P.scheme != ADV_WENO5 || P.tilted) return 0;
-    if (g.topo[0] != OB_PERIODIC || (g.topo[1] != OB_PERIODIC && g.topo[1] != OB_COMM)) return 0;
-    for (int d = 0; d < 3; ++d)
-        if (g.H[d] < 3 || (d < 2 && (!g.regular[d] || P.wc[d][0] || P.wc[d][1]))) return 0;
-    if (g.N[0] % TX || (g.S[0] * sizeof(FT)) % 16 || g.total >= (1LL << 31)) return 0;
-    if (a.nf < 3) return 0;
+    bool native;
+    const int zt = classify(P, a.nf, native);
+    if (zt < 0 || (!native && !a.accumulate)) return 0;
     const int nt = std::min(a.nf - 3, 1);
-    // ZT = 1: Bounded z (stretched with WENO5(grid) tables, or regular) with ScalarDiffusivity (or no closure) and constant
-    // Flux BCs in z
-    int zt;
-    if (g.topo[2] == OB_PERIODIC) {
-        if (!g.regular[2] || P.wc[2][0] || P.wc[2][1] || P.closure != CLO_NONE) return 0;
-        zt = 0;
-    } else if (g.topo[2] == OB_BOUNDED) {
-        if (offb || nt == 0 || !g.izC || !g.izF || !P.wzp[0] || !P.wzp[1] || g.N[2] < 6) return 0;
-        if (!g.regular[2] && (!P.wc[2][0] || !P.wc[2][1])) return 0;      // stretched z without coefficient tables
-        if ((P.closure != CLO_NONE && P.closure != CLO_3D) || P.vitd) return 0;
+    if (zt == 1)
         for (int s = 4; s < 6; ++s)
             if (a.fbc[2].kind[s] == 2 && a.fbc[2].val[s] != FT(0)) return 0;      // w has no Flux BCs on a Bounded z
-        zt = 1;
-    } else {
-        return 0;
-    }
+    (void)g;
     bool ok = false;
 #define GO(ZTV, NTV, RV)                                                                        \
     { ok = P.zweno ? launch_gm<FT, true, ZTV, NTV, RV>(P, a, part) : launch_gm<FT, false, ZTV, NTV, RV>(P, a, part); }

@@ -244,6 +244,18 @@ CONFIGS = {
                                        bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"bottom": ("Flux", -1e-4)}}),
     "ppb_regular_fused_nz12_ab2": dict(size=(32, 16, 12), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(1, 1, 0.5),
                                        adv="WENO5", tracers=("b",), buoyancy=True, ts="QuasiAdamsBashforth2", dt=4e-3),
+    # closures the fused kernel does not evaluate itself: their flux divergence alone goes through the general shared-face kernel
+    # into G^n, the fused kernel adds advection, Coriolis, pressure gradient, BC fluxes and the substep
+    "amd_c3_fused_split": dict(size=(32, 16, 14), topology=(O.Periodic, O.Periodic, O.Bounded),
+                               coords=dict(x=(0, 1), y=(0, 1), z=_zf(14)), adv="WENO5grid", tracers=("b",), buoyancy=True,
+                               amd=dict(Cb=1.0), f=1e-2, ts="RungeKutta3", dt=5e-3,
+                               bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"top": ("Flux", 1e-4), "bottom": ("Gradient", 1e-2)}}),
+    "smagorinsky_ppb_fused_split_ab2": dict(size=(32, 16, 16), topology=(O.Periodic, O.Periodic, O.Bounded), extent=(2, 1, 1),
+                                            adv="WENO5", tracers=("b", "c"), buoyancy=True, smagorinsky={}, ts="QuasiAdamsBashforth2",
+                                            dt=4e-3, bcs={"b": {"bottom": ("Flux", -1e-4)}}),
+    "scalar3d_periodic_fused_split": dict(size=(32, 12, 16), topology=(O.Periodic,) * 3, extent=(1, 1, 1), adv="WENO5",
+                                          tracers=("b",), buoyancy=True, closure=("ThreeDimensional", 1e-3, 2e-3), f=0.3,
+                                          ts="RungeKutta3", dt=2e-3),
     "channel_bounded_yz_weno": dict(size=(8, 12, 10), topology=(O.Periodic, O.Bounded, O.Bounded), extent=(1, 1, 1),
                                     adv="WENO5", tracers=("b",), buoyancy=True, closure=("Horizontal", 1e-3, 1e-3),
                                     ts="RungeKutta3", dt=2e-3),
