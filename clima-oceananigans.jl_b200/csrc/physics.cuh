@@ -101,6 +101,7 @@ template <class FT> OBD FT deriv(const GridD<FT>& g, const FT* f, Pt q, int d, i
     FT del = loc == OB_C ? dC(g, f, q, d) : dFc(g, f, q, d);
 #ifndef OB200_STRICT
     if (g.regular[d]) return del * g.invd[d];       // one rounding instead of a Float64 division (~20 instructions)
+    if (d == 2 && g.izC) return del * (loc == OB_F ? g.izF[q.i[2]] : g.izC[q.i[2]]);      // stretched z: tabulated reciprocals
 #endif
     return del / spacing(g, d, loc, q.i[d]);
 }
