@@ -91,3 +91,14 @@ def test_host_weno_tables_match_oracle():
         for ri, r in enumerate((-1, 0, 1, 2)):
             for i in range(14):
                 assert np.allclose(s.coeff[2][li][ri][i], _eno_weights(r, nodes, i), rtol=0, atol=0)
+
+
+def test_field_slicer_index_boxes():
+    """FieldSlicer (OutputWriters/field_slicer.jl): host logic only -- index ranges with and without halos"""
+    import types
+    from ocean_b200.output_writers import FieldSlicer
+    f = types.SimpleNamespace(size=lambda: (8, 6, 5), grid=types.SimpleNamespace(H=(3, 2, 1)))
+    assert FieldSlicer().box(f) == ([1, 1, 1], [8, 6, 5])
+    assert FieldSlicer(with_halos=True).box(f) == ([-2, -1, 0], [11, 8, 6])
+    assert FieldSlicer(k=3).box(f) == ([1, 1, 3], [8, 6, 3])
+    assert FieldSlicer(i=(2, 4), j=5, with_halos=True).box(f) == ([2, 5, 0], [4, 5, 6])
