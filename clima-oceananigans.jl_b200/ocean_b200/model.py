@@ -451,8 +451,9 @@ class NonhydrostaticModel:
     """NonhydrostaticModel(; grid, advection, closure, coriolis, buoyancy, tracers, timestepper,
     boundary_conditions) (src/Models/NonhydrostaticModels/nonhydrostatic_model.jl:102-203).
     Defaults as in the reference: advection = CenteredSecondOrder(), timestepper =
-    :QuasiAdamsBashforth2.  Unsupported pieces (forcings, function BCs, LES closures, immersed
-    boundaries, background fields, particles) raise ArgumentError-like ValueErrors."""
+    :QuasiAdamsBashforth2.  Unsupported pieces (forcings, function BCs, immersed boundaries, background
+    fields, particles, closures other than ScalarDiffusivity / SmagorinskyLilly / AnisotropicMinimumDissipation)
+    raise ArgumentError-like ValueErrors."""
 
     def __init__(self, grid, advection="default", closure=None, coriolis=None, buoyancy=None, tracers=(),
                  timestepper="QuasiAdamsBashforth2", boundary_conditions=None, forcing=None,

@@ -786,3 +786,29 @@ def test_fourier_tridiagonal_solve_is_history_free_and_well_conditioned(ob):
         O.FourierTridiagonalPoissonSolver(go).solve(po, rc)
         ob.solve(p1, s1, rc)
         assert relerr(p1.interior(), po.interior) < 1e-11
+
+
+@pytest.mark.parametrize("form,ν,κ,want", [("ThreeDimensional", 0.3, 0.7, dict(T=2 * 0.7, u=2 * 0.3, v=4 * 0.3, w=6 * 0.3)),
+                                           ("Horizontal", 0.3, 0.7, dict(T=8 * 0.7, u=2 * 0.3, v=4 * 0.3, w=6 * 0.3)),
+                                           ("Vertical", 0.1, 0.5, dict(T=10 * 0.5, u=4 * 0.1, v=6 * 0.1, w=8 * 0.1))])
+def test_closure_flux_divergence_known_answers_on_cuda(ob, form, ν, κ, want):
+    """the reference's hand-computed closure flux divergences (test/test_turbulence_closures.jl:26-101: -2κ, -2ν, -4ν, -6ν for the
+    isotropic closure; -8κh, -10κz, ... for the horizontal / vertical ones) as the TENDENCIES of a model with nothing but the
+    closure, through the CUDA path; independent of the oracle"""
+    gb = ob.RectilinearGrid(ob.arch, np.float64, size=(3, 1, 4), extent=(3, 1, 4), topology=("Periodic", "Periodic", "Bounded"))
+    m = ob.NonhydrostaticModel(gb, advection=None, closure=ob.ScalarDiffusivity(form, ν=ν, κ=κ), tracers=("T",))
+    if form == "ThreeDimensional":
+        lines = {n: {k: [0, c, 0] for k in (1, 2, 3, 4)} for n, c in (("u", -0.5), ("v", -2), ("w", -3), ("T", -1))}
+    else:
+        lines = {n: {2: [0, 1, 0], 3: [0, c, 0], 4: [0, 1, 0]} for n, c in (("u", -1), ("v", -2), ("w", -3), ("T", -4))}
+    for n, prof in lines.items():
+        f = m.fields[n]
+        a = np.zeros(f.size())
+        for k, line in prof.items():
+            a[:, 0, k - 1] = line
+        f.set(a)                                  # no projection: the reference test sets the arrays directly
+    ob.update_state(m)
+    ob.calculate_tendencies(m)
+    for n, val in want.items():
+        got = m.Gn[n].interior()[1, 0, 2]         # Julia (2, 1, 3); tendency = -(flux divergence)
+        assert abs(got - val) <= 4e-16 * abs(val), (n, got, val)

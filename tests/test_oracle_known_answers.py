@@ -462,3 +462,51 @@ def test_amd_known_answers():
     inner = (slice(2, -2),) * 3
     assert np.allclose(m.νe.interior[inner], (1 / 12) * 4 * D * D, rtol=1e-12)
     assert np.allclose(m.κe["c"].interior[inner], 8 * (1 / 6) * D * D, rtol=1e-12)
+
+
+# ---- closure flux divergences with hand-computed answers (test/test_turbulence_closures.jl:26-101) -------------------------------
+def _closure_fixture(values):
+    """grid (3, 1, 4), extent (3, 1, 4) (unit spacings); values: field name -> {k (1-based): [x-line]}"""
+    from oracle.fields import fill_halo_regions
+    g = O.RectilinearGrid(np.float64, size=(3, 1, 4), extent=(3, 1, 4), topology=(O.Periodic, O.Periodic, O.Bounded))
+    F = {"u": O.Field(g, ("f", "c", "c")), "v": O.Field(g, ("c", "f", "c")), "w": O.Field(g, ("c", "c", "f")),
+         "T": O.Field(g, ("c", "c", "c"))}
+    for n, f in F.items():
+        a = np.zeros(f.size())
+        for kk, line in values.get(n, {}).items():
+            a[:, 0, kk - 1] = line
+        f.set(a)
+    fill_halo_regions(list(F.values()))
+    return g, F
+
+
+def test_constant_isotropic_diffusivity_flux_divergence_known_answers():
+    """run_constant_isotropic_diffusivity_fluxdiv_tests (:26-56): the reference asserts EXACT equality with -2κ, -2ν, -4ν, -6ν"""
+    from oracle import closures as CL
+    ν, κ = 0.3, 0.7
+    every = lambda line: {k: line for k in (1, 2, 3, 4)}
+    g, F = _closure_fixture({"u": every([0, -1 / 2, 0]), "v": every([0, -2, 0]), "w": every([0, -3, 0]), "T": every([0, -1, 0])})
+    clo = CL.ScalarDiffusivity(ν=ν, κ=κ)
+    i, j, k = O.R(2, 2), O.R(1, 1), O.R(3, 3)
+    assert CL.div_q(i, j, k, g, clo, κ, F["T"]).item() == -2 * κ
+    assert CL.div_τ(0, i, j, k, g, clo, F["u"], F["v"], F["w"]).item() == -2 * ν
+    assert CL.div_τ(1, i, j, k, g, clo, F["u"], F["v"], F["w"]).item() == -4 * ν
+    assert CL.div_τ(2, i, j, k, g, clo, F["u"], F["v"], F["w"]).item() == -6 * ν
+
+
+@pytest.mark.parametrize("νh,νz", [(0.3, 0.1), (0.0, 0.0)])
+def test_horizontal_and_vertical_diffusivity_flux_divergence_known_answers(νh, νz):
+    """horizontal_diffusivity_fluxdiv (:58-101): HorizontalScalarDiffusivity and VerticalScalarDiffusivity, exact equality"""
+    from oracle import closures as CL
+    κh, κz = 0.7, 0.5
+    prof = lambda c: {2: [0, 1, 0], 3: [0, c, 0], 4: [0, 1, 0]}
+    g, F = _closure_fixture({"u": prof(-1), "v": prof(-2), "w": prof(-3), "T": prof(-4)})
+    H = CL.ScalarDiffusivity("Horizontal", ν=νh, κ=κh)
+    V = CL.ScalarDiffusivity("Vertical", ν=νz, κ=κz)
+    i, j, k = O.R(2, 2), O.R(1, 1), O.R(3, 3)
+    U = (F["u"], F["v"], F["w"])
+    assert CL.div_q(i, j, k, g, H, κh, F["T"]).item() == -8 * κh
+    assert CL.div_q(i, j, k, g, V, κz, F["T"]).item() == -10 * κz
+    for comp, (ah, az) in enumerate(((2, 4), (4, 6), (6, 8))):
+        assert CL.div_τ(comp, i, j, k, g, H, *U).item() == -(ah * νh)
+        assert CL.div_τ(comp, i, j, k, g, V, *U).item() == -(az * νz)
