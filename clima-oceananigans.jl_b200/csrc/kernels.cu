@@ -400,7 +400,9 @@ __global__ void __launch_bounds__(128) tendency_general_kernel(const __grid_cons
 // SPEC = 1: the configuration class of BASELINE config 3 (x, y Periodic and regular, z Bounded, WENO5, vertical gravity,
 // explicit closure): the kernel works on a LOCAL copy of the physics descriptor whose flags are overwritten with these
 // constants, so that after inlining every run-time scheme / topology / regularity branch of the operator tree folds away.
-template <class FT, int COMP, int SPEC>
+// CO = 1: closure-only (TendArgs::closure_only) as a compile-time flag, so that the advection operators are not part of the
+// kernel at all (registers, occupancy)
+template <class FT, int COMP, int SPEC, int CO = 0>
 __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_constant__ Phys<FT> Pin, const __grid_constant__ TendArgs<FT> A, int Kc) {
     Phys<FT> Pl;
     if constexpr (SPEC == 1) {
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
     const bool need_x = outy && i <= g.N[0] + 1, need_y = outx && j <= g.N[1] + 1;
     const FT* U[3] = {A.U[0], A.U[1], A.U[2]};
     const int comp = COMP == 3 ? A.comp : COMP;
-    const bool visc = P.closure != CLO_NONE, adv = P.scheme != ADV_NONE && !A.closure_only;
+    const bool visc = P.closure != CLO_NONE, adv = !CO && P.scheme != ADV_NONE && !A.closure_only;
     const FT kappa = COMP == 3 ? Pin.kappa[comp - 3] : FT(0);
     const FT* kappae = COMP == 3 ? Pin.kappae[comp - 3] : nullptr;
     auto face = [&](int d, Pt q) -> FT {       // area-weighted advective + viscous / diffusive flux at q along d
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_co
             int l[3] = {OB_C, OB_C, OB_C};
             if (COMP < 3) l[COMP] = OB_F;
             FT G = -((1 / volume(g, q, l[0], l[1], l[2])) * ((dFx + dFy) + dFz));
-            if (A.closure_only) {
+            if (CO || A.closure_only) {
                 A.Gn[q.p] = G;
             } else {
             if (COMP == 0) {
@@ -541,7 +543,8 @@ void launch_tendency_general(const Phys<FT>& P, int comp, const FT* const U[3], 
         const int Kc = 32;
         dim3 bs(32, 8, 1), gs(cdiv(P.g.N[0], 31), cdiv(P.g.N[1], 7), cdiv(P.g.N[2], Kc));
         switch (comp) {
-#define SHK(C, S) tendency_shared_kernel<FT, C, S><<<gs, bs, 0, stream()>>>(P, A, Kc)
+#define SHK(C, S) do { if (closure_only) tendency_shared_kernel<FT, C, S, 1><<<gs, bs, 0, stream()>>>(P, A, Kc); \
+                       else tendency_shared_kernel<FT, C, S, 0><<<gs, bs, 0, stream()>>>(P, A, Kc); } while (0)
             case 0: if (spec) SHK(0, 1); else SHK(0, 0); break;
             case 1: if (spec) SHK(1, 1); else SHK(1, 0); break;
             case 2: if (spec) SHK(2, 1); else SHK(2, 0); break;
