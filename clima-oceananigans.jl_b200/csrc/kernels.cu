@@ -401,9 +401,9 @@ __global__ void __launch_bounds__(128) tendency_general_kernel(const __grid_cons
 // explicit closure): the kernel works on a LOCAL copy of the physics descriptor whose flags are overwritten with these
 // constants, so that after inlining every run-time scheme / topology / regularity branch of the operator tree folds away.
 // CO = 1: closure-only (TendArgs::closure_only) as a compile-time flag, so that the advection operators are not part of the
-// kernel at all (registers, occupancy)
+// kernel at all, with 4 resident blocks per SM (64 registers; C3 with AMD: 3 blocks 64.3, 4 blocks 60.5, 5 blocks 62.0 ms per step)
 template <class FT, int COMP, int SPEC, int CO = 0>
-__global__ void __launch_bounds__(256, 3) tendency_shared_kernel(const __grid_constant__ Phys<FT> Pin, const __grid_constant__ TendArgs<FT> A, int Kc) {
+__global__ void __launch_bounds__(256, (CO ? 4 : 3)) tendency_shared_kernel(const __grid_constant__ Phys<FT> Pin, const __grid_constant__ TendArgs<FT> A, int Kc) {
     Phys<FT> Pl;
     if constexpr (SPEC == 1) {
         Pl = Pin;
