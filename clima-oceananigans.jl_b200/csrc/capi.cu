@@ -1157,6 +1157,7 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
     }
     model_halo_join(m);
     if (fork) OB_CUDA(cudaEventRecord(ev_fork, g_stream));
+    bool lane_forked[3] = {false, false, false};        // a side stream waits for the fork event before its first launch
     for (int q = first; q < m->nf; ++q) {
         ob200_field* f = m->F[q].get();
         FluxBC<FT> fbc;
@@ -1165,7 +1166,7 @@ static void model_tendencies(ob200_model* m, const Substep<FT>& ss) {
         bool done = false;
         const int lane = fork ? q % 4 : 0;               // lane 0 = the library stream itself
         if (lane > 0) {
-            if (q < 4) OB_CUDA(cudaStreamWaitEvent(side[lane - 1], ev_fork, 0));
+            if (!lane_forked[lane - 1]) { OB_CUDA(cudaStreamWaitEvent(side[lane - 1], ev_fork, 0)); lane_forked[lane - 1] = true; }
             g_override = side[lane - 1];
         }
         try {
